@@ -1,0 +1,203 @@
+/*
+ * stroke_b200.h — C-ABI of libstroke_b200.so (sm_100a kernels for the volumetric CAE / U-Net hot path).
+ *
+ * The reference (multimodallearning/stroke-prediction) has no FFI: every arithmetic op on its hot path is a call
+ * into the torch 0.3.1 wheel from common/model/Cae3D.py, common/model/Unet3D.py, common/metrics.py and
+ * learner/*.py.  Each entry point below therefore cites the reference call-site(s) (file:line, relative to the
+ * reference root) whose torch op it replaces.
+ *
+ * Conventions
+ *   - All tensors are fp32, dense NDHWC ("channels_last_3d"): element (n,d,h,w,c) lives at
+ *     (((n*D + d)*H + h)*W + w)*ld + c, where ld (floats per voxel) >= C lets a kernel address a channel slice
+ *     of a wider (concatenated) buffer.  Pointers are device pointers, 16-byte aligned.
+ *   - The library never allocates tensor memory.  Workspaces are sized by the *_workspace_bytes query and
+ *     passed in by the caller.
+ *   - Every call is asynchronous on `stream` (a cudaStream_t passed as void*), never synchronises the device,
+ *     is re-entrant and CUDA-graph-capture safe.
+ *   - Return value: 0 = success; negative = argument/shape error (nothing launched); positive = cudaError_t of
+ *     the failed launch.  sp_last_error() returns a thread-local message.
+ *   - "G" (statistic groups): a batch of N samples may be G independent BatchNorm calls stacked along N
+ *     (the CAE runs its encoder 3x and decoder 4x per step with separate batch statistics,
+ *     Cae3D.py:105-110,230-233).  Per-channel BN vectors are laid out [G][C]; sample n belongs to group n/(N/G).
+ */
+#ifndef STROKE_B200_H
+#define STROKE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SP_VERSION 100
+
+/* activation codes (epilogues / derivative-from-output rules) */
+enum SpAct {
+    SP_ACT_NONE = 0,
+    SP_ACT_ELU = 1,      /* nn.ELU(alpha)        Cae3D.py:42..216                      */
+    SP_ACT_LEAKY = 2,    /* nn.LeakyReLU(alpha)  Unet3D.py:20,23,51                    */
+    SP_ACT_SIGMOID = 3   /* nn.Sigmoid           Cae3D.py:136,219; Unet3D.py:53        */
+};
+
+/*
+ * Geometry of one cubic convolution, stated for the *correlation* direction:
+ *   O[n,o,co] = sum_{tap,ci} I[n, o*s - p + tap, ci] * W[co,ci,tap]
+ * I ("I-side") is the larger tensor of a strided conv, O ("O-side") the smaller.
+ *   nn.Conv3d forward            = sp_corr        (src = I-side, dst = O-side)
+ *   nn.Conv3d dgrad              = sp_corrT       (src = O-side, dst = I-side)
+ *   nn.ConvTranspose3d forward   = sp_corrT       (its weight (Cin_T,Cout_T,k,k,k) is exactly W[co][ci][tap])
+ *   nn.ConvTranspose3d dgrad     = sp_corr
+ *   weight gradient of either    = sp_wgrad
+ */
+typedef struct SpConvDesc {
+    int32_t N;                      /* samples (all groups stacked)                                   */
+    int32_t Di, Hi, Wi, Ci, ldi;    /* I-side extents, channels, floats per voxel                     */
+    int32_t Do, Ho, Wo, Co, ldo;    /* O-side extents, channels, floats per voxel                     */
+    int32_t k;                      /* cubic kernel extent: 1, 2 or 3                                 */
+    int32_t s;                      /* stride (same on all axes): 1 or 2                              */
+    int32_t pd, ph, pw;             /* zero padding of the I-side per axis (may exceed (k-1)/2)       */
+    int32_t act;                    /* SpAct applied to dst after bias                                */
+    float   alpha;                  /* ELU alpha / LeakyReLU slope                                    */
+} SpConvDesc;
+
+int         sp_version(void);
+const char* sp_last_error(void);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Convolution family.  Replaces nn.Conv3d (Cae3D.py:41,44,48,52,55,59,63,66,70,74,126,128,132,186,189,197,200,
+ * 208,211,215,218; Unet3D.py:19,22,50,52) and nn.ConvTranspose3d (Cae3D.py:178,182,193,204), forward + backward.
+ *
+ * Weights are consumed in a packed layout produced by sp_pack_weights from the torch layout W[co][ci][k^3]
+ * (for ConvTranspose3d the torch layout (Cin_T,Cout_T,k,k,k) is already W[co][ci][tap] of the equivalent
+ * correlation).  `which`: 0 = for sp_corr, 1 = for sp_corrT.
+ *
+ * Source prologue (optional, scale != NULL): v <- v*scale[g][c] + shift[g][c] applied to real voxels only, so
+ * zero padding stays zero *after* BatchNorm (Cae3D.py:40-41 ordering BN -> padded conv).
+ * Destination epilogue: + bias[c] (optional), then desc->act.
+ * ---------------------------------------------------------------------------------------------------------- */
+size_t sp_packed_weight_floats(const SpConvDesc* d, int which);
+int    sp_pack_weights(const SpConvDesc* d, int which, const float* w_torch, float* w_packed, void* stream);
+
+int sp_corr (const SpConvDesc* d, const float* src_iside, const float* w_packed, const float* bias,
+             const float* scale, const float* shift, int G, float* dst_oside, void* stream);
+int sp_corrT(const SpConvDesc* d, const float* src_oside, const float* w_packed, const float* bias,
+             const float* scale, const float* shift, int G, float* dst_iside, void* stream);
+
+/* dW[co][ci][tap] (torch layout) = beta*dW + sum_{n,o} O'[n,o,co] * I'[n,o*s-p+tap,ci], where I' / O' are the
+ * I-side / O-side tensors after their optional per-(group,channel) affine prologue (BatchNorm of the layer
+ * input; zero padding stays zero).  Deterministic two-stage reduction through `ws`. */
+size_t sp_wgrad_workspace_bytes(const SpConvDesc* d);
+int    sp_wgrad(const SpConvDesc* d, const float* iside, const float* i_scale, const float* i_shift,
+                const float* oside, const float* o_scale, const float* o_shift, int G,
+                float* dw_torch, float beta, void* ws, size_t ws_bytes, void* stream);
+
+/* db[c] = beta*db[c] + sum over rows of g[row*ld + c]   (bias gradient of Conv3d / ConvTranspose3d);
+ * ws: C doubles of scratch */
+int sp_bias_grad(const float* g, int64_t rows, int C, int ld, float* db, float beta, double* ws, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * BatchNorm3d (Cae3D.py:40..217, Unet3D.py:18,21), training and eval mode, forward statistics and backward.
+ * The normalisation itself is never materialised: sp_bn_finalize emits scale/shift that the consuming
+ * convolution applies while staging its input.
+ * ---------------------------------------------------------------------------------------------------------- */
+/* sums[g][c][0..1] (fp64) = sum x, sum x^2 over the group's voxels.  x: [N][vox][ld] */
+int sp_bn_stats(const float* x, int N, int64_t vox, int C, int ld, int G, double* sums, void* stream);
+/* training != 0: batch statistics (biased var for normalisation), running stats updated group after group with
+ * momentum (unbiased var), num_batches_tracked += G.  training == 0: running stats.
+ * Outputs scale/shift/mean/invstd as [G][C] floats. */
+int sp_bn_finalize(const double* sums, int64_t count_per_group, int C, int G, const float* gamma,
+                   const float* beta, float* running_mean, float* running_var, int64_t* num_batches_tracked,
+                   float momentum, float eps, int training, float* scale, float* shift, float* mean,
+                   float* invstd, void* stream);
+/* bsums[g][c][0..1] (fp64) = sum gxh, sum gxh*x  (gxh = gradient w.r.t. the BN output) */
+int sp_bn_bwd_reduce(const float* gxh, int ldg, const float* x, int ldx, int N, int64_t vox, int C, int G,
+                     double* bsums, void* stream);
+/* dgamma/dbeta (accumulated with `beta_acc`, NULL to skip) and the coefficients of
+ *   gx = A[g][c]*gxh + B[g][c]*x + Cc[g][c]        (coef layout [3][G][C]) */
+int sp_bn_bwd_finalize(const double* bsums, int64_t count_per_group, int C, int G, const float* gamma,
+                       const float* mean, const float* invstd, int training, float* dgamma, float* dbeta,
+                       float beta_acc, float* coef, void* stream);
+/* out = (A*gxh + B*x + Cc) * act'(x)   — BN backward apply fused with the backward of the activation that
+ * produced x (derivative computed from the activation output).  coef == NULL: out = gxh*act'(x).
+ * `accumulate` != 0: out += ...  */
+int sp_bn_act_bwd_apply(const float* gxh, int ldg, const float* x, int ldx, const float* coef, int N,
+                        int64_t vox, int C, int G, int act, float alpha, float* out, int ldout, int accumulate,
+                        void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Resampling ops of the U-Net (Unet3D.py:39,41 MaxPool3d(2,2); :44,46 Upsample(x2, trilinear); :6-11,66-67,71-72
+ * crop + cat) and layout glue.
+ * ---------------------------------------------------------------------------------------------------------- */
+int sp_maxpool2_fwd(const float* x, int N, int D, int H, int W, int C, int ldx, float* y, int ldy, void* stream);
+/* gx (dense, ld = C) = route gy to the first maximum of each 2x2x2 window in d->h->w scan order, 0 elsewhere */
+int sp_maxpool2_bwd(const float* x, const float* y, const float* gy, int N, int D, int H, int W, int C,
+                    float* gx, void* stream);
+int sp_upsample2_fwd(const float* x, int N, int D, int H, int W, int C, int ldx, float* y, int ldy,
+                     int align_corners, void* stream);
+int sp_upsample2_bwd(const float* gy, int ldgy, int N, int D, int H, int W, int C, float* gx, int ldgx,
+                     int align_corners, void* stream);
+/* dst[n, d, h, w, 0:C] (ld = ldd) (+)= src[n, d+od, h+oh, w+ow, 0:C] (ld = lds) over the dst extents;
+ * used for centre-crop into a concat slice (forward) */
+int sp_crop_copy(const float* src, int Ds, int Hs, int Ws, int lds, float* dst, int Dd, int Hd, int Wd, int ldd,
+                 int N, int C, int od, int oh, int ow, void* stream);
+/* big[n, d+od, h+oh, w+ow, 0:C] += small[n,d,h,w,0:C]  (gradient of the centre-crop, accumulated in place) */
+int sp_crop_add(float* big, int Db, int Hb, int Wb, int ldb, const float* small, int Ds, int Hs, int Ws, int lds,
+                int N, int C, int od, int oh, int ow, void* stream);
+/* dense NCDHW <-> NDHWC */
+int sp_ncdhw_to_ndhwc(const float* src, float* dst, int N, int C, int64_t vox, void* stream);
+int sp_ndhwc_to_ncdhw(const float* src, float* dst, int N, int C, int64_t vox, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Losses.  BatchDiceLoss (metrics.py:16-28), hinge mean(abs(d)-d) and L1 mean(abs(a-b))
+ * (CaeReconstructionLearner.py:59-62,68; CaeStepLearner.py:18-19; CaePredictionLearner.py:46-55).
+ * Reductions accumulate in fp64 on the device; no host synchronisation.
+ * ---------------------------------------------------------------------------------------------------------- */
+/* sums[0..2] (fp64, must be zeroed by the call itself) = sum o*t, sum o*o, sum t*t over n elements */
+int sp_dice_sums(const float* o, const float* t, int64_t n, double* sums, void* stream);
+/* loss[0] = 1 - w*(2*sums[0]+eps)/(sums[1]+sums[2]+eps) */
+int sp_dice_loss(const double* sums, float w, float eps, float* loss, void* stream);
+/* go[i] (+)= gscale[0]*gmul * ( -w*(2*t*den - 2*o*num)/den^2 ) */
+int sp_dice_bwd(const float* o, const float* t, int64_t n, const double* sums, float w, float eps,
+                const float* gscale, float gmul, float* go, int accumulate, void* stream);
+/* mode 0: hinge  out = mean(|a-b| - (a-b));  mode 1: L1  out = mean(|a-b|) */
+int sp_absdiff_mean(const float* a, const float* b, int64_t n, int mode, double* sum_ws, float* out, void* stream);
+/* ga (+)= g*gmul/n * dmode(a-b), gb (+)= -(same); either may be NULL.  sign(0) = 0. */
+int sp_absdiff_bwd(const float* a, const float* b, int64_t n, int mode, const float* gscale, float gmul,
+                   float* ga, int acc_a, float* gb, int acc_b, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Latent interpolation z_c + s*(z_p - z_c), s per sample (Cae3D.py:78-89).
+ * ---------------------------------------------------------------------------------------------------------- */
+int sp_latent_interp_fwd(const float* zc, const float* zp, const float* step, int B, int64_t per_sample,
+                         float* out, void* stream);
+/* dzc (+)= g*(1-s), dzp (+)= g*s, dstep[b] = sum g*(zp-zc)  (any output may be NULL; ws: B doubles when
+ * dstep is requested) */
+int sp_latent_interp_bwd(const float* g, const float* zc, const float* zp, const float* step, int B,
+                         int64_t per_sample, float* dzc, int acc_c, float* dzp, int acc_p, float* dstep,
+                         double* ws, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Fused multi-tensor Adam step (torch.optim.Adam as configured at train_shape_reconstruction.py:40,
+ * train_unet_segmentation.py:32; beta1 schedule CaeReconstructionLearner.py:28-40):
+ *   g += wd*p; m += (g-m)(1-b1); v = b2*v + (1-b2) g^2; p -= (lr/(1-b1^t)) * m / (sqrt(v)/sqrt(1-b2^t) + eps)
+ * `table` is a device array of SpAdamTensor; one launch updates all tensors.  grad_scale multiplies g first
+ * (1/world_size after a sum all-reduce).  zero_grad != 0 clears g afterwards (optimizer.zero_grad, Learner.py:120).
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct SpAdamTensor {
+    float*  p;
+    float*  g;
+    float*  m;
+    float*  v;
+    int64_t n;
+    int64_t block_start;   /* first CTA index that works on this tensor (prefix sum of ceil(n/SP_ADAM_CHUNK)) */
+} SpAdamTensor;
+#define SP_ADAM_CHUNK 4096
+int sp_adam_multi(const SpAdamTensor* table, int n_tensors, int64_t total_blocks, float lr, float beta1,
+                  float beta2, float eps, float weight_decay, int64_t step, float grad_scale, int zero_grad,
+                  void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* STROKE_B200_H */

@@ -1,0 +1,521 @@
+// sp_conv.cu — correlation / transposed correlation / weight-gradient kernels (fp32, NDHWC) and their C-ABI.
+//
+// Reference call sites replaced: nn.Conv3d and nn.ConvTranspose3d forward/backward at
+// common/model/Cae3D.py:41-74,126-132,178-218 and common/model/Unet3D.py:19,22,50,52 (see include/stroke_b200.h).
+//
+// Two kernel tiers:
+//   * generic kernels (this file, *_generic_kernel): any k in {1,2,3}, s in {1,2}, any padding / channel count.
+//     One thread owns one destination voxel x 8 destination channels and walks the taps straight from global
+//     memory.  They are the correctness baseline and serve the HBM-bound layers (1x1x1, k2s2, C<=3).
+//   * tiled kernels (sp_conv_tiled.cuh): 3x3x3 stride-1 correlation on shared-memory halo tiles with an 8x8
+//     register micro-tile per thread — the FFMA-bound 16..96-channel layers.
+#include "sp_common.cuh"
+#include "sp_conv_tiled.cuh"
+
+namespace {
+
+constexpr int kPad = 16;  // packed weights pad the fastest (destination-channel) axis to a multiple of 16
+
+__host__ __device__ inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
+
+int check_desc(const SpConvDesc* d) {
+    SP_REQUIRE(d != nullptr, "SpConvDesc is NULL");
+    SP_REQUIRE(d->N > 0 && d->Ci > 0 && d->Co > 0, "conv: N, Ci, Co must be positive (N=%d Ci=%d Co=%d)", d->N, d->Ci, d->Co);
+    SP_REQUIRE(d->k >= 1 && d->k <= 3, "conv: kernel extent %d not in {1,2,3}", d->k);
+    SP_REQUIRE(d->s == 1 || d->s == 2, "conv: stride %d not in {1,2}", d->s);
+    SP_REQUIRE(d->pd >= 0 && d->ph >= 0 && d->pw >= 0, "conv: negative padding");
+    SP_REQUIRE(d->ldi >= d->Ci && d->ldo >= d->Co, "conv: ld smaller than channel count");
+    SP_REQUIRE(d->Di > 0 && d->Hi > 0 && d->Wi > 0 && d->Do > 0 && d->Ho > 0 && d->Wo > 0, "conv: empty extent");
+    // O-side extents are the floor-mode output size of the I-side (the same relation ConvTranspose3d inverts).
+    SP_REQUIRE(d->Di + 2 * d->pd >= d->k && d->Hi + 2 * d->ph >= d->k && d->Wi + 2 * d->pw >= d->k,
+               "conv: kernel larger than padded I-side");
+    SP_REQUIRE(d->Do == (d->Di + 2 * d->pd - d->k) / d->s + 1 && d->Ho == (d->Hi + 2 * d->ph - d->k) / d->s + 1 &&
+                   d->Wo == (d->Wi + 2 * d->pw - d->k) / d->s + 1,
+               "conv: O-side %dx%dx%d inconsistent with I-side %dx%dx%d (k=%d s=%d p=%d,%d,%d)", d->Do, d->Ho, d->Wo,
+               d->Di, d->Hi, d->Wi, d->k, d->s, d->pd, d->ph, d->pw);
+    SP_REQUIRE(d->act >= SP_ACT_NONE && d->act <= SP_ACT_SIGMOID, "conv: unknown activation %d", d->act);
+    return 0;
+}
+
+// ---- weight packing -----------------------------------------------------------------------------------------
+// which = 0: Wc[tap][ci][coP]   (sp_corr:  destination channel = co)
+// which = 1: Wt[tap][co][ciP]   (sp_corrT: destination channel = ci)
+__global__ void pack_weights_kernel(const float* __restrict__ w, float* __restrict__ wp, int Co, int Ci, int k3,
+                                    int which, int dP) {
+    const int64_t total = (int64_t)k3 * (which == 0 ? Ci : Co) * dP;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int dch = (int)(i % dP);
+        int64_t t = i / dP;
+        float v = 0.f;
+        if (which == 0) {
+            const int ci = (int)(t % Ci), tap = (int)(t / Ci);
+            if (dch < Co) v = w[((int64_t)dch * Ci + ci) * k3 + tap];
+        } else {
+            const int co = (int)(t % Co), tap = (int)(t / Co);
+            if (dch < Ci) v = w[((int64_t)co * Ci + dch) * k3 + tap];
+        }
+        wp[i] = v;
+    }
+}
+
+// ---- generic correlation: one thread = one O-side voxel x COT output channels ------------------------------------
+template <int COT>
+__global__ void __launch_bounds__(256)
+corr_generic_kernel(SpConvDesc d, int nPerG, int coP, const float* __restrict__ src, const float* __restrict__ wp,
+                    const float* __restrict__ bias, const float* __restrict__ scale, const float* __restrict__ shift,
+                    float* __restrict__ dst) {
+    const int ncg = coP / COT;
+    const int64_t total = (int64_t)d.N * d.Do * d.Ho * d.Wo * ncg;
+    const bool vec = (d.Ci % 4 == 0) && (d.ldi % 4 == 0);
+    for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int cg = (int)(idx % ncg);
+        const int64_t v = idx / ncg;
+        int64_t t = v;
+        const int ow = (int)(t % d.Wo); t /= d.Wo;
+        const int oh = (int)(t % d.Ho); t /= d.Ho;
+        const int od = (int)(t % d.Do);
+        const int n = (int)(t / d.Do);
+        const int g = n / nPerG;
+        const float* sc = scale ? scale + (int64_t)g * d.Ci : nullptr;
+        const float* sh = scale ? shift + (int64_t)g * d.Ci : nullptr;
+        float acc[COT];
+#pragma unroll
+        for (int j = 0; j < COT; ++j) acc[j] = 0.f;
+        for (int kd = 0; kd < d.k; ++kd) {
+            const int id = od * d.s - d.pd + kd;
+            if (id < 0 || id >= d.Di) continue;
+            for (int kh = 0; kh < d.k; ++kh) {
+                const int ih = oh * d.s - d.ph + kh;
+                if (ih < 0 || ih >= d.Hi) continue;
+                for (int kw = 0; kw < d.k; ++kw) {
+                    const int iw = ow * d.s - d.pw + kw;
+                    if (iw < 0 || iw >= d.Wi) continue;
+                    const int tap = (kd * d.k + kh) * d.k + kw;
+                    const float* xp = src + ((((int64_t)n * d.Di + id) * d.Hi + ih) * d.Wi + iw) * d.ldi;
+                    const float* wq = wp + (int64_t)tap * d.Ci * coP + cg * COT;
+                    if (vec) {
+                        for (int ci = 0; ci < d.Ci; ci += 4) {
+                            float4 xv = *reinterpret_cast<const float4*>(xp + ci);
+                            if (sc) {
+                                xv.x = fmaf(xv.x, sc[ci + 0], sh[ci + 0]);
+                                xv.y = fmaf(xv.y, sc[ci + 1], sh[ci + 1]);
+                                xv.z = fmaf(xv.z, sc[ci + 2], sh[ci + 2]);
+                                xv.w = fmaf(xv.w, sc[ci + 3], sh[ci + 3]);
+                            }
+                            const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                const float* wr = wq + (int64_t)(ci + q) * coP;
+#pragma unroll
+                                for (int j = 0; j < COT; j += 4) {
+                                    const float4 wv = *reinterpret_cast<const float4*>(wr + j);
+                                    acc[j + 0] = fmaf(xs[q], wv.x, acc[j + 0]);
+                                    acc[j + 1] = fmaf(xs[q], wv.y, acc[j + 1]);
+                                    acc[j + 2] = fmaf(xs[q], wv.z, acc[j + 2]);
+                                    acc[j + 3] = fmaf(xs[q], wv.w, acc[j + 3]);
+                                }
+                            }
+                        }
+                    } else {
+                        for (int ci = 0; ci < d.Ci; ++ci) {
+                            float xv = xp[ci];
+                            if (sc) xv = fmaf(xv, sc[ci], sh[ci]);
+                            const float* wr = wq + (int64_t)ci * coP;
+#pragma unroll
+                            for (int j = 0; j < COT; j += 4) {
+                                const float4 wv = *reinterpret_cast<const float4*>(wr + j);
+                                acc[j + 0] = fmaf(xv, wv.x, acc[j + 0]);
+                                acc[j + 1] = fmaf(xv, wv.y, acc[j + 1]);
+                                acc[j + 2] = fmaf(xv, wv.z, acc[j + 2]);
+                                acc[j + 3] = fmaf(xv, wv.w, acc[j + 3]);
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        float* yp = dst + v * d.ldo;
+#pragma unroll
+        for (int j = 0; j < COT; ++j) {
+            const int co = cg * COT + j;
+            if (co < d.Co) {
+                float r = acc[j] + (bias ? bias[co] : 0.f);
+                yp[co] = sp_act_fwd(r, d.act, d.alpha);
+            }
+        }
+    }
+}
+
+// ---- generic transposed correlation (gather form): one thread = one I-side voxel x CIT channels -------------------
+template <int CIT>
+__global__ void __launch_bounds__(256)
+corrT_generic_kernel(SpConvDesc d, int nPerG, int ciP, const float* __restrict__ src, const float* __restrict__ wp,
+                     const float* __restrict__ bias, const float* __restrict__ scale, const float* __restrict__ shift,
+                     float* __restrict__ dst) {
+    const int ncg = ciP / CIT;
+    const int64_t total = (int64_t)d.N * d.Di * d.Hi * d.Wi * ncg;
+    const bool vec = (d.Co % 4 == 0) && (d.ldo % 4 == 0);
+    for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int cg = (int)(idx % ncg);
+        const int64_t v = idx / ncg;
+        int64_t t = v;
+        const int iw = (int)(t % d.Wi); t /= d.Wi;
+        const int ih = (int)(t % d.Hi); t /= d.Hi;
+        const int id = (int)(t % d.Di);
+        const int n = (int)(t / d.Di);
+        const int g = n / nPerG;
+        const float* sc = scale ? scale + (int64_t)g * d.Co : nullptr;
+        const float* sh = scale ? shift + (int64_t)g * d.Co : nullptr;
+        float acc[CIT];
+#pragma unroll
+        for (int j = 0; j < CIT; ++j) acc[j] = 0.f;
+        for (int kd = 0; kd < d.k; ++kd) {
+            const int td = id + d.pd - kd;
+            if (td < 0 || (td % d.s) != 0) continue;
+            const int od = td / d.s;
+            if (od >= d.Do) continue;
+            for (int kh = 0; kh < d.k; ++kh) {
+                const int th = ih + d.ph - kh;
+                if (th < 0 || (th % d.s) != 0) continue;
+                const int oh = th / d.s;
+                if (oh >= d.Ho) continue;
+                for (int kw = 0; kw < d.k; ++kw) {
+                    const int tw = iw + d.pw - kw;
+                    if (tw < 0 || (tw % d.s) != 0) continue;
+                    const int ow = tw / d.s;
+                    if (ow >= d.Wo) continue;
+                    const int tap = (kd * d.k + kh) * d.k + kw;
+                    const float* op = src + ((((int64_t)n * d.Do + od) * d.Ho + oh) * d.Wo + ow) * d.ldo;
+                    const float* wq = wp + (int64_t)tap * d.Co * ciP + cg * CIT;
+                    if (vec) {
+                        for (int co = 0; co < d.Co; co += 4) {
+                            float4 ov = *reinterpret_cast<const float4*>(op + co);
+                            if (sc) {
+                                ov.x = fmaf(ov.x, sc[co + 0], sh[co + 0]);
+                                ov.y = fmaf(ov.y, sc[co + 1], sh[co + 1]);
+                                ov.z = fmaf(ov.z, sc[co + 2], sh[co + 2]);
+                                ov.w = fmaf(ov.w, sc[co + 3], sh[co + 3]);
+                            }
+                            const float os[4] = {ov.x, ov.y, ov.z, ov.w};
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                const float* wr = wq + (int64_t)(co + q) * ciP;
+#pragma unroll
+                                for (int j = 0; j < CIT; j += 4) {
+                                    const float4 wv = *reinterpret_cast<const float4*>(wr + j);
+                                    acc[j + 0] = fmaf(os[q], wv.x, acc[j + 0]);
+                                    acc[j + 1] = fmaf(os[q], wv.y, acc[j + 1]);
+                                    acc[j + 2] = fmaf(os[q], wv.z, acc[j + 2]);
+                                    acc[j + 3] = fmaf(os[q], wv.w, acc[j + 3]);
+                                }
+                            }
+                        }
+                    } else {
+                        for (int co = 0; co < d.Co; ++co) {
+                            float ov = op[co];
+                            if (sc) ov = fmaf(ov, sc[co], sh[co]);
+                            const float* wr = wq + (int64_t)co * ciP;
+#pragma unroll
+                            for (int j = 0; j < CIT; j += 4) {
+                                const float4 wv = *reinterpret_cast<const float4*>(wr + j);
+                                acc[j + 0] = fmaf(ov, wv.x, acc[j + 0]);
+                                acc[j + 1] = fmaf(ov, wv.y, acc[j + 1]);
+                                acc[j + 2] = fmaf(ov, wv.z, acc[j + 2]);
+                                acc[j + 3] = fmaf(ov, wv.w, acc[j + 3]);
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        float* yp = dst + v * d.ldi;
+#pragma unroll
+        for (int j = 0; j < CIT; ++j) {
+            const int ci = cg * CIT + j;
+            if (ci < d.Ci) {
+                float r = acc[j] + (bias ? bias[ci] : 0.f);
+                yp[ci] = sp_act_fwd(r, d.act, d.alpha);
+            }
+        }
+    }
+}
+
+// ---- generic weight gradient --------------------------------------------------------------------------------
+// Work item = (tap, ci-quad, co-quad): a 4x4 register tile of dW.  grid.x covers the items, grid.y splits the
+// O-side voxels into chunks; each block writes its partial dW into ws[chunk] and a second kernel reduces the
+// chunks in fixed order (deterministic, no float atomics).
+struct WgradPlan {
+    int ciQ, coQ, items, blocks_x, chunks;
+    int64_t ov, per_chunk, wn;
+};
+
+WgradPlan wgrad_plan(const SpConvDesc* d) {
+    WgradPlan p;
+    p.ciQ = (d->Ci + 3) / 4;
+    p.coQ = (d->Co + 3) / 4;
+    const int k3 = d->k * d->k * d->k;
+    p.items = k3 * p.ciQ * p.coQ;
+    p.blocks_x = (p.items + 255) / 256;
+    p.ov = (int64_t)d->N * d->Do * d->Ho * d->Wo;
+    p.wn = (int64_t)d->Co * d->Ci * k3;
+    int64_t chunks = sp_cdiv(4 * 148, p.blocks_x);                 // ~4 CTAs per SM in flight
+    chunks = chunks < sp_cdiv(p.ov, 32) ? chunks : sp_cdiv(p.ov, 32);   // at least 32 voxels per chunk
+    const int64_t cap = (int64_t)(96u << 20) / (p.wn * 4);         // keep partials under 96 MB
+    if (chunks > cap) chunks = cap;
+    if (chunks < 1) chunks = 1;
+    p.chunks = (int)chunks;
+    p.per_chunk = sp_cdiv(p.ov, p.chunks);
+    return p;
+}
+
+template <bool VEC_I, bool VEC_O>
+__global__ void __launch_bounds__(256)
+wgrad_generic_kernel(SpConvDesc d, int nPerG, int ciQ, int coQ, int items, int64_t ov, int64_t per_chunk,
+                     const float* __restrict__ iside, const float* __restrict__ i_scale, const float* __restrict__ i_shift,
+                     const float* __restrict__ oside, const float* __restrict__ o_scale, const float* __restrict__ o_shift,
+                     float* __restrict__ ws) {
+    const int item = blockIdx.x * blockDim.x + threadIdx.x;
+    if (item >= items) return;
+    const int coq = item % coQ;
+    const int ciq = (item / coQ) % ciQ;
+    const int tap = item / (coQ * ciQ);
+    const int kw = tap % d.k, kh = (tap / d.k) % d.k, kd = tap / (d.k * d.k);
+    const int ci0 = ciq * 4, co0 = coq * 4;
+    const int k3 = d.k * d.k * d.k;
+
+    float acc[4][4];  // [co][ci]
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+
+    const int64_t v0 = (int64_t)blockIdx.y * per_chunk;
+    const int64_t v1 = (v0 + per_chunk < ov) ? v0 + per_chunk : ov;
+    // decode the first voxel, then advance incrementally
+    int64_t t = v0;
+    int ow = (int)(t % d.Wo); t /= d.Wo;
+    int oh = (int)(t % d.Ho); t /= d.Ho;
+    int od = (int)(t % d.Do);
+    int n = (int)(t / d.Do);
+
+    for (int64_t v = v0; v < v1; ++v) {
+        const int id = od * d.s - d.pd + kd, ih = oh * d.s - d.ph + kh, iw = ow * d.s - d.pw + kw;
+        if (id >= 0 && id < d.Di && ih >= 0 && ih < d.Hi && iw >= 0 && iw < d.Wi) {
+            const int g = n / nPerG;
+            const float* ip = iside + ((((int64_t)n * d.Di + id) * d.Hi + ih) * d.Wi + iw) * d.ldi + ci0;
+            const float* op = oside + v * d.ldo + co0;
+            float xi[4], xo[4];
+            if (VEC_I) {
+                const float4 a = *reinterpret_cast<const float4*>(ip);
+                xi[0] = a.x; xi[1] = a.y; xi[2] = a.z; xi[3] = a.w;
+            } else {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) xi[q] = (ci0 + q < d.Ci) ? ip[q] : 0.f;
+            }
+            if (VEC_O) {
+                const float4 a = *reinterpret_cast<const float4*>(op);
+                xo[0] = a.x; xo[1] = a.y; xo[2] = a.z; xo[3] = a.w;
+            } else {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) xo[q] = (co0 + q < d.Co) ? op[q] : 0.f;
+            }
+            if (i_scale) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    if (ci0 + q < d.Ci) xi[q] = fmaf(xi[q], i_scale[g * d.Ci + ci0 + q], i_shift[g * d.Ci + ci0 + q]);
+            }
+            if (o_scale) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    if (co0 + q < d.Co) xo[q] = fmaf(xo[q], o_scale[g * d.Co + co0 + q], o_shift[g * d.Co + co0 + q]);
+            }
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int b = 0; b < 4; ++b) acc[a][b] = fmaf(xo[a], xi[b], acc[a][b]);
+        }
+        if (++ow == d.Wo) {
+            ow = 0;
+            if (++oh == d.Ho) {
+                oh = 0;
+                if (++od == d.Do) { od = 0; ++n; }
+            }
+        }
+    }
+    float* wsp = ws + (int64_t)blockIdx.y * ((int64_t)d.Co * d.Ci * k3);
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b)
+            if (co0 + a < d.Co && ci0 + b < d.Ci) wsp[((int64_t)(co0 + a) * d.Ci + (ci0 + b)) * k3 + tap] = acc[a][b];
+}
+
+__global__ void wgrad_reduce_kernel(const float* __restrict__ ws, int chunks, int64_t wn, float* __restrict__ dw, float beta) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < wn; i += (int64_t)gridDim.x * blockDim.x) {
+        float s = 0.f;
+        for (int c = 0; c < chunks; ++c) s += ws[(int64_t)c * wn + i];
+        dw[i] = (beta == 0.f) ? s : fmaf(beta, dw[i], s);
+    }
+}
+
+// ---- bias gradient: column sums of a [rows][ld] matrix -----------------------------------------------------------
+__global__ void __launch_bounds__(256)
+bias_grad_partial_kernel(const float* __restrict__ g, int64_t rows, int C, int ld, int64_t rows_per_block, double* __restrict__ acc) {
+    // thread (r, c): c = tid % C-lanes; accumulate in fp64, block reduce through shared memory, fp64 atomics
+    extern __shared__ double sm[];
+    const int lanesC = C < 256 ? C : 256;
+    const int R = 256 / lanesC;
+    const int c_l = threadIdx.x % lanesC, r_l = threadIdx.x / lanesC;
+    const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
+    const int64_t r1 = (r0 + rows_per_block < rows) ? r0 + rows_per_block : rows;
+    for (int cb = 0; cb < C; cb += lanesC) {   // uniform trip count: every thread reaches the barriers below
+        const int c = cb + c_l;
+        double s = 0.0;
+        if (r_l < R && c < C)
+            for (int64_t r = r0 + r_l; r < r1; r += R) s += (double)g[r * ld + c];
+        sm[threadIdx.x] = s;
+        __syncthreads();
+        if (r_l == 0 && c < C) {
+            for (int q = 1; q < R; ++q) s += sm[q * lanesC + c_l];
+            atomicAdd(&acc[c], s);
+        }
+        __syncthreads();
+    }
+}
+__global__ void bias_grad_final_kernel(const double* __restrict__ acc, int C, float* __restrict__ db, float beta) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < C) db[c] = (beta == 0.f) ? (float)acc[c] : fmaf(beta, db[c], (float)acc[c]);
+}
+
+int grid_for(int64_t work_items, int threads = 256, int waves = 16) {
+    int64_t b = sp_cdiv(work_items, threads);
+    const int64_t cap = (int64_t)sp_num_sms() * waves;
+    if (b > cap) b = cap;
+    if (b < 1) b = 1;
+    return (int)b;
+}
+
+}  // namespace
+
+// =============================================================================================================
+extern "C" {
+
+size_t sp_packed_weight_floats(const SpConvDesc* d, int which) {
+    if (!d) return 0;
+    const int k3 = d->k * d->k * d->k;
+    return which == 0 ? (size_t)k3 * d->Ci * round_up(d->Co, kPad) : (size_t)k3 * d->Co * round_up(d->Ci, kPad);
+}
+
+int sp_pack_weights(const SpConvDesc* d, int which, const float* w_torch, float* w_packed, void* stream) {
+    if (int e = check_desc(d)) return e;
+    SP_REQUIRE(which == 0 || which == 1, "sp_pack_weights: which must be 0 (corr) or 1 (corrT)");
+    SP_REQUIRE(w_torch && w_packed, "sp_pack_weights: NULL pointer");
+    const int k3 = d->k * d->k * d->k;
+    const int dP = round_up(which == 0 ? d->Co : d->Ci, kPad);
+    const int64_t total = (int64_t)sp_packed_weight_floats(d, which);
+    pack_weights_kernel<<<grid_for(total), 256, 0, sp_stream(stream)>>>(w_torch, w_packed, d->Co, d->Ci, k3, which, dP);
+    SP_LAUNCH_OK("pack_weights_kernel");
+    return 0;
+}
+
+int sp_corr(const SpConvDesc* d, const float* src, const float* wp, const float* bias, const float* scale,
+            const float* shift, int G, float* dst, void* stream) {
+    if (int e = check_desc(d)) return e;
+    SP_REQUIRE(src && wp && dst, "sp_corr: NULL pointer");
+    SP_REQUIRE((scale == nullptr) == (shift == nullptr), "sp_corr: scale and shift must be given together");
+    SP_REQUIRE(G >= 1 && d->N % G == 0, "sp_corr: N=%d not divisible by G=%d", d->N, G);
+    const int coP = round_up(d->Co, kPad);
+    const int nPerG = d->N / G;
+    if (sp_tiled_corr_supported(d)) return sp_tiled_corr_launch(d, nPerG, src, wp, /*flip=*/0, bias, scale, shift, dst, sp_stream(stream));
+    const int64_t work = (int64_t)d->N * d->Do * d->Ho * d->Wo * (coP / 8);
+    corr_generic_kernel<8><<<grid_for(work), 256, 0, sp_stream(stream)>>>(*d, nPerG, coP, src, wp, bias, scale, shift, dst);
+    SP_LAUNCH_OK("corr_generic_kernel");
+    return 0;
+}
+
+int sp_corrT(const SpConvDesc* d, const float* src, const float* wp, const float* bias, const float* scale,
+             const float* shift, int G, float* dst, void* stream) {
+    if (int e = check_desc(d)) return e;
+    SP_REQUIRE(src && wp && dst, "sp_corrT: NULL pointer");
+    SP_REQUIRE((scale == nullptr) == (shift == nullptr), "sp_corrT: scale and shift must be given together");
+    SP_REQUIRE(G >= 1 && d->N % G == 0, "sp_corrT: N=%d not divisible by G=%d", d->N, G);
+    const int ciP = round_up(d->Ci, kPad);
+    const int nPerG = d->N / G;
+    if (d->s == 1) {
+        // stride 1: the transposed correlation is a correlation with flipped taps, swapped channel roles and
+        // padding k-1-p; Wt[tap][co][ciP] read with flipped tap index is exactly that correlation's Wc.
+        SpConvDesc f = *d;
+        f.Di = d->Do; f.Hi = d->Ho; f.Wi = d->Wo; f.Ci = d->Co; f.ldi = d->ldo;
+        f.Do = d->Di; f.Ho = d->Hi; f.Wo = d->Wi; f.Co = d->Ci; f.ldo = d->ldi;
+        f.pd = d->k - 1 - d->pd; f.ph = d->k - 1 - d->ph; f.pw = d->k - 1 - d->pw;
+        if (f.pd >= 0 && f.ph >= 0 && f.pw >= 0 && sp_tiled_corr_supported(&f))
+            return sp_tiled_corr_launch(&f, nPerG, src, wp, /*flip=*/1, bias, scale, shift, dst, sp_stream(stream));
+    }
+    const int64_t work = (int64_t)d->N * d->Di * d->Hi * d->Wi * (ciP / 8);
+    corrT_generic_kernel<8><<<grid_for(work), 256, 0, sp_stream(stream)>>>(*d, nPerG, ciP, src, wp, bias, scale, shift, dst);
+    SP_LAUNCH_OK("corrT_generic_kernel");
+    return 0;
+}
+
+size_t sp_wgrad_workspace_bytes(const SpConvDesc* d) {
+    if (!d || d->N <= 0) return 0;
+    size_t generic = 0, tiled = 0;
+    {
+        const WgradPlan p = wgrad_plan(d);
+        generic = (size_t)p.chunks * p.wn * sizeof(float);
+    }
+    tiled = sp_tiled_wgrad_workspace_bytes(d);
+    return (generic > tiled ? generic : tiled) + 256;
+}
+
+int sp_wgrad(const SpConvDesc* d, const float* iside, const float* i_scale, const float* i_shift, const float* oside,
+             const float* o_scale, const float* o_shift, int G, float* dw, float beta, void* ws, size_t ws_bytes,
+             void* stream) {
+    if (int e = check_desc(d)) return e;
+    SP_REQUIRE(iside && oside && dw && ws, "sp_wgrad: NULL pointer");
+    SP_REQUIRE((i_scale == nullptr) == (i_shift == nullptr) && (o_scale == nullptr) == (o_shift == nullptr),
+               "sp_wgrad: scale and shift must be given together");
+    SP_REQUIRE(G >= 1 && d->N % G == 0, "sp_wgrad: N=%d not divisible by G=%d", d->N, G);
+    SP_REQUIRE(ws_bytes >= sp_wgrad_workspace_bytes(d), "sp_wgrad: workspace too small (%zu < %zu)", ws_bytes,
+               sp_wgrad_workspace_bytes(d));
+    const int nPerG = d->N / G;
+    if (sp_tiled_wgrad_supported(d) && o_scale == nullptr)
+        return sp_tiled_wgrad_launch(d, nPerG, iside, i_scale, i_shift, oside, dw, beta, (float*)ws, sp_stream(stream));
+    const WgradPlan p = wgrad_plan(d);
+    const bool vi = (d->Ci % 4 == 0) && (d->ldi % 4 == 0);
+    const bool vo = (d->Co % 4 == 0) && (d->ldo % 4 == 0);
+    dim3 grid(p.blocks_x, p.chunks);
+    float* wsf = (float*)ws;
+#define SP_WG(VI, VO)                                                                                             \
+    wgrad_generic_kernel<VI, VO><<<grid, 256, 0, sp_stream(stream)>>>(*d, nPerG, p.ciQ, p.coQ, p.items, p.ov,     \
+                                                                      p.per_chunk, iside, i_scale, i_shift, oside, \
+                                                                      o_scale, o_shift, wsf)
+    if (vi && vo) SP_WG(true, true);
+    else if (vi) SP_WG(true, false);
+    else if (vo) SP_WG(false, true);
+    else SP_WG(false, false);
+#undef SP_WG
+    SP_LAUNCH_OK("wgrad_generic_kernel");
+    wgrad_reduce_kernel<<<grid_for(p.wn), 256, 0, sp_stream(stream)>>>(wsf, p.chunks, p.wn, dw, beta);
+    SP_LAUNCH_OK("wgrad_reduce_kernel");
+    return 0;
+}
+
+int sp_bias_grad(const float* g, int64_t rows, int C, int ld, float* db, float beta, double* acc, void* stream) {
+    SP_REQUIRE(g && db && rows > 0 && C > 0 && ld >= C, "sp_bias_grad: bad arguments");
+    SP_REQUIRE(C <= 4096, "sp_bias_grad: C=%d too large", C);
+    SP_REQUIRE(acc != nullptr, "sp_bias_grad: workspace of C doubles required");
+    SP_CUDA(cudaMemsetAsync(acc, 0, sizeof(double) * C, sp_stream(stream)));
+    int64_t blocks = sp_cdiv(rows, 64);
+    const int64_t cap = (int64_t)sp_num_sms() * 8;
+    if (blocks > cap) blocks = cap;
+    const int64_t rpb = sp_cdiv(rows, blocks);
+    blocks = sp_cdiv(rows, rpb);
+    bias_grad_partial_kernel<<<(int)blocks, 256, 256 * sizeof(double), sp_stream(stream)>>>(g, rows, C, ld, rpb, acc);
+    SP_LAUNCH_OK("bias_grad_partial_kernel");
+    bias_grad_final_kernel<<<(C + 255) / 256, 256, 0, sp_stream(stream)>>>(acc, C, db, beta);
+    SP_LAUNCH_OK("bias_grad_final_kernel");
+    return 0;
+}
+
+}  // extern "C"

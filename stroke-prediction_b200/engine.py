@@ -1,0 +1,379 @@
+"""Layer plans and hand-written forward/backward chains over the sm_100a kernels.
+
+A reference ``nn.Sequential`` on the hot path is a chain of pre-norm units ``[BatchNorm3d] -> Conv3d |
+ConvTranspose3d -> [ELU | LeakyReLU | Sigmoid]`` (Cae3D.py:39-76,176-220; Unet3D.py:17-24,49-54).  ``SeqPlan`` parses
+such a Sequential (whose modules keep owning the parameters, so ``state_dict`` names/shapes stay those of the
+reference) into fused units and runs them through the C-ABI:
+
+forward per unit   : bn_stats -> bn_finalize (scale/shift)  ->  corr / corrT with BN applied while staging the
+                     source and bias + activation fused in the epilogue.  Only the activation output is stored.
+backward per unit  : wgrad (BN re-applied on the fly) + bias_grad, corrT / corr for the gradient w.r.t. the BN output,
+                     bn_bwd_reduce -> bn_bwd_finalize (dgamma, dbeta, coefficients) -> bn_act_bwd_apply, which fuses
+                     the BN backward with the derivative of the *previous* unit's activation.
+
+``SeqFunction`` / ``UnetFunction`` expose the chains to autograd as single nodes.
+"""
+import torch
+import torch.nn as nn
+
+from . import ops
+from .ops import ACT_ELU, ACT_LEAKY, ACT_NONE, ACT_SIGMOID
+
+_weights_epoch = 0
+
+
+def bump_weights_epoch():
+    """Called by the fused optimizer after it has rewritten parameters behind autograd's back."""
+    global _weights_epoch
+    _weights_epoch += 1
+
+
+def _triple(v):
+    return tuple(v) if isinstance(v, (tuple, list)) else (v, v, v)
+
+
+def _act_of(m):
+    if m is None:
+        return ACT_NONE, 0.0
+    if isinstance(m, nn.ELU):
+        return ACT_ELU, float(m.alpha)
+    if isinstance(m, nn.LeakyReLU):
+        return ACT_LEAKY, float(m.negative_slope)
+    if isinstance(m, nn.Sigmoid):
+        return ACT_SIGMOID, 0.0
+    raise TypeError("unsupported activation %r" % (m,))
+
+
+class FusedUnit:
+    """One [BN] -> conv/convT -> [act] unit."""
+
+    def __init__(self, bn, conv, act_module):
+        self.bn = bn
+        self.conv = conv
+        self.transposed = isinstance(conv, nn.ConvTranspose3d)
+        k, s, p = _triple(conv.kernel_size), _triple(conv.stride), _triple(conv.padding)
+        if not (k[0] == k[1] == k[2] and s[0] == s[1] == s[2]):
+            raise ValueError("only cubic kernels / isotropic strides are on the hot path")
+        if _triple(conv.dilation) != (1, 1, 1) or conv.groups != 1:
+            raise ValueError("dilation/groups are not used by the reference and not supported")
+        if self.transposed and _triple(conv.output_padding) != (0, 0, 0):
+            raise ValueError("output_padding is not used by the reference and not supported")
+        self.k, self.s, self.pad = k[0], s[0], p
+        self.act, self.alpha = _act_of(act_module)
+        self.cin, self.cout = conv.in_channels, conv.out_channels
+        self._packed = {}
+
+    def out_size(self, size):
+        if self.transposed:
+            return tuple((i - 1) * self.s - 2 * p + self.k for i, p in zip(size, self.pad))
+        return tuple((i + 2 * p - self.k) // self.s + 1 for i, p in zip(size, self.pad))
+
+    def desc(self, N, in_size, act=None, alpha=None):
+        """Correlation-geometry descriptor; conv: I-side = input, convT: O-side = input."""
+        out_size = self.out_size(in_size)
+        a = self.act if act is None else act
+        al = self.alpha if alpha is None else alpha
+        if self.transposed:
+            return ops.conv_desc(N, out_size, self.cout, in_size, self.cin, self.k, self.s, self.pad, a, al)
+        return ops.conv_desc(N, in_size, self.cin, out_size, self.cout, self.k, self.s, self.pad, a, al)
+
+    def packed(self, d, which):
+        w = self.conv.weight
+        key = (w._version, w.data_ptr(), _weights_epoch)
+        hit = self._packed.get(which)
+        if hit is not None and hit[0] == key:
+            return hit[1]
+        wp = ops.pack_weights(d, which, w)
+        self._packed[which] = (key, wp)
+        return wp
+
+    def params(self):
+        ps = []
+        if self.bn is not None and self.bn.affine:
+            ps += [self.bn.weight, self.bn.bias]
+        ps.append(self.conv.weight)
+        if self.conv.bias is not None:
+            ps.append(self.conv.bias)
+        return ps
+
+
+class SeqPlan:
+    def __init__(self, seq):
+        mods = list(seq.children()) if isinstance(seq, nn.Sequential) else list(seq)
+        self.units = []
+        i = 0
+        while i < len(mods):
+            bn = None
+            if isinstance(mods[i], nn.BatchNorm3d):
+                bn = mods[i]
+                i += 1
+            if i >= len(mods) or not isinstance(mods[i], (nn.Conv3d, nn.ConvTranspose3d)):
+                raise TypeError("expected Conv3d/ConvTranspose3d at position %d of the Sequential" % i)
+            conv = mods[i]
+            i += 1
+            act = None
+            if i < len(mods) and isinstance(mods[i], (nn.ELU, nn.LeakyReLU, nn.Sigmoid)):
+                act = mods[i]
+                i += 1
+            self.units.append(FusedUnit(bn, conv, act))
+
+    def params(self):
+        ps = []
+        for u in self.units:
+            ps += u.params()
+        return ps
+
+    def out_shape(self, shape):
+        N, C, D, H, W = shape
+        size = (D, H, W)
+        for u in self.units:
+            size = u.out_size(size)
+        return (N, self.units[-1].cout) + size
+
+
+class SeqSaved:
+    __slots__ = ("acts", "bn", "G")
+
+    def __init__(self):
+        self.acts = []   # input + every unit's activation output
+        self.bn = []     # per unit: None or (scale, shift, mean, invstd, training)
+        self.G = 1
+
+
+def seq_forward(plan, x, G=1):
+    """x: NDHWC volume with N = G * B.  Returns (y, SeqSaved)."""
+    saved = SeqSaved()
+    saved.G = G
+    saved.acts.append(x)
+    for u in plan.units:
+        N, C, D, H, W = x.shape
+        if C != u.cin:
+            raise RuntimeError("channel mismatch: unit expects %d, got %d" % (u.cin, C))
+        scale = shift = None
+        if u.bn is not None:
+            bn = u.bn
+            training = bn.training or bn.running_mean is None
+            mom = 0.1 if bn.momentum is None else bn.momentum
+            scale, shift, mean, invstd = ops.bn_forward(
+                x, G, bn.weight if bn.affine else None, bn.bias if bn.affine else None,
+                bn.running_mean, bn.running_var, bn.num_batches_tracked, mom, bn.eps, training)
+            saved.bn.append((scale, shift, mean, invstd, training))
+        else:
+            saved.bn.append(None)
+        d = u.desc(N, (D, H, W))
+        osz = u.out_size((D, H, W))
+        y = ops.new_vol(N, u.cout, osz[0], osz[1], osz[2], x.device)
+        bias = u.conv.bias
+        if u.transposed:
+            ops.corrT(d, x, u.packed(d, 1), bias, scale, shift, G, y)
+        else:
+            ops.corr(d, x, u.packed(d, 0), bias, scale, shift, G, y)
+        saved.acts.append(y)
+        x = y
+    return x, saved
+
+
+def seq_backward(plan, saved, gy, need_input_grad, want):
+    """gy: gradient w.r.t. the chain output (post-activation).  `want(param)` tells whether a parameter gradient is
+    needed.  Returns (gx or None, {param: grad})."""
+    G = saved.G
+    grads = {}
+    units = plan.units
+    last = units[-1]
+    # gradient w.r.t. the last conv output: gy * act'(y)
+    if last.act != ACT_NONE:
+        gz = ops.bn_act_bwd_apply(gy, saved.acts[-1], None, G, last.act, last.alpha)
+    else:
+        gz = gy if ops.is_ndhwc(gy) else ops.as_vol(gy)
+    for i in range(len(units) - 1, -1, -1):
+        u = units[i]
+        x = saved.acts[i]
+        N, C, D, H, W = x.shape
+        bnrec = saved.bn[i]
+        scale = shift = None
+        if bnrec is not None:
+            scale, shift = bnrec[0], bnrec[1]
+        d = u.desc(N, (D, H, W), ACT_NONE, 0.0)
+        conv = u.conv
+        # ---- parameter gradients
+        if want(conv.weight):
+            dw = torch.empty_like(conv.weight, memory_format=torch.contiguous_format)
+            if u.transposed:
+                ops.wgrad(d, gz, None, None, x, scale, shift, G, dw)
+            else:
+                ops.wgrad(d, x, scale, shift, gz, None, None, G, dw)
+            grads[conv.weight] = dw
+        if conv.bias is not None and want(conv.bias):
+            db = torch.empty_like(conv.bias)
+            gN, gC = gz.shape[0], gz.shape[1]
+            ops.bias_grad(gz, gz.numel() // gC, gC, gC, db)
+            grads[conv.bias] = db
+        bn_grads = u.bn is not None and u.bn.affine and (want(u.bn.weight) or want(u.bn.bias))
+        need_dx = need_input_grad if i == 0 else True
+        if not (need_dx or bn_grads):
+            break
+        # ---- gradient w.r.t. the BN output (= conv input)
+        gxh = ops.new_vol(N, C, D, H, W, x.device)
+        if u.transposed:
+            ops.corr(d, gz, u.packed(d, 0), None, None, None, G, gxh)
+        else:
+            ops.corrT(d, gz, u.packed(d, 1), None, None, None, G, gxh)
+        coef = None
+        if bnrec is not None:
+            bn = u.bn
+            dgamma = torch.empty_like(bn.weight) if (bn.affine and want(bn.weight)) else None
+            dbeta = torch.empty_like(bn.bias) if (bn.affine and want(bn.bias)) else None
+            coef = ops.bn_backward_coef(gxh, x, G, bn.weight if bn.affine else None, bnrec[2], bnrec[3], bnrec[4],
+                                        dgamma, dbeta)
+            if dgamma is not None:
+                grads[bn.weight] = dgamma
+            if dbeta is not None:
+                grads[bn.bias] = dbeta
+        if not need_dx:
+            break
+        prev_act, prev_alpha = (units[i - 1].act, units[i - 1].alpha) if i > 0 else (ACT_NONE, 0.0)
+        if coef is None and prev_act == ACT_NONE:
+            gz = gxh
+        else:
+            gz = ops.bn_act_bwd_apply(gxh, x, coef, G, prev_act, prev_alpha)
+    else:
+        return gz, grads
+    return None, grads
+
+
+class SeqFunction(torch.autograd.Function):
+    """autograd node for one pass of a whole Sequential (encoder / decoder / step MLP)."""
+
+    @staticmethod
+    def forward(ctx, x, plan, G, *params):
+        xv = ops.as_vol(x)
+        y, saved = seq_forward(plan, xv, G)
+        ctx.plan, ctx.saved, ctx.params = plan, saved, params
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        params = ctx.params
+        needs = ctx.needs_input_grad
+        wanted = {id(p) for j, p in enumerate(params) if needs[3 + j]}
+        gy = ops.as_vol(gy)
+        gx, grads = seq_backward(ctx.plan, ctx.saved, gy, needs[0], lambda p: id(p) in wanted)
+        ctx.saved = None
+        return (gx, None, None) + tuple(grads.get(p) for p in params)
+
+
+def run_sequential(plan, x, G=1):
+    return SeqFunction.apply(x, plan, G, *plan.params())
+
+
+# =====================================================================================================================
+class UnetPlan:
+    """The 3-scale U-Net graph of Unet3D.forward (Unet3D.py:56-79)."""
+
+    def __init__(self, unet):
+        self.blocks = [SeqPlan(getattr(unet, "block%d" % i).bn_conv_relu_2x) for i in range(1, 6)]
+        self.classify = SeqPlan(unet.classify)
+        self.unet = unet
+
+    def params(self):
+        ps = []
+        for b in self.blocks:
+            ps += b.params()
+        return ps + self.classify.params()
+
+
+def _align(unet, name):
+    ac = getattr(getattr(unet, name), "align_corners", None)
+    return bool(ac)  # None (installed default) == False
+
+
+def _crop_offsets(big, small):
+    return tuple((b - s) // 2 for b, s in zip(big.shape[2:], small.shape[2:]))
+
+
+def unet_forward(plan, x):
+    b = plan.blocks
+    S = {}
+    y1, S["b1"] = seq_forward(b[0], x)
+    p1 = ops.maxpool2_fwd(y1)
+    y2, S["b2"] = seq_forward(b[1], p1)
+    p2 = ops.maxpool2_fwd(y2)
+    y3, S["b3"] = seq_forward(b[2], p2)
+    N, C3, D3, H3, W3 = y3.shape
+    C2 = y2.shape[1]
+    cat4 = ops.new_vol(N, C3 + C2, 2 * D3, 2 * H3, 2 * W3, x.device)
+    ops.upsample2_fwd(y3, cat4, 0, _align(plan.unet, "upsa34"))
+    off4 = _crop_offsets(y2, cat4)
+    ops.crop_into(y2, cat4, C3, off4)
+    y4, S["b4"] = seq_forward(b[3], cat4)
+    N, C4, D4, H4, W4 = y4.shape
+    C1 = y1.shape[1]
+    cat5 = ops.new_vol(N, C4 + C1, 2 * D4, 2 * H4, 2 * W4, x.device)
+    ops.upsample2_fwd(y4, cat5, 0, _align(plan.unet, "upsa45"))
+    off5 = _crop_offsets(y1, cat5)
+    ops.crop_into(y1, cat5, C4, off5)
+    y5, S["b5"] = seq_forward(b[4], cat5)
+    seg, S["cls"] = seq_forward(plan.classify, y5)
+    S.update(p1=p1, p2=p2, off4=off4, off5=off5, C1=C1, C2=C2, C3=C3, C4=C4)
+    return seg, S
+
+
+def unet_backward(plan, S, gseg, need_input_grad, want):
+    b = plan.blocks
+    grads = {}
+
+    def run(p, key, g, need=True):
+        gx, gr = seq_backward(p, S[key], g, need, want)
+        grads.update(gr)
+        return gx
+
+    g5 = run(plan.classify, "cls", gseg)
+    gcat5 = run(b[4], "b5", g5)
+    g4 = ops.upsample2_bwd(gcat5, 0, S["C4"], _align(plan.unet, "upsa45"))
+    gcat4 = run(b[3], "b4", g4)
+    g3 = ops.upsample2_bwd(gcat4, 0, S["C3"], _align(plan.unet, "upsa34"))
+    gp2 = run(b[2], "b3", g3)
+    y2 = S["b2"].acts[-1]
+    g2 = ops.maxpool2_bwd(y2, S["p2"], gp2)
+    ops.crop_add(g2, gcat4, S["C3"], S["off4"])
+    gp1 = run(b[1], "b2", g2)
+    y1 = S["b1"].acts[-1]
+    g1 = ops.maxpool2_bwd(y1, S["p1"], gp1)
+    ops.crop_add(g1, gcat5, S["C4"], S["off5"])
+    gx = run(b[0], "b1", g1, need_input_grad)
+    return gx, grads
+
+
+class UnetFunction(torch.autograd.Function):
+    """autograd node for the whole U-Net: returns the two dense single-channel probability volumes."""
+
+    @staticmethod
+    def forward(ctx, x, plan, *params):
+        xv = ops.as_vol(x)
+        seg, S = unet_forward(plan, xv)
+        ctx.plan, ctx.S, ctx.params = plan, S, params
+        ctx.seg_shape = seg.shape
+        outs = tuple(ops.extract_channel(seg, c) for c in range(seg.shape[1]))
+        return outs
+
+    @staticmethod
+    def backward(ctx, *gouts):
+        params = ctx.params
+        needs = ctx.needs_input_grad
+        wanted = {id(p) for j, p in enumerate(params) if needs[2 + j]}
+        N, C, D, H, W = ctx.seg_shape
+        dev = ctx.S["p1"].device
+        if any(g is None for g in gouts):
+            gseg = ops.zeros_vol(N, C, D, H, W, dev)
+        else:
+            gseg = ops.new_vol(N, C, D, H, W, dev)
+        for c, g in enumerate(gouts):
+            if g is not None:
+                ops.insert_channel(ops.as_vol(g), gseg, c)
+        gx, grads = unet_backward(ctx.plan, ctx.S, gseg, needs[0], lambda p: id(p) in wanted)
+        ctx.S = None
+        return (gx, None) + tuple(grads.get(p) for p in params)
+
+
+def run_unet(plan, x):
+    return UnetFunction.apply(x, plan, *plan.params())

@@ -1,0 +1,219 @@
+"""Training procedure skeleton (API of the reference's learner/Learner.py:16-226).
+
+Hot path = ``train_batch`` / ``validate_batch`` (Learner.py:116-142): forward through the fused engine, the
+subclass's ``loss_step``, ``zero_grad`` / ``backward`` / fused Adam step, one scalar D2H for the loss.  A
+``torch.optim.Adam`` handed in by a reference-style script is adopted by :class:`FusedAdam` (same param_groups and
+state objects).  Plotting (matplotlib) and jsonpickle history files are host-side orchestration outside the hot-path
+scope; they are used when those packages are importable and skipped otherwise.
+"""
+import json
+from abc import abstractmethod
+
+import numpy
+import torch
+
+from ..common.dto.Dto import Dto
+from ..common.dto import MetricMeasuresDto as MetricMeasuresDtoInit
+from ..common.dto.MetricMeasuresDto import MetricMeasuresDto
+from ..common.inference.Inference import Inference
+from ..optim import FusedAdam
+
+
+def _history_to_json(history):
+    def enc(d):
+        return {k: (enc(v) if isinstance(v, Dto) else (None if v is None else float(v))) for k, v in d}
+    return json.dumps({phase: [enc(m) for m in metrics] for phase, metrics in history.items()})
+
+
+def _history_from_json(text):
+    def dec(d):
+        b = lambda x: MetricMeasuresDtoInit.BinaryMeasuresDto(x['dc'], x['hd'], x['assd'], x['precision'],
+                                                                x['sensitivity'], x['specificity'])
+        return MetricMeasuresDto(d['loss'], b(d['core']), b(d['penu']), b(d['lesion']))
+    raw = json.loads(text)
+    return {phase: [dec(m) for m in metrics] for phase, metrics in raw.items()}
+
+
+class Learner(Inference):
+    FNB_MODEL = 'model'
+    FNB_OPTIM = 'optimizer'
+    FNB_TRAIN = 'training'
+    FNB_PLOTS = 'plots'
+    FNB_IMAGE = 'visual'
+    FNB_MARKS = '_learner'
+    EXT_MODEL = '.model'
+    EXT_OPTIM = '.optim'
+    EXT_TRAIN = '.json'
+    EXT_IMAGE = '.png'
+
+    def __init__(self, dataloader_training, dataloader_validation, model, optimizer, scheduler, n_epochs: int,
+                 path_previous_base: str = None, path_outputs_base: str = '/tmp/stroke-prediction'):
+        Inference.__init__(self, model)
+
+        assert dataloader_training is None or dataloader_training.batch_size > 1, \
+            'For normalization layers batch_size > 1 is required.'
+        self._dataloader_training = dataloader_training
+        self._dataloader_validation = dataloader_validation
+        self._optimizer = FusedAdam.from_torch(optimizer) if isinstance(optimizer, torch.optim.Adam) else optimizer
+        self._scheduler = scheduler
+        self._n_epochs = n_epochs
+
+        self._path_outputs_base = path_outputs_base
+        self._path_previous_base = path_previous_base
+
+        if path_previous_base is not None:
+            self.load_model(self.is_cuda)
+            self.load_training()
+            print('Continue training', path_previous_base, '...')
+        else:
+            self._metric_dtos = {'training': [], 'validate': []}
+        assert len(self._metric_dtos['training']) == len(self._metric_dtos['validate']), 'Incomplete training data!'
+
+    def path(self, mode: str, type: str, suffix: str = ''):
+        base_path = {'load': self._path_previous_base, 'save': self._path_outputs_base}.get(mode)
+        ext = {self.FNB_MODEL: self.EXT_MODEL, self.FNB_OPTIM: self.EXT_OPTIM, self.FNB_TRAIN: self.EXT_TRAIN,
+               self.FNB_PLOTS: self.EXT_IMAGE, self.FNB_IMAGE: self.EXT_IMAGE}.get(type)
+        if base_path is None or ext is None:
+            return None
+        return base_path + self.FNB_MARKS + suffix + ext
+
+    @abstractmethod
+    def loss_step(self, dto: Dto, epoch):
+        pass
+
+    def get_start_epoch(self):
+        return 0
+
+    def get_start_min_loss(self):
+        return numpy.inf
+
+    def load_model(self, cuda=True):
+        model = torch.load(self.path('load', self.FNB_MODEL), weights_only=False)
+        self._model = model.cuda() if cuda else model
+
+    def load_training(self):
+        path_training = self.path('load', self.FNB_TRAIN)
+        path_optimizer = self.path('load', self.FNB_OPTIM)
+        print('Loading:', path_training, path_optimizer)
+        self._optimizer.load_state_dict(torch.load(path_optimizer, weights_only=False))
+        with open(path_training, 'r') as fp:
+            text = fp.read()
+        try:
+            import jsonpickle
+            self._metric_dtos = jsonpickle.decode(text)
+        except ImportError:
+            self._metric_dtos = _history_from_json(text)
+
+    def save_training(self):
+        torch.save(self._optimizer.state_dict(), self.path('save', self.FNB_OPTIM))
+        try:
+            import jsonpickle
+            text = jsonpickle.encode(self._metric_dtos)
+        except ImportError:
+            text = _history_to_json(self._metric_dtos)
+        with open(self.path('save', self.FNB_TRAIN), 'w') as fp:
+            fp.write(text)
+
+    def save_model(self, suffix=''):
+        device = self.device
+        torch.save(self._model.cpu(), self.path('save', self.FNB_MODEL, suffix))
+        self._model.to(device)
+
+    # ------------------------------------------------------------------------------------------ hot path
+    def train_batch(self, batch: dict, epoch) -> MetricMeasuresDto:
+        dto = self.inference_step(batch)
+        loss = self.loss_step(dto, epoch)
+
+        self._optimizer.zero_grad()
+        loss.backward()
+        self._optimizer.step()
+
+        batch_metrics = self.batch_metrics_step(dto, epoch)
+        batch_metrics.loss = float(loss.detach().reshape(-1)[0].cpu())   # the step's single D2H read
+
+        del loss
+        del dto
+        return batch_metrics
+
+    def validate_batch(self, batch: dict, epoch) -> MetricMeasuresDto:
+        with torch.no_grad():   # the reference builds a graph here for nothing
+            dto = self.inference_step(batch)
+            loss = self.loss_step(dto, epoch)
+            batch_metrics = self.batch_metrics_step(dto, epoch)
+            batch_metrics.loss = float(loss.detach().reshape(-1)[0].cpu())
+        del loss
+        del dto
+        return batch_metrics
+
+    def batch_metrics_step(self, dto: Dto, epoch) -> MetricMeasuresDto:
+        return MetricMeasuresDtoInit.init_dto()
+
+    def print_epoch(self, epoch, phase, epoch_metrics: MetricMeasuresDto):
+        pass
+
+    def plot_epoch(self, plotter, epochs):
+        pass
+
+    def visualize_epoch(self, epoch):
+        pass
+
+    def adapt_lr(self, epoch):
+        if self._scheduler is not None:
+            self._scheduler.step()
+
+    def adapt_betas(self, epoch):
+        pass
+
+    def run_training(self):
+        min_loss = self.get_start_min_loss()
+        epoch = self.get_start_epoch()
+        for epoch in range(self.get_start_epoch(), self._n_epochs):
+            self.adapt_lr(epoch)
+            self.adapt_betas(epoch)
+
+            # (1) training
+            self._model.train()
+            epoch_metrics = MetricMeasuresDtoInit.init_dto()
+            for batch in self._dataloader_training:
+                epoch_metrics.add(self.train_batch(batch, epoch))
+            epoch_metrics.div(len(self._dataloader_training))
+            self.print_epoch(epoch, 'training', epoch_metrics)
+            self._metric_dtos['training'].append(epoch_metrics)
+
+            # (2) validation
+            self._model.eval()
+            if self._dataloader_validation is None:
+                epoch_metrics = MetricMeasuresDtoInit.init_dto(*([0.0] * 13))
+            else:
+                epoch_metrics = MetricMeasuresDtoInit.init_dto()
+                for batch in self._dataloader_validation:
+                    epoch_metrics.add(self.validate_batch(batch, epoch))
+                epoch_metrics.div(len(self._dataloader_validation))
+            self.print_epoch(epoch, 'validate', epoch_metrics)
+            self._metric_dtos['validate'].append(epoch_metrics)
+
+            # (3) checkpoint on a new validation optimum
+            if self._metric_dtos['validate'] and self._metric_dtos['validate'][-1].loss < min_loss:
+                min_loss = self._metric_dtos['validate'][-1].loss
+                self.save_model()
+                self.save_training()
+                print('(New optimum: Training saved)', end=' ')
+                self.visualize_epoch(epoch)
+            if epoch % 50 == 0:
+                self.visualize_epoch(epoch)
+
+            # (4) curves
+            if epoch > 0:
+                try:
+                    import matplotlib.pyplot as plt
+                except ImportError:
+                    plt = None
+                if plt is not None:
+                    fig, plot = plt.subplots()
+                    self.plot_epoch(plot, range(1, epoch + 2))
+                    fig.savefig(self._path_outputs_base + self.FN_VIS_BASE + 'plots.png', bbox_inches='tight', dpi=300)
+                    plt.close(fig)
+
+        # (5) final model
+        self.save_model('_final')
+        self.visualize_epoch(epoch)

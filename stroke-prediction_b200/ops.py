@@ -1,0 +1,342 @@
+"""Thin Python wrappers over the C-ABI (include/stroke_b200.h): argument checking, pointers, current stream.
+
+Volumes are torch tensors of *logical* shape N x C x D x H x W whose memory is dense NDHWC (what torch calls
+``channels_last_3d``), so the reference's B x C x D x H x W API (README.md:13) is unchanged while the kernels see
+channel-innermost voxels.  Nothing in this module computes on the CPU: a CUDA tensor is required everywhere.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import ACT_ELU, ACT_LEAKY, ACT_NONE, ACT_SIGMOID, SpAdamTensor, SpConvDesc, check
+
+__all__ = ["ACT_NONE", "ACT_ELU", "ACT_LEAKY", "ACT_SIGMOID"]
+
+
+def _L():
+    return _lib.load()
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _req_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("stroke_prediction_b200 ops run on CUDA tensors only (no CPU fallback)")
+
+
+# ---------------------------------------------------------------------------------------------------- volumes
+def new_vol(N, C, D, H, W, device, dtype=torch.float32):
+    """Uninitialised volume: logical (N,C,D,H,W), memory NDHWC dense."""
+    return torch.empty((N, D, H, W, C), device=device, dtype=dtype).permute(0, 4, 1, 2, 3)
+
+
+def zeros_vol(N, C, D, H, W, device, dtype=torch.float32):
+    return torch.zeros((N, D, H, W, C), device=device, dtype=dtype).permute(0, 4, 1, 2, 3)
+
+
+def is_ndhwc(x):
+    return x.dim() == 5 and x.permute(0, 2, 3, 4, 1).is_contiguous()
+
+
+def as_vol(x):
+    """Return x as a dense-NDHWC fp32 CUDA volume (converting from dense NCDHW with our transpose kernel)."""
+    _req_cuda(x)
+    if x.dtype != torch.float32:
+        x = x.float()
+    if is_ndhwc(x):
+        return x
+    if not x.is_contiguous():
+        x = x.contiguous()
+    N, C, D, H, W = x.shape
+    out = new_vol(N, C, D, H, W, x.device)
+    check(_L().sp_ncdhw_to_ndhwc(_p(x), _p(out), N, C, D * H * W, _stream()), "sp_ncdhw_to_ndhwc")
+    return out
+
+
+def to_ncdhw(x):
+    """Dense NCDHW copy of an NDHWC volume (for users who need torch-contiguous results)."""
+    _req_cuda(x)
+    N, C, D, H, W = x.shape
+    if not is_ndhwc(x):
+        return x.contiguous()
+    out = torch.empty((N, C, D, H, W), device=x.device, dtype=x.dtype)
+    check(_L().sp_ndhwc_to_ncdhw(_p(x), _p(out), N, C, D * H * W, _stream()), "sp_ndhwc_to_ncdhw")
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------- conv family
+def conv_desc(N, isize, Ci, osize, Co, k, s, pad, act=ACT_NONE, alpha=0.0, ldi=None, ldo=None):
+    d = SpConvDesc()
+    d.N = N
+    d.Di, d.Hi, d.Wi = isize
+    d.Ci = Ci
+    d.ldi = Ci if ldi is None else ldi
+    d.Do, d.Ho, d.Wo = osize
+    d.Co = Co
+    d.ldo = Co if ldo is None else ldo
+    d.k = k
+    d.s = s
+    d.pd, d.ph, d.pw = pad
+    d.act = act
+    d.alpha = alpha
+    return d
+
+
+def with_act(d, act, alpha):
+    e = SpConvDesc.from_buffer_copy(d)
+    e.act = act
+    e.alpha = alpha
+    return e
+
+
+def pack_weights(d, which, w):
+    """w: torch-layout weight (Co,Ci,k,k,k) of the correlation geometry -> packed fp32 tensor."""
+    _req_cuda(w)
+    w = w.detach()
+    if not w.is_contiguous():
+        w = w.contiguous()
+    n = _L().sp_packed_weight_floats(ctypes.byref(d), which)
+    out = torch.empty(n, device=w.device, dtype=torch.float32)
+    check(_L().sp_pack_weights(ctypes.byref(d), which, _p(w), _p(out), _stream()), "sp_pack_weights")
+    return out
+
+
+def corr(d, src, wp, bias, scale, shift, G, dst):
+    _req_cuda(src, wp, dst)
+    check(_L().sp_corr(ctypes.byref(d), _p(src), _p(wp), _p(bias), _p(scale), _p(shift), G, _p(dst), _stream()), "sp_corr")
+    return dst
+
+
+def corrT(d, src, wp, bias, scale, shift, G, dst):
+    _req_cuda(src, wp, dst)
+    check(_L().sp_corrT(ctypes.byref(d), _p(src), _p(wp), _p(bias), _p(scale), _p(shift), G, _p(dst), _stream()), "sp_corrT")
+    return dst
+
+
+_ws_cache = {}
+
+
+def workspace(nbytes, device, tag="ws"):
+    """Grow-only scratch buffer per (device, tag); stream-ordered reuse on the current stream."""
+    key = (device.index if device.index is not None else torch.cuda.current_device(), tag)
+    buf = _ws_cache.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(int(nbytes), 1 << 20), device=device, dtype=torch.uint8)
+        _ws_cache[key] = buf
+    return buf
+
+
+def wgrad(d, iside, i_scale, i_shift, oside, o_scale, o_shift, G, dw, beta=0.0):
+    _req_cuda(iside, oside, dw)
+    assert dw.is_contiguous()
+    nbytes = _L().sp_wgrad_workspace_bytes(ctypes.byref(d))
+    ws = workspace(nbytes, dw.device, "wgrad")
+    check(_L().sp_wgrad(ctypes.byref(d), _p(iside), _p(i_scale), _p(i_shift), _p(oside), _p(o_scale), _p(o_shift), G,
+                        _p(dw), beta, _p(ws), ws.numel(), _stream()), "sp_wgrad")
+    return dw
+
+
+def bias_grad(g, rows, C, ld, db, beta=0.0):
+    ws = workspace(8 * C, db.device, "f64")
+    check(_L().sp_bias_grad(_p(g), rows, C, ld, _p(db), beta, _p(ws), _stream()), "sp_bias_grad")
+    return db
+
+
+# ---------------------------------------------------------------------------------------------------- batch norm
+def bn_forward(x, G, gamma, beta, running_mean, running_var, nbt, momentum, eps, training):
+    """x: volume (N = G*B).  Returns (scale, shift, mean, invstd), each [G, C]; updates running stats in training."""
+    N, C, D, H, W = x.shape
+    vox = D * H * W
+    dev = x.device
+    sums = None
+    if training:
+        sums = torch.empty((G, C, 2), device=dev, dtype=torch.float64)
+        check(_L().sp_bn_stats(_p(x), N, vox, C, C, G, _p(sums), _stream()), "sp_bn_stats")
+    out = torch.empty((4, G, C), device=dev, dtype=torch.float32)
+    check(_L().sp_bn_finalize(_p(sums), (N // G) * vox, C, G, _p(gamma), _p(beta), _p(running_mean), _p(running_var),
+                              _p(nbt), float(momentum), float(eps), int(bool(training)),
+                              _p(out[0]), _p(out[1]), _p(out[2]), _p(out[3]), _stream()), "sp_bn_finalize")
+    return out[0], out[1], out[2], out[3]
+
+
+def bn_backward_coef(gxh, x, G, gamma, mean, invstd, training, dgamma, dbeta, beta_acc=0.0):
+    """Reduce + finalise BN backward.  Returns coef [3, G, C]; writes dgamma / dbeta when given."""
+    N, C, D, H, W = x.shape
+    vox = D * H * W
+    bsums = torch.empty((G, C, 2), device=x.device, dtype=torch.float64)
+    check(_L().sp_bn_bwd_reduce(_p(gxh), C, _p(x), C, N, vox, C, G, _p(bsums), _stream()), "sp_bn_bwd_reduce")
+    coef = torch.empty((3, G, C), device=x.device, dtype=torch.float32)
+    check(_L().sp_bn_bwd_finalize(_p(bsums), (N // G) * vox, C, G, _p(gamma), _p(mean), _p(invstd), int(bool(training)),
+                                  _p(dgamma), _p(dbeta), beta_acc, _p(coef), _stream()), "sp_bn_bwd_finalize")
+    return coef
+
+
+def bn_act_bwd_apply(gxh, x, coef, G, act, alpha, out=None, accumulate=False):
+    """out (+)= (A*gxh + B*x + C) * act'(x); coef None -> gxh * act'(x)."""
+    N, C, D, H, W = gxh.shape
+    if out is None:
+        out = new_vol(N, C, D, H, W, gxh.device)
+        accumulate = False
+    check(_L().sp_bn_act_bwd_apply(_p(gxh), C, _p(x), C, _p(coef), N, D * H * W, C, G, act, float(alpha), _p(out), C,
+                                   int(accumulate), _stream()), "sp_bn_act_bwd_apply")
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------- resampling
+def maxpool2_fwd(x):
+    N, C, D, H, W = x.shape
+    y = new_vol(N, C, D // 2, H // 2, W // 2, x.device)
+    check(_L().sp_maxpool2_fwd(_p(x), N, D, H, W, C, C, _p(y), C, _stream()), "sp_maxpool2_fwd")
+    return y
+
+
+def maxpool2_bwd(x, y, gy):
+    N, C, D, H, W = x.shape
+    gx = new_vol(N, C, D, H, W, x.device)
+    check(_L().sp_maxpool2_bwd(_p(x), _p(y), _p(gy), N, D, H, W, C, _p(gx), _stream()), "sp_maxpool2_bwd")
+    return gx
+
+
+def _chan_ptr(t, c0):
+    return ctypes.c_void_p(t.data_ptr() + 4 * c0)
+
+
+def upsample2_fwd(x, out, c0, align_corners):
+    """Trilinear x2 of x into channels [c0, c0+C) of the (wider) volume `out`."""
+    N, C, D, H, W = x.shape
+    ldy = out.shape[1]
+    check(_L().sp_upsample2_fwd(_p(x), N, D, H, W, C, C, _chan_ptr(out, c0), ldy, int(align_corners), _stream()),
+          "sp_upsample2_fwd")
+    return out
+
+
+def upsample2_bwd(gcat, c0, C, align_corners):
+    """Gradient w.r.t. the low-resolution input from channels [c0, c0+C) of the concat-buffer gradient."""
+    N, Ct, Do, Ho, Wo = gcat.shape
+    D, H, W = Do // 2, Ho // 2, Wo // 2
+    gx = new_vol(N, C, D, H, W, gcat.device)
+    check(_L().sp_upsample2_bwd(_chan_ptr(gcat, c0), Ct, N, D, H, W, C, _p(gx), C, int(align_corners), _stream()),
+          "sp_upsample2_bwd")
+    return gx
+
+
+def crop_into(src, out, c0, offs):
+    """out[:, c0:c0+C] = centre crop of src (offsets offs) — the skip connection half of the virtual concat."""
+    N, C, Ds, Hs, Ws = src.shape
+    _, Ct, Dd, Hd, Wd = out.shape
+    check(_L().sp_crop_copy(_p(src), Ds, Hs, Ws, C, _chan_ptr(out, c0), Dd, Hd, Wd, Ct, N, C, offs[0], offs[1], offs[2],
+                            _stream()), "sp_crop_copy")
+    return out
+
+
+def crop_add(big, gcat, c0, offs):
+    """big[crop window] += gcat[:, c0:c0+C]  (gradient of crop_into, accumulated into the skip tensor's gradient)."""
+    N, C, Db, Hb, Wb = big.shape
+    _, Ct, Ds, Hs, Ws = gcat.shape
+    check(_L().sp_crop_add(_p(big), Db, Hb, Wb, C, _chan_ptr(gcat, c0), Ds, Hs, Ws, Ct, N, C, offs[0], offs[1], offs[2],
+                           _stream()), "sp_crop_add")
+    return big
+
+
+def extract_channel(x, c):
+    """Dense (N,1,D,H,W) copy of channel c of an NDHWC volume."""
+    N, C, D, H, W = x.shape
+    out = new_vol(N, 1, D, H, W, x.device)
+    check(_L().sp_crop_copy(_chan_ptr(x, c), D, H, W, C, _p(out), D, H, W, 1, N, 1, 0, 0, 0, _stream()), "sp_crop_copy")
+    return out
+
+
+def insert_channel(src, out, c):
+    """out[:, c] = src (src dense single-channel volume)."""
+    N, C, D, H, W = out.shape
+    check(_L().sp_crop_copy(_p(src), D, H, W, 1, _chan_ptr(out, c), D, H, W, C, N, 1, 0, 0, 0, _stream()), "sp_crop_copy")
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------- losses
+def _dense(t):
+    """1-D view semantics: any tensor whose elements are densely packed (any dim order) is fine for reductions."""
+    if t.is_contiguous() or (t.dim() == 5 and is_ndhwc(t)):
+        return t
+    return t.contiguous()
+
+
+def dice_sums(o, t):
+    _req_cuda(o, t)
+    sums = torch.empty(3, device=o.device, dtype=torch.float64)
+    check(_L().sp_dice_sums(_p(o), _p(t), o.numel(), _p(sums), _stream()), "sp_dice_sums")
+    return sums
+
+
+def dice_loss(sums, w, eps):
+    loss = torch.empty((), device=sums.device, dtype=torch.float32)
+    check(_L().sp_dice_loss(_p(sums), float(w), float(eps), _p(loss), _stream()), "sp_dice_loss")
+    return loss
+
+
+def dice_bwd(o, t, sums, w, eps, gscale, gmul, go, accumulate):
+    check(_L().sp_dice_bwd(_p(o), _p(t), o.numel(), _p(sums), float(w), float(eps), _p(gscale), float(gmul), _p(go),
+                           int(accumulate), _stream()), "sp_dice_bwd")
+    return go
+
+
+def absdiff_mean(a, b, mode):
+    ws = torch.empty(1, device=a.device, dtype=torch.float64)
+    out = torch.empty((), device=a.device, dtype=torch.float32)
+    check(_L().sp_absdiff_mean(_p(a), _p(b), a.numel(), mode, _p(ws), _p(out), _stream()), "sp_absdiff_mean")
+    return out
+
+
+def absdiff_bwd(a, b, mode, gscale, gmul, ga, acc_a, gb, acc_b):
+    check(_L().sp_absdiff_bwd(_p(a), _p(b), a.numel(), mode, _p(gscale), float(gmul), _p(ga), int(acc_a), _p(gb),
+                              int(acc_b), _stream()), "sp_absdiff_bwd")
+
+
+# ---------------------------------------------------------------------------------------------------- interpolation
+def latent_interp_fwd(zc, zp, step):
+    B = zc.shape[0]
+    per = zc.numel() // B
+    out = torch.empty_like(zc)
+    check(_L().sp_latent_interp_fwd(_p(zc), _p(zp), _p(step), B, per, _p(out), _stream()), "sp_latent_interp_fwd")
+    return out
+
+
+def latent_interp_bwd(g, zc, zp, step, need_c, need_p, need_s):
+    B = zc.shape[0]
+    per = zc.numel() // B
+    dzc = torch.empty_like(zc) if need_c else None
+    dzp = torch.empty_like(zp) if need_p else None
+    ds = torch.empty(B, device=zc.device, dtype=torch.float32) if need_s else None
+    ws = torch.empty(B, device=zc.device, dtype=torch.float64) if need_s else None
+    check(_L().sp_latent_interp_bwd(_p(g), _p(zc), _p(zp), _p(step), B, per, _p(dzc), 0, _p(dzp), 0, _p(ds), _p(ws),
+                                    _stream()), "sp_latent_interp_bwd")
+    return dzc, dzp, ds
+
+
+# ---------------------------------------------------------------------------------------------------- optimizer
+def adam_multi(table_dev, n_tensors, total_blocks, lr, beta1, beta2, eps, wd, step, grad_scale, zero_grad):
+    check(_L().sp_adam_multi(_p(table_dev), n_tensors, total_blocks, float(lr), float(beta1), float(beta2), float(eps),
+                             float(wd), int(step), float(grad_scale), int(zero_grad), _stream()), "sp_adam_multi")
+
+
+def make_adam_table(entries, device):
+    """entries: list of (p, g, m, v) fp32 contiguous CUDA tensors -> (device uint8 tensor holding the table, blocks)."""
+    arr = (SpAdamTensor * len(entries))()
+    start = 0
+    for i, (p, g, m, v) in enumerate(entries):
+        n = p.numel()
+        arr[i].p, arr[i].g, arr[i].m, arr[i].v = p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr()
+        arr[i].n = n
+        arr[i].block_start = start
+        start += (n + _lib.SP_ADAM_CHUNK - 1) // _lib.SP_ADAM_CHUNK
+    raw = bytes(arr)
+    host = torch.frombuffer(bytearray(raw), dtype=torch.uint8)
+    return host.to(device), start

@@ -1,0 +1,329 @@
+"""GPU parity, model level: the drop-in modules / learners on cuda:0 against (a) the committed fixtures produced by
+the reference's own modules (tests/golden, see oracle/make_golden.py) and (b) the CPU oracle on fresh seeded inputs,
+including the BASELINE.json shapes.  Everything goes through the public host API -> autograd nodes -> C-ABI."""
+import numpy as np
+import pytest
+import torch
+
+import stroke_oracle as O
+from util import TOL_ACT, TOL_DICE, TOL_GRAD, load, rel_l2, rel_max, state_from, unpack_masks
+
+pytestmark = pytest.mark.gpu
+
+
+def _api():
+    from stroke_prediction_b200.common import data
+    from stroke_prediction_b200.common.inference.CaeEncInference import CaeEncInference
+    from stroke_prediction_b200.common.inference.CaeInference import CaeInference
+    from stroke_prediction_b200.common.inference.UnetInference import UnetInference
+    from stroke_prediction_b200.common.metrics import BatchDiceLoss
+    from stroke_prediction_b200.common.model.Cae3D import Cae3D, Dec3D, Enc3D, Enc3DCtp, Enc3DStep
+    from stroke_prediction_b200.common.model.Unet3D import Unet3D
+    from stroke_prediction_b200.learner.CaePredictionLearner import CaePredictionLearner
+    from stroke_prediction_b200.learner.CaeReconstructionLearner import CaeReconstructionLearner
+    from stroke_prediction_b200.learner.CaeStepLearner import CaeStepLearner
+    from stroke_prediction_b200.learner.UnetSegmentationLearner import UnetSegmentationLearner
+    from stroke_prediction_b200.optim import FusedAdam
+    from stroke_prediction_b200.tester.Tester import Tester
+    import types
+    return types.SimpleNamespace(**locals())
+
+
+def _dice_binary(a, b):
+    a, b = (torch.as_tensor(a) > 0.5), (torch.as_tensor(b) > 0.5)
+    den = a.sum().item() + b.sum().item()
+    return 2.0 * (a & b).sum().item() / den if den else 0.0
+
+
+def _check_grads(model, fx, tol=TOL_GRAD, prefix="grad/"):
+    named = dict(model.named_parameters())
+    n = 0
+    for k, v in fx.items():
+        if k.startswith(prefix):
+            p = named[k[len(prefix):]]
+            assert p.grad is not None, k
+            err = rel_l2(p.grad, v)
+            assert err < tol, "%s: rel-L2 %g" % (k, err)
+            n += 1
+    assert n > 0
+
+
+def test_cae_reconstruction_step_against_reference_fixture():
+    A = _api()
+    fx = load("cae_rec_tiny")
+    ch = [int(c) for c in fx["channels"]]
+    D, H, W = (int(v) for v in fx["size"])
+    cae = A.Cae3D(A.Enc3D(H, D, ch, 5, float(fx["alpha"])), A.Dec3D(H, D, ch, 5, float(fx["alpha"])))
+    cae.load_state_dict(state_from(fx, "sd0/"))
+    cae = cae.cuda().train()
+    batch = {A.data.KEY_IMAGES: torch.zeros(2, 2, 1, 1, 1), A.data.KEY_LABELS: unpack_masks(fx),
+             A.data.KEY_GLOBAL: torch.from_numpy(fx["clinical"])}
+    opt = torch.optim.Adam([p for p in cae.parameters() if p.requires_grad], lr=1e-3, weight_decay=1e-5, betas=(0.9, 0.999))
+    learner = A.CaeReconstructionLearner(None, None, cae, opt, None, 1, None, "/tmp/x", A.BatchDiceLoss([1.0]))
+    dto = learner.inference_step(batch)
+    assert rel_max(dto.given_variables.time_to_treatment, fx["step"]) < 1e-6
+    loss = learner.loss_step(dto, int(fx["epoch"]))
+    assert abs(loss.item() - float(fx["loss"])) < 1e-5
+    for k in ("core", "penu", "lesion", "interpolation"):
+        assert rel_l2(getattr(dto.latents.gtruth, k), fx["lat/" + k]) < TOL_ACT, k
+        r = getattr(dto.reconstructions.gtruth, k)
+        assert r.shape == (2, 1, D, H, W)
+        assert rel_l2(r.detach().cpu().reshape(-1)[::13], fx["rec_sample/" + k]) < TOL_ACT, k
+        m = fx["rec_moments/" + k]
+        assert abs(r.double().sum().item() - m[0]) < 1e-4 * abs(m[0])
+        assert abs((r.double() ** 2).sum().item() - m[1]) < 1e-4 * abs(m[1])
+    learner._optimizer.zero_grad()
+    loss.backward()
+    _check_grads(cae, fx)
+    learner._optimizer.step()
+    torch.cuda.synchronize()
+    sd1 = cae.state_dict()
+    for k, v in fx.items():
+        if not k.startswith("sd1/"):
+            continue
+        name = k[4:]
+        if "num_batches" in name:
+            assert int(sd1[name]) == int(v), name
+        elif "running_" in name:
+            assert rel_max(sd1[name], v) < 1e-5, name
+        else:   # parameters after one Adam step: compare the UPDATE (Adam's first step is lr * sign-like, so be lenient)
+            before = state_from(fx, "sd0/")[name]
+            upd_ref = torch.from_numpy(np.array(v)) - before
+            upd = sd1[name].cpu() - before
+            assert (upd - upd_ref).abs().max().item() < 2e-5, name
+
+
+def test_cae_step_learner_against_reference_fixture():
+    A = _api()
+    fx = load("cae_step_tiny")
+    ch = [int(c) for c in fx["channels"]]
+    D, H, W = (int(v) for v in fx["size"])
+    cae = A.Cae3D(A.Enc3DStep(H, D, ch, 5, 1.0), A.Dec3D(H, D, ch, 5, 1.0))
+    cae.load_state_dict(state_from(fx, "sd0/"))
+    cae.freeze(True)
+    for p in list(cae.enc.reduce.parameters()) + list(cae.enc.step.parameters()):
+        p.requires_grad = True
+    cae = cae.cuda().train()
+    batch = {A.data.KEY_IMAGES: torch.zeros(2, 2, 1, 1, 1), A.data.KEY_LABELS: unpack_masks(fx),
+             A.data.KEY_GLOBAL: torch.from_numpy(fx["clinical"])}
+    opt = A.FusedAdam([p for p in cae.parameters() if p.requires_grad], lr=1e-3, weight_decay=1e-5)
+    learner = A.CaeStepLearner(None, None, cae, opt, None, 1, None, "/tmp/x", A.BatchDiceLoss([1.0]))
+    dto = learner.inference_step(batch)
+    assert dto.given_variables.time_to_treatment is None
+    loss = learner.loss_step(dto, 0)
+    assert abs(loss.item() - float(fx["loss"])) < 1e-5
+    assert rel_l2(dto.latents.gtruth.interpolation, fx["lat/interpolation"]) < TOL_ACT
+    loss.backward()
+    _check_grads(cae, fx, tol=5e-4)    # 45-parameter MLP behind a full decoder dgrad: fp32 accumulation-order noise
+    frozen = [n for n, p in cae.named_parameters() if not p.requires_grad]
+    assert frozen and all(dict(cae.named_parameters())[n].grad is None for n in frozen)
+    # frozen BN layers still ran in train mode: running stats drift exactly like the reference
+    for k, v in fx.items():
+        if k.startswith("sd1/") and "running_" in k:
+            assert rel_max(cae.state_dict()[k[4:]], v) < 1e-5, k
+
+
+def test_cae_prediction_learner_against_reference_fixture():
+    A = _api()
+    fx = load("cae_pred_tiny")
+    ch = [int(c) for c in fx["channels"]]
+    D, H, W = (int(v) for v in fx["size"])
+    cae = A.Cae3D(A.Enc3D(H, D, ch, 5, 1.0), A.Dec3D(H, D, ch, 5, 1.0))
+    cae.load_state_dict(state_from(fx, "cae0/"))
+    new_enc = A.Enc3D(H, D, ch, 5, 1.0)
+    new_enc.load_state_dict(state_from(fx, "enc0/"))
+    cae, new_enc = cae.cuda().train(), new_enc.cuda().train()
+    batch = {A.data.KEY_IMAGES: torch.from_numpy(fx["soft"].astype(np.float32)), A.data.KEY_LABELS: unpack_masks(fx),
+             A.data.KEY_GLOBAL: torch.from_numpy(fx["clinical"])}
+    opt = A.FusedAdam(new_enc.parameters(), lr=1e-3, weight_decay=1e-5)
+    learner = A.CaePredictionLearner(None, None, cae, new_enc, opt, None, 1, None, "/tmp/x", A.BatchDiceLoss([1.0]))
+    dto = learner.inference_step(batch)
+    loss = learner.loss_step(dto, 0)
+    assert abs(loss.item() - float(fx["loss"])) < 1e-5
+    for k in ("core", "penu", "interpolation"):
+        assert rel_l2(getattr(dto.latents.inputs, k), fx["lat_in/" + k]) < TOL_ACT
+    loss.backward()
+    _check_grads(new_enc, fx, tol=3e-4)
+    assert all(p.grad is None for p in cae.parameters())
+    for k, v in fx.items():
+        if k.startswith("cae1/"):
+            assert rel_max(cae.state_dict()[k[5:]], v) < 1e-5, k
+    # the reference's literal flag bug is available behind the switch and fails like the reference does
+    strict = A.CaeEncInference(cae, new_enc, 10, compat_reference_flag_bug=True)
+    with pytest.raises(AssertionError):
+        strict.inference_step(batch)
+
+
+def test_unet_step_against_reference_fixture():
+    A = _api()
+    fx = load("unet_tiny")
+    unet = A.Unet3D([int(c) for c in fx["channels"]])
+    unet.load_state_dict(state_from(fx, "sd0/"))
+    unet = unet.cuda().train()
+    interior = torch.from_numpy(fx["images_interior"])
+    B, _, D, H, W = interior.shape
+    img = torch.zeros(B, 2, D + 40, H + 40, W + 40)
+    img[:, :, 20:-20, 20:-20, 20:-20] = interior
+    batch = {A.data.KEY_IMAGES: img, A.data.KEY_LABELS: unpack_masks(fx)}
+    opt = torch.optim.Adam(unet.parameters(), lr=1e-3, weight_decay=1e-5, betas=(0.99, 0.999))
+    learner = A.UnetSegmentationLearner(None, None, unet, opt, None, 1, A.BatchDiceLoss([1.0]))
+    dto = learner.inference_step(batch)
+    assert dto.outputs.core.shape == (B, 1, D, H, W)
+    assert rel_l2(dto.outputs.core, fx["core"]) < TOL_ACT and rel_l2(dto.outputs.penu, fx["penu"]) < TOL_ACT
+    assert abs(_dice_binary(dto.outputs.penu.cpu(), fx["penu"]) - 1.0) < TOL_DICE
+    loss = learner.loss_step(dto, 0)
+    assert abs(loss.item() - float(fx["loss"])) < 1e-5
+    learner._optimizer.zero_grad()
+    loss.backward()
+    # U-Net gradients: judge against an fp64 oracle run with the CPU-fp32 noise floor (SURVEY fact 9 / §8c rule 3)
+    sd64 = O.clone_state(state_from(fx, "sd0/"), requires_grad=True, dtype=torch.float64)
+    labels = unpack_masks(fx).double()
+    c64, p64 = O.unet_forward(sd64, img.double(), True)
+    g64 = O.grads_of(O.unet_loss(c64, p64, labels[:, 0:1], labels[:, 1:2]), sd64)
+    for n, p in unet.named_parameters():
+        e_gpu, e_cpu = rel_l2(p.grad, g64[n]), rel_l2(fx["grad/" + n], g64[n])
+        assert e_gpu <= max(TOL_GRAD, 2 * e_cpu), "%s: gpu %g cpu32 %g" % (n, e_gpu, e_cpu)
+    learner._optimizer.step()
+    for k, v in fx.items():
+        if k.startswith("sd1/") and "running_" in k:
+            assert rel_max(unet.state_dict()[k[4:]], v) < 1e-5, k
+    # eval mode (running statistics) — Tester path
+    unet.load_state_dict(state_from(fx, "sd0/"))
+    unet.eval()
+    with torch.no_grad():
+        d2 = A.UnetInference(unet).inference_step(batch)
+    assert rel_l2(d2.outputs.core, fx["eval_core"]) < TOL_ACT and rel_l2(d2.outputs.penu, fx["eval_penu"]) < TOL_ACT
+
+
+def test_three_training_steps_track_the_oracle():
+    """Loss trajectory of Learner.train_batch (forward, loss, backward, fused Adam, beta1 schedule) vs the oracle loop."""
+    A = _api()
+    ch = [1, 4, 6, 8, 10, 12, 1]
+    torch.manual_seed(21)
+    cae = A.Cae3D(A.Enc3D(56, 28, ch, 5, 1.0), A.Dec3D(56, 28, ch, 5, 1.0))
+    sd = O.clone_state(cae.state_dict(), requires_grad=True)
+    cae = cae.cuda().train()
+    opt = torch.optim.Adam(cae.parameters(), lr=1e-3, weight_decay=1e-5, betas=(0.9, 0.999))
+    learner = A.CaeReconstructionLearner(None, None, cae, opt, None, 10, None, "/tmp/x", A.BatchDiceLoss([1.0]))
+    names = [k for k, v in sd.items() if v.requires_grad]
+    m = {k: torch.zeros_like(sd[k]) for k in names}
+    v = {k: torch.zeros_like(sd[k]) for k in names}
+    for it in range(3):
+        epoch = it          # adapt_betas: beta1 = 0.5, 0.6, 0.7 (CaeReconstructionLearner.py:28-40)
+        learner.adapt_betas(epoch)
+        batch = A.data.synthetic_cae_batch(2, size=(28, 56, 56), seed=40 + it)
+        got = learner.train_batch(batch, epoch).loss
+        labels = batch[A.data.KEY_LABELS]
+        step = O.time_to_treatment(batch[A.data.KEY_GLOBAL])
+        lat, rec = O.cae_forward(sd, ch, 1.0, True, labels[:, 0:1], labels[:, 1:2], labels[:, 2:3], step)
+        loss = O.cae_reconstruction_loss(lat, rec, labels[:, 0:1], labels[:, 1:2], labels[:, 2:3], epoch)
+        grads = O.grads_of(loss, sd)
+        beta1 = 0.9 - 0.1 * (4 - epoch)
+        with torch.no_grad():
+            for k in names:
+                newp, m[k], v[k] = O.adam_step(sd[k], grads[k], m[k], v[k], it + 1, beta1=beta1)
+                sd[k].copy_(newp)
+        assert abs(got - loss.item()) < 2e-4 * max(1.0, abs(loss.item())), (it, got, loss.item())
+
+
+def test_tester_eval_batch_one():
+    """Tester path: eval mode, batch size 1 (breaks in the reference on current torch)."""
+    A = _api()
+    ch = [1, 4, 6, 8, 10, 12, 1]
+    torch.manual_seed(23)
+    cae = A.Cae3D(A.Enc3D(56, 28, ch, 5, 1.0), A.Dec3D(56, 28, ch, 5, 1.0))
+    sd = O.clone_state(cae.state_dict())
+    cae = cae.cuda()
+
+    class T(A.Tester, A.CaeInference):
+        def __init__(self, model):
+            A.Tester.__init__(self, None, model, "/tmp/x")
+            A.CaeInference.__init__(self, model, 10)
+
+    t = T(cae)
+    batch = A.data.synthetic_cae_batch(1, size=(28, 56, 56), seed=3)
+    _, dto = t.infer_batch(batch)
+    labels = batch[A.data.KEY_LABELS]
+    step = O.time_to_treatment(batch[A.data.KEY_GLOBAL])
+    lat, rec = O.cae_forward(sd, ch, 1.0, False, labels[:, 0:1], labels[:, 1:2], labels[:, 2:3], step)
+    for k in ("core", "penu", "lesion", "interpolation"):
+        assert rel_l2(getattr(dto.reconstructions.gtruth, k), rec[k]) < TOL_ACT
+    assert not any(p.requires_grad for p in cae.parameters())
+
+
+def test_enc3dctp_virtual_concat():
+    A = _api()
+    ch = [3, 4, 6, 8, 10, 12, 1]
+    torch.manual_seed(25)
+    enc = A.Enc3DCtp(56, 28, ch, 5, 1.0, [20, 20, 20])
+    sd = O.clone_state({"enc." + k: v for k, v in enc.state_dict().items()})
+    enc = enc.cuda().train()
+    from stroke_prediction_b200.common.dto import CaeDto as U
+    mask = (torch.rand(2, 3, 28, 56, 56) > 0.7).float()
+    cbv, ttd = torch.rand(2, 1, 68, 96, 96), torch.rand(2, 1, 68, 96, 96)
+    step = torch.rand(2, 1, 1, 1, 1)
+    dto = U.init_dto(None, step.cuda(), None, None, cbv.cuda(), ttd.cuda(), mask[:, 0:1].cuda(), mask[:, 1:2].cuda(), mask[:, 2:3].cuda())
+    dto = enc(dto)
+    crop = lambda t: t[:, :, 20:-20, 20:-20, 20:-20]
+    for j, k in enumerate(("core", "penu", "lesion")):
+        ref = O.encoder_pass(torch.cat((mask[:, j:j + 1], crop(cbv), crop(ttd)), 1), sd, ch, 1.0, True, "enc.encoder")
+        assert rel_l2(getattr(dto.latents.gtruth, k), ref) < TOL_ACT, k
+
+
+@pytest.mark.parametrize("fc", [200, 800])
+def test_cae_named_config_full_size_against_oracle(fc):
+    """BASELINE configs 2/3: channels 1 16 24 32 100 fc 1 on 28 x 128 x 128, B = 2: forward, loss and gradients."""
+    A = _api()
+    ch = [1, 16, 24, 32, 100, fc, 1]
+    torch.manual_seed(31)
+    cae = A.Cae3D(A.Enc3D(128, 28, ch, 5, 1.0), A.Dec3D(128, 28, ch, 5, 1.0))
+    sd = O.clone_state(cae.state_dict(), requires_grad=True)
+    cae = cae.cuda().train()
+    batch = A.data.synthetic_cae_batch(2, seed=4)
+    opt = A.FusedAdam(cae.parameters(), lr=1e-3, weight_decay=1e-5)
+    learner = A.CaeReconstructionLearner(None, None, cae, opt, None, 1, None, "/tmp/x", A.BatchDiceLoss([1.0]))
+    dto = learner.inference_step(batch)
+    loss = learner.loss_step(dto, 60)
+    loss.backward()
+    labels = batch[A.data.KEY_LABELS]
+    step = O.time_to_treatment(batch[A.data.KEY_GLOBAL])
+    torch.set_num_threads(max(1, torch.get_num_threads()))
+    lat, rec = O.cae_forward(sd, ch, 1.0, True, labels[:, 0:1], labels[:, 1:2], labels[:, 2:3], step)
+    oloss = O.cae_reconstruction_loss(lat, rec, labels[:, 0:1], labels[:, 1:2], labels[:, 2:3], 60)
+    grads = O.grads_of(oloss, sd)
+    assert abs(loss.item() - oloss.item()) < 1e-5
+    for k in ("core", "penu", "lesion", "interpolation"):
+        assert rel_l2(getattr(dto.latents.gtruth, k), lat[k]) < TOL_ACT, k
+        r = getattr(dto.reconstructions.gtruth, k)
+        assert rel_l2(r, rec[k]) < TOL_ACT, k
+        assert abs(_dice_binary(r.cpu(), rec[k]) - 1.0) < TOL_DICE or float((rec[k] > 0.5).sum()) == 0
+    worst = max(rel_l2(p.grad, grads[n]) for n, p in cae.named_parameters())
+    assert worst < 5e-4, worst      # vs the fp32 CPU oracle, whose own noise floor here is <= 7e-5
+
+
+def test_unet_named_config_patch_size_against_oracle():
+    """BASELINE config 1 channels on the reference's training patch 2 x 68 x 104 x 104 -> 28 x 64 x 64, B = 2."""
+    A = _api()
+    torch.manual_seed(33)
+    unet = A.Unet3D([2, 16, 32, 64, 32, 16, 32, 2])
+    sd = O.clone_state(unet.state_dict())
+    unet = unet.cuda().train()
+    batch = A.data.synthetic_unet_batch(2, out_size=(28, 64, 64), seed=4)
+    opt = A.FusedAdam(unet.parameters(), lr=1e-3, weight_decay=1e-5, betas=(0.99, 0.999))
+    learner = A.UnetSegmentationLearner(None, None, unet, opt, None, 1, A.BatchDiceLoss([1.0]))
+    dto = learner.inference_step(batch)
+    loss = learner.loss_step(dto, 0)
+    loss.backward()
+    labels = batch[A.data.KEY_LABELS]
+    sd32 = O.clone_state(sd, requires_grad=True)
+    c32, p32 = O.unet_forward(sd32, batch[A.data.KEY_IMAGES], True)
+    l32 = O.unet_loss(c32, p32, labels[:, 0:1], labels[:, 1:2])
+    g32 = O.grads_of(l32, sd32)
+    sd64 = O.clone_state(sd, requires_grad=True, dtype=torch.float64)
+    c64, p64 = O.unet_forward(sd64, batch[A.data.KEY_IMAGES].double(), True)
+    g64 = O.grads_of(O.unet_loss(c64, p64, labels[:, 0:1].double(), labels[:, 1:2].double()), sd64)
+    assert rel_l2(dto.outputs.core, c32) < TOL_ACT and rel_l2(dto.outputs.penu, p32) < TOL_ACT
+    assert abs(loss.item() - l32.item()) < 1e-5
+    for n, p in unet.named_parameters():
+        e_gpu, e_cpu = rel_l2(p.grad, g64[n]), rel_l2(g32[n], g64[n])
+        assert e_gpu <= max(TOL_GRAD, 2 * e_cpu), "%s: gpu %g cpu32 %g" % (n, e_gpu, e_cpu)

@@ -1,0 +1,349 @@
+"""GPU parity, op level: every kernel family behind the C-ABI against the CPU oracle (plain torch ops on the host)
+on identical seeded inputs.  fp32 bar: 1e-4 relative (BASELINE.json north_star); gradients are additionally judged
+against an fp64 CPU run with `err_gpu <= max(1e-4, 2 * err_cpu32)` (noise-floor rule)."""
+import copy
+
+import pytest
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from util import TOL_ACT, TOL_GRAD, rel_l2, rel_max
+
+pytestmark = pytest.mark.gpu
+
+
+def _mods():
+    from stroke_prediction_b200 import engine, functions, ops
+    return engine, functions, ops
+
+
+def _randomize_bn(seq, gen):
+    for m in seq.modules():
+        if isinstance(m, nn.BatchNorm3d):
+            with torch.no_grad():
+                m.weight.copy_(0.5 + torch.rand(m.weight.shape, generator=gen))
+                m.bias.copy_(0.2 * torch.randn(m.bias.shape, generator=gen))
+                m.running_mean.copy_(0.1 * torch.randn(m.running_mean.shape, generator=gen))
+                m.running_var.copy_(0.5 + torch.rand(m.running_var.shape, generator=gen))
+
+
+def _check_sequential(seq, x, training=True, G=1, check_input_grad=True, tol_act=TOL_ACT, tol_grad=TOL_GRAD):
+    """Run `seq` (a plain torch nn.Sequential) on the CPU in fp32 and fp64 and through the fused engine on the GPU."""
+    engine, _, ops = _mods()
+    gen = torch.Generator().manual_seed(1234)
+    _randomize_bn(seq, gen)
+    seq.train(training)
+    ref32 = copy.deepcopy(seq)
+    ref64 = copy.deepcopy(seq).double()
+    mine = copy.deepcopy(seq).cuda()
+
+    B = x.shape[0] // G
+    outs = {}
+    for name, mod, xin in (("f32", ref32, x.clone()), ("f64", ref64, x.double())):
+        xin.requires_grad_(check_input_grad)
+        ys = [mod(xin[g * B:(g + 1) * B]) for g in range(G)]   # G separate calls: separate statistics, sequential running stats
+        y = torch.cat(ys, 0)
+        gy = torch.randn(y.shape, generator=torch.Generator().manual_seed(99)).to(y.dtype)
+        y.backward(gy)
+        outs[name] = (y.detach(), xin.grad, {n: p.grad for n, p in mod.named_parameters()}, dict(mod.named_buffers()))
+    y64, gx64, gp64, _ = outs["f64"]
+    y32, gx32, gp32, buf32 = outs["f32"]
+
+    xg = x.clone().cuda().requires_grad_(check_input_grad)
+    plan = engine.SeqPlan(mine)
+    y = engine.run_sequential(plan, xg, G)
+    gy = torch.randn(y.shape, generator=torch.Generator().manual_seed(99)).cuda()
+    y.backward(gy)
+    torch.cuda.synchronize()
+
+    assert tuple(y.shape) == tuple(y32.shape)
+    assert rel_l2(y, y32) < tol_act, "forward: %g" % rel_l2(y, y32)
+
+    def judge(mine_t, t32, t64, what):
+        e_gpu, e_cpu = rel_l2(mine_t, t64), rel_l2(t32, t64)
+        assert e_gpu <= max(tol_grad, 2 * e_cpu), "%s: gpu-vs-fp64 %g, cpu32-vs-fp64 %g" % (what, e_gpu, e_cpu)
+
+    if check_input_grad:
+        judge(xg.grad, gx32, gx64, "input grad")
+    for n, p in mine.named_parameters():
+        assert p.grad is not None, n
+        judge(p.grad, gp32[n], gp64[n], "grad " + n)
+    for n, b in mine.named_buffers():
+        if "running" in n:
+            assert rel_max(b, buf32[n]) < 1e-5, n
+        if "num_batches" in n:
+            assert int(b) == int(buf32[n]), n
+
+
+# ---------------------------------------------------------------------------------------------------- layout
+def test_layout_roundtrip():
+    _, _, ops = _mods()
+    x = torch.randn(2, 3, 5, 7, 9).cuda()
+    v = ops.as_vol(x)
+    assert ops.is_ndhwc(v) and torch.equal(v, x)
+    assert torch.equal(v.permute(0, 2, 3, 4, 1).contiguous(), x.permute(0, 2, 3, 4, 1).contiguous())
+    back = ops.to_ncdhw(v)
+    assert back.is_contiguous() and torch.equal(back, x)
+    big = torch.randn(1, 2, 40, 70, 50).cuda()   # > 65535 tiles-of-32 rows would break a 2-D grid
+    assert torch.equal(ops.to_ncdhw(ops.as_vol(big)), big)
+
+
+# ---------------------------------------------------------------------------------------------------- conv units
+CONV_CASES = [
+    # (kind, cin, cout, k, stride, padding, act, in_size)      reference call site
+    ("C", 1, 16, 3, 1, (1, 0, 0), "elu", (6, 12, 11)),         # Cae3D.py:41   first encoder conv, Cin = 1
+    ("C", 16, 16, 3, 1, (1, 0, 0), "elu", (5, 10, 13)),        # Cae3D.py:44
+    ("C", 16, 24, 3, 2, 1, "elu", (8, 12, 10)),                # Cae3D.py:48   stride 2 pad 1
+    ("C", 24, 24, 3, 1, (1, 0, 0), "elu", (4, 9, 9)),          # Cae3D.py:52
+    ("C", 24, 32, 3, 2, 1, "elu", (7, 9, 11)),                 # Cae3D.py:59   odd extents, stride 2
+    ("C", 32, 100, 3, 2, 0, "elu", (7, 9, 9)),                 # Cae3D.py:70   stride 2 pad 0
+    ("C", 100, 40, 3, 1, 0, "elu", (3, 5, 4)),                 # Cae3D.py:74   bottleneck (fc reduced to 40 for speed)
+    ("T", 40, 100, 3, 1, 0, "elu", (1, 3, 2)),                 # Cae3D.py:178  convT k3 s1
+    ("T", 100, 32, 3, 2, 0, "elu", (3, 4, 5)),                 # Cae3D.py:182  convT k3 s2
+    ("C", 32, 24, 3, 1, (1, 2, 2), "elu", (4, 6, 7)),          # Cae3D.py:189  pad > (k-1)/2
+    ("T", 24, 24, 2, 2, 0, "elu", (3, 5, 4)),                  # Cae3D.py:193  convT k2 s2
+    ("C", 16, 16, 1, 1, 0, "elu", (3, 6, 5)),                  # Cae3D.py:215  1x1
+    ("C", 16, 1, 1, 1, 0, "sigmoid", (3, 6, 5)),               # Cae3D.py:218  1x1 + sigmoid
+    ("C", 2, 16, 3, 1, 0, "leaky", (7, 9, 10)),                # Unet3D.py:19  valid conv, Cin = 2
+    ("C", 96, 32, 3, 1, 0, "leaky", (5, 6, 7)),                # Unet3D.py:19  block4 on the concat
+    ("C", 3, 8, 3, 1, (1, 0, 0), "elu", (4, 8, 8)),            # Enc3DCtp first conv, Cin = 3
+    ("C", 5, 5, 1, 1, 0, "elu", (1, 1, 1)),                    # Cae3D.py:126  step MLP on B x 5 x 1 x 1 x 1
+]
+
+
+def _act(name):
+    return {"elu": nn.ELU(1.0, True), "leaky": nn.LeakyReLU(0.01, True), "sigmoid": nn.Sigmoid(), "none": None}[name]
+
+
+@pytest.mark.parametrize("case", CONV_CASES, ids=lambda c: "%s%d-%d_k%ds%d" % (c[0], c[1], c[2], c[3], c[4]))
+@pytest.mark.parametrize("with_bn", [True, False])
+def test_fused_unit_forward_backward(case, with_bn):
+    kind, cin, cout, k, s, p, act, size = case
+    torch.manual_seed(100 + CONV_CASES.index(case))
+    conv = nn.ConvTranspose3d(cin, cout, k, stride=s, padding=p) if kind == "T" else nn.Conv3d(cin, cout, k, stride=s, padding=p)
+    mods = ([nn.BatchNorm3d(cin)] if with_bn else []) + [conv] + ([_act(act)] if _act(act) is not None else [])
+    x = torch.randn(3, cin, *size) * 2.0 + 0.5
+    _check_sequential(nn.Sequential(*mods), x)
+
+
+def test_unit_eval_mode_uses_running_stats():
+    seq = nn.Sequential(nn.BatchNorm3d(6), nn.Conv3d(6, 10, 3, padding=(1, 0, 0)), nn.ELU(1.0, True),
+                        nn.BatchNorm3d(10), nn.Conv3d(10, 4, 3, padding=(1, 2, 2)), nn.ELU(1.0, True))
+    _check_sequential(seq, torch.randn(2, 6, 4, 7, 8), training=False)
+
+
+def test_chain_with_grouped_statistics():
+    """G = 3 passes stacked along the batch == 3 separate calls (separate batch statistics, sequential running-stat
+    updates, summed parameter gradients) — the CAE's core / penumbra / lesion encoder passes (Cae3D.py:105-107)."""
+    seq = nn.Sequential(nn.BatchNorm3d(1), nn.Conv3d(1, 8, 3, padding=(1, 0, 0)), nn.ELU(1.0, True),
+                        nn.BatchNorm3d(8), nn.Conv3d(8, 12, 3, stride=2, padding=1), nn.ELU(1.0, True),
+                        nn.BatchNorm3d(12), nn.ConvTranspose3d(12, 6, 2, stride=2), nn.ELU(1.0, True),
+                        nn.BatchNorm3d(6), nn.Conv3d(6, 1, 1), nn.Sigmoid())
+    x = (torch.rand(6, 1, 6, 10, 10) > 0.6).float()
+    _check_sequential(seq, x, G=3, check_input_grad=False)
+
+
+def test_frozen_parameters_get_no_gradient():
+    engine, _, _ = _mods()
+    seq = nn.Sequential(nn.BatchNorm3d(4), nn.Conv3d(4, 6, 3), nn.ELU(1.0, True), nn.BatchNorm3d(6), nn.Conv3d(6, 2, 1), nn.Sigmoid()).cuda()
+    for p in seq.parameters():
+        p.requires_grad = False
+    x = torch.randn(2, 4, 5, 6, 7).cuda().requires_grad_(True)
+    y = engine.run_sequential(engine.SeqPlan(seq), x)
+    y.sum().backward()
+    assert all(p.grad is None for p in seq.parameters()) and x.grad is not None
+    ref = copy.deepcopy(seq).cpu()
+    xr = x.detach().cpu().requires_grad_(True)
+    ref(xr).sum().backward()
+    assert rel_l2(x.grad, xr.grad) < TOL_GRAD
+
+
+def test_large_channel_count_statistics():
+    """C = 800 (paper config fc) exercises the channel loop of the statistics kernels."""
+    seq = nn.Sequential(nn.BatchNorm3d(800), nn.ConvTranspose3d(800, 12, 3), nn.ELU(1.0, True))
+    _check_sequential(seq, torch.randn(2, 800, 1, 3, 3))
+
+
+def test_raw_perfusion_statistics_do_not_cancel():
+    """First U-Net BN sees raw CBV/TTD (mean far from 0, 20-voxel zero border): variance must not lose digits."""
+    seq = nn.Sequential(nn.BatchNorm3d(2), nn.Conv3d(2, 4, 3), nn.LeakyReLU(0.01, True))
+    x = torch.zeros(2, 2, 12, 14, 16)
+    x[:, 0, 4:-4, 4:-4, 4:-4] = 1000.0 + torch.rand(2, 4, 6, 8)
+    x[:, 1, 4:-4, 4:-4, 4:-4] = 40 * torch.rand(2, 4, 6, 8)
+    _check_sequential(seq, x, check_input_grad=False)
+
+
+# ---------------------------------------------------------------------------------------------------- resampling
+@pytest.mark.parametrize("size", [(4, 6, 8), (5, 7, 9), (2, 2, 2)])
+def test_maxpool_with_ties(size):
+    _, _, ops = _mods()
+    torch.manual_seed(3)
+    x = torch.randn(2, 5, *size)
+    x[:, :, :, : size[1] // 2] = 0.25            # constant region -> every window there is an 8-way tie
+    x[0, 0] = torch.round(x[0, 0])               # many partial ties
+    xr = x.clone().requires_grad_(True)
+    yr = F.max_pool3d(xr, 2, 2)
+    gy = torch.randn(yr.shape)
+    yr.backward(gy)
+    xv = ops.as_vol(x.cuda())
+    y = ops.maxpool2_fwd(xv)
+    gx = ops.maxpool2_bwd(xv, y, ops.as_vol(gy.cuda()))
+    assert torch.equal(y.cpu(), yr.detach())
+    assert torch.equal(gx.cpu(), xr.grad)      # bit exact: pure routing
+
+
+@pytest.mark.parametrize("align", [False, True])
+@pytest.mark.parametrize("size", [(3, 4, 5), (1, 2, 7), (10, 35, 35)])
+def test_trilinear_upsample(align, size):
+    _, _, ops = _mods()
+    torch.manual_seed(5)
+    C = 6
+    x = torch.randn(2, C, *size)
+    xr = x.clone().requires_grad_(True)
+    yr = F.interpolate(xr, scale_factor=2, mode="trilinear", align_corners=align)
+    gy = torch.randn(yr.shape)
+    yr.backward(gy)
+    xv = ops.as_vol(x.cuda())
+    N, _, D, H, W = x.shape
+    cat = ops.zeros_vol(N, C + 3, 2 * D, 2 * H, 2 * W, "cuda")     # write into a channel slice of a wider buffer
+    ops.upsample2_fwd(xv, cat, 2, align)
+    assert rel_l2(cat[:, 2:2 + C], yr) < 1e-6
+    assert float(cat[:, :2].abs().max()) == 0.0 and float(cat[:, 2 + C:].abs().max()) == 0.0
+    gcat = ops.zeros_vol(N, C + 3, 2 * D, 2 * H, 2 * W, "cuda")
+    gcat[:, 2:2 + C] = gy.cuda()
+    gx = ops.upsample2_bwd(gcat, 2, C, align)
+    assert rel_l2(gx, xr.grad) < 1e-5
+
+
+def test_crop_concat_and_channel_helpers():
+    _, _, ops = _mods()
+    torch.manual_seed(7)
+    src = torch.randn(2, 4, 9, 10, 11).cuda()
+    out = ops.zeros_vol(2, 7, 5, 6, 7, "cuda")
+    offs = (2, 2, 2)
+    ops.crop_into(ops.as_vol(src), out, 3, offs)
+    assert torch.equal(out[:, 3:], src[:, :, 2:7, 2:8, 2:9]) and float(out[:, :3].abs().max()) == 0.0
+    big = ops.as_vol(torch.randn(2, 4, 9, 10, 11).cuda())
+    before = big.clone()
+    g = ops.as_vol(torch.randn(2, 7, 5, 6, 7).cuda())
+    ops.crop_add(big, g, 3, offs)
+    want = before.clone()
+    want[:, :, 2:7, 2:8, 2:9] += g[:, 3:]
+    assert torch.allclose(big, want, atol=0, rtol=0)
+    ch = ops.extract_channel(g, 5)
+    assert ch.shape == (2, 1, 5, 6, 7) and ch.is_contiguous() and torch.equal(ch[:, 0], g[:, 5])
+    tgt = ops.zeros_vol(2, 7, 5, 6, 7, "cuda")
+    ops.insert_channel(ch, tgt, 1)
+    assert torch.equal(tgt[:, 1], g[:, 5]) and float(tgt[:, 2:].abs().max()) == 0.0
+
+
+# ---------------------------------------------------------------------------------------------------- losses
+def test_dice_term():
+    _, functions, _ = _mods()
+    torch.manual_seed(11)
+    for n in (1, 5, 4096, 100003):
+        o = torch.rand(n)
+        t = (torch.rand(n) > 0.7).float()
+        orf = o.clone().double().requires_grad_(True)
+        lr = 1.0 - (2.0 * (orf * t.double()).sum() + 1e-7) / ((orf * orf).sum() + (t.double() * t.double()).sum() + 1e-7)
+        (lr * 0.37).backward()
+        og = o.clone().cuda().requires_grad_(True)
+        lg = functions.dice_term(og, t.cuda(), 1.0, 1e-7)
+        (lg * 0.37).backward()
+        assert abs(lg.item() - lr.item()) < 2e-6
+        assert rel_l2(og.grad, orf.grad) < 1e-5
+
+
+def test_dice_all_zero_prediction_and_target():
+    _, functions, _ = _mods()
+    o = torch.zeros(1000).cuda().requires_grad_(True)
+    t = torch.zeros(1000).cuda()
+    l = functions.dice_term(o, t, 1.0, 1e-7)
+    l.backward()
+    assert abs(l.item() - 0.0) < 1e-6 and torch.isfinite(o.grad).all()   # (0 + eps) / (0 + eps) = 1 -> loss 0
+
+
+def test_hinge_and_l1_including_exact_zeros():
+    _, functions, _ = _mods()
+    torch.manual_seed(13)
+    a = torch.rand(3, 1, 4, 5, 6)
+    b = torch.rand(3, 1, 4, 5, 6)
+    b.view(-1)[::3] = a.view(-1)[::3]            # d == 0 exactly where both sigmoids saturate
+    for mode, fn in ((0, lambda d: torch.mean(torch.abs(d) - d)), (1, lambda d: torch.mean(torch.abs(d)))):
+        ar, br = a.clone().requires_grad_(True), b.clone().requires_grad_(True)
+        lr = fn(ar - br)
+        (2.5 * lr).backward()
+        ag, bg = a.clone().cuda().requires_grad_(True), b.clone().cuda().requires_grad_(True)
+        lg = functions.hinge_mean(ag, bg) if mode == 0 else functions.l1_mean(ag, bg)
+        (2.5 * lg).backward()
+        assert abs(lg.item() - lr.item()) < 1e-6
+        assert rel_max(ag.grad, ar.grad) < 1e-6 and rel_max(bg.grad, br.grad) < 1e-6
+
+
+def test_latent_interpolation():
+    _, functions, _ = _mods()
+    torch.manual_seed(17)
+    zc, zp = torch.randn(4, 12, 1, 3, 3), torch.randn(4, 12, 1, 3, 3)
+    s = torch.tensor([-1.0, 0.0, 0.4, 2.0]).reshape(4, 1, 1, 1, 1)     # no clamping of the step (Cae3D.py:78-89)
+    zcr, zpr, sr = zc.clone().requires_grad_(True), zp.clone().requires_grad_(True), s.clone().requires_grad_(True)
+    out_r = zcr + sr * (zpr - zcr)
+    g = torch.randn(out_r.shape)
+    out_r.backward(g)
+    zcg, zpg, sg = (t.clone().cuda().requires_grad_(True) for t in (zc, zp, s))
+    out_g = functions.latent_interp(zcg, zpg, sg)
+    out_g.backward(g.cuda())
+    assert rel_max(out_g, out_r) < 1e-6
+    assert rel_max(zcg.grad, zcr.grad) < 1e-6 and rel_max(zpg.grad, zpr.grad) < 1e-6
+    assert sg.grad.shape == s.shape and rel_max(sg.grad, sr.grad) < 1e-5
+
+
+# ---------------------------------------------------------------------------------------------------- optimizer
+def test_fused_adam_matches_torch_adam():
+    from stroke_prediction_b200.optim import FusedAdam
+    torch.manual_seed(19)
+    shapes = [(16, 1, 3, 3, 3), (16,), (5000,), (1,), (100, 40, 3, 3, 3)]
+    ref = [torch.randn(s).requires_grad_(True) for s in shapes]
+    mine = [p.detach().clone().cuda().requires_grad_(True) for p in ref]
+    o_ref = torch.optim.Adam(ref, lr=1e-3, betas=(0.9, 0.999), weight_decay=1e-5)
+    o_mine = FusedAdam(mine, lr=1e-3, betas=(0.9, 0.999), weight_decay=1e-5)
+    for t in range(5):
+        beta1 = 0.5 + 0.1 * t if t < 4 else 0.9          # adapt_betas schedule, CaeReconstructionLearner.py:28-40
+        for o in (o_ref, o_mine):
+            for g in o.param_groups:
+                g["betas"] = (beta1, 0.999)
+        for p, q in zip(ref, mine):
+            gr = torch.randn(p.shape)
+            p.grad = gr.clone()
+            q.grad = gr.clone().cuda()
+        o_ref.step()
+        o_mine.step()
+    for p, q in zip(ref, mine):
+        assert rel_max(q, p) < 2e-6
+    sd = o_mine.state_dict()
+    assert set(sd["state"][0].keys()) == {"step", "exp_avg", "exp_avg_sq"}
+    assert rel_max(sd["state"][2]["exp_avg_sq"], o_ref.state_dict()["state"][2]["exp_avg_sq"]) < 1e-6
+
+
+def test_fused_adam_adopts_torch_adam():
+    from stroke_prediction_b200.optim import FusedAdam
+    p = torch.randn(300).cuda().requires_grad_(True)
+    ref = p.detach().clone().cpu().requires_grad_(True)
+    o = torch.optim.Adam([p], lr=1e-3, betas=(0.99, 0.999), weight_decay=1e-5)
+    f = FusedAdam.from_torch(o)
+    assert f.param_groups is o.param_groups
+    o2 = torch.optim.Adam([ref], lr=1e-3, betas=(0.99, 0.999), weight_decay=1e-5)
+    for _ in range(2):
+        g = torch.randn(300)
+        p.grad, ref.grad = g.cuda(), g.clone()
+        f.step()
+        o2.step()
+    assert rel_max(p, ref) < 2e-6
+
+
+def test_no_cpu_fallback():
+    _, functions, ops = _mods()
+    with pytest.raises(RuntimeError):
+        ops.as_vol(torch.zeros(1, 1, 2, 2, 2))
+    with pytest.raises(RuntimeError):
+        functions.dice_term(torch.rand(10), torch.rand(10))
