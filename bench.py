@@ -1,0 +1,337 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the hot path: CAE shape-space training throughput in volumes/s.
+
+Workload at every N: BASELINE.json configs[1] — CAE `1 16 24 32 100 200 1`, synthetic 1 x 28 x 128 x 128 core /
+penumbra / follow-up masks, batch 8 PER GPU (weak scaling), fp32, one full training step = 3 encoder + 4 decoder
+passes, CaeReconstructionLearner.loss_step (epoch 60 -> ramp factor 1), backward, gradient all-reduce (N > 1), fused
+Adam.  A "volume" is one patient sample (one batch element).
+
+  value  : whole-job volumes/s with the masks already resident in HBM (CUDA events, max over ranks)
+  e2e    : the same step through the public API `CaeReconstructionLearner.train_batch(batch, epoch)` with a HOST
+           (pinned) batch: H2D of labels + clinical and the D2H loss read are inside the timed region
+  roofline / cpu_baseline / clocks / gpu_launches : see DESIGN.md §Measurement
+
+`--impl reference` times the reference algorithm's CPU path (the oracle port, all host threads) on a bounded sample.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "oracle")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import torch  # noqa: E402
+
+CHANNELS = {"cae200": [1, 16, 24, 32, 100, 200, 1], "cae800": [1, 16, 24, 32, 100, 800, 1]}
+SIZE = (28, 128, 128)
+EPOCH = 60            # ramp factor f = 1 (CaeReconstructionLearner.py:53)
+METRIC = "cae_train_volumes_per_s"
+UNIT = "volumes/s"
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = float(r[1])
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except (ValueError, IndexError):
+                continue
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------------- CPU arm
+def cpu_reference_step_time(channels, batch, steps, warmup):
+    """Reference algorithm on the host cores: oracle port of the CAE train step (forward, loss_step, backward, Adam)."""
+    import stroke_oracle as O
+    from stroke_prediction_b200.common import data
+    from stroke_prediction_b200.common.model.Cae3D import Cae3D, Dec3D, Enc3D
+    torch.manual_seed(4)
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    cae = Cae3D(Enc3D(SIZE[1], SIZE[0], channels, 5, 1.0), Dec3D(SIZE[1], SIZE[0], channels, 5, 1.0))
+    sd = O.clone_state(cae.state_dict(), requires_grad=True)
+    names = [k for k, v in sd.items() if v.requires_grad]
+    m = {k: torch.zeros_like(sd[k]) for k in names}
+    v = {k: torch.zeros_like(sd[k]) for k in names}
+    b = data.synthetic_cae_batch(batch, size=SIZE, seed=4)
+    labels = b[data.KEY_LABELS]
+    core, penu, lesion = labels[:, 0:1].contiguous(), labels[:, 1:2].contiguous(), labels[:, 2:3].contiguous()
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        step = O.time_to_treatment(b[data.KEY_GLOBAL])
+        lat, rec = O.cae_forward(sd, channels, 1.0, True, core, penu, lesion, step)
+        loss = O.cae_reconstruction_loss(lat, rec, core, penu, lesion, EPOCH)
+        grads = O.grads_of(loss, sd)
+        with torch.no_grad():
+            for k in names:
+                newp, m[k], v[k] = O.adam_step(sd[k], grads[k], m[k], v[k], it + 1)
+                sd[k].copy_(newp)
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    return sum(times) / len(times), threads
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    channels = CHANNELS[args.workload]
+    sample_b = 2
+    steps, warmup = max(1, min(args.steps, 2)), 1 if args.warmup > 0 else 0
+    sec, threads = cpu_reference_step_time(channels, sample_b, steps, warmup)
+    val = sample_b / sec
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, per_gpu_batch=sample_b),
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": "oracle port of the reference CAE train step (torch %s CPU), batch %d x 1x28x128x128, "
+                                   "%d timed step(s) after %d warm-up" % (torch.__version__, sample_b, steps, warmup)},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, per_gpu_batch):
+    return {"workload": "BASELINE configs[1]: CAE channels %s, 1x28x128x128 core/penumbra/lesion masks, "
+                        "3 encoder + 4 decoder passes + loss_step + backward + Adam" % " ".join(map(str, CHANNELS[args.workload])),
+            "per_gpu_batch": per_gpu_batch, "global_batch": per_gpu_batch * args.gpus, "volume": "1x28x128x128",
+            "parallelism": "dp%d (batch-sharded, gradient all-reduce, local BN/Dice statistics)" % args.gpus,
+            "l2": "per-step working set (saved activations ~0.75 GB per volume) exceeds the 126 MB L2; no explicit flush"}
+
+
+# ----------------------------------------------------------------------------------------------------- GPU arm
+def algorithmic_bytes(name, key):
+    """fwd 4(|X|+|Y|) + 4|W|; wgrad 4(|X|+|dY|) + 4|W| per launch, from the descriptor key."""
+    try:
+        parts = key.split()
+        n = int(parts[0][1:])
+        di, hi, wi, ci = (int(v) for v in parts[1][1:].split("x"))
+        do, ho, wo, co = (int(v) for v in parts[2][1:].split("x"))
+        k = int(parts[3][1:])
+    except (ValueError, IndexError):
+        return None
+    return 4.0 * (n * di * hi * wi * ci + n * do * ho * wo * co) + 4.0 * (co * ci * k ** 3)
+
+
+def run_b200(args):
+    import torch.distributed as dist
+    from stroke_prediction_b200 import ops
+    from stroke_prediction_b200.common import data
+    from stroke_prediction_b200.common.dto import CaeDto as CaeDtoUtil
+    from stroke_prediction_b200.common.metrics import BatchDiceLoss
+    from stroke_prediction_b200.common.model.Cae3D import Cae3D, Dec3D, Enc3D
+    from stroke_prediction_b200.learner.CaeReconstructionLearner import CaeReconstructionLearner
+    from stroke_prediction_b200.optim import FusedAdam
+    from stroke_prediction_b200.parallel import broadcast_parameters
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the hot path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    if world != args.gpus and rank == 0:
+        print("warning: --gpus %d but WORLD_SIZE %d" % (args.gpus, world), file=sys.stderr)
+
+    channels = CHANNELS[args.workload]
+    B = args.batch
+    torch.manual_seed(4)
+    cae = Cae3D(Enc3D(SIZE[1], SIZE[0], channels, 5, 1.0), Dec3D(SIZE[1], SIZE[0], channels, 5, 1.0)).to(dev).train()
+    broadcast_parameters(cae)
+    opt = FusedAdam([p for p in cae.parameters() if p.requires_grad], lr=1e-3, weight_decay=1e-5, betas=(0.9, 0.999))
+    learner = CaeReconstructionLearner(None, None, cae, opt, None, 1, None, "/tmp/bench", BatchDiceLoss([1.0]))
+    if world > 1:
+        learner.enable_data_parallel()
+
+    host = data.synthetic_cae_batch(B, size=SIZE, seed=4 + rank)
+    host = {k: (v.pin_memory() if torch.is_tensor(v) else v) for k, v in host.items()}
+    h2d = host[data.KEY_LABELS].numel() * 4 + host[data.KEY_GLOBAL].numel() * 4 + 3 * B * 4
+    d2h = 4
+
+    # device-resident inputs for `value`
+    with torch.no_grad():
+        dto0 = learner.init_clinical_variables(host, None)
+        dto0 = learner.init_gtruth_segm_variables(host, dto0)
+    res = dto0.given_variables
+
+    def step_resident():
+        dto = CaeDtoUtil.init_dto(res.globals, res.time_to_treatment, res.scalar_types.core, res.scalar_types.penu,
+                                  None, None, res.gtruth.core, res.gtruth.penu, res.gtruth.lesion)
+        dto = cae(dto)
+        loss = learner.loss_step(dto, EPOCH)
+        opt.zero_grad()
+        loss.backward()
+        if learner._grad_sync is not None:
+            learner._grad_sync()
+        opt.step()
+        return loss
+
+    def step_e2e():
+        return learner.train_batch(host, EPOCH).loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    import contextlib
+    with contextlib.redirect_stdout(open(os.devnull, "w")):   # loss_step-style prints must not pollute the JSON line
+        for _ in range(max(args.warmup, 3)):
+            step_resident()
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()
+        ops.reset_launch_count()
+        ms_total = timed(step_resident, args.steps)
+        launches = ops.launch_count()
+        clocks = sampler.stop() if rank == 0 else None
+        for _ in range(2):
+            step_e2e()
+        ms_e2e = timed(step_e2e, args.steps)
+
+        # per-kernel attribution with CUDA events on the launching stream (one extra step, not part of `value`)
+        prof = None
+        if rank == 0:
+            ops.start_profile()
+            step_resident()
+            prof = ops.stop_profile()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    ms_step = ms_total / args.steps
+    value = world * B / (ms_step * 1e-3)
+    e2e_val = world * B / (ms_e2e / args.steps * 1e-3)
+
+    hbm_peak, peak_src = peaks()
+    fam = {}
+    for (name, key), ts in prof.items():
+        f = fam.setdefault((name, key), [0.0, 0])
+        f[0] += sum(ts)
+        f[1] += len(ts)
+    total_prof = sum(v[0] for v in fam.values())
+    (top_name, top_key), (top_ms, top_n) = max(fam.items(), key=lambda kv: kv[1][0])
+    abytes = algorithmic_bytes(top_name, top_key)
+    avg_ms = top_ms / top_n
+    achieved = (abytes / (avg_ms * 1e-3) / 1e9) if abytes else None
+    roofline = {"bound": "hbm", "kernel": "%s [%s]" % (top_name, top_key), "achieved": achieved, "peak": hbm_peak,
+                "peak_source": peak_src, "unit": "GB/s", "frac": (achieved / hbm_peak) if achieved else None,
+                "traffic": None, "avg_launch_ms": avg_ms, "launches_per_step": top_n,
+                "share_of_step": top_ms / total_prof if total_prof else None,
+                "algorithmic_bytes_per_launch": abytes,
+                "note": "fp32 FFMA direct convolution: arithmetic intensity of this layer is above the FFMA ridge, so the "
+                        "HBM fraction is reported for the contract while the binding roof is FP32 FFMA (see DESIGN.md)"}
+    top5 = sorted(fam.items(), key=lambda kv: -kv[1][0])[:8]
+    breakdown = [{"kernel": "%s [%s]" % k, "ms_per_step": round(v[0], 3), "launches": v[1]} for k, v in top5]
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        sec, threads = cpu_reference_step_time(channels, 2, 1, 1)
+        cpu = {"value": 2 / sec, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": "oracle port of the reference CAE train step (torch %s CPU), batch 2 x 1x28x128x128, 1 timed step "
+                         "after 1 warm-up" % torch.__version__}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": workload_config(args, B),
+            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": ms_e2e / args.steps, "api": "CaeReconstructionLearner.train_batch(host_batch, epoch)"},
+            "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "kernel_breakdown": breakdown,
+            "cpu_baseline": cpu}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="cae200", choices=sorted(CHANNELS))
+    ap.add_argument("--batch", type=int, default=8, help="per-GPU batch")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

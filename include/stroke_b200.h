@@ -182,7 +182,7 @@ int sp_latent_interp_bwd(const float* g, const float* zc, const float* zp, const
  * train_unet_segmentation.py:32; beta1 schedule CaeReconstructionLearner.py:28-40):
  *   g += wd*p; m += (g-m)(1-b1); v = b2*v + (1-b2) g^2; p -= (lr/(1-b1^t)) * m / (sqrt(v)/sqrt(1-b2^t) + eps)
  * `table` is a device array of SpAdamTensor; one launch updates all tensors.  grad_scale multiplies g first
- * (1/world_size after a sum all-reduce).  zero_grad != 0 clears g afterwards (optimizer.zero_grad, Learner.py:120).
+ * (1/world_size after a sum all-reduce).  Hyper-parameters are doubles because torch forms 1 - beta in double.  zero_grad != 0 clears g afterwards (optimizer.zero_grad, Learner.py:120).
  * ---------------------------------------------------------------------------------------------------------- */
 typedef struct SpAdamTensor {
     float*  p;
@@ -193,8 +193,8 @@ typedef struct SpAdamTensor {
     int64_t block_start;   /* first CTA index that works on this tensor (prefix sum of ceil(n/SP_ADAM_CHUNK)) */
 } SpAdamTensor;
 #define SP_ADAM_CHUNK 4096
-int sp_adam_multi(const SpAdamTensor* table, int n_tensors, int64_t total_blocks, float lr, float beta1,
-                  float beta2, float eps, float weight_decay, int64_t step, float grad_scale, int zero_grad,
+int sp_adam_multi(const SpAdamTensor* table, int n_tensors, int64_t total_blocks, double lr, double beta1,
+                  double beta2, double eps, double weight_decay, int64_t step, double grad_scale, int zero_grad,
                   void* stream);
 
 #ifdef __cplusplus

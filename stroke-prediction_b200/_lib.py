@@ -21,6 +21,7 @@ c_f32p = ctypes.c_void_p
 c_i64 = ctypes.c_int64
 c_int = ctypes.c_int
 c_float = ctypes.c_float
+c_double = ctypes.c_double
 c_vp = ctypes.c_void_p
 c_size = ctypes.c_size_t
 
@@ -81,7 +82,7 @@ SIGNATURES = {
     "sp_absdiff_bwd": (c_int, [c_vp, c_vp, c_i64, c_int, c_vp, c_float, c_vp, c_int, c_vp, c_int, c_vp]),
     "sp_latent_interp_fwd": (c_int, [c_vp, c_vp, c_vp, c_int, c_i64, c_vp, c_vp]),
     "sp_latent_interp_bwd": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_i64, c_vp, c_int, c_vp, c_int, c_vp, c_vp, c_vp]),
-    "sp_adam_multi": (c_int, [c_vp, c_int, c_i64, c_float, c_float, c_float, c_float, c_float, c_i64, c_float,
+    "sp_adam_multi": (c_int, [c_vp, c_int, c_i64, c_double, c_double, c_double, c_double, c_double, c_i64, c_double,
                               c_int, c_vp]),
 }
 

@@ -13,8 +13,8 @@
 namespace {
 
 __global__ void __launch_bounds__(256)
-adam_multi_kernel(const SpAdamTensor* __restrict__ table, int n_tensors, float step_size, float beta1, float beta2,
-                  float inv_sqrt_bc2, float eps, float wd, float grad_scale, int zero_grad) {
+adam_multi_kernel(const SpAdamTensor* __restrict__ table, int n_tensors, float step_size, float omb1, float beta2,
+                  float omb2, float inv_sqrt_bc2, float eps, float wd, float grad_scale, int zero_grad) {
     // locate the tensor of this CTA
     int lo = 0, hi = n_tensors - 1;
     const int64_t b = blockIdx.x;
@@ -31,8 +31,8 @@ adam_multi_kernel(const SpAdamTensor* __restrict__ table, int n_tensors, float s
         g = fmaf(wd, p, g);
         float m = T.m[i];
         float v = T.v[i];
-        m = m + (g - m) * (1.f - beta1);                    // torch: exp_avg.lerp_(grad, 1 - beta1)
-        v = beta2 * v + (1.f - beta2) * g * g;              // torch: exp_avg_sq.mul_(b2).addcmul_(g, g, 1 - b2)
+        m = m + (g - m) * omb1;                             // torch: exp_avg.lerp_(grad, 1 - beta1)
+        v = beta2 * v + omb2 * g * g;                       // torch: exp_avg_sq.mul_(b2).addcmul_(g, g, 1 - b2)
         const float denom = sqrtf(v) * inv_sqrt_bc2 + eps;  // torch: (sqrt(v) / sqrt(bc2)).add_(eps)
         T.p[i] = p - step_size * (m / denom);
         T.m[i] = m;
@@ -43,19 +43,21 @@ adam_multi_kernel(const SpAdamTensor* __restrict__ table, int n_tensors, float s
 
 }  // namespace
 
-extern "C" int sp_adam_multi(const SpAdamTensor* table, int n_tensors, int64_t total_blocks, float lr, float beta1,
-                             float beta2, float eps, float weight_decay, int64_t step, float grad_scale, int zero_grad,
-                             void* stream) {
+extern "C" int sp_adam_multi(const SpAdamTensor* table, int n_tensors, int64_t total_blocks, double lr, double beta1,
+                             double beta2, double eps, double weight_decay, int64_t step, double grad_scale,
+                             int zero_grad, void* stream) {
     SP_REQUIRE(table && n_tensors > 0 && total_blocks > 0, "sp_adam_multi: empty table");
     SP_REQUIRE(step >= 1, "sp_adam_multi: step counts from 1");
     SP_REQUIRE(total_blocks < (1LL << 31), "sp_adam_multi: too many blocks");
-    const double bc1 = 1.0 - pow((double)beta1, (double)step);
-    const double bc2 = 1.0 - pow((double)beta2, (double)step);
-    const float step_size = (float)((double)lr / bc1);
+    // hyper-parameters arrive as doubles: torch forms 1 - beta in double before rounding to fp32 (1 - 0.999f would be
+    // off by 1.3e-5 relative)
+    const double bc1 = 1.0 - pow(beta1, (double)step);
+    const double bc2 = 1.0 - pow(beta2, (double)step);
+    const float step_size = (float)(lr / bc1);
     const float inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2));
-    adam_multi_kernel<<<(unsigned)total_blocks, 256, 0, sp_stream(stream)>>>(table, n_tensors, step_size, beta1, beta2,
-                                                                          inv_sqrt_bc2, eps, weight_decay, grad_scale,
-                                                                          zero_grad);
+    adam_multi_kernel<<<(unsigned)total_blocks, 256, 0, sp_stream(stream)>>>(
+        table, n_tensors, step_size, (float)(1.0 - beta1), (float)beta2, (float)(1.0 - beta2), inv_sqrt_bc2, (float)eps,
+        (float)weight_decay, (float)grad_scale, zero_grad);
     SP_LAUNCH_OK("adam_multi_kernel");
     return 0;
 }

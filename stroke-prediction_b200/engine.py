@@ -28,6 +28,69 @@ def bump_weights_epoch():
     _weights_epoch += 1
 
 
+class GradSink:
+    """Persistent flat gradient buffer.
+
+    Every trainable parameter's ``.grad`` is a view into one fp32 buffer; the backward chains accumulate weight /
+    bias / BN-affine gradients straight into these views (kernel-side ``beta = 1``) instead of returning fresh
+    tensors to autograd's AccumulateGrad.  Consequences: the CAE's 3 encoder / 4 decoder passes sum their parameter
+    gradients inside the wgrad kernels, gradient pointers are stable (the fused Adam pointer table is built once),
+    clearing is one memset (or fused into the Adam kernel), and data-parallel training all-reduces ONE tensor.
+    """
+
+    def __init__(self, params):
+        params = [p for p in params if p.requires_grad]
+        if not params:
+            raise ValueError("GradSink: no trainable parameters")
+        dev = params[0].device
+        offs, total = [], 0
+        for p in params:
+            if not p.is_cuda or p.dtype != torch.float32:
+                raise RuntimeError("GradSink: fp32 CUDA parameters expected")
+            offs.append(total)
+            total += (p.numel() + 3) // 4 * 4          # keep every view 16-byte aligned
+        self.flat = torch.zeros(total, device=dev, dtype=torch.float32)
+        self.params = params
+        self._views = {}
+        for p, o in zip(params, offs):
+            v = self.flat[o:o + p.numel()].view(p.shape)
+            p.grad = v
+            self._views[id(p)] = v
+        self.dirty = False
+
+    def view(self, p):
+        v = self._views.get(id(p))
+        if v is not None and p.grad is not v:
+            p.grad = v        # somebody set .grad = None (zero_grad(set_to_none=True)): re-attach
+        return v
+
+    def zero(self):
+        self.flat.zero_()
+        self.dirty = False
+
+
+_sinks = []
+
+
+def register_grad_sink(sink):
+    _sinks.append(sink)
+    return sink
+
+
+def unregister_grad_sink(sink):
+    if sink in _sinks:
+        _sinks.remove(sink)
+
+
+def _sink_view(p):
+    for s in _sinks:
+        v = s.view(p)
+        if v is not None:
+            s.dirty = True
+            return v
+    return None
+
+
 def _triple(v):
     return tuple(v) if isinstance(v, (tuple, list)) else (v, v, v)
 
@@ -197,17 +260,21 @@ def seq_backward(plan, saved, gy, need_input_grad, want):
         conv = u.conv
         # ---- parameter gradients
         if want(conv.weight):
-            dw = torch.empty_like(conv.weight, memory_format=torch.contiguous_format)
+            dw, beta = _sink_view(conv.weight), 1.0
+            if dw is None:
+                dw, beta = torch.empty_like(conv.weight, memory_format=torch.contiguous_format), 0.0
+                grads[conv.weight] = dw
             if u.transposed:
-                ops.wgrad(d, gz, None, None, x, scale, shift, G, dw)
+                ops.wgrad(d, gz, None, None, x, scale, shift, G, dw, beta)
             else:
-                ops.wgrad(d, x, scale, shift, gz, None, None, G, dw)
-            grads[conv.weight] = dw
+                ops.wgrad(d, x, scale, shift, gz, None, None, G, dw, beta)
         if conv.bias is not None and want(conv.bias):
-            db = torch.empty_like(conv.bias)
-            gN, gC = gz.shape[0], gz.shape[1]
-            ops.bias_grad(gz, gz.numel() // gC, gC, gC, db)
-            grads[conv.bias] = db
+            db, beta = _sink_view(conv.bias), 1.0
+            if db is None:
+                db, beta = torch.empty_like(conv.bias), 0.0
+                grads[conv.bias] = db
+            gC = gz.shape[1]
+            ops.bias_grad(gz, gz.numel() // gC, gC, gC, db, beta)
         bn_grads = u.bn is not None and u.bn.affine and (want(u.bn.weight) or want(u.bn.bias))
         need_dx = need_input_grad if i == 0 else True
         if not (need_dx or bn_grads):
@@ -221,14 +288,17 @@ def seq_backward(plan, saved, gy, need_input_grad, want):
         coef = None
         if bnrec is not None:
             bn = u.bn
-            dgamma = torch.empty_like(bn.weight) if (bn.affine and want(bn.weight)) else None
-            dbeta = torch.empty_like(bn.bias) if (bn.affine and want(bn.bias)) else None
+            dgamma = dbeta = None
+            beta_acc = 0.0
+            if bn.affine and (want(bn.weight) or want(bn.bias)):
+                dgamma, dbeta = _sink_view(bn.weight), _sink_view(bn.bias)
+                if dgamma is not None and dbeta is not None:
+                    beta_acc = 1.0
+                else:
+                    dgamma, dbeta = torch.empty_like(bn.weight), torch.empty_like(bn.bias)
+                    grads[bn.weight], grads[bn.bias] = dgamma, dbeta
             coef = ops.bn_backward_coef(gxh, x, G, bn.weight if bn.affine else None, bnrec[2], bnrec[3], bnrec[4],
-                                        dgamma, dbeta)
-            if dgamma is not None:
-                grads[bn.weight] = dgamma
-            if dbeta is not None:
-                grads[bn.bias] = dbeta
+                                        dgamma, dbeta, beta_acc)
         if not need_dx:
             break
         prev_act, prev_alpha = (units[i - 1].act, units[i - 1].alpha) if i > 0 else (ACT_NONE, 0.0)

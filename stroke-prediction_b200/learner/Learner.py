@@ -57,6 +57,11 @@ class Learner(Inference):
         self._optimizer = FusedAdam.from_torch(optimizer) if isinstance(optimizer, torch.optim.Adam) else optimizer
         self._scheduler = scheduler
         self._n_epochs = n_epochs
+        self._grad_sync = None   # data-parallel hook (parallel.GradientAllReduce), called between backward and step
+        if isinstance(self._optimizer, FusedAdam) and self.is_cuda:
+            # gradients accumulate straight into one flat buffer and are cleared inside the Adam kernel
+            self._optimizer.attach_grad_sink()
+            self._optimizer.fuse_zero_grad = True
 
         self._path_outputs_base = path_outputs_base
         self._path_previous_base = path_previous_base
@@ -126,6 +131,8 @@ class Learner(Inference):
 
         self._optimizer.zero_grad()
         loss.backward()
+        if self._grad_sync is not None:
+            self._grad_sync()
         self._optimizer.step()
 
         batch_metrics = self.batch_metrics_step(dto, epoch)
@@ -134,6 +141,13 @@ class Learner(Inference):
         del loss
         del dto
         return batch_metrics
+
+    def enable_data_parallel(self, process_group=None):
+        """Batch-sharded training over torch.distributed (one process per GPU): gradients are summed with one
+        all-reduce of the flat gradient buffer and averaged inside the Adam kernel (DDP semantics)."""
+        from ..parallel import GradientAllReduce
+        self._grad_sync = GradientAllReduce(self._optimizer, process_group)
+        return self._grad_sync
 
     def validate_batch(self, batch: dict, epoch) -> MetricMeasuresDto:
         with torch.no_grad():   # the reference builds a graph here for nothing (SURVEY App. B D10)

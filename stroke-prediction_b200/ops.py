@@ -14,8 +14,92 @@ from ._lib import ACT_ELU, ACT_LEAKY, ACT_NONE, ACT_SIGMOID, SpAdamTensor, SpCon
 __all__ = ["ACT_NONE", "ACT_ELU", "ACT_LEAKY", "ACT_SIGMOID"]
 
 
+# ---------------------------------------------------------------------------------------------------- call proxy
+# kernels launched per C-ABI entry point (for the `gpu_launches` figure bench.py reports)
+_KERNELS_PER_CALL = {
+    "sp_pack_weights": 1, "sp_corr": 1, "sp_corrT": 1, "sp_wgrad": 2, "sp_bias_grad": 2, "sp_bn_stats": 1,
+    "sp_bn_finalize": 1, "sp_bn_bwd_reduce": 1, "sp_bn_bwd_finalize": 1, "sp_bn_act_bwd_apply": 1,
+    "sp_maxpool2_fwd": 1, "sp_maxpool2_bwd": 1, "sp_upsample2_fwd": 1, "sp_upsample2_bwd": 1, "sp_crop_copy": 1,
+    "sp_crop_add": 1, "sp_ncdhw_to_ndhwc": 1, "sp_ndhwc_to_ncdhw": 1, "sp_dice_sums": 1, "sp_dice_loss": 1,
+    "sp_dice_bwd": 1, "sp_absdiff_mean": 2, "sp_absdiff_bwd": 1, "sp_latent_interp_fwd": 1,
+    "sp_latent_interp_bwd": 1, "sp_adam_multi": 1,
+}
+
+
+class _Stats:
+    launches = 0          # kernels launched through the C-ABI since the last reset
+    calls = 0
+    profile = None        # None, or a list receiving (name, key, start_event, end_event)
+
+
+def reset_launch_count():
+    _Stats.launches = 0
+    _Stats.calls = 0
+
+
+def launch_count():
+    return _Stats.launches
+
+
+def start_profile():
+    """Record a CUDA-event pair around every C-ABI call on the current stream (bench.py's per-kernel attribution)."""
+    _Stats.profile = []
+
+
+def stop_profile():
+    """-> {(name, key): [ms, ...]} ; synchronises."""
+    rec, _Stats.profile = _Stats.profile, None
+    torch.cuda.synchronize()
+    out = {}
+    for name, key, e0, e1 in rec or []:
+        out.setdefault((name, key), []).append(e0.elapsed_time(e1))
+    return out
+
+
+def _desc_key(args):
+    a0 = args[0] if args else None
+    d = getattr(a0, "_obj", None)
+    if isinstance(d, SpConvDesc):
+        return "N%d I%dx%dx%dx%d O%dx%dx%dx%d k%d s%d" % (d.N, d.Di, d.Hi, d.Wi, d.Ci, d.Do, d.Ho, d.Wo, d.Co, d.k, d.s)
+    return ""
+
+
+class _Proxy:
+    def __init__(self, lib):
+        self._lib = lib
+
+    def __getattr__(self, name):
+        fn = getattr(self._lib, name)
+        nk = _KERNELS_PER_CALL.get(name, 0)
+        if nk == 0:
+            setattr(self, name, fn)
+            return fn
+
+        def call(*args):
+            _Stats.launches += nk
+            _Stats.calls += 1
+            if _Stats.profile is None:
+                return fn(*args)
+            e0 = torch.cuda.Event(enable_timing=True)
+            e1 = torch.cuda.Event(enable_timing=True)
+            e0.record()
+            rc = fn(*args)
+            e1.record()
+            _Stats.profile.append((name, _desc_key(args), e0, e1))
+            return rc
+
+        setattr(self, name, call)
+        return call
+
+
+_proxy = None
+
+
 def _L():
-    return _lib.load()
+    global _proxy
+    if _proxy is None:
+        _proxy = _Proxy(_lib.load())
+    return _proxy
 
 
 def _stream():

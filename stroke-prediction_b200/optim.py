@@ -22,6 +22,7 @@ class FusedAdam(Optimizer):
         defaults = dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay)
         super().__init__(params, defaults)
         self._tables = {}
+        self._sink = None
         self.grad_scale = 1.0       # multiplied into every gradient (1/world_size after a sum all-reduce)
         self.fuse_zero_grad = False  # clear gradients inside the update kernel (saves the separate memset pass)
         self.launches = 0
@@ -42,10 +43,34 @@ class FusedAdam(Optimizer):
         new.state = opt.state
         new.defaults = opt.defaults
         new._tables = {}
+        new._sink = None
         new.grad_scale = 1.0
         new.fuse_zero_grad = False
         new.launches = 0
         return new
+
+    # ------------------------------------------------------------------------------------------ gradient sink
+    def attach_grad_sink(self):
+        """Route all gradients of this optimizer's parameters into one persistent flat buffer (engine.GradSink)."""
+        if getattr(self, '_sink', None) is None:
+            params = [p for g in self.param_groups for p in g['params'] if p.requires_grad]
+            self._sink = engine.register_grad_sink(engine.GradSink(params))
+        return self._sink
+
+    def detach_grad_sink(self):
+        sink = getattr(self, '_sink', None)
+        if sink is not None:
+            engine.unregister_grad_sink(sink)
+            for p in sink.params:
+                p.grad = None
+            self._sink = None
+
+    def zero_grad(self, set_to_none=True):
+        sink = getattr(self, '_sink', None)
+        if sink is None:
+            return super().zero_grad(set_to_none=set_to_none)
+        if sink.dirty or not self.fuse_zero_grad:
+            sink.zero()
 
     @torch.no_grad()
     def step(self, closure=None):
@@ -95,5 +120,8 @@ class FusedAdam(Optimizer):
                 ops.adam_multi(hit[1], len(ents), hit[2], group['lr'], b1, b2, group['eps'], group['weight_decay'],
                                t, self.grad_scale, self.fuse_zero_grad)
                 self.launches += 1
+        sink = getattr(self, '_sink', None)
+        if sink is not None and self.fuse_zero_grad:
+            sink.dirty = False          # the update kernel cleared the gradients it consumed
         engine.bump_weights_epoch()
         return loss
