@@ -127,6 +127,37 @@ def test_fused_unit_forward_backward(case, with_bn):
     _check_sequential(nn.Sequential(*mods), x)
 
 
+TILED_CASES = [
+    # big enough (>= 2048 output voxels, Wo >= 8) to take the shared-memory tiled 3x3x3 path, with ragged tile edges
+    ("C", 16, 16, 3, 1, (1, 0, 0), "elu", (9, 20, 37)),        # Cae3D.py:44
+    ("C", 1, 16, 3, 1, (1, 0, 0), "elu", (9, 18, 35)),         # Cae3D.py:41   Cin = 1 -> CK = 4 kernel
+    ("C", 2, 16, 3, 1, 0, "leaky", (12, 19, 33)),              # Unet3D.py:19  Cin = 2
+    ("C", 3, 8, 3, 1, (1, 0, 0), "elu", (8, 18, 20)),          # Enc3DCtp, Cout = 8 < 16
+    ("C", 24, 24, 3, 1, (1, 0, 0), "elu", (10, 17, 19)),       # Cae3D.py:52   Cout = 24 -> two passes, second ragged
+    ("C", 32, 24, 3, 1, (1, 2, 2), "elu", (7, 14, 15)),        # Cae3D.py:189  pad 2: transposed pass has pad 0
+    ("C", 96, 32, 3, 1, 0, "leaky", (10, 18, 18)),             # Unet3D.py:19  block4 conv a
+    ("C", 16, 100, 3, 1, 0, "elu", (10, 14, 20)),              # Cout = 100 (not a multiple of 16)
+    ("T", 12, 20, 3, 1, 0, "elu", (8, 14, 16)),                # convT k3 s1 forward = flipped correlation, pad 2
+]
+
+
+@pytest.mark.parametrize("case", TILED_CASES, ids=lambda c: "%s%d-%d_p%s" % (c[0], c[1], c[2], str(c[5]).replace(" ", "")))
+def test_tiled_corr_paths(case):
+    kind, cin, cout, k, s, p, act, size = case
+    torch.manual_seed(200 + TILED_CASES.index(case))
+    conv = nn.ConvTranspose3d(cin, cout, k, stride=s, padding=p) if kind == "T" else nn.Conv3d(cin, cout, k, stride=s, padding=p)
+    x = torch.randn(2, cin, *size) * 1.5 + 0.3
+    _check_sequential(nn.Sequential(nn.BatchNorm3d(cin), conv, _act(act)), x)
+
+
+def test_tiled_chain_grouped():
+    seq = nn.Sequential(nn.BatchNorm3d(1), nn.Conv3d(1, 16, 3, padding=(1, 0, 0)), nn.ELU(1.0, True),
+                        nn.BatchNorm3d(16), nn.Conv3d(16, 16, 3, padding=(1, 0, 0)), nn.ELU(1.0, True),
+                        nn.BatchNorm3d(16), nn.Conv3d(16, 16, 3, padding=(1, 2, 2)), nn.ELU(1.0, True))
+    x = (torch.rand(4, 1, 8, 24, 24) > 0.6).float()
+    _check_sequential(seq, x, G=2, check_input_grad=False)
+
+
 def test_unit_eval_mode_uses_running_stats():
     seq = nn.Sequential(nn.BatchNorm3d(6), nn.Conv3d(6, 10, 3, padding=(1, 0, 0)), nn.ELU(1.0, True),
                         nn.BatchNorm3d(10), nn.Conv3d(10, 4, 3, padding=(1, 2, 2)), nn.ELU(1.0, True))
