@@ -114,11 +114,12 @@ int sp_bn_finalize(const double* sums, int64_t count_per_group, int C, int G, co
 int sp_bn_bwd_reduce(const float* gxh, int ldg, const float* x, int ldx, int N, int64_t vox, int C, int G,
                      double* bsums, void* stream);
 /* dgamma/dbeta (accumulated with `beta_acc`, NULL to skip) and the coefficients of
- *   gx = A[g][c]*gxh + B[g][c]*x + Cc[g][c]        (coef layout [3][G][C]) */
+ *   gx = A*((gxh - m1) - (x - mu)*k)        (coef layout [4][G][C]: A, m1, mu, k; same association as ATen so a
+ *   large common mode of gxh cancels exactly) */
 int sp_bn_bwd_finalize(const double* bsums, int64_t count_per_group, int C, int G, const float* gamma,
                        const float* mean, const float* invstd, int training, float* dgamma, float* dbeta,
                        float beta_acc, float* coef, void* stream);
-/* out = (A*gxh + B*x + Cc) * act'(x)   — BN backward apply fused with the backward of the activation that
+/* out = A*((gxh - m1) - (x - mu)*k) * act'(x)   — BN backward apply fused with the backward of the activation that
  * produced x (derivative computed from the activation output).  coef == NULL: out = gxh*act'(x).
  * `accumulate` != 0: out += ...  */
 int sp_bn_act_bwd_apply(const float* gxh, int ldg, const float* x, int ldx, const float* coef, int N,

@@ -12,6 +12,16 @@
 #include "sp_common.cuh"
 #include "sp_conv_tiled.cuh"
 
+// fixed-order sum of per-CTA partial weight-gradient slabs (fp64 accumulation: the partials carry the rounding of long
+// fp32 chains already, the cross-CTA sum should not add to it)
+__global__ void wgrad_reduce_kernel(const float* __restrict__ ws, int chunks, int64_t wn, float* __restrict__ dw, float beta) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < wn; i += (int64_t)gridDim.x * blockDim.x) {
+        double s = 0.0;
+        for (int c = 0; c < chunks; ++c) s += (double)ws[(int64_t)c * wn + i];
+        dw[i] = (beta == 0.f) ? (float)s : fmaf(beta, dw[i], (float)s);
+    }
+}
+
 namespace {
 
 constexpr int kPad = 16;  // packed weights pad the fastest (destination-channel) axis to a multiple of 16
@@ -348,14 +358,6 @@ wgrad_generic_kernel(SpConvDesc d, int nPerG, int ciQ, int coQ, int items, int64
 #pragma unroll
         for (int b = 0; b < 4; ++b)
             if (co0 + a < d.Co && ci0 + b < d.Ci) wsp[((int64_t)(co0 + a) * d.Ci + (ci0 + b)) * k3 + tap] = acc[a][b];
-}
-
-__global__ void wgrad_reduce_kernel(const float* __restrict__ ws, int chunks, int64_t wn, float* __restrict__ dw, float beta) {
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < wn; i += (int64_t)gridDim.x * blockDim.x) {
-        float s = 0.f;
-        for (int c = 0; c < chunks; ++c) s += ws[(int64_t)c * wn + i];
-        dw[i] = (beta == 0.f) ? s : fmaf(beta, dw[i], s);
-    }
 }
 
 // ---- bias gradient: column sums of a [rows][ld] matrix -----------------------------------------------------------

@@ -226,8 +226,244 @@ static inline int sp_tiled_corr_launch(const SpConvDesc* d, int nPerG, const flo
     return 0;
 }
 
-// ---- tiled wgrad: not enabled yet (generic two-stage kernel is used) ------------------------------------------------
-static inline bool sp_tiled_wgrad_supported(const SpConvDesc*) { return false; }
-static inline size_t sp_tiled_wgrad_workspace_bytes(const SpConvDesc*) { return 0; }
-static inline int sp_tiled_wgrad_launch(const SpConvDesc*, int, const float*, const float*, const float*, const float*,
-                                        float*, float, float*, cudaStream_t) { return -1; }
+// =====================================================================================================================
+// Tiled weight gradient for the same 3x3x3 stride-1 layers:
+//   dW[co][ci][tap] = sum_{n,o} gz[n,o,co] * xbn[n, o - p + tap, ci]
+// A CTA owns one (input-channel chunk of CK, output-channel pass of 16) slab of dW and walks over output tiles of
+// 16(w) x 8(h) x 4(d) voxels (grid-strided, so the register accumulators live across many tiles and only
+// gridDim.x partial slabs reach memory).  Per tile it stages the BN-applied, zero-padded input halo (18 x 10 x 6) as
+// channel-quad planes and the gz tile as [voxel][16].  Thread = (sub-group sg = depth plane 0..3, item = (tap, quad)):
+// a 4(ci) x 16(co) register tile, fed per voxel by one LDS.128 of x (tap-shifted) and four warp-broadcast LDS.128 of
+// gz: 64 FFMA per 5 LDS.  The four sub-groups are summed through shared memory at the end (fixed order), partial
+// slabs are reduced across CTAs by wgrad_reduce_kernel in fixed order: deterministic, no atomics.
+namespace sp_tiled {
+
+constexpr int WTD = 4;                               // output tile depth for wgrad
+constexpr int WID = WTD + 2;
+constexpr int WPLANE = WID * IH * RW;                // 1140 float4 per channel-quad plane
+constexpr int WVOX = TW * TH * WTD;                  // 512 output voxels per tile
+
+template <int CK>
+constexpr size_t wgrad_smem_bytes() {
+    size_t stage = (size_t)(CK / 4) * WPLANE * 16 + (size_t)WVOX * COT * 4;
+    size_t red = (size_t)4 * 27 * (CK / 4) * 64 * 4;
+    return stage > red ? stage : red;
+}
+
+template <int CK>
+__global__ void __launch_bounds__(256, 2)
+wgrad3_tiled_kernel(SpConvDesc d, int nPerG, int tiles_w, int tiles_h, int tiles_d, int total_tiles, int n_co_pass,
+                    const float* __restrict__ iside, const float* __restrict__ scale, const float* __restrict__ shift,
+                    const float* __restrict__ oside, float* __restrict__ ws) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int NQ = CK / 4;
+    constexpr int NITEM = 27 * NQ;
+    float4* xs = reinterpret_cast<float4*>(smem_raw);                                  // [NQ][WID][IH][RW]
+    float4* gs = reinterpret_cast<float4*>(smem_raw + (size_t)NQ * WPLANE * 16);       // [WVOX][4]
+
+    const int c0 = (blockIdx.y / n_co_pass) * CK;
+    const int co0 = (blockIdx.y % n_co_pass) * COT;
+    const int sg = threadIdx.x >> 6;            // depth plane of the tile handled by this 64-thread sub-group
+    const int item = threadIdx.x & 63;
+    const bool active = item < NITEM;
+    const int tap = active ? item / NQ : 0;
+    const int q = active ? item % NQ : 0;
+    const int kw = tap % 3, kh = (tap / 3) % 3, kd = tap / 9;
+
+    float acc[4][COT];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < COT; ++b) acc[a][b] = 0.f;
+
+    const bool vec_i = (d.Ci % 4 == 0) && (d.ldi % 4 == 0);
+    const bool vec_o = (d.ldo % 4 == 0) && (co0 + COT <= d.Co);
+
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        int t = tile;
+        const int tw = t % tiles_w; t /= tiles_w;
+        const int th_ = t % tiles_h; t /= tiles_h;
+        const int td_ = t % tiles_d;
+        const int n = t / tiles_d;
+        const int ow0 = tw * TW, oh0 = th_ * TH, od0 = td_ * WTD;
+        const int id0 = od0 - d.pd, ih0 = oh0 - d.ph, iw0 = ow0 - d.pw;
+        const int g = n / nPerG;
+        const float* srcn = iside + (int64_t)n * d.Di * d.Hi * d.Wi * d.ldi;
+        const float* gzn = oside + (int64_t)n * d.Do * d.Ho * d.Wo * d.ldo;
+        __syncthreads();   // previous tile fully consumed
+        for (int i = threadIdx.x; i < WID * IH * IW * NQ; i += 256) {
+            const int qq = i % NQ;
+            int r = i / NQ;
+            const int iw = r % IW; r /= IW;
+            const int ih = r % IH;
+            const int idd = r / IH;
+            const int gd = id0 + idd, gh = ih0 + ih, gw = iw0 + iw;
+            const int c = c0 + qq * 4;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (gd >= 0 && gd < d.Di && gh >= 0 && gh < d.Hi && gw >= 0 && gw < d.Wi && c < d.Ci) {
+                const float* p = srcn + (((int64_t)gd * d.Hi + gh) * d.Wi + gw) * d.ldi + c;
+                if (vec_i) {
+                    v = *reinterpret_cast<const float4*>(p);
+                    if (scale) {
+                        const float4 sc = *reinterpret_cast<const float4*>(scale + (int64_t)g * d.Ci + c);
+                        const float4 sh = *reinterpret_cast<const float4*>(shift + (int64_t)g * d.Ci + c);
+                        v.x = fmaf(v.x, sc.x, sh.x); v.y = fmaf(v.y, sc.y, sh.y);
+                        v.z = fmaf(v.z, sc.z, sh.z); v.w = fmaf(v.w, sc.w, sh.w);
+                    }
+                } else {
+                    float e[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        e[u] = 0.f;
+                        if (c + u < d.Ci) {
+                            e[u] = p[u];
+                            if (scale) e[u] = fmaf(e[u], scale[(int64_t)g * d.Ci + c + u], shift[(int64_t)g * d.Ci + c + u]);
+                        }
+                    }
+                    v = make_float4(e[0], e[1], e[2], e[3]);
+                }
+            }
+            xs[qq * WPLANE + (idd * IH + ih) * RW + iw] = v;
+        }
+        for (int i = threadIdx.x; i < WVOX * (COT / 4); i += 256) {
+            const int j4 = i % (COT / 4);
+            int r = i / (COT / 4);
+            const int w = r % TW; r /= TW;
+            const int h = r % TH;
+            const int dd = r / TH;
+            const int od = od0 + dd, oh = oh0 + h, ow = ow0 + w;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (od < d.Do && oh < d.Ho && ow < d.Wo) {
+                const float* p = gzn + (((int64_t)od * d.Ho + oh) * d.Wo + ow) * d.ldo + co0 + j4 * 4;
+                if (vec_o) {
+                    v = *reinterpret_cast<const float4*>(p);
+                } else {
+                    float e[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) e[u] = (co0 + j4 * 4 + u < d.Co) ? p[u] : 0.f;
+                    v = make_float4(e[0], e[1], e[2], e[3]);
+                }
+            }
+            gs[i] = v;    // i == ((dd*TH + h)*TW + w)*4 + j4
+        }
+        __syncthreads();
+        if (active) {
+            const float4* xrow = xs + q * WPLANE + ((sg + kd) * IH + kh) * RW + kw;
+            const float4* grow = gs + (sg * TH * TW) * (COT / 4);
+#pragma unroll 1
+            for (int h = 0; h < TH; ++h) {
+#pragma unroll 4
+                for (int w = 0; w < TW; ++w) {
+                    const float4 xv = xrow[h * RW + w];
+                    const float4* gp = grow + (h * TW + w) * (COT / 4);
+                    float gzv[COT];
+#pragma unroll
+                    for (int j4 = 0; j4 < COT / 4; ++j4) {
+                        const float4 t4 = gp[j4];
+                        gzv[j4 * 4 + 0] = t4.x; gzv[j4 * 4 + 1] = t4.y; gzv[j4 * 4 + 2] = t4.z; gzv[j4 * 4 + 3] = t4.w;
+                    }
+#pragma unroll
+                    for (int b = 0; b < COT; ++b) {
+                        acc[0][b] = fmaf(xv.x, gzv[b], acc[0][b]);
+                        acc[1][b] = fmaf(xv.y, gzv[b], acc[1][b]);
+                        acc[2][b] = fmaf(xv.z, gzv[b], acc[2][b]);
+                        acc[3][b] = fmaf(xv.w, gzv[b], acc[3][b]);
+                    }
+                }
+            }
+        }
+    }
+
+    // ---- reduce the four sub-groups through shared memory (fixed order) and emit this CTA's partial slab
+    __syncthreads();
+    float* red = reinterpret_cast<float*>(smem_raw);     // [4][NITEM][4][COT]
+    if (active) {
+        float* r = red + ((size_t)sg * NITEM + item) * 64;
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < COT; ++b) r[a * COT + b] = acc[a][b];
+    }
+    __syncthreads();
+    const int64_t wn = (int64_t)d.Co * d.Ci * 27;
+    float* wsp = ws + (int64_t)blockIdx.x * wn;
+    for (int i = threadIdx.x; i < NITEM * 64; i += 256) {
+        const int b = i % COT;
+        const int a = (i / COT) % 4;
+        const int it = i / 64;
+        const int tp = it / NQ, qq = it % NQ;
+        const int ci = c0 + qq * 4 + a, co = co0 + b;
+        if (ci < d.Ci && co < d.Co) {
+            const float v = ((red[(0 * NITEM + it) * 64 + a * COT + b] + red[(1 * NITEM + it) * 64 + a * COT + b]) +
+                             red[(2 * NITEM + it) * 64 + a * COT + b]) + red[(3 * NITEM + it) * 64 + a * COT + b];
+            wsp[((int64_t)co * d.Ci + ci) * 27 + tp] = v;
+        }
+    }
+}
+
+struct WgradTiledPlan {
+    int ck, n_chunks, n_co_pass, tiles_w, tiles_h, tiles_d, total_tiles, grid_x;
+};
+
+static inline WgradTiledPlan wgrad_tiled_plan(const SpConvDesc* d) {
+    WgradTiledPlan p;
+    p.ck = d->Ci > 4 ? 8 : 4;
+    p.n_chunks = (d->Ci + p.ck - 1) / p.ck;
+    p.n_co_pass = (d->Co + COT - 1) / COT;
+    p.tiles_w = (d->Wo + TW - 1) / TW;
+    p.tiles_h = (d->Ho + TH - 1) / TH;
+    p.tiles_d = (d->Do + WTD - 1) / WTD;
+    p.total_tiles = p.tiles_w * p.tiles_h * p.tiles_d * d->N;
+    int gx = (2 * 148) / (p.n_chunks * p.n_co_pass);     // ~2 resident CTAs per SM over all slabs
+    if (gx < 1) gx = 1;
+    if (gx > p.total_tiles) gx = p.total_tiles;
+    p.grid_x = gx;
+    return p;
+}
+
+}  // namespace sp_tiled
+
+__global__ void wgrad_reduce_kernel(const float* __restrict__ ws, int chunks, int64_t wn, float* __restrict__ dw, float beta);
+
+static inline bool sp_tiled_wgrad_supported(const SpConvDesc* d) {
+    if (d->k != 3 || d->s != 1 || sp_tiled_disabled()) return false;
+    const int64_t ov = (int64_t)d->Do * d->Ho * d->Wo;
+    return ov >= 2048 && d->Wo >= 8 && d->Ho >= 4;
+}
+
+static inline size_t sp_tiled_wgrad_workspace_bytes(const SpConvDesc* d) {
+    if (!sp_tiled_wgrad_supported(d)) return 0;
+    const sp_tiled::WgradTiledPlan p = sp_tiled::wgrad_tiled_plan(d);
+    return (size_t)p.grid_x * d->Co * d->Ci * 27 * sizeof(float);
+}
+
+static inline int sp_tiled_wgrad_launch(const SpConvDesc* d, int nPerG, const float* iside, const float* scale,
+                                        const float* shift, const float* oside, float* dw, float beta, float* ws,
+                                        cudaStream_t st) {
+    using namespace sp_tiled;
+    const WgradTiledPlan p = wgrad_tiled_plan(d);
+    dim3 grid(p.grid_x, p.n_chunks * p.n_co_pass);
+    static bool attr8 = false, attr4 = false;
+    if (p.ck == 8) {
+        if (!attr8) {
+            SP_CUDA(cudaFuncSetAttribute(wgrad3_tiled_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wgrad_smem_bytes<8>()));
+            attr8 = true;
+        }
+        wgrad3_tiled_kernel<8><<<grid, 256, wgrad_smem_bytes<8>(), st>>>(*d, nPerG, p.tiles_w, p.tiles_h, p.tiles_d, p.total_tiles,
+                                                                        p.n_co_pass, iside, scale, shift, oside, ws);
+    } else {
+        if (!attr4) {
+            SP_CUDA(cudaFuncSetAttribute(wgrad3_tiled_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wgrad_smem_bytes<4>()));
+            attr4 = true;
+        }
+        wgrad3_tiled_kernel<4><<<grid, 256, wgrad_smem_bytes<4>(), st>>>(*d, nPerG, p.tiles_w, p.tiles_h, p.tiles_d, p.total_tiles,
+                                                                        p.n_co_pass, iside, scale, shift, oside, ws);
+    }
+    SP_LAUNCH_OK("wgrad3_tiled_kernel");
+    const int64_t wn = (int64_t)d->Co * d->Ci * 27;
+    int64_t rb = (wn + 255) / 256;
+    if (rb > 148 * 16) rb = 148 * 16;
+    wgrad_reduce_kernel<<<(int)rb, 256, 0, st>>>(ws, p.grid_x, wn, dw, beta);
+    SP_LAUNCH_OK("wgrad_reduce_kernel");
+    return 0;
+}

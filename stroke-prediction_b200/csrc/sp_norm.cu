@@ -3,7 +3,7 @@
 //
 // The normalised tensor is never written: forward produces per-(group,channel) scale/shift that the consuming
 // convolution applies while staging its input; backward produces the coefficients of
-//   gx = A*gxh + B*x + C   (gxh = gradient w.r.t. the BN output)
+//   gx = A*((gxh - m1) - (x - mu)*k)   (gxh = gradient w.r.t. the BN output)
 // which sp_bn_act_bwd_apply fuses with the derivative of the activation that produced x.
 //
 // All channel reductions accumulate in fp64 (the variance sum x^2 - n*mean^2 cancels catastrophically in fp32 for
@@ -112,7 +112,12 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sums, double count
     }
 }
 
-// coef layout [3][G][C]: A, B, Cc
+// coef layout [4][G][C]: A, m1, mu, k  with   gx = A * ((gxh - m1) - (x - mu) * k)
+//   training: A = gamma*invstd, m1 = mean(gxh), mu = batch mean, k = invstd^2 * mean(gxh * (x - mu))
+//   eval    : A = gamma*invstd(running), m1 = 0, k = 0
+// The subtraction (gxh - m1) is done first and in fp32 exactly like ATen's batch_norm_backward: when the incoming
+// gradient has a large common mode (the hinge term seeds -2/N on half of all voxels) it cancels without rounding;
+// folding m1 into a pre-rounded constant would lose |m1| / |gxh - m1| digits.
 __global__ void bn_bwd_finalize_kernel(const double* __restrict__ bsums, double count, int C, int G,
                                        const float* __restrict__ gamma, const float* __restrict__ mean,
                                        const float* __restrict__ invstd, int training, float* __restrict__ dgamma,
@@ -126,28 +131,19 @@ __global__ void bn_bwd_finalize_kernel(const double* __restrict__ bsums, double 
         const double sx = bsums[((int64_t)g * C + c) * 2 + 1];       // sum gxh*x
         const double mu = (double)mean[g * C + c];
         const double is = (double)invstd[g * C + c];
-        const double s2 = is * (sx - mu * s1);                       // sum gxh*xhat
-        dg += s2;
+        const double dotp = sx - mu * s1;                            // sum gxh*(x - mu)
+        dg += is * dotp;                                             // sum gxh*xhat
         db += s1;
-        double A, B, Cc;
-        if (training) {
-            A = (double)gm * is;
-            B = -(double)gm * is * is * s2 / count;
-            Cc = (double)gm * is * (-s1 / count + mu * is * s2 / count);
-        } else {
-            A = (double)gm * is;
-            B = 0.0;
-            Cc = 0.0;
-        }
-        coef[(0 * G + g) * C + c] = (float)A;
-        coef[(1 * G + g) * C + c] = (float)B;
-        coef[(2 * G + g) * C + c] = (float)Cc;
+        coef[(0 * G + g) * C + c] = (float)((double)gm * is);
+        coef[(1 * G + g) * C + c] = training ? (float)(s1 / count) : 0.f;
+        coef[(2 * G + g) * C + c] = (float)mu;
+        coef[(3 * G + g) * C + c] = training ? (float)(is * is * dotp / count) : 0.f;
     }
     if (dgamma) dgamma[c] = (beta_acc == 0.f) ? (float)dg : fmaf(beta_acc, dgamma[c], (float)dg);
     if (dbeta) dbeta[c] = (beta_acc == 0.f) ? (float)db : fmaf(beta_acc, dbeta[c], (float)db);
 }
 
-// out[v][c] (+)= (A*gxh + B*x + Cc) * act'(x); elementwise over [N*vox][C]
+// out[v][c] (+)= A * ((gxh - m1) - (x - mu) * k) * act'(x); elementwise over [N*vox][C]
 __global__ void __launch_bounds__(256)
 bn_act_bwd_apply_kernel(const float* __restrict__ gxh, int ldg, const float* __restrict__ x, int ldx,
                         const float* __restrict__ coef, int64_t rows, int64_t rows_per_group, int C, int G, int act,
@@ -162,8 +158,9 @@ bn_act_bwd_apply_kernel(const float* __restrict__ gxh, int ldg, const float* __r
         if (coef || act != SP_ACT_NONE) xv = x[r * ldx + c];
         if (coef) {
             const int g = (int)(r / rows_per_group);
-            const float A = coef[(0 * G + g) * C + c], B = coef[(1 * G + g) * C + c], Cc = coef[(2 * G + g) * C + c];
-            res = fmaf(A, gv, fmaf(B, xv, Cc));
+            const float A = coef[(0 * G + g) * C + c], m1 = coef[(1 * G + g) * C + c];
+            const float mu = coef[(2 * G + g) * C + c], k = coef[(3 * G + g) * C + c];
+            res = A * ((gv - m1) - (xv - mu) * k);
         }
         res *= sp_act_bwd(xv, act, alpha);
         float* o = out + r * ldout + c;

@@ -252,19 +252,19 @@ def bn_forward(x, G, gamma, beta, running_mean, running_var, nbt, momentum, eps,
 
 
 def bn_backward_coef(gxh, x, G, gamma, mean, invstd, training, dgamma, dbeta, beta_acc=0.0):
-    """Reduce + finalise BN backward.  Returns coef [3, G, C]; writes dgamma / dbeta when given."""
+    """Reduce + finalise BN backward.  Returns coef [4, G, C]; writes dgamma / dbeta when given."""
     N, C, D, H, W = x.shape
     vox = D * H * W
     bsums = torch.empty((G, C, 2), device=x.device, dtype=torch.float64)
     check(_L().sp_bn_bwd_reduce(_p(gxh), C, _p(x), C, N, vox, C, G, _p(bsums), _stream()), "sp_bn_bwd_reduce")
-    coef = torch.empty((3, G, C), device=x.device, dtype=torch.float32)
+    coef = torch.empty((4, G, C), device=x.device, dtype=torch.float32)
     check(_L().sp_bn_bwd_finalize(_p(bsums), (N // G) * vox, C, G, _p(gamma), _p(mean), _p(invstd), int(bool(training)),
                                   _p(dgamma), _p(dbeta), beta_acc, _p(coef), _stream()), "sp_bn_bwd_finalize")
     return coef
 
 
 def bn_act_bwd_apply(gxh, x, coef, G, act, alpha, out=None, accumulate=False):
-    """out (+)= (A*gxh + B*x + C) * act'(x); coef None -> gxh * act'(x)."""
+    """out (+)= A*((gxh - m1) - (x - mu)*k) * act'(x); coef None -> gxh * act'(x)."""
     N, C, D, H, W = gxh.shape
     if out is None:
         out = new_vol(N, C, D, H, W, gxh.device)
