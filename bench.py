@@ -258,6 +258,12 @@ def run_b200(args):
         ms_total = timed(step_resident, args.steps)
         launches = ops.launch_count()
         clocks = sampler.stop() if rank == 0 else None
+        if args.quick:
+            if rank == 0:
+                sys.stderr.write("quick: %.3f ms/step, %.2f volumes/s\n" % (ms_total / args.steps, world * B / (ms_total / args.steps * 1e-3)))
+            if world > 1:
+                dist.destroy_process_group()
+            return
         for _ in range(2):
             step_e2e()
         ms_e2e = timed(step_e2e, args.steps)
@@ -326,6 +332,7 @@ def main():
     ap.add_argument("--workload", default="cae200", choices=sorted(CHANNELS))
     ap.add_argument("--batch", type=int, default=8, help="per-GPU batch")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--quick", action="store_true", help="profiling aid: resident-input steps only (no e2e / attribution / CPU legs)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -255,7 +255,7 @@ corrT_generic_kernel(SpConvDesc d, int nPerG, int ciP, const float* __restrict__
 // O-side voxels into chunks; each block writes its partial dW into ws[chunk] and a second kernel reduces the
 // chunks in fixed order (deterministic, no float atomics).
 struct WgradPlan {
-    int ciQ, coQ, items, blocks_x, chunks;
+    int ciQ, coQ, items, ipb, vl, blocks_x, chunks;
     int64_t ov, per_chunk, wn;
 };
 
@@ -265,11 +265,17 @@ WgradPlan wgrad_plan(const SpConvDesc* d) {
     p.coQ = (d->Co + 3) / 4;
     const int k3 = d->k * d->k * d->k;
     p.items = k3 * p.ciQ * p.coQ;
-    p.blocks_x = (p.items + 255) / 256;
+    // few work items (1x1x1 layers: 16 or 4): split the voxels of a chunk over `vl` lanes per item so that the CTA
+    // still has 256 busy threads; the lanes are summed through shared memory at the end
+    p.ipb = p.items < 256 ? p.items : 256;
+    p.vl = 1;
+    while (p.vl * 2 * p.ipb <= 256) p.vl *= 2;
+    p.blocks_x = (p.items + p.ipb - 1) / p.ipb;
     p.ov = (int64_t)d->N * d->Do * d->Ho * d->Wo;
     p.wn = (int64_t)d->Co * d->Ci * k3;
     int64_t chunks = sp_cdiv(4 * 148, p.blocks_x);                 // ~4 CTAs per SM in flight
-    chunks = chunks < sp_cdiv(p.ov, 32) ? chunks : sp_cdiv(p.ov, 32);   // at least 32 voxels per chunk
+    const int64_t min_vox = 32 * p.vl;
+    chunks = chunks < sp_cdiv(p.ov, min_vox) ? chunks : sp_cdiv(p.ov, min_vox);
     const int64_t cap = (int64_t)(96u << 20) / (p.wn * 4);         // keep partials under 96 MB
     if (chunks > cap) chunks = cap;
     if (chunks < 1) chunks = 1;
@@ -280,15 +286,19 @@ WgradPlan wgrad_plan(const SpConvDesc* d) {
 
 template <bool VEC_I, bool VEC_O>
 __global__ void __launch_bounds__(256)
-wgrad_generic_kernel(SpConvDesc d, int nPerG, int ciQ, int coQ, int items, int64_t ov, int64_t per_chunk,
+wgrad_generic_kernel(SpConvDesc d, int nPerG, int ciQ, int coQ, int items, int ipb, int vl, int64_t ov, int64_t per_chunk,
                      const float* __restrict__ iside, const float* __restrict__ i_scale, const float* __restrict__ i_shift,
                      const float* __restrict__ oside, const float* __restrict__ o_scale, const float* __restrict__ o_shift,
                      float* __restrict__ ws) {
-    const int item = blockIdx.x * blockDim.x + threadIdx.x;
-    if (item >= items) return;
-    const int coq = item % coQ;
-    const int ciq = (item / coQ) % ciQ;
-    const int tap = item / (coQ * ciQ);
+    __shared__ float red[256 * 16];
+    const int il = threadIdx.x % ipb;           // item within the CTA
+    const int lane_v = threadIdx.x / ipb;       // voxel lane (0 .. vl-1; threads beyond ipb*vl idle)
+    const int item = blockIdx.x * ipb + il;
+    const bool live = (item < items) && (lane_v < vl);
+    const int it = live ? item : 0;
+    const int coq = it % coQ;
+    const int ciq = (it / coQ) % ciQ;
+    const int tap = it / (coQ * ciQ);
     const int kw = tap % d.k, kh = (tap / d.k) % d.k, kd = tap / (d.k * d.k);
     const int ci0 = ciq * 4, co0 = coq * 4;
     const int k3 = d.k * d.k * d.k;
@@ -301,16 +311,15 @@ wgrad_generic_kernel(SpConvDesc d, int nPerG, int ciQ, int coQ, int items, int64
 
     const int64_t v0 = (int64_t)blockIdx.y * per_chunk;
     const int64_t v1 = (v0 + per_chunk < ov) ? v0 + per_chunk : ov;
-    // decode the first voxel, then advance incrementally
-    int64_t t = v0;
-    int ow = (int)(t % d.Wo); t /= d.Wo;
-    int oh = (int)(t % d.Ho); t /= d.Ho;
-    int od = (int)(t % d.Do);
-    int n = (int)(t / d.Do);
-
-    for (int64_t v = v0; v < v1; ++v) {
-        const int id = od * d.s - d.pd + kd, ih = oh * d.s - d.ph + kh, iw = ow * d.s - d.pw + kw;
-        if (id >= 0 && id < d.Di && ih >= 0 && ih < d.Hi && iw >= 0 && iw < d.Wi) {
+    if (live) {
+        for (int64_t v = v0 + lane_v; v < v1; v += vl) {
+            int64_t t = v;
+            const int ow = (int)(t % d.Wo); t /= d.Wo;
+            const int oh = (int)(t % d.Ho); t /= d.Ho;
+            const int od = (int)(t % d.Do);
+            const int n = (int)(t / d.Do);
+            const int id = od * d.s - d.pd + kd, ih = oh * d.s - d.ph + kh, iw = ow * d.s - d.pw + kw;
+            if (id < 0 || id >= d.Di || ih < 0 || ih >= d.Hi || iw < 0 || iw >= d.Wi) continue;
             const int g = n / nPerG;
             const float* ip = iside + ((((int64_t)n * d.Di + id) * d.Hi + ih) * d.Wi + iw) * d.ldi + ci0;
             const float* op = oside + v * d.ldo + co0;
@@ -344,20 +353,24 @@ wgrad_generic_kernel(SpConvDesc d, int nPerG, int ciQ, int coQ, int items, int64
 #pragma unroll
                 for (int b = 0; b < 4; ++b) acc[a][b] = fmaf(xo[a], xi[b], acc[a][b]);
         }
-        if (++ow == d.Wo) {
-            ow = 0;
-            if (++oh == d.Ho) {
-                oh = 0;
-                if (++od == d.Do) { od = 0; ++n; }
-            }
-        }
     }
-    float* wsp = ws + (int64_t)blockIdx.y * ((int64_t)d.Co * d.Ci * k3);
+    // sum the voxel lanes of each item (fixed order) and write the CTA's partial
 #pragma unroll
     for (int a = 0; a < 4; ++a)
 #pragma unroll
-        for (int b = 0; b < 4; ++b)
-            if (co0 + a < d.Co && ci0 + b < d.Ci) wsp[((int64_t)(co0 + a) * d.Ci + (ci0 + b)) * k3 + tap] = acc[a][b];
+        for (int b = 0; b < 4; ++b) red[threadIdx.x * 16 + a * 4 + b] = acc[a][b];
+    __syncthreads();
+    if (lane_v == 0 && item < items) {
+        float* wsp = ws + (int64_t)blockIdx.y * ((int64_t)d.Co * d.Ci * k3);
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                float s = acc[a][b];
+                for (int l = 1; l < vl; ++l) s += red[(l * ipb + il) * 16 + a * 4 + b];
+                if (co0 + a < d.Co && ci0 + b < d.Ci) wsp[((int64_t)(co0 + a) * d.Ci + (ci0 + b)) * k3 + tap] = s;
+            }
+    }
 }
 
 // ---- bias gradient: column sums of a [rows][ld] matrix -----------------------------------------------------------
@@ -489,9 +502,9 @@ int sp_wgrad(const SpConvDesc* d, const float* iside, const float* i_scale, cons
     dim3 grid(p.blocks_x, p.chunks);
     float* wsf = (float*)ws;
 #define SP_WG(VI, VO)                                                                                             \
-    wgrad_generic_kernel<VI, VO><<<grid, 256, 0, sp_stream(stream)>>>(*d, nPerG, p.ciQ, p.coQ, p.items, p.ov,     \
-                                                                      p.per_chunk, iside, i_scale, i_shift, oside, \
-                                                                      o_scale, o_shift, wsf)
+    wgrad_generic_kernel<VI, VO><<<grid, 256, 0, sp_stream(stream)>>>(*d, nPerG, p.ciQ, p.coQ, p.items, p.ipb, p.vl, \
+                                                                      p.ov, p.per_chunk, iside, i_scale, i_shift,   \
+                                                                      oside, o_scale, o_shift, wsf)
     if (vi && vo) SP_WG(true, true);
     else if (vi) SP_WG(true, false);
     else if (vo) SP_WG(false, true);

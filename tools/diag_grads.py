@@ -35,6 +35,12 @@ def pick_gpu(dto):
         return Fn.hinge_mean(rec.penu, rec.interpolation) + Fn.hinge_mean(rec.penu, rec.core)
     if TERMS == "l1":
         return Fn.l1_mean(lat.interpolation, lat.lesion)
+    if TERMS == "hinge_a":
+        return Fn.hinge_mean(rec.penu, rec.core.detach())
+    if TERMS == "hinge_b":
+        return Fn.hinge_mean(rec.penu.detach(), rec.core)
+    if TERMS == "hinge_ab":
+        return Fn.hinge_mean(rec.penu, rec.core)
     return learner.loss_step(dto, 60)
 
 
@@ -45,6 +51,12 @@ def pick_cpu(lat, rec, lab):
         return O.hinge(rec["penu"], rec["interpolation"]) + O.hinge(rec["penu"], rec["core"])
     if TERMS == "l1":
         return O.l1(lat["interpolation"], lat["lesion"])
+    if TERMS == "hinge_a":
+        return O.hinge(rec["penu"], rec["core"].detach())
+    if TERMS == "hinge_b":
+        return O.hinge(rec["penu"].detach(), rec["core"])
+    if TERMS == "hinge_ab":
+        return O.hinge(rec["penu"], rec["core"])
     return O.cae_reconstruction_loss(lat, rec, lab[:, 0:1], lab[:, 1:2], lab[:, 2:3], 60)
 
 
