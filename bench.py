@@ -249,7 +249,7 @@ def run_b200(args):
 
     import contextlib
     with contextlib.redirect_stdout(open(os.devnull, "w")):   # loss_step-style prints must not pollute the JSON line
-        for _ in range(max(args.warmup, 3)):
+        for _ in range(args.warmup if args.quick else max(args.warmup, 3)):
             step_resident()
         sampler = ClockSampler(local)
         if rank == 0:
@@ -301,8 +301,14 @@ def run_b200(args):
                 "algorithmic_bytes_per_launch": abytes,
                 "note": "fp32 FFMA direct convolution: arithmetic intensity of this layer is above the FFMA ridge, so the "
                         "HBM fraction is reported for the contract while the binding roof is FP32 FFMA (see DESIGN.md)"}
-    top5 = sorted(fam.items(), key=lambda kv: -kv[1][0])[:8]
+    top5 = sorted(fam.items(), key=lambda kv: -kv[1][0])[:12]
     breakdown = [{"kernel": "%s [%s]" % k, "ms_per_step": round(v[0], 3), "launches": v[1]} for k, v in top5]
+    by_op = {}
+    for (name, key), v in fam.items():
+        o = by_op.setdefault(name, [0.0, 0])
+        o[0] += v[0]
+        o[1] += v[1]
+    op_breakdown = {k: {"ms_per_step": round(v[0], 3), "launches": v[1]} for k, v in sorted(by_op.items(), key=lambda kv: -kv[1][0])}
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
@@ -316,7 +322,7 @@ def run_b200(args):
             "data": "synthetic", "config": workload_config(args, B),
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / args.steps, "api": "CaeReconstructionLearner.train_batch(host_batch, epoch)"},
-            "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "kernel_breakdown": breakdown,
+            "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "kernel_breakdown": breakdown, "op_breakdown": op_breakdown,
             "cpu_baseline": cpu}
     print(json.dumps(line), flush=True)
     if world > 1:

