@@ -53,11 +53,21 @@ class CaeInference(Inference):
                                    None, None, None, None, None)
 
     def init_gtruth_segm_variables(self, batch: dict, dto: CaeDto):
-        labels = self._to_device(batch[data.KEY_LABELS])
-        vol = ops.as_vol(labels)                       # one transpose kernel: N x 3 x D x H x W -> NDHWC
-        dto.given_variables.gtruth.core = ops.extract_channel(vol, 0)
-        dto.given_variables.gtruth.penu = ops.extract_channel(vol, 1)
-        dto.given_variables.gtruth.lesion = ops.extract_channel(vol, 2)
+        labels = batch[data.KEY_LABELS]
+        if not self.is_cuda:
+            raise RuntimeError("model is not on a CUDA device — stroke_prediction_b200 has no CPU path")
+        if labels.dtype != torch.float32:
+            labels = labels.float()
+        B, C, D, H, W = labels.shape
+        # The three masks land in ONE [3B, 1, D, H, W] buffer, channel-major, as three strided copies (for a pinned
+        # host batch that is three 2-D DMA transfers, no kernel).  The encoder recognises the adjacent slices and runs
+        # core / penumbra / lesion as one stacked pass.
+        buf = torch.empty((3 * B, 1, D, H, W), device=self.device, dtype=torch.float32)
+        for c in range(3):
+            buf[c * B:(c + 1) * B].copy_(labels[:, c:c + 1], non_blocking=True)
+        dto.given_variables.gtruth.core = buf[0:B]
+        dto.given_variables.gtruth.penu = buf[B:2 * B]
+        dto.given_variables.gtruth.lesion = buf[2 * B:3 * B]
         return dto
 
     def infer(self, dto: CaeDto):

@@ -36,6 +36,27 @@ class _PlanCache:
 _plans = _PlanCache()
 
 
+def _run_grouped(owner, attr, inputs, what):
+    """Run owner.<attr> (a Sequential) on every non-None input; same-shaped ones share one stacked pass."""
+    present = [(i, t) for i, t in enumerate(inputs) if t is not None]
+    outs = [None] * len(inputs)
+    if not present:
+        return outs
+    for _, t in present:
+        _require_cuda(t, what)
+    plan = _plans.get(owner, attr)
+    if GROUP_PASSES and len({tuple(t.shape) for _, t in present}) == 1:
+        ys = engine.run_sequential_grouped(plan, [t for _, t in present])
+    else:
+        ys = [engine.run_sequential(plan, t) for _, t in present]
+    for (i, _), y in zip(present, ys):
+        outs[i] = y
+    return outs
+
+
+GROUP_PASSES = True   # False: one launch sequence per pass, literally like the reference (used by A/B tests)
+
+
 class CaeBase(nn.Module):
 
     def __init__(self, size_input_xy=128, size_input_z=28, channels=[1, 16, 32, 64, 128, 1024, 128, 1], n_ch_global=2,
@@ -109,20 +130,24 @@ class Enc3D(CaeBase):
     def _get_step(self, dto: CaeDto):
         return dto.given_variables.time_to_treatment
 
+    def _forward_group(self, inputs):
+        """The reference calls the encoder once per input, in order (Cae3D.py:105-107,113-114).  Same-shaped inputs
+        are stacked along the batch and run as ONE pass with per-call BatchNorm statistics and sequential
+        running-stat updates, which is numerically the same thing with a third of the launches."""
+        return _run_grouped(self, 'encoder', inputs, 'Enc3D')
+
     def forward(self, dto: CaeDto):
         step = self._get_step(dto)
         given, latents = dto.given_variables, dto.latents
 
         if dto.flag == CaeDtoUtil.FLAG_GTRUTH or dto.flag == CaeDtoUtil.FLAG_DEFAULT:
             assert latents.gtruth._is_empty()  # do not overwrite earlier results
-            latents.gtruth.core = self._forward_single(given.gtruth.core)
-            latents.gtruth.penu = self._forward_single(given.gtruth.penu)
-            latents.gtruth.lesion = self._forward_single(given.gtruth.lesion)
+            latents.gtruth.core, latents.gtruth.penu, latents.gtruth.lesion = self._forward_group(
+                [given.gtruth.core, given.gtruth.penu, given.gtruth.lesion])
             latents.gtruth.interpolation = self._interpolate(latents.gtruth.core, latents.gtruth.penu, step)
         if dto.flag == CaeDtoUtil.FLAG_INPUTS or dto.flag == CaeDtoUtil.FLAG_DEFAULT:
             assert latents.inputs._is_empty()
-            latents.inputs.core = self._forward_single(given.inputs.core)
-            latents.inputs.penu = self._forward_single(given.inputs.penu)
+            latents.inputs.core, latents.inputs.penu = self._forward_group([given.inputs.core, given.inputs.penu])
             latents.inputs.interpolation = self._interpolate(latents.inputs.core, latents.inputs.penu, step)
         return dto
 
@@ -185,9 +210,9 @@ class Enc3DCtp(Enc3D):
         cbv, ttd = given.inputs.core, given.inputs.penu
         if dto.flag == CaeDtoUtil.FLAG_GTRUTH or dto.flag == CaeDtoUtil.FLAG_DEFAULT:
             lat = dto.latents.gtruth
-            lat.core = self._forward_single(self._stack(given.gtruth.core, cbv, ttd))
-            lat.penu = self._forward_single(self._stack(given.gtruth.penu, cbv, ttd))
-            lat.lesion = self._forward_single(self._stack(given.gtruth.lesion, cbv, ttd))
+            lat.core, lat.penu, lat.lesion = self._forward_group(
+                [self._stack(given.gtruth.core, cbv, ttd), self._stack(given.gtruth.penu, cbv, ttd),
+                 self._stack(given.gtruth.lesion, cbv, ttd)])
             lat.interpolation = self._interpolate(lat.core, lat.penu, step)
         return dto
 
@@ -217,19 +242,19 @@ class Dec3D(CaeBase):
         _require_cuda(input_latent, 'Dec3D')
         return engine.run_sequential(_plans.get(self, 'decoder'), input_latent)
 
+    def _forward_group(self, latents):
+        return _run_grouped(self, 'decoder', latents, 'Dec3D')
+
     def forward(self, dto: CaeDto):
         lat, rec = dto.latents, dto.reconstructions
         if dto.flag == CaeDtoUtil.FLAG_GTRUTH or dto.flag == CaeDtoUtil.FLAG_DEFAULT:
             assert rec.gtruth._is_empty()  # do not overwrite earlier results
-            rec.gtruth.core = self._forward_single(lat.gtruth.core)
-            rec.gtruth.penu = self._forward_single(lat.gtruth.penu)
-            rec.gtruth.lesion = self._forward_single(lat.gtruth.lesion)
-            rec.gtruth.interpolation = self._forward_single(lat.gtruth.interpolation)
+            rec.gtruth.core, rec.gtruth.penu, rec.gtruth.lesion, rec.gtruth.interpolation = self._forward_group(
+                [lat.gtruth.core, lat.gtruth.penu, lat.gtruth.lesion, lat.gtruth.interpolation])
         if dto.flag == CaeDtoUtil.FLAG_INPUTS or dto.flag == CaeDtoUtil.FLAG_DEFAULT:
             assert rec.inputs._is_empty()
-            rec.inputs.core = self._forward_single(lat.inputs.core)
-            rec.inputs.penu = self._forward_single(lat.inputs.penu)
-            rec.inputs.interpolation = self._forward_single(lat.inputs.interpolation)
+            rec.inputs.core, rec.inputs.penu, rec.inputs.interpolation = self._forward_group(
+                [lat.inputs.core, lat.inputs.penu, lat.inputs.interpolation])
         return dto
 
 

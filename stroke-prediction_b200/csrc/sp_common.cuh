@@ -72,6 +72,18 @@ __device__ __forceinline__ float sp_act_bwd(float y, int act, float alpha) {
     }
 }
 
+// ---- packed fp32 FMA (Blackwell FFMA2): {acc.x, acc.y} += x * {w.x, w.y} -------------------------------------------
+// One instruction, two FMAs per lane; ptxas folds the (x, x) pair into a scalar-broadcast operand (`Rx.F32`), so the
+// FMA pipe still retires 128 FMA/clk/SM while only every second issue slot is an FFMA and every operand is one
+// aligned 64-bit register read (no even/odd bank conflicts).
+__device__ __forceinline__ float2 sp_ffma2(float x, float2 w, float2 acc) {
+    float2 xx = make_float2(x, x);
+    unsigned long long ra = *reinterpret_cast<unsigned long long*>(&xx), rb = *reinterpret_cast<unsigned long long*>(&w),
+                       rc = *reinterpret_cast<unsigned long long*>(&acc), rd;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+    return *reinterpret_cast<float2*>(&rd);
+}
+
 // ---- reductions ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ double sp_warp_sum(double v) {
 #pragma unroll

@@ -18,23 +18,29 @@
 
 namespace sp_tiled {
 
-constexpr int TW = 16, TH = 8, TD = 8;           // output tile
-constexpr int IW = TW + 2, IH = TH + 2, ID = TD + 2;
+constexpr int TW = 16, TH = 8;                   // output tile in w, h; depth TD (4 or 8) is a template parameter
+constexpr int IW = TW + 2, IH = TH + 2;
 constexpr int RW = 19;                           // padded row length (float4 units), odd -> conflict-free row stride
-constexpr int PLANE = ID * IH * RW;              // 1900 float4 per channel-quad plane; 1900 % 8 == 4 -> conflict-free staging
 constexpr int COT = 16;                          // output channels per thread / per CTA pass
 constexpr int VT = 4;                            // voxels per thread along w
 
-template <int CK>
-constexpr size_t smem_bytes() { return (size_t)(CK / 4) * PLANE * 16 + (size_t)27 * CK * COT * 4; }
+// float4 per channel-quad plane; (TD+2)*190 is 1900 (TD=8) or 1140 (TD=4), both == 4 mod 8 -> conflict-free staging
+template <int TD>
+__host__ __device__ constexpr int plane_f4() { return (TD + 2) * IH * RW; }
+
+template <int CK, int TD>
+constexpr size_t smem_bytes() { return (size_t)(CK / 4) * plane_f4<TD>() * 16 + (size_t)27 * CK * COT * 4; }
 
 // d: correlation geometry (k = 3, s = 1).  wp: packed [tap][src channel][dstP]; flip != 0 reads tap 26 - t.
-template <int CK>
-__global__ void __launch_bounds__(256, 2)
+template <int CK, int TD>
+__global__ void __launch_bounds__(32 * TD, 512 / (32 * TD))
 corr3_tiled_kernel(SpConvDesc d, int nPerG, int dstP, int tiles_w, int tiles_h, int tiles_d, const float* __restrict__ src,
                    const float* __restrict__ wp, int flip, const float* __restrict__ bias, const float* __restrict__ scale,
                    const float* __restrict__ shift, float* __restrict__ dst) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int ID = TD + 2;
+    constexpr int PLANE = plane_f4<TD>();
+    constexpr int NT = 32 * TD;
     float4* xs = reinterpret_cast<float4*>(smem_raw);                                   // [CK/4][ID][IH][RW]
     float* wsm = reinterpret_cast<float*>(smem_raw + (size_t)(CK / 4) * PLANE * 16);    // [27][CK][COT]
 
@@ -50,11 +56,11 @@ corr3_tiled_kernel(SpConvDesc d, int nPerG, int dstP, int tiles_w, int tiles_h, 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int ltd = warp, lth = lane & 7, lw0 = (lane >> 3) * VT;
 
-    float acc[VT][COT];
+    float2 acc[VT][COT / 2];
 #pragma unroll
     for (int v = 0; v < VT; ++v)
 #pragma unroll
-        for (int j = 0; j < COT; ++j) acc[v][j] = 0.f;
+        for (int j = 0; j < COT / 2; ++j) acc[v][j] = make_float2(0.f, 0.f);
 
     const bool vec = (d.Ci % 4 == 0) && (d.ldi % 4 == 0);
     const int id0 = od0 - d.pd, ih0 = oh0 - d.ph, iw0 = ow0 - d.pw;
@@ -64,7 +70,7 @@ corr3_tiled_kernel(SpConvDesc d, int nPerG, int dstP, int tiles_w, int tiles_h, 
         __syncthreads();   // previous chunk fully consumed
         // ---- stage the input halo tile of channels [c0, c0 + CK): BN applied, padding written as zeros
         constexpr int NQ = CK / 4;
-        for (int i = threadIdx.x; i < ID * IH * IW * NQ; i += 256) {
+        for (int i = threadIdx.x; i < ID * IH * IW * NQ; i += NT) {
             const int q = i % NQ;
             int r = i / NQ;
             const int iw = r % IW; r /= IW;
@@ -99,7 +105,7 @@ corr3_tiled_kernel(SpConvDesc d, int nPerG, int dstP, int tiles_w, int tiles_h, 
             xs[q * PLANE + (idd * IH + ih) * RW + iw] = v;
         }
         // ---- stage the weight slab [27][CK][COT] of this chunk / output-channel pass
-        for (int i = threadIdx.x; i < 27 * CK * (COT / 4); i += 256) {
+        for (int i = threadIdx.x; i < 27 * CK * (COT / 4); i += NT) {
             const int j4 = i % (COT / 4);
             int r = i / (COT / 4);
             const int cl = r % CK;
@@ -128,18 +134,19 @@ corr3_tiled_kernel(SpConvDesc d, int nPerG, int dstP, int tiles_w, int tiles_h, 
 #pragma unroll
                         for (int c = 0; c < 4; ++c) {
                             const float4* wv = reinterpret_cast<const float4*>(wtap + (kw * CK + q * 4 + c) * COT);
-                            float w[COT];
+                            float2 w[COT / 2];
 #pragma unroll
                             for (int j4 = 0; j4 < COT / 4; ++j4) {
                                 const float4 t4 = wv[j4];
-                                w[j4 * 4 + 0] = t4.x; w[j4 * 4 + 1] = t4.y; w[j4 * 4 + 2] = t4.z; w[j4 * 4 + 3] = t4.w;
+                                w[j4 * 2 + 0] = make_float2(t4.x, t4.y);
+                                w[j4 * 2 + 1] = make_float2(t4.z, t4.w);
                             }
 #pragma unroll
                             for (int v = 0; v < VT; ++v) {
                                 const float4 xv = xin[v + kw];
                                 const float x = (c == 0) ? xv.x : (c == 1) ? xv.y : (c == 2) ? xv.z : xv.w;
 #pragma unroll
-                                for (int j = 0; j < COT; ++j) acc[v][j] = fmaf(x, w[j], acc[v][j]);
+                                for (int j = 0; j < COT / 2; ++j) acc[v][j] = sp_ffma2(x, w[j], acc[v][j]);
                             }
                         }
                     }
@@ -164,16 +171,16 @@ corr3_tiled_kernel(SpConvDesc d, int nPerG, int dstP, int tiles_w, int tiles_h, 
 #pragma unroll
             for (int j4 = 0; j4 < COT / 4; ++j4) {
                 float4 o;
-                o.x = sp_act_fwd(acc[v][j4 * 4 + 0] + b[j4 * 4 + 0], d.act, d.alpha);
-                o.y = sp_act_fwd(acc[v][j4 * 4 + 1] + b[j4 * 4 + 1], d.act, d.alpha);
-                o.z = sp_act_fwd(acc[v][j4 * 4 + 2] + b[j4 * 4 + 2], d.act, d.alpha);
-                o.w = sp_act_fwd(acc[v][j4 * 4 + 3] + b[j4 * 4 + 3], d.act, d.alpha);
+                o.x = sp_act_fwd(acc[v][j4 * 2 + 0].x + b[j4 * 4 + 0], d.act, d.alpha);
+                o.y = sp_act_fwd(acc[v][j4 * 2 + 0].y + b[j4 * 4 + 1], d.act, d.alpha);
+                o.z = sp_act_fwd(acc[v][j4 * 2 + 1].x + b[j4 * 4 + 2], d.act, d.alpha);
+                o.w = sp_act_fwd(acc[v][j4 * 2 + 1].y + b[j4 * 4 + 3], d.act, d.alpha);
                 reinterpret_cast<float4*>(yp)[j4] = o;
             }
         } else {
 #pragma unroll
             for (int j = 0; j < COT; ++j)
-                if (co0 + j < d.Co) yp[j] = sp_act_fwd(acc[v][j] + b[j], d.act, d.alpha);
+                if (co0 + j < d.Co) yp[j] = sp_act_fwd(((j & 1) ? acc[v][j >> 1].y : acc[v][j >> 1].x) + b[j], d.act, d.alpha);
         }
     }
 }
@@ -197,33 +204,39 @@ static inline bool sp_tiled_corr_supported(const SpConvDesc* d) {
     return ov >= 2048 && d->Wo >= 8 && d->Ho >= 4;
 }
 
-static inline int sp_tiled_corr_launch(const SpConvDesc* d, int nPerG, const float* src, const float* wp, int flip,
-                                       const float* bias, const float* scale, const float* shift, float* dst,
-                                       cudaStream_t st) {
+template <int CK, int TD>
+static inline int sp_tiled_corr_launch_t(const SpConvDesc* d, int nPerG, const float* src, const float* wp, int flip,
+                                         const float* bias, const float* scale, const float* shift, float* dst,
+                                         cudaStream_t st) {
     using namespace sp_tiled;
     const int tiles_w = (d->Wo + TW - 1) / TW, tiles_h = (d->Ho + TH - 1) / TH, tiles_d = (d->Do + TD - 1) / TD;
     const int64_t nblk = (int64_t)tiles_w * tiles_h * tiles_d * d->N;
     SP_REQUIRE(nblk < (1LL << 31), "tiled corr: too many tiles");
     const int dstP = (d->Co + 15) / 16 * 16;
     dim3 grid((unsigned)nblk, (unsigned)(dstP / COT));
-    static bool attr8 = false, attr4 = false;
-    if (d->Ci > 4) {
-        if (!attr8) {
-            SP_CUDA(cudaFuncSetAttribute(corr3_tiled_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<8>()));
-            attr8 = true;
-        }
-        corr3_tiled_kernel<8><<<grid, 256, smem_bytes<8>(), st>>>(*d, nPerG, dstP, tiles_w, tiles_h, tiles_d, src, wp, flip, bias,
-                                                                 scale, shift, dst);
-    } else {
-        if (!attr4) {
-            SP_CUDA(cudaFuncSetAttribute(corr3_tiled_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<4>()));
-            attr4 = true;
-        }
-        corr3_tiled_kernel<4><<<grid, 256, smem_bytes<4>(), st>>>(*d, nPerG, dstP, tiles_w, tiles_h, tiles_d, src, wp, flip, bias,
-                                                                 scale, shift, dst);
+    static bool attr = false;
+    if (!attr) {
+        SP_CUDA(cudaFuncSetAttribute(corr3_tiled_kernel<CK, TD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)smem_bytes<CK, TD>()));
+        attr = true;
     }
+    corr3_tiled_kernel<CK, TD><<<grid, 32 * TD, smem_bytes<CK, TD>(), st>>>(*d, nPerG, dstP, tiles_w, tiles_h, tiles_d, src, wp,
+                                                                          flip, bias, scale, shift, dst);
     SP_LAUNCH_OK("corr3_tiled_kernel");
     return 0;
+}
+
+static inline int sp_tiled_corr_launch(const SpConvDesc* d, int nPerG, const float* src, const float* wp, int flip,
+                                       const float* bias, const float* scale, const float* shift, float* dst,
+                                       cudaStream_t st) {
+    // depth tile: 4 planes (128-thread CTAs, 4 per SM) when that wastes fewer padded planes than 8 (D = 28: 0 vs 4)
+    const bool td4 = ((d->Do + 3) / 4 * 4) < ((d->Do + 7) / 8 * 8);
+    if (d->Ci > 4) {
+        return td4 ? sp_tiled_corr_launch_t<8, 4>(d, nPerG, src, wp, flip, bias, scale, shift, dst, st)
+                   : sp_tiled_corr_launch_t<8, 8>(d, nPerG, src, wp, flip, bias, scale, shift, dst, st);
+    }
+    return td4 ? sp_tiled_corr_launch_t<4, 4>(d, nPerG, src, wp, flip, bias, scale, shift, dst, st)
+               : sp_tiled_corr_launch_t<4, 8>(d, nPerG, src, wp, flip, bias, scale, shift, dst, st);
 }
 
 // =====================================================================================================================
@@ -270,11 +283,11 @@ wgrad3_tiled_kernel(SpConvDesc d, int nPerG, int tiles_w, int tiles_h, int tiles
     const int q = active ? item % NQ : 0;
     const int kw = tap % 3, kh = (tap / 3) % 3, kd = tap / 9;
 
-    float acc[4][COT];
+    float2 acc[4][COT / 2];
 #pragma unroll
     for (int a = 0; a < 4; ++a)
 #pragma unroll
-        for (int b = 0; b < COT; ++b) acc[a][b] = 0.f;
+        for (int b = 0; b < COT / 2; ++b) acc[a][b] = make_float2(0.f, 0.f);
 
     const bool vec_i = (d.Ci % 4 == 0) && (d.ldi % 4 == 0);
     const bool vec_o = (d.ldo % 4 == 0) && (co0 + COT <= d.Co);
@@ -356,18 +369,19 @@ wgrad3_tiled_kernel(SpConvDesc d, int nPerG, int tiles_w, int tiles_h, int tiles
                 for (int w = 0; w < TW; ++w) {
                     const float4 xv = xrow[h * RW + w];
                     const float4* gp = grow + (h * TW + w) * (COT / 4);
-                    float gzv[COT];
+                    float2 gzv[COT / 2];
 #pragma unroll
                     for (int j4 = 0; j4 < COT / 4; ++j4) {
                         const float4 t4 = gp[j4];
-                        gzv[j4 * 4 + 0] = t4.x; gzv[j4 * 4 + 1] = t4.y; gzv[j4 * 4 + 2] = t4.z; gzv[j4 * 4 + 3] = t4.w;
+                        gzv[j4 * 2 + 0] = make_float2(t4.x, t4.y);
+                        gzv[j4 * 2 + 1] = make_float2(t4.z, t4.w);
                     }
 #pragma unroll
-                    for (int b = 0; b < COT; ++b) {
-                        acc[0][b] = fmaf(xv.x, gzv[b], acc[0][b]);
-                        acc[1][b] = fmaf(xv.y, gzv[b], acc[1][b]);
-                        acc[2][b] = fmaf(xv.z, gzv[b], acc[2][b]);
-                        acc[3][b] = fmaf(xv.w, gzv[b], acc[3][b]);
+                    for (int b = 0; b < COT / 2; ++b) {
+                        acc[0][b] = sp_ffma2(xv.x, gzv[b], acc[0][b]);
+                        acc[1][b] = sp_ffma2(xv.y, gzv[b], acc[1][b]);
+                        acc[2][b] = sp_ffma2(xv.z, gzv[b], acc[2][b]);
+                        acc[3][b] = sp_ffma2(xv.w, gzv[b], acc[3][b]);
                     }
                 }
             }
@@ -382,7 +396,10 @@ wgrad3_tiled_kernel(SpConvDesc d, int nPerG, int tiles_w, int tiles_h, int tiles
 #pragma unroll
         for (int a = 0; a < 4; ++a)
 #pragma unroll
-            for (int b = 0; b < COT; ++b) r[a * COT + b] = acc[a][b];
+            for (int b = 0; b < COT / 2; ++b) {
+                r[a * COT + 2 * b] = acc[a][b].x;
+                r[a * COT + 2 * b + 1] = acc[a][b].y;
+            }
     }
     __syncthreads();
     const int64_t wn = (int64_t)d.Co * d.Ci * 27;

@@ -336,6 +336,66 @@ def run_sequential(plan, x, G=1):
     return SeqFunction.apply(x, plan, G, *plan.params())
 
 
+def _adjacent_views(ts):
+    """True when the NDHWC volumes `ts` are consecutive batch slices of one dense buffer (zero-copy grouping)."""
+    t0 = ts[0]
+    if not ops.is_ndhwc(t0):
+        return False
+    base = t0.untyped_storage().data_ptr()
+    off = t0.storage_offset()
+    for t in ts:
+        if (t.shape != t0.shape or t.dtype != t0.dtype or not ops.is_ndhwc(t) or t.untyped_storage().data_ptr() != base
+                or t.storage_offset() != off or t.requires_grad):
+            return False
+        off += t.numel()
+    return off * t0.element_size() <= t0.untyped_storage().nbytes()
+
+
+def group_volumes(ts):
+    """Stack same-shaped volumes along the batch axis as one NDHWC volume [G*B, C, D, H, W]."""
+    if len(ts) == 1:
+        return ts[0]
+    if all(t.is_cuda for t in ts) and _adjacent_views(ts):
+        B, C, D, H, W = ts[0].shape
+        return ts[0].as_strided((len(ts) * B, C, D, H, W), ts[0].stride())
+    return torch.cat([ops.as_vol(t) if t.is_cuda else t for t in ts], dim=0)
+
+
+class _SplitGroups(torch.autograd.Function):
+    """[G*B, ...] -> G batch slices (views); the backward stitches the G incoming gradients into one volume."""
+
+    @staticmethod
+    def forward(ctx, y, G):
+        ctx.G = G
+        ctx.shape = y.shape
+        B = y.shape[0] // G
+        return tuple(y.narrow(0, g * B, B) for g in range(G))
+
+    @staticmethod
+    def backward(ctx, *gs):
+        N, C, D, H, W = ctx.shape
+        B = N // ctx.G
+        dev = next(g for g in gs if g is not None).device
+        out = ops.new_vol(N, C, D, H, W, dev)
+        for i, g in enumerate(gs):
+            dst = out.narrow(0, i * B, B)
+            if g is None:
+                dst.zero_()
+            else:
+                dst.copy_(g)
+        return out, None
+
+
+def run_sequential_grouped(plan, xs):
+    """Run `plan` on G same-shaped inputs as ONE stacked pass with per-group BatchNorm statistics (identical to G
+    separate calls in the reference's order, Cae3D.py:105-110,230-233).  Returns the G outputs."""
+    G = len(xs)
+    if G == 1:
+        return [run_sequential(plan, xs[0], 1)]
+    y = run_sequential(plan, group_volumes(xs), G)
+    return list(_SplitGroups.apply(y, G))
+
+
 # =====================================================================================================================
 class UnetPlan:
     """The 3-scale U-Net graph of Unet3D.forward (Unet3D.py:56-79)."""

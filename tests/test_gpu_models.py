@@ -373,3 +373,37 @@ def test_unet_named_config_patch_size_against_oracle():
     for n, p in unet.named_parameters():
         e_gpu, e_cpu = rel_l2(p.grad, g64[n]), rel_l2(g32[n], g64[n])
         assert e_gpu <= max(TOL_GRAD, 2 * e_cpu), "%s: gpu %g cpu32 %g" % (n, e_gpu, e_cpu)
+
+
+def test_stacked_passes_equal_separate_passes():
+    """Running core / penumbra / lesion (/ interpolation) as one stacked pass with per-group BatchNorm statistics is
+    the same computation as the reference's separate calls: compare the two execution modes of the drop-in."""
+    A = _api()
+    import stroke_prediction_b200.common.model.Cae3D as M
+    ch = [1, 4, 6, 8, 10, 12, 1]
+    results = []
+    for grouped in (True, False):
+        M.GROUP_PASSES = grouped
+        try:
+            torch.manual_seed(41)
+            cae = A.Cae3D(A.Enc3D(56, 28, ch, 5, 1.0), A.Dec3D(56, 28, ch, 5, 1.0)).cuda().train()
+            opt = A.FusedAdam(cae.parameters(), lr=1e-3, weight_decay=1e-5)
+            learner = A.CaeReconstructionLearner(None, None, cae, opt, None, 1, None, "/tmp/x", A.BatchDiceLoss([1.0]))
+            batch = A.data.synthetic_cae_batch(2, size=(28, 56, 56), seed=5)
+            dto = learner.inference_step(batch)
+            loss = learner.loss_step(dto, 60)
+            opt.zero_grad()
+            loss.backward()
+            results.append((loss.item(), {n: p.grad.clone() for n, p in cae.named_parameters()},
+                            {k: v.clone() for k, v in cae.state_dict().items() if "running" in k or "num_batches" in k},
+                            dto.reconstructions.gtruth.interpolation.detach().clone()))
+            opt.detach_grad_sink()
+        finally:
+            M.GROUP_PASSES = True
+    (l1, g1, b1, r1), (l2, g2, b2, r2) = results
+    assert abs(l1 - l2) < 1e-6
+    assert rel_l2(r1, r2) < 1e-6
+    for k in b1:
+        assert rel_max(b1[k].double(), b2[k].double()) < 1e-6, k
+    for n in g1:
+        assert rel_l2(g1[n], g2[n]) < 2e-4, n      # fp32 reduction partition differs (one 3B-sample wgrad vs three B-sample ones)
