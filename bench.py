@@ -301,6 +301,10 @@ def run_b200(args):
                 "algorithmic_bytes_per_launch": abytes,
                 "note": "fp32 FFMA direct convolution: arithmetic intensity of this layer is above the FFMA ridge, so the "
                         "HBM fraction is reported for the contract while the binding roof is FP32 FFMA (see DESIGN.md)"}
+    if args.dump_breakdown:
+        with open(args.dump_breakdown, "w") as f:
+            for k, v in sorted(fam.items(), key=lambda kv: -kv[1][0]):
+                f.write("%9.3f ms  x%-3d %s [%s]\n" % (v[0], v[1], k[0], k[1]))
     top5 = sorted(fam.items(), key=lambda kv: -kv[1][0])[:12]
     breakdown = [{"kernel": "%s [%s]" % k, "ms_per_step": round(v[0], 3), "launches": v[1]} for k, v in top5]
     by_op = {}
@@ -338,6 +342,7 @@ def main():
     ap.add_argument("--workload", default="cae200", choices=sorted(CHANNELS))
     ap.add_argument("--batch", type=int, default=8, help="per-GPU batch")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--dump-breakdown", default=None, help="write the full per-kernel CUDA-event attribution to this file")
     ap.add_argument("--quick", action="store_true", help="profiling aid: resident-input steps only (no e2e / attribution / CPU legs)")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -64,6 +64,16 @@ typedef struct SpConvDesc {
 int         sp_version(void);
 const char* sp_last_error(void);
 
+/*
+ * Numeric mode of the 3x3x3 stride-1 correlations with 8..16 channels (Cae3D.py:44,208,211; Unet3D.py:22):
+ *   0 (default)  exact fp32: FFMA tier, IEEE round-to-nearest accumulation (what the parity tests are calibrated on)
+ *   2 / 3        split-precision tcgen05 tier: every fp32 operand is staged as 2 / 3 bf16 terms, products of order < terms
+ *                are accumulated in fp32 in TMEM (per-layer forward rel-L2 ~5e-6 / ~1.4e-6).
+ * Packed weights depend on the mode: re-pack (sp_packed_weight_floats / sp_pack_weights) after changing it.
+ */
+int         sp_get_tc_terms(void);
+int         sp_set_tc_terms(int terms);
+
 /* ------------------------------------------------------------------------------------------------------------
  * Convolution family.  Replaces nn.Conv3d (Cae3D.py:41,44,48,52,55,59,63,66,70,74,126,128,132,186,189,197,200,
  * 208,211,215,218; Unet3D.py:19,22,50,52) and nn.ConvTranspose3d (Cae3D.py:178,182,193,204), forward + backward.

@@ -154,32 +154,41 @@ def dice_loss(o, t, w=1.0, eps=1e-7):
     return 1.0 - w * (2.0 * (o * t).sum() + eps) / ((o * o).sum() + (t * t).sum() + eps)
 
 
-def hinge(a, b):
+def hinge(a, b, sign=None):
+    """mean(|d| - d), d = a - b (CaeReconstructionLearner.py:59-62).  `sign` (tests only): evaluate the kink with a GIVEN
+    sign pattern, i.e. mean(sign * d - d).  Where sign == sign(d) this is the same value and the same gradient
+    (sign(d) - 1) / N; the parity tests use it to take the decision at |d| ~ 0 from the implementation under test, so
+    that a gradient comparison is not dominated by voxels where two correct fp32 forwards land on opposite sides."""
     d = a - b
-    return torch.mean(torch.abs(d) - d)
+    if sign is None:
+        return torch.mean(torch.abs(d) - d)
+    return torch.mean(sign.to(d.dtype) * d - d)
 
 
 def l1(a, b):
     return torch.mean(torch.abs(a - b))
 
 
-def cae_reconstruction_loss(lat, rec, core, penu, lesion, epoch):
-    """CaeReconstructionLearner.loss_step (:52-70)."""
+def cae_reconstruction_loss(lat, rec, core, penu, lesion, epoch, signs=None):
+    """CaeReconstructionLearner.loss_step (:52-70).  signs: optional (sign(penu - interpolation), sign(penu - core))."""
     f = min(0.04 * max(0, epoch - 25), 1)
-    loss = hinge(rec['penu'], rec['interpolation']) + hinge(rec['penu'], rec['core'])
+    s0, s1 = signs if signs is not None else (None, None)
+    loss = hinge(rec['penu'], rec['interpolation'], s0) + hinge(rec['penu'], rec['core'], s1)
     loss = loss + dice_loss(rec['core'], core) + dice_loss(rec['penu'], penu) + dice_loss(rec['lesion'], lesion)
     loss = loss + f * l1(lat['interpolation'], lat['lesion'])
     return loss / (5 + f)
 
 
-def cae_step_loss(rec, lesion):
+def cae_step_loss(rec, lesion, signs=None):
     """CaeStepLearner.loss_step (:15-21)."""
-    return (hinge(rec['penu'], rec['interpolation']) + dice_loss(rec['interpolation'], lesion)) / 2
+    s0 = signs[0] if signs is not None else None
+    return (hinge(rec['penu'], rec['interpolation'], s0) + dice_loss(rec['interpolation'], lesion)) / 2
 
 
-def cae_prediction_loss(lat_in, rec_in, lat_gt, lesion):
+def cae_prediction_loss(lat_in, rec_in, lat_gt, lesion, signs=None):
     """CaePredictionLearner.loss_step (:42-57)."""
-    loss = hinge(rec_in['penu'], rec_in['interpolation']) + hinge(rec_in['penu'], rec_in['core'])
+    s0, s1 = signs if signs is not None else (None, None)
+    loss = hinge(rec_in['penu'], rec_in['interpolation'], s0) + hinge(rec_in['penu'], rec_in['core'], s1)
     loss = loss + dice_loss(rec_in['interpolation'], lesion)
     loss = loss + l1(lat_gt['interpolation'], lat_in['interpolation']) + l1(lat_gt['core'], lat_in['core'])
     loss = loss + l1(lat_gt['penu'], lat_in['penu'])
@@ -220,6 +229,30 @@ def grads_of(loss, sd):
     names = [k for k, v in sd.items() if v.requires_grad]
     gs = torch.autograd.grad(loss, [sd[k] for k in names], allow_unused=True)
     return {k: g for k, g in zip(names, gs)}
+
+
+def hinge_signs(rec):
+    """(sign(penu - interpolation), sign(penu - core)) of a dict / DTO-like set of reconstructions, on the CPU."""
+    get = (lambda k: rec[k]) if isinstance(rec, dict) else (lambda k: getattr(rec, k))
+    p = get('penu').detach().cpu()
+    return torch.sign(p - get('interpolation').detach().cpu()), torch.sign(p - get('core').detach().cpu())
+
+
+def ulp_perturbed(sd, names, gen):
+    """Copy of `sd` with every fp32 tensor listed in `names` moved one ulp up or down at random (tests only).
+
+    Used to SAMPLE the fp32 noise floor of an ill-conditioned case: re-running the fp32 CPU oracle on parameters that
+    differ in the last bit changes every rounding decision downstream, so the spread of |fp32 - fp64| over a few such
+    runs is the accuracy the reference's own fp32 arithmetic has on that case (tests/test_gpu_models.py)."""
+    out = {}
+    for n, v in sd.items():
+        if n in names and v.dtype == torch.float32:
+            up = torch.nextafter(v, torch.full_like(v, float('inf')))
+            dn = torch.nextafter(v, torch.full_like(v, -float('inf')))
+            out[n] = torch.where(torch.randint(0, 2, v.shape, generator=gen).bool(), up, dn)
+        else:
+            out[n] = v.clone()
+    return out
 
 
 def rel_l2(a, b):

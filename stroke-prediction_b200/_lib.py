@@ -51,6 +51,8 @@ _D = ctypes.POINTER(SpConvDesc)
 SIGNATURES = {
     "sp_version": (c_int, []),
     "sp_last_error": (ctypes.c_char_p, []),
+    "sp_get_tc_terms": (c_int, []),
+    "sp_set_tc_terms": (c_int, [c_int]),
     "sp_packed_weight_floats": (c_size, [_D, c_int]),
     "sp_pack_weights": (c_int, [_D, c_int, c_vp, c_vp, c_vp]),
     "sp_corr": (c_int, [_D, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_vp, c_vp]),

@@ -11,6 +11,7 @@
 //     register micro-tile per thread — the FFMA-bound 16..96-channel layers.
 #include "sp_common.cuh"
 #include "sp_conv_tiled.cuh"
+#include "sp_conv_tc.cuh"
 
 // fixed-order sum of per-CTA partial weight-gradient slabs (fp64 accumulation: the partials carry the rounding of long
 // fp32 chains already, the cross-CTA sum should not add to it)
@@ -412,13 +413,58 @@ int grid_for(int64_t work_items, int threads = 256, int waves = 16) {
 
 }  // namespace
 
+// ---- tensor-core tier plumbing ------------------------------------------------------------------------------------------
+// The packed weight buffer of a layer the tcgen05 tier serves is [fp32 FFMA layout | bf16-split UMMA image]: the image
+// travels with the fp32 pack so the C-ABI (and its host-side per-parameter-version cache) stays unchanged.
+namespace {
+
+size_t ffma_packed_floats(const SpConvDesc* d, int which) {
+    const int k3 = d->k * d->k * d->k;
+    return which == 0 ? (size_t)k3 * d->Ci * round_up(d->Co, kPad) : (size_t)k3 * d->Co * round_up(d->Ci, kPad);
+}
+
+// geometry seen by the correlation kernels when sp_corrT (stride 1) is run as a flipped correlation
+SpConvDesc flipped_desc(const SpConvDesc* d) {
+    SpConvDesc f = *d;
+    f.Di = d->Do; f.Hi = d->Ho; f.Wi = d->Wo; f.Ci = d->Co; f.ldi = d->ldo;
+    f.Do = d->Di; f.Ho = d->Hi; f.Wo = d->Wi; f.Co = d->Ci; f.ldo = d->ldi;
+    f.pd = d->k - 1 - d->pd; f.ph = d->k - 1 - d->ph; f.pw = d->k - 1 - d->pw;
+    return f;
+}
+
+bool tc_serves(const SpConvDesc* d, int which, SpTcCfg* cfg) {
+    if (which == 0) return sp_tc_corr_supported(d, cfg);
+    if (d->s != 1) return false;
+    const SpConvDesc f = flipped_desc(d);
+    return f.pd >= 0 && f.ph >= 0 && f.pw >= 0 && sp_tc_corr_supported(&f, cfg);
+}
+
+int tc_corr_launch(const SpConvDesc* d, const SpTcCfg& cfg, int nPerG, const float* src, const float* wimg, const float* bias,
+                   const float* scale, const float* shift, float* dst, cudaStream_t st) {
+    const uint4* img = reinterpret_cast<const uint4*>(wimg);
+    if (sp_tc_terms() == 2) return sp_tc_corr_launch_t<16, 16, 2, 4>(d, nPerG, src, img, bias, scale, shift, dst, st);
+    return sp_tc_corr_launch_t<16, 16, 3, 2>(d, nPerG, src, img, bias, scale, shift, dst, st);
+}
+
+}  // namespace
+
 // =============================================================================================================
 extern "C" {
 
+int sp_get_tc_terms(void) { return sp_tc_terms(); }
+
+int sp_set_tc_terms(int terms) {
+    SP_REQUIRE(terms == 0 || terms == 2 || terms == 3, "sp_set_tc_terms: terms must be 0 (off), 2 or 3, got %d", terms);
+    sp_tc_terms_ref() = terms;
+    return 0;
+}
+
 size_t sp_packed_weight_floats(const SpConvDesc* d, int which) {
     if (!d) return 0;
-    const int k3 = d->k * d->k * d->k;
-    return which == 0 ? (size_t)k3 * d->Ci * round_up(d->Co, kPad) : (size_t)k3 * d->Co * round_up(d->Ci, kPad);
+    size_t n = ffma_packed_floats(d, which);
+    SpTcCfg cfg;
+    if (tc_serves(d, which, &cfg)) n += sp_tc_wimg_bytes(cfg.cip, cfg.cop, sp_tc_terms()) / sizeof(float);
+    return n;
 }
 
 int sp_pack_weights(const SpConvDesc* d, int which, const float* w_torch, float* w_packed, void* stream) {
@@ -427,9 +473,12 @@ int sp_pack_weights(const SpConvDesc* d, int which, const float* w_torch, float*
     SP_REQUIRE(w_torch && w_packed, "sp_pack_weights: NULL pointer");
     const int k3 = d->k * d->k * d->k;
     const int dP = round_up(which == 0 ? d->Co : d->Ci, kPad);
-    const int64_t total = (int64_t)sp_packed_weight_floats(d, which);
+    const int64_t total = (int64_t)ffma_packed_floats(d, which);
     pack_weights_kernel<<<grid_for(total), 256, 0, sp_stream(stream)>>>(w_torch, w_packed, d->Co, d->Ci, k3, which, dP);
     SP_LAUNCH_OK("pack_weights_kernel");
+    SpTcCfg cfg;
+    if (tc_serves(d, which, &cfg))
+        return sp_tc_pack_launch(d, which, sp_tc_terms(), cfg.cip, cfg.cop, w_torch, w_packed + total, sp_stream(stream));
     return 0;
 }
 
@@ -441,6 +490,9 @@ int sp_corr(const SpConvDesc* d, const float* src, const float* wp, const float*
     SP_REQUIRE(G >= 1 && d->N % G == 0, "sp_corr: N=%d not divisible by G=%d", d->N, G);
     const int coP = round_up(d->Co, kPad);
     const int nPerG = d->N / G;
+    SpTcCfg cfg;
+    if (tc_serves(d, 0, &cfg))
+        return tc_corr_launch(d, cfg, nPerG, src, wp + ffma_packed_floats(d, 0), bias, scale, shift, dst, sp_stream(stream));
     if (sp_tiled_corr_supported(d)) return sp_tiled_corr_launch(d, nPerG, src, wp, /*flip=*/0, bias, scale, shift, dst, sp_stream(stream));
     const int64_t work = (int64_t)d->N * d->Do * d->Ho * d->Wo * (coP / 8);
     corr_generic_kernel<8><<<grid_for(work), 256, 0, sp_stream(stream)>>>(*d, nPerG, coP, src, wp, bias, scale, shift, dst);
@@ -459,10 +511,10 @@ int sp_corrT(const SpConvDesc* d, const float* src, const float* wp, const float
     if (d->s == 1) {
         // stride 1: the transposed correlation is a correlation with flipped taps, swapped channel roles and
         // padding k-1-p; Wt[tap][co][ciP] read with flipped tap index is exactly that correlation's Wc.
-        SpConvDesc f = *d;
-        f.Di = d->Do; f.Hi = d->Ho; f.Wi = d->Wo; f.Ci = d->Co; f.ldi = d->ldo;
-        f.Do = d->Di; f.Ho = d->Hi; f.Wo = d->Wi; f.Co = d->Ci; f.ldo = d->ldi;
-        f.pd = d->k - 1 - d->pd; f.ph = d->k - 1 - d->ph; f.pw = d->k - 1 - d->pw;
+        const SpConvDesc f = flipped_desc(d);
+        SpTcCfg cfg;
+        if (tc_serves(d, 1, &cfg))
+            return tc_corr_launch(&f, cfg, nPerG, src, wp + ffma_packed_floats(d, 1), bias, scale, shift, dst, sp_stream(stream));
         if (f.pd >= 0 && f.ph >= 0 && f.pw >= 0 && sp_tiled_corr_supported(&f))
             return sp_tiled_corr_launch(&f, nPerG, src, wp, /*flip=*/1, bias, scale, shift, dst, sp_stream(stream));
     }

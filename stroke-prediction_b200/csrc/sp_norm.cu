@@ -36,22 +36,15 @@ channel_sums_kernel(const float* __restrict__ a, int lda, const float* __restric
         const bool live = (c < C) && (r_l < R);
         double s0 = 0.0, s1 = 0.0;
         if (live) {
-            // fp32 accumulation over runs of 8 rows, folded into fp64: exact enough and 4x fewer DADDs
-            int64_t r = r0 + r_l;
-            while (r < r1) {
-                float f0 = 0.f, f1 = 0.f;
-#pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    if (r < r1) {
-                        const float va = ag[r * lda + c];
-                        const float vb = (MODE == 1) ? va : bgp[r * ldb + c];
-                        f0 += va;
-                        f1 = fmaf(va, vb, f1);
-                        r += R;
-                    }
-                }
-                s0 += (double)f0;
-                s1 += (double)f1;
+            // straight fp64 accumulation: the product of two floats is exact in double, so sum(a*b) - mu*sum(a) and
+            // sum(x^2) - n*mean^2 cancel without loss whatever |mean| / std of the tensor is (B200 runs DFMA at half the
+            // FFMA rate; the kernel stays HBM-bound).  fp32 partial sums here cost |mean|/std digits of the BN backward
+            // dot product and showed up as 4-5x the CPU's gradient noise on nets with non-trivial BN affine parameters.
+            for (int64_t r = r0 + r_l; r < r1; r += R) {
+                const double va = (double)ag[r * lda + c];
+                const double vb = (MODE == 1) ? va : (double)bgp[r * ldb + c];
+                s0 += va;
+                s1 = fma(va, vb, s1);
             }
         }
         sm0[threadIdx.x] = s0;
@@ -102,7 +95,9 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sums, double count
         }
         const float sc = gm * invstd;
         scale[g * C + c] = sc;
-        shift[g * C + c] = bt - mean * sc;
+        // shift is formed in double from the ROUNDED scale and mean, so that x*sc + shift == (x - mean)*sc + beta up to
+        // the one rounding of shift itself
+        shift[g * C + c] = (float)((double)bt - (double)mean * (double)sc);
         mean_out[g * C + c] = mean;
         invstd_out[g * C + c] = invstd;
     }

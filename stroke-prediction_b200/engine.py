@@ -20,6 +20,8 @@ from . import ops
 from .ops import ACT_ELU, ACT_LEAKY, ACT_NONE, ACT_SIGMOID
 
 _weights_epoch = 0
+DEBUG_GZ = None     # diagnostics only (tools/diag_chain.py): a list receiving (plan, unit index, dL/d(conv output))
+DEBUG_ACTS = None   # diagnostics only: a list receiving (plan, [input, unit outputs...]) per forward pass
 
 
 def bump_weights_epoch():
@@ -233,6 +235,8 @@ def seq_forward(plan, x, G=1):
             ops.corr(d, x, u.packed(d, 0), bias, scale, shift, G, y)
         saved.acts.append(y)
         x = y
+    if DEBUG_ACTS is not None:
+        DEBUG_ACTS.append((plan, list(saved.acts)))
     return x, saved
 
 
@@ -251,6 +255,8 @@ def seq_backward(plan, saved, gy, need_input_grad, want):
     for i in range(len(units) - 1, -1, -1):
         u = units[i]
         x = saved.acts[i]
+        if DEBUG_GZ is not None:
+            DEBUG_GZ.append((plan, i, gz))
         N, C, D, H, W = x.shape
         bnrec = saved.bn[i]
         scale = shift = None

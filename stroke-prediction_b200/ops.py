@@ -193,6 +193,18 @@ def pack_weights(d, which, w):
     return out
 
 
+def set_tc_terms(terms):
+    """Numeric mode of the 16-channel 3x3x3 stride-1 correlations (include/stroke_b200.h): 0 = exact fp32 FFMA tier
+    (default), 2 / 3 = split-precision tcgen05 tier.  Packed weights depend on the mode, so cached packs are dropped."""
+    check(_L().sp_set_tc_terms(int(terms)), "sp_set_tc_terms")
+    from . import engine
+    engine.bump_weights_epoch()
+
+
+def get_tc_terms():
+    return int(_L().sp_get_tc_terms())
+
+
 def corr(d, src, wp, bias, scale, shift, G, dst):
     _req_cuda(src, wp, dst)
     check(_L().sp_corr(ctypes.byref(d), _p(src), _p(wp), _p(bias), _p(scale), _p(shift), G, _p(dst), _stream()), "sp_corr")

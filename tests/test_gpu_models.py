@@ -55,23 +55,91 @@ def _fixture_grads(fx, prefix="grad/"):
     return {k[len(prefix):]: torch.from_numpy(np.array(v)) for k, v in fx.items() if k.startswith(prefix)}
 
 
-def _cae_oracle_grads64(fx, mode):
-    """fp64 oracle run of a CAE fixture case -> {param: grad}."""
+def _cae_oracle_grads(fx, mode, dtype=torch.float64, signs=None, sd0=None):
+    """Oracle run (fp64 or fp32) of a CAE fixture case -> ({param: grad}, reconstructions).
+
+    `signs`: hinge decisions taken from the implementation under test (O.hinge_signs).  The monotonicity hinge
+    mean(|d| - d) has a kink at d = 0 and, for near-identical penumbra / core / interpolation reconstructions, many
+    voxels with |d| of a few fp32 ulps: two correct fp32 forwards put some of them on opposite sides, which moves whole
+    -2/N gradient quanta around and would dominate a gradient comparison.  Aligning the decision makes the comparison
+    measure the backward arithmetic; `_check_signs` separately proves that decisions only differ at such near-ties.
+    `sd0`: parameters to use instead of the fixture's (noise-floor sampling, see `_fp32_noise_floor`)."""
     ch = [int(c) for c in fx["channels"]]
-    labels = unpack_masks(fx).double()
+    labels = unpack_masks(fx).to(dtype)
     clinical = torch.from_numpy(fx["clinical"])
-    sd = O.clone_state(state_from(fx, "sd0/"), dtype=torch.float64)
+    sd = O.clone_state(state_from(fx, "sd0/") if sd0 is None else sd0, dtype=dtype)
     names = list(_fixture_grads(fx))
     for n in names:
         sd[n].requires_grad_(True)
     core, penu, lesion = labels[:, 0:1], labels[:, 1:2], labels[:, 2:3]
     if mode == "step":
-        step = O.step_from_globals(clinical.double(), sd, 1.0)
+        step = O.step_from_globals(clinical.to(dtype), sd, 1.0)
     else:
-        step = O.time_to_treatment(clinical).double()
+        step = O.time_to_treatment(clinical).to(dtype)
     lat, rec = O.cae_forward(sd, ch, 1.0, True, core, penu, lesion, step)
-    loss = O.cae_step_loss(rec, lesion) if mode == "step" else O.cae_reconstruction_loss(lat, rec, core, penu, lesion, int(fx["epoch"]))
-    return O.grads_of(loss, sd)
+    loss = (O.cae_step_loss(rec, lesion, signs) if mode == "step"
+            else O.cae_reconstruction_loss(lat, rec, core, penu, lesion, int(fx["epoch"]), signs))
+    return O.grads_of(loss, sd), rec
+
+
+NOISE_SAMPLES = 6
+
+
+def _fp32_noise_floor(fx, mode, samples=NOISE_SAMPLES):
+    """Per-tensor fp32 noise floor of a fixture case: the LARGEST distance |fp32 CPU oracle - fp64 oracle| over the
+    fixture's parameters and `samples - 1` copies of them moved by one ulp at random (O.ulp_perturbed).
+
+    Why a sampled floor: the tiny fixtures decode a 1x1x1 latent at batch 2, i.e. the decoder's first BatchNorm
+    normalises TWO values per channel with |mean|/std up to 56 (profiles/r01_diag_fwd_units.log).  Every fp32
+    implementation is ill-conditioned there, and the distance of one fp32 run from fp64 is a draw from a wide
+    distribution: the reference's own CPU arithmetic lands anywhere between 1.5e-5 and 1.4e-4 (encoder weights, median
+    over tensors) when its parameters move by one ulp.  A single CPU draw is therefore not a bound for another correct
+    implementation; the maximum over a few draws is."""
+    names = set(_fixture_grads(fx))
+    gen = torch.Generator().manual_seed(7)
+    base = state_from(fx, "sd0/")
+    floor = {}
+    for k in range(samples):
+        sd0 = base if k == 0 else O.ulp_perturbed(base, names, gen)
+        g32, rec32 = _cae_oracle_grads(fx, mode, torch.float32, sd0=sd0)
+        g64, _ = _cae_oracle_grads(fx, mode, torch.float64, O.hinge_signs(rec32), sd0=sd0)
+        for n in names:
+            if g64.get(n) is not None:
+                floor[n] = max(floor.get(n, 0.0), rel_l2(g32[n], g64[n]))
+    return floor
+
+
+NEAR_TIE = 1e-5   # |d| below which a hinge decision may legitimately differ between two fp32 forwards (outputs in [0,1])
+
+
+def _check_signs(signs, rec64, pairs=(("penu", "interpolation"), ("penu", "core"))):
+    """Hinge decisions of the implementation under test may differ from the fp64 oracle's only at near-ties."""
+    for s, (a, b) in zip(signs, pairs):
+        d = (rec64[a] - rec64[b]).detach()
+        differ = torch.sign(d) != s.to(d.dtype)
+        assert float(d[differ].abs().max() if differ.any() else 0.0) < NEAR_TIE, (a, b, int(differ.sum()))
+
+
+def _aligned_cae_check(model, fx, mode, rec_gpu, tol=TOL_GRAD, strip=""):
+    """Noise-floor gradient check with the hinge decisions aligned: CUDA path vs fp64 oracle (CUDA's decisions) against
+    the sampled fp32 floor of the reference arithmetic (`_fp32_noise_floor`): err_gpu <= max(tol, 2 x floor)."""
+    s_gpu = O.hinge_signs(rec_gpu)
+    g64_gpu, rec64 = _cae_oracle_grads(fx, mode, torch.float64, s_gpu)
+    _check_signs(s_gpu, rec64)
+    floor = _fp32_noise_floor(fx, mode)
+    n, bad = 0, []
+    for name, p in model.named_parameters():
+        key = strip + name
+        if g64_gpu.get(key) is None:
+            assert p.grad is None or not p.requires_grad, name
+            continue
+        assert p.grad is not None, name
+        e_gpu, e_cpu = rel_l2(p.grad, g64_gpu[key]), floor[key]
+        print("%-28s gpu/f64 %.2e cpu32-floor/f64 %.2e |g| %.3e" % (name, e_gpu, e_cpu, g64_gpu[key].norm().item()))
+        if e_gpu > max(tol, 2 * e_cpu):
+            bad.append("%s: gpu-vs-fp64 %g, cpu32 floor %g" % (name, e_gpu, e_cpu))
+        n += 1
+    assert n > 0 and not bad, bad
 
 
 def test_cae_reconstruction_step_against_reference_fixture():
@@ -100,7 +168,7 @@ def test_cae_reconstruction_step_against_reference_fixture():
         assert abs((r.double() ** 2).sum().item() - m[1]) < 1e-4 * abs(m[1])
     learner._optimizer.zero_grad()
     loss.backward()
-    _check_grads(cae, _cae_oracle_grads64(fx, "reconstruction"), _fixture_grads(fx))
+    _aligned_cae_check(cae, fx, "reconstruction", dto.reconstructions.gtruth)
     learner._optimizer.step()
     torch.cuda.synchronize()
     sd1 = cae.state_dict()
@@ -140,7 +208,7 @@ def test_cae_step_learner_against_reference_fixture():
     assert abs(loss.item() - float(fx["loss"])) < 1e-5
     assert rel_l2(dto.latents.gtruth.interpolation, fx["lat/interpolation"]) < TOL_ACT
     loss.backward()
-    _check_grads(cae, _cae_oracle_grads64(fx, "step"), _fixture_grads(fx))
+    _aligned_cae_check(cae, fx, "step", dto.reconstructions.gtruth)
     frozen = [n for n, p in cae.named_parameters() if not p.requires_grad]
     assert frozen and all(dict(cae.named_parameters())[n].grad is None for n in frozen)
     # frozen BN layers still ran in train mode: running stats drift exactly like the reference
@@ -180,7 +248,9 @@ def test_cae_prediction_learner_against_reference_fixture():
     li["interpolation"] = O.interpolate(li["core"], li["penu"], step64)
     ri = {k: O.decoder_pass(li[k], sd_cae, ch, 1.0, True) for k in ("core", "penu", "interpolation")}
     lg, _ = O.cae_forward(sd_cae, ch, 1.0, True, labels64[:, 0:1], labels64[:, 1:2], labels64[:, 2:3], step64)
-    g64 = O.grads_of(O.cae_prediction_loss(li, ri, lg, labels64[:, 2:3]), sd_enc)
+    signs = O.hinge_signs(dto.reconstructions.inputs)
+    _check_signs(signs, ri)
+    g64 = O.grads_of(O.cae_prediction_loss(li, ri, lg, labels64[:, 2:3], signs), sd_enc)
     _check_grads(new_enc, g64, {"enc." + k: v for k, v in _fixture_grads(fx).items()}, strip="enc.")
     assert all(p.grad is None for p in cae.parameters())
     for k, v in fx.items():
@@ -332,19 +402,29 @@ def test_cae_named_config_full_size_against_oracle(fc):
     lat, rec = O.cae_forward(sd, ch, 1.0, True, labels[:, 0:1], labels[:, 1:2], labels[:, 2:3], step)
     oloss = O.cae_reconstruction_loss(lat, rec, labels[:, 0:1], labels[:, 1:2], labels[:, 2:3], 60)
     grads = O.grads_of(oloss, sd)
-    sd64 = O.clone_state({k: v.detach() for k, v in sd.items()}, requires_grad=True, dtype=torch.float64)
     l64 = labels.double()
-    lat64, rec64 = O.cae_forward(sd64, ch, 1.0, True, l64[:, 0:1], l64[:, 1:2], l64[:, 2:3], step.double())
-    grads64 = O.grads_of(O.cae_reconstruction_loss(lat64, rec64, l64[:, 0:1], l64[:, 1:2], l64[:, 2:3], 60), sd64)
+
+    def grads64_with(signs):
+        sd64 = O.clone_state({k: v.detach() for k, v in sd.items()}, requires_grad=True, dtype=torch.float64)
+        lat64, rec64 = O.cae_forward(sd64, ch, 1.0, True, l64[:, 0:1], l64[:, 1:2], l64[:, 2:3], step.double())
+        return O.grads_of(O.cae_reconstruction_loss(lat64, rec64, l64[:, 0:1], l64[:, 1:2], l64[:, 2:3], 60, signs), sd64), rec64
+
+    s_gpu = O.hinge_signs(dto.reconstructions.gtruth)
+    grads64, rec64 = grads64_with(s_gpu)                 # hinge decisions of the CUDA forward (see _cae_oracle_grads)
+    _check_signs(s_gpu, rec64)
+    grads64_cpu, _ = grads64_with(O.hinge_signs(rec))    # noise floor: CPU fp32 against fp64 with the CPU run's decisions
     assert abs(loss.item() - oloss.item()) < 1e-5
     for k in ("core", "penu", "lesion", "interpolation"):
         assert rel_l2(getattr(dto.latents.gtruth, k), lat[k]) < TOL_ACT, k
         r = getattr(dto.reconstructions.gtruth, k)
         assert rel_l2(r, rec[k]) < TOL_ACT, k
         assert abs(_dice_binary(r.cpu(), rec[k]) - 1.0) < TOL_DICE or float((rec[k] > 0.5).sum()) == 0
-    # hinge-seeded gradients are ill-conditioned in fp32 for every implementation: measured worst
-    # tensor 1.5e-4 from fp64 here vs 1.2e-4 for the reference's own CPU run on the isolated hinge term
-    _check_grads(cae, grads64, grads, tol=3e-4)
+    n = 0
+    for name, p in cae.named_parameters():
+        e_gpu, e_cpu = rel_l2(p.grad, grads64[name]), rel_l2(grads[name], grads64_cpu[name])
+        assert e_gpu <= max(TOL_GRAD, 2 * e_cpu), "%s: gpu-vs-fp64 %g, cpu32-vs-fp64 %g" % (name, e_gpu, e_cpu)
+        n += 1
+    assert n > 0
 
 
 def test_unet_named_config_patch_size_against_oracle():
@@ -361,18 +441,36 @@ def test_unet_named_config_patch_size_against_oracle():
     loss = learner.loss_step(dto, 0)
     loss.backward()
     labels = batch[A.data.KEY_LABELS]
-    sd32 = O.clone_state(sd, requires_grad=True)
-    c32, p32 = O.unet_forward(sd32, batch[A.data.KEY_IMAGES], True)
-    l32 = O.unet_loss(c32, p32, labels[:, 0:1], labels[:, 1:2])
-    g32 = O.grads_of(l32, sd32)
-    sd64 = O.clone_state(sd, requires_grad=True, dtype=torch.float64)
-    c64, p64 = O.unet_forward(sd64, batch[A.data.KEY_IMAGES].double(), True)
-    g64 = O.grads_of(O.unet_loss(c64, p64, labels[:, 0:1].double(), labels[:, 1:2].double()), sd64)
+    x = batch[A.data.KEY_IMAGES]
+
+    def oracle(sd0, dtype):
+        s = O.clone_state(sd0, requires_grad=True, dtype=dtype)
+        c, p_ = O.unet_forward(s, x.to(dtype), True)
+        l = O.unet_loss(c, p_, labels[:, 0:1].to(dtype), labels[:, 1:2].to(dtype))
+        return c, p_, l, O.grads_of(l, s)
+
+    c32, p32, l32, g32 = oracle(sd, torch.float32)
+    _, _, _, g64 = oracle(sd, torch.float64)
     assert rel_l2(dto.outputs.core, c32) < TOL_ACT and rel_l2(dto.outputs.penu, p32) < TOL_ACT
     assert abs(loss.item() - l32.item()) < 1e-5
+    # sampled fp32 noise floor (see _fp32_noise_floor): the U-Net backward crosses two max-pools and ten LeakyReLU kinks
+    # and ends in BatchNorm backward cancellations; the reference's own fp32 CPU gradient of block1's first BN weight is
+    # anywhere between 1.6e-5 and 1.2e-3 from fp64 when the parameters move by one ulp, so one draw is not a bound.
+    names = set(g64)
+    floor = {n: rel_l2(g32[n], g64[n]) for n in names}
+    gen = torch.Generator().manual_seed(7)
+    for _ in range(3):
+        sdk = O.ulp_perturbed(sd, names, gen)
+        g32k, g64k = oracle(sdk, torch.float32)[3], oracle(sdk, torch.float64)[3]
+        for n in names:
+            floor[n] = max(floor[n], rel_l2(g32k[n], g64k[n]))
+    bad = []
     for n, p in unet.named_parameters():
-        e_gpu, e_cpu = rel_l2(p.grad, g64[n]), rel_l2(g32[n], g64[n])
-        assert e_gpu <= max(TOL_GRAD, 2 * e_cpu), "%s: gpu %g cpu32 %g" % (n, e_gpu, e_cpu)
+        e_gpu = rel_l2(p.grad, g64[n])
+        print("%-36s gpu/f64 %.2e cpu32-floor/f64 %.2e" % (n, e_gpu, floor[n]))
+        if e_gpu > max(TOL_GRAD, 2 * floor[n]):
+            bad.append("%s: gpu %g cpu32 floor %g" % (n, e_gpu, floor[n]))
+    assert not bad, bad
 
 
 def test_stacked_passes_equal_separate_passes():

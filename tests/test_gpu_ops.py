@@ -150,6 +150,36 @@ def test_tiled_corr_paths(case):
     _check_sequential(nn.Sequential(nn.BatchNorm3d(cin), conv, _act(act)), x)
 
 
+TC_CASES = [
+    # >= 8192 output voxels, 8..16 channels on both sides, Ho >= 16: the tcgen05 / TMEM tier (sp_conv_tc.cuh) serves the
+    # forward and — through flipped taps — the dgrad; ragged tiles in w, h and d
+    ("C", 16, 16, 3, 1, (1, 0, 0), "elu", (9, 40, 29)),        # Cae3D.py:44   encoder 16->16
+    ("C", 16, 16, 3, 1, (1, 2, 2), "elu", (9, 30, 30)),        # Cae3D.py:208  decoder 16->16, pad 2 (dgrad has pad 0)
+    ("C", 16, 16, 3, 1, 0, "leaky", (12, 34, 30)),             # Unet3D.py:22  valid conv (dgrad has pad 2)
+    ("C", 12, 10, 3, 1, (1, 1, 1), "elu", (10, 33, 31)),       # channel counts that are not multiples of 8
+    ("T", 16, 16, 3, 1, 0, "elu", (8, 30, 36)),                # convT k3 s1 forward = flipped correlation
+]
+
+
+@pytest.mark.parametrize("terms", [3, 2])
+@pytest.mark.parametrize("case", TC_CASES, ids=lambda c: "%s%d-%d_p%s" % (c[0], c[1], c[2], str(c[5]).replace(" ", "")))
+def test_tensor_core_corr_paths(case, terms):
+    """Opt-in split-precision tcgen05 tier (ops.set_tc_terms): activations within the 1e-4 bar; its truncating fp32
+    accumulator is 5-20x noisier than IEEE FFMA chains, so gradients are held to 1e-4 / 1e-5-per-term-scaled bounds
+    instead of the CPU noise floor."""
+    _, _, ops = _mods()
+    kind, cin, cout, k, s, p, act, size = case
+    torch.manual_seed(300 + TC_CASES.index(case))
+    conv = nn.ConvTranspose3d(cin, cout, k, stride=s, padding=p) if kind == "T" else nn.Conv3d(cin, cout, k, stride=s, padding=p)
+    x = torch.randn(2, cin, *size) * 1.5 + 0.3
+    ops.set_tc_terms(terms)
+    try:
+        assert ops.get_tc_terms() == terms
+        _check_sequential(nn.Sequential(nn.BatchNorm3d(cin), conv, _act(act)), x, G=2, tol_grad=1e-4 if terms == 3 else 3e-4)
+    finally:
+        ops.set_tc_terms(0)
+
+
 def test_tiled_chain_grouped():
     seq = nn.Sequential(nn.BatchNorm3d(1), nn.Conv3d(1, 16, 3, padding=(1, 0, 0)), nn.ELU(1.0, True),
                         nn.BatchNorm3d(16), nn.Conv3d(16, 16, 3, padding=(1, 0, 0)), nn.ELU(1.0, True),
