@@ -11,6 +11,7 @@
 //     register micro-tile per thread — the FFMA-bound 16..96-channel layers.
 #include "sp_common.cuh"
 #include "sp_conv_tiled.cuh"
+#include "sp_conv_tiledT.cuh"
 #include "sp_conv_tc.cuh"
 
 // fixed-order sum of per-CTA partial weight-gradient slabs (fp64 accumulation: the partials carry the rounding of long
@@ -518,6 +519,7 @@ int sp_corrT(const SpConvDesc* d, const float* src, const float* wp, const float
         if (f.pd >= 0 && f.ph >= 0 && f.pw >= 0 && sp_tiled_corr_supported(&f))
             return sp_tiled_corr_launch(&f, nPerG, src, wp, /*flip=*/1, bias, scale, shift, dst, sp_stream(stream));
     }
+    if (sp_tiledT_supported(d)) return sp_tiledT_launch(d, nPerG, src, wp, bias, scale, shift, dst, sp_stream(stream));
     const int64_t work = (int64_t)d->N * d->Di * d->Hi * d->Wi * (ciP / 8);
     corrT_generic_kernel<8><<<grid_for(work), 256, 0, sp_stream(stream)>>>(*d, nPerG, ciP, src, wp, bias, scale, shift, dst);
     SP_LAUNCH_OK("corrT_generic_kernel");
@@ -546,8 +548,8 @@ int sp_wgrad(const SpConvDesc* d, const float* iside, const float* i_scale, cons
     SP_REQUIRE(ws_bytes >= sp_wgrad_workspace_bytes(d), "sp_wgrad: workspace too small (%zu < %zu)", ws_bytes,
                sp_wgrad_workspace_bytes(d));
     const int nPerG = d->N / G;
-    if (sp_tiled_wgrad_supported(d) && o_scale == nullptr)
-        return sp_tiled_wgrad_launch(d, nPerG, iside, i_scale, i_shift, oside, dw, beta, (float*)ws, sp_stream(stream));
+    if (sp_tiled_wgrad_supported(d))
+        return sp_tiled_wgrad_launch(d, nPerG, iside, i_scale, i_shift, oside, o_scale, o_shift, dw, beta, (float*)ws, sp_stream(stream));
     const WgradPlan p = wgrad_plan(d);
     const bool vi = (d->Ci % 4 == 0) && (d->ldi % 4 == 0);
     const bool vo = (d->Co % 4 == 0) && (d->ldo % 4 == 0);

@@ -1,48 +1,102 @@
-// sp_conv_tiled.cuh — shared-memory tiled fast path for the FFMA-bound 3x3x3 stride-1 correlations
-// (Cae3D.py:44,52,55,63,66,186-211 and every Block3x3x3 conv of Unet3D.py:19,22; also their stride-1 dgrads, which
-// sp_corrT maps onto the same kernel with flipped taps).
+// sp_conv_tiled.cuh — shared-memory tiled FFMA tier for the FFMA-bound correlations:
+//   * K = 3, S = 1 : Cae3D.py:44,52,55,63,66,186-211 and every Block3x3x3 conv of Unet3D.py:19,22; also their stride-1
+//                    dgrads / ConvTranspose3d k3 s1 (Cae3D.py:178), which sp_corrT maps here with flipped taps
+//   * K = 3, S = 2 : the strided down-sampling convs Cae3D.py:48,59,70
+//   * K = 2, S = 2 : the dgrad of the k2 s2 ConvTranspose3d up-sampling layers Cae3D.py:193,204
+// and the weight gradients of all of them.
 //
-// Tile: one CTA (256 threads, 8 warps) produces a 16(w) x 8(h) x 8(d) block of output voxels x 16 output channels.
-//   warp  -> output depth plane td (0..7)
+// Tile: one CTA (32 x TD threads) produces a 16(w) x 8(h) x TD(d) block of output voxels x 16 output channels.
+//   warp  -> output depth plane td
 //   lane  -> row th = lane & 7, column group wcol = lane >> 3 (4 groups of 4 consecutive w)
-//   thread micro-tile: 4 voxels x 16 channels = 64 fp32 accumulators.
-// The input halo tile (18 x 10 x 10 voxels) is staged per chunk of CK input channels as CK/4 planes of float4
-// ("channel-quad planes"): BatchNorm scale/shift is applied while staging and out-of-range voxels are written as 0,
-// so zero padding stays zero *after* the normalisation.  Rows are padded to 19 float4 so that the 8 lanes of a
-// quarter-warp (8 different rows) hit 8 different 16-byte bank groups: conflict-free LDS.128.  The 27 x CK x 16
-// weight slab of the chunk sits next to it and is read with warp-uniform (broadcast) LDS.128.
-// Per (kd, kh, channel quad) a thread issues 6 + 48 LDS.128 and 768 FFMA.
+//   thread micro-tile: 4 voxels x 16 channels = 64 fp32 accumulators (32 FFMA2 registers pairs).
+// The input halo tile is staged per chunk of CK input channels as CK/4 planes of float4 ("channel-quad planes"):
+// BatchNorm scale/shift is applied while staging and out-of-range voxels are written as 0, so zero padding stays zero
+// *after* the normalisation.  Rows are padded to an odd number of float4 so that the 8 lanes of a quarter-warp (8
+// different rows) hit 8 different 16-byte bank groups: conflict-free LDS.128.
+//
+// Stride 2 uses a PARITY-SPLIT tile: along every axis the even input coordinates of the tile are stored first, then
+// the odd ones (slot(i) = i/2 or NE + i/2).  Output o reads input 2o + t, i.e. parity t&1 at index o + t/2 — so inside
+// a parity block consecutive outputs read consecutive slots and the kernel body (and its bank behaviour) is that of the
+// stride-1 case with a different per-tap base offset.
 #pragma once
 #include <stdlib.h>
 #include "sp_common.cuh"
 
 namespace sp_tiled {
 
-constexpr int TW = 16, TH = 8;                   // output tile in w, h; depth TD (4 or 8) is a template parameter
-constexpr int IW = TW + 2, IH = TH + 2;
-constexpr int RW = 19;                           // padded row length (float4 units), odd -> conflict-free row stride
+constexpr int TW = 16, TH = 8;                   // output tile in w, h; depth TD is a template parameter
 constexpr int COT = 16;                          // output channels per thread / per CTA pass
 constexpr int VT = 4;                            // voxels per thread along w
 
-// float4 per channel-quad plane; (TD+2)*190 is 1900 (TD=8) or 1140 (TD=4), both == 4 mod 8 -> conflict-free staging
-template <int TD>
-__host__ __device__ constexpr int plane_f4() { return (TD + 2) * IH * RW; }
+// one axis of the (parity-split) input tile of an output tile of extent T
+template <int K, int S, int T>
+struct Axis {
+    static constexpr int IN = S * (T - 1) + K;                       // input extent
+    static constexpr int NE = (S == 1) ? IN : (IN + 1) / 2;          // slots holding even coordinates (S = 2)
+    __host__ __device__ static constexpr int slot(int i) { return S == 1 ? i : ((i & 1) ? NE + (i >> 1) : (i >> 1)); }
+    __host__ __device__ static constexpr int tap(int t) { return slot(t); }   // base slot of tap t for output 0
+};
 
-template <int CK, int TD>
-constexpr size_t smem_bytes() { return (size_t)(CK / 4) * plane_f4<TD>() * 16 + (size_t)27 * CK * COT * 4; }
+template <int K, int S>
+__host__ __device__ constexpr int row_f4() {      // padded row length (float4 units), odd
+    return Axis<K, S, TW>::IN | 1;
+}
+// S = 1, K = 3: IN = 18 -> 19.  S = 2, K = 3: IN = 33 -> 33.  S = 2, K = 2: IN = 32 -> 33.
 
-// d: correlation geometry (k = 3, s = 1).  wp: packed [tap][src channel][dstP]; flip != 0 reads tap 26 - t.
-template <int CK, int TD>
-__global__ void __launch_bounds__(32 * TD, 512 / (32 * TD))
-corr3_tiled_kernel(SpConvDesc d, int nPerG, int dstP, int tiles_w, int tiles_h, int tiles_d, const float* __restrict__ src,
-                   const float* __restrict__ wp, int flip, const float* __restrict__ bias, const float* __restrict__ scale,
-                   const float* __restrict__ shift, float* __restrict__ dst) {
+template <int K, int S, int TD>
+__host__ __device__ constexpr int plane_f4() { return Axis<K, S, TD>::IN * Axis<K, S, TH>::IN * row_f4<K, S>(); }
+
+template <int CK, int TD, int K, int S>
+constexpr size_t smem_bytes() { return (size_t)(CK / 4) * plane_f4<K, S, TD>() * 16 + (size_t)K * K * K * CK * COT * 4; }
+
+// stage one channel-quad of one input voxel: BN applied, zeros outside the volume / beyond Ci
+__device__ __forceinline__ float4 stage_quad(const float* __restrict__ srcn, const SpConvDesc& d, int gd, int gh, int gw, int c,
+                                             bool vec, const float* __restrict__ scale, const float* __restrict__ shift, int g) {
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (gd >= 0 && gd < d.Di && gh >= 0 && gh < d.Hi && gw >= 0 && gw < d.Wi && c < d.Ci) {
+        const float* p = srcn + (((int64_t)gd * d.Hi + gh) * d.Wi + gw) * d.ldi + c;
+        if (vec) {
+            v = *reinterpret_cast<const float4*>(p);
+            if (scale) {
+                const float4 sc = *reinterpret_cast<const float4*>(scale + (int64_t)g * d.Ci + c);
+                const float4 sh = *reinterpret_cast<const float4*>(shift + (int64_t)g * d.Ci + c);
+                v.x = fmaf(v.x, sc.x, sh.x); v.y = fmaf(v.y, sc.y, sh.y);
+                v.z = fmaf(v.z, sc.z, sh.z); v.w = fmaf(v.w, sc.w, sh.w);
+            }
+        } else {
+            float e[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                e[u] = 0.f;
+                if (c + u < d.Ci) {
+                    e[u] = p[u];
+                    if (scale) e[u] = fmaf(e[u], scale[(int64_t)g * d.Ci + c + u], shift[(int64_t)g * d.Ci + c + u]);
+                }
+            }
+            v = make_float4(e[0], e[1], e[2], e[3]);
+        }
+    }
+    return v;
+}
+
+// d: correlation geometry (k = K, s = S).  wp: packed [tap][src channel][dstP]; flip != 0 reads tap K^3 - 1 - t.
+template <int CK, int TD, int K, int S>
+__global__ void __launch_bounds__(32 * TD, (S == 1 ? 512 : 256) / (32 * TD))
+corr_tiled_kernel(SpConvDesc d, int nPerG, int dstP, int tiles_w, int tiles_h, int tiles_d, const float* __restrict__ src,
+                  const float* __restrict__ wp, int flip, const float* __restrict__ bias, const float* __restrict__ scale,
+                  const float* __restrict__ shift, float* __restrict__ dst) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    constexpr int ID = TD + 2;
-    constexpr int PLANE = plane_f4<TD>();
+    using AW = Axis<K, S, TW>;
+    using AH = Axis<K, S, TH>;
+    using AD = Axis<K, S, TD>;
+    constexpr int IW = AW::IN, IH = AH::IN, ID = AD::IN;
+    constexpr int RW = row_f4<K, S>();
+    constexpr int PLANE = plane_f4<K, S, TD>();
     constexpr int NT = 32 * TD;
-    float4* xs = reinterpret_cast<float4*>(smem_raw);                                   // [CK/4][ID][IH][RW]
-    float* wsm = reinterpret_cast<float*>(smem_raw + (size_t)(CK / 4) * PLANE * 16);    // [27][CK][COT]
+    constexpr int K3 = K * K * K;
+    constexpr int NQ = CK / 4;
+    float4* xs = reinterpret_cast<float4*>(smem_raw);                                   // [NQ][ID][IH][RW]
+    float* wsm = reinterpret_cast<float*>(smem_raw + (size_t)NQ * PLANE * 16);          // [K3][CK][COT]
 
     int t = blockIdx.x;
     const int tw = t % tiles_w; t /= tiles_w;
@@ -63,54 +117,28 @@ corr3_tiled_kernel(SpConvDesc d, int nPerG, int dstP, int tiles_w, int tiles_h, 
         for (int j = 0; j < COT / 2; ++j) acc[v][j] = make_float2(0.f, 0.f);
 
     const bool vec = (d.Ci % 4 == 0) && (d.ldi % 4 == 0);
-    const int id0 = od0 - d.pd, ih0 = oh0 - d.ph, iw0 = ow0 - d.pw;
+    const int id0 = od0 * S - d.pd, ih0 = oh0 * S - d.ph, iw0 = ow0 * S - d.pw;
     const float* srcn = src + (int64_t)n * d.Di * d.Hi * d.Wi * d.ldi;
 
     for (int c0 = 0; c0 < d.Ci; c0 += CK) {
         __syncthreads();   // previous chunk fully consumed
         // ---- stage the input halo tile of channels [c0, c0 + CK): BN applied, padding written as zeros
-        constexpr int NQ = CK / 4;
         for (int i = threadIdx.x; i < ID * IH * IW * NQ; i += NT) {
             const int q = i % NQ;
             int r = i / NQ;
             const int iw = r % IW; r /= IW;
             const int ih = r % IH;
             const int idd = r / IH;
-            const int gd = id0 + idd, gh = ih0 + ih, gw = iw0 + iw;
-            const int c = c0 + q * 4;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (gd >= 0 && gd < d.Di && gh >= 0 && gh < d.Hi && gw >= 0 && gw < d.Wi && c < d.Ci) {
-                const float* p = srcn + (((int64_t)gd * d.Hi + gh) * d.Wi + gw) * d.ldi + c;
-                if (vec) {
-                    v = *reinterpret_cast<const float4*>(p);
-                    if (scale) {
-                        const float4 sc = *reinterpret_cast<const float4*>(scale + (int64_t)g * d.Ci + c);
-                        const float4 sh = *reinterpret_cast<const float4*>(shift + (int64_t)g * d.Ci + c);
-                        v.x = fmaf(v.x, sc.x, sh.x); v.y = fmaf(v.y, sc.y, sh.y);
-                        v.z = fmaf(v.z, sc.z, sh.z); v.w = fmaf(v.w, sc.w, sh.w);
-                    }
-                } else {
-                    float e[4];
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        e[u] = 0.f;
-                        if (c + u < d.Ci) {
-                            e[u] = p[u];
-                            if (scale) e[u] = fmaf(e[u], scale[(int64_t)g * d.Ci + c + u], shift[(int64_t)g * d.Ci + c + u]);
-                        }
-                    }
-                    v = make_float4(e[0], e[1], e[2], e[3]);
-                }
-            }
-            xs[q * PLANE + (idd * IH + ih) * RW + iw] = v;
+            const float4 v = stage_quad(srcn, d, id0 + idd, ih0 + ih, iw0 + iw, c0 + q * 4, vec, scale, shift, g);
+            xs[q * PLANE + (AD::slot(idd) * IH + AH::slot(ih)) * RW + AW::slot(iw)] = v;
         }
-        // ---- stage the weight slab [27][CK][COT] of this chunk / output-channel pass
-        for (int i = threadIdx.x; i < 27 * CK * (COT / 4); i += NT) {
+        // ---- stage the weight slab [K3][CK][COT] of this chunk / output-channel pass
+        for (int i = threadIdx.x; i < K3 * CK * (COT / 4); i += NT) {
             const int j4 = i % (COT / 4);
             int r = i / (COT / 4);
             const int cl = r % CK;
             const int tap = r / CK;
-            const int st = flip ? 26 - tap : tap;
+            const int st = flip ? K3 - 1 - tap : tap;
             float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
             if (c0 + cl < d.Ci) w = *reinterpret_cast<const float4*>(wp + ((int64_t)st * d.Ci + c0 + cl) * dstP + co0 + j4 * 4);
             reinterpret_cast<float4*>(wsm)[(tap * CK + cl) * (COT / 4) + j4] = w;
@@ -119,18 +147,25 @@ corr3_tiled_kernel(SpConvDesc d, int nPerG, int dstP, int tiles_w, int tiles_h, 
 
         // ---- accumulate
 #pragma unroll 1
-        for (int kd = 0; kd < 3; ++kd) {
+        for (int kd = 0; kd < K; ++kd) {
 #pragma unroll 1
-            for (int kh = 0; kh < 3; ++kh) {
-                const float4* row = xs + ((ltd + kd) * IH + (lth + kh)) * RW + lw0;
-                const float* wtap = wsm + ((kd * 3 + kh) * 3) * CK * COT;
+            for (int kh = 0; kh < K; ++kh) {
+                const float4* row = xs + ((ltd + AD::tap(kd)) * IH + (lth + AH::tap(kh))) * RW + lw0;
+                const float* wtap = wsm + ((kd * K + kh) * K) * CK * COT;
 #pragma unroll
                 for (int q = 0; q < NQ; ++q) {
-                    float4 xin[VT + 2];
+                    // S = 1: xin[j] = input lw0 + j.  S = 2: xin[j] = even slot lw0 + j (taps 0, 2), xodd[j] = odd slot (tap 1)
+                    constexpr int NXE = (S == 1) ? VT + K - 1 : VT + (K - 1) / 2;
+                    float4 xin[NXE];
+                    float4 xodd[VT];
 #pragma unroll
-                    for (int j = 0; j < VT + 2; ++j) xin[j] = row[q * PLANE + j];
+                    for (int j = 0; j < NXE; ++j) xin[j] = row[q * PLANE + j];
+                    if (S == 2) {
 #pragma unroll
-                    for (int kw = 0; kw < 3; ++kw) {
+                        for (int j = 0; j < VT; ++j) xodd[j] = row[q * PLANE + AW::NE + j];
+                    }
+#pragma unroll
+                    for (int kw = 0; kw < K; ++kw) {
 #pragma unroll
                         for (int c = 0; c < 4; ++c) {
                             const float4* wv = reinterpret_cast<const float4*>(wtap + (kw * CK + q * 4 + c) * COT);
@@ -143,7 +178,7 @@ corr3_tiled_kernel(SpConvDesc d, int nPerG, int dstP, int tiles_w, int tiles_h, 
                             }
 #pragma unroll
                             for (int v = 0; v < VT; ++v) {
-                                const float4 xv = xin[v + kw];
+                                const float4 xv = (S == 1) ? xin[v + kw] : ((kw & 1) ? xodd[v] : xin[v + (kw >> 1)]);
                                 const float x = (c == 0) ? xv.x : (c == 1) ? xv.y : (c == 2) ? xv.z : xv.w;
 #pragma unroll
                                 for (int j = 0; j < COT / 2; ++j) acc[v][j] = sp_ffma2(x, w[j], acc[v][j]);
@@ -187,8 +222,8 @@ corr3_tiled_kernel(SpConvDesc d, int nPerG, int dstP, int tiles_w, int tiles_h, 
 
 }  // namespace sp_tiled
 
-// Route a correlation to the tiled kernel when it is a 3x3x3 stride-1 layer with enough output voxels per sample to
-// fill tiles; tiny-plane layers (bottleneck 3x12x12 / 1x10x10) stay on the generic kernel.
+// Route a correlation to the tiled kernel when it has enough output voxels per sample to fill tiles; tiny-plane layers
+// (bottleneck 3x12x12 / 1x10x10) stay on the generic kernel.
 static inline bool sp_tiled_disabled() {
     static int v = -1;   // SP_DISABLE_TILED=1 forces the generic kernels (A/B parity checks of the two tiers)
     if (v < 0) {
@@ -198,13 +233,17 @@ static inline bool sp_tiled_disabled() {
     return v == 1;
 }
 
+static inline bool sp_tiled_geometry(const SpConvDesc* d) {
+    return (d->k == 3 && d->s == 1) || (d->k == 3 && d->s == 2) || (d->k == 2 && d->s == 2);
+}
+
 static inline bool sp_tiled_corr_supported(const SpConvDesc* d) {
-    if (d->k != 3 || d->s != 1 || sp_tiled_disabled()) return false;
+    if (!sp_tiled_geometry(d) || sp_tiled_disabled()) return false;
     const int64_t ov = (int64_t)d->Do * d->Ho * d->Wo;
     return ov >= 2048 && d->Wo >= 8 && d->Ho >= 4;
 }
 
-template <int CK, int TD>
+template <int CK, int TD, int K, int S>
 static inline int sp_tiled_corr_launch_t(const SpConvDesc* d, int nPerG, const float* src, const float* wp, int flip,
                                          const float* bias, const float* scale, const float* shift, float* dst,
                                          cudaStream_t st) {
@@ -216,72 +255,91 @@ static inline int sp_tiled_corr_launch_t(const SpConvDesc* d, int nPerG, const f
     dim3 grid((unsigned)nblk, (unsigned)(dstP / COT));
     static bool attr = false;
     if (!attr) {
-        SP_CUDA(cudaFuncSetAttribute(corr3_tiled_kernel<CK, TD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)smem_bytes<CK, TD>()));
+        SP_CUDA(cudaFuncSetAttribute(corr_tiled_kernel<CK, TD, K, S>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)smem_bytes<CK, TD, K, S>()));
         attr = true;
     }
-    corr3_tiled_kernel<CK, TD><<<grid, 32 * TD, smem_bytes<CK, TD>(), st>>>(*d, nPerG, dstP, tiles_w, tiles_h, tiles_d, src, wp,
-                                                                          flip, bias, scale, shift, dst);
-    SP_LAUNCH_OK("corr3_tiled_kernel");
+    corr_tiled_kernel<CK, TD, K, S><<<grid, 32 * TD, smem_bytes<CK, TD, K, S>(), st>>>(*d, nPerG, dstP, tiles_w, tiles_h, tiles_d,
+                                                                                     src, wp, flip, bias, scale, shift, dst);
+    SP_LAUNCH_OK("corr_tiled_kernel");
     return 0;
 }
 
 static inline int sp_tiled_corr_launch(const SpConvDesc* d, int nPerG, const float* src, const float* wp, int flip,
                                        const float* bias, const float* scale, const float* shift, float* dst,
                                        cudaStream_t st) {
+    if (d->s == 2) {   // parity-split tile: one channel quad per chunk (81 KB / 68 KB of shared memory), 2 CTAs per SM
+        if (d->k == 3) return sp_tiled_corr_launch_t<4, 4, 3, 2>(d, nPerG, src, wp, flip, bias, scale, shift, dst, st);
+        return sp_tiled_corr_launch_t<4, 4, 2, 2>(d, nPerG, src, wp, flip, bias, scale, shift, dst, st);
+    }
     // depth tile: 4 planes (128-thread CTAs, 4 per SM) when that wastes fewer padded planes than 8 (D = 28: 0 vs 4)
     const bool td4 = ((d->Do + 3) / 4 * 4) < ((d->Do + 7) / 8 * 8);
     if (d->Ci > 4) {
-        return td4 ? sp_tiled_corr_launch_t<8, 4>(d, nPerG, src, wp, flip, bias, scale, shift, dst, st)
-                   : sp_tiled_corr_launch_t<8, 8>(d, nPerG, src, wp, flip, bias, scale, shift, dst, st);
+        return td4 ? sp_tiled_corr_launch_t<8, 4, 3, 1>(d, nPerG, src, wp, flip, bias, scale, shift, dst, st)
+                   : sp_tiled_corr_launch_t<8, 8, 3, 1>(d, nPerG, src, wp, flip, bias, scale, shift, dst, st);
     }
-    return td4 ? sp_tiled_corr_launch_t<4, 4>(d, nPerG, src, wp, flip, bias, scale, shift, dst, st)
-               : sp_tiled_corr_launch_t<4, 8>(d, nPerG, src, wp, flip, bias, scale, shift, dst, st);
+    return td4 ? sp_tiled_corr_launch_t<4, 4, 3, 1>(d, nPerG, src, wp, flip, bias, scale, shift, dst, st)
+               : sp_tiled_corr_launch_t<4, 8, 3, 1>(d, nPerG, src, wp, flip, bias, scale, shift, dst, st);
 }
 
 // =====================================================================================================================
-// Tiled weight gradient for the same 3x3x3 stride-1 layers:
-//   dW[co][ci][tap] = sum_{n,o} gz[n,o,co] * xbn[n, o - p + tap, ci]
+// Tiled weight gradient for the same layer geometries:
+//   dW[co][ci][tap] = sum_{n,o} O[n,o,co] * I[n, o*S - p + tap, ci]          (O-side / I-side of SpConvDesc)
 // A CTA owns one (input-channel chunk of CK, output-channel pass of 16) slab of dW and walks over output tiles of
-// 16(w) x 8(h) x 4(d) voxels (grid-strided, so the register accumulators live across many tiles and only
-// gridDim.x partial slabs reach memory).  Per tile it stages the BN-applied, zero-padded input halo (18 x 10 x 6) as
-// channel-quad planes and the gz tile as [voxel][16].  Thread = (sub-group sg = depth plane 0..3, item = (tap, quad)):
-// a 4(ci) x 16(co) register tile, fed per voxel by one LDS.128 of x (tap-shifted) and four warp-broadcast LDS.128 of
-// gz: 64 FFMA per 5 LDS.  The four sub-groups are summed through shared memory at the end (fixed order), partial
-// slabs are reduced across CTAs by wgrad_reduce_kernel in fixed order: deterministic, no atomics.
+// 16(w) x 8(h) x 4(d) voxels (grid-strided, so the register accumulators live across many tiles and only gridDim.x
+// partial slabs reach memory).  Per tile it stages the (BN-applied, zero-padded, parity-split for S = 2) I-side halo as
+// channel-quad planes and the O-side tile as [voxel][16].  Thread = (sub-group sg, item = (tap, quad)): a 4(ci) x 16(co)
+// register tile, fed per voxel by one LDS.128 of I (tap-shifted) and four warp-broadcast LDS.128 of O: 64 FFMA per 5
+// LDS.  A sub-group is 32 or 64 threads (K^3 * CK/4 items rounded up) and owns a slice of the tile's voxels; the
+// sub-groups are summed through shared memory at the end (fixed order), partial slabs are reduced across CTAs by
+// wgrad_reduce_kernel in fixed order: deterministic, no atomics.
 namespace sp_tiled {
 
 constexpr int WTD = 4;                               // output tile depth for wgrad
-constexpr int WID = WTD + 2;
-constexpr int WPLANE = WID * IH * RW;                // 1140 float4 per channel-quad plane
 constexpr int WVOX = TW * TH * WTD;                  // 512 output voxels per tile
 
-template <int CK>
-constexpr size_t wgrad_smem_bytes() {
-    size_t stage = (size_t)(CK / 4) * WPLANE * 16 + (size_t)WVOX * COT * 4;
-    size_t red = (size_t)4 * 27 * (CK / 4) * 64 * 4;
-    return stage > red ? stage : red;
-}
+template <int CK, int K, int S>
+struct WgradCfg {
+    static constexpr int NQ = CK / 4;
+    static constexpr int NITEM = K * K * K * NQ;
+    static constexpr int SGT = NITEM <= 32 ? 32 : 64;         // threads per sub-group
+    static constexpr int NSG = 256 / SGT;                     // 4 or 8 sub-groups
+    static constexpr int HSPLIT = NSG / WTD;                  // sub-groups per depth plane (1 or 2): split of the h rows
+    static constexpr int HROWS = TH / HSPLIT;
+    static constexpr int PLANE = plane_f4<K, S, WTD>();
+    static constexpr size_t stage_bytes = (size_t)NQ * PLANE * 16 + (size_t)WVOX * COT * 4;
+    static constexpr size_t red_bytes = (size_t)NSG * NITEM * 64 * 4;
+    static constexpr size_t smem = stage_bytes > red_bytes ? stage_bytes : red_bytes;
+    static_assert(NITEM <= 64, "too many items per sub-group");
+};
 
-template <int CK>
-__global__ void __launch_bounds__(256, 2)
-wgrad3_tiled_kernel(SpConvDesc d, int nPerG, int tiles_w, int tiles_h, int tiles_d, int total_tiles, int n_co_pass,
-                    const float* __restrict__ iside, const float* __restrict__ scale, const float* __restrict__ shift,
-                    const float* __restrict__ oside, float* __restrict__ ws) {
+template <int CK, int K, int S>
+__global__ void __launch_bounds__(256, (WgradCfg<CK, K, S>::smem > 112 * 1024) ? 1 : 2)
+wgrad_tiled_kernel(SpConvDesc d, int nPerG, int tiles_w, int tiles_h, int tiles_d, int total_tiles, int n_co_pass,
+                   const float* __restrict__ iside, const float* __restrict__ scale, const float* __restrict__ shift,
+                   const float* __restrict__ oside, const float* __restrict__ o_scale, const float* __restrict__ o_shift,
+                   float* __restrict__ ws) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    constexpr int NQ = CK / 4;
-    constexpr int NITEM = 27 * NQ;
-    float4* xs = reinterpret_cast<float4*>(smem_raw);                                  // [NQ][WID][IH][RW]
-    float4* gs = reinterpret_cast<float4*>(smem_raw + (size_t)NQ * WPLANE * 16);       // [WVOX][4]
+    using C = WgradCfg<CK, K, S>;
+    using AW = Axis<K, S, TW>;
+    using AH = Axis<K, S, TH>;
+    using AD = Axis<K, S, WTD>;
+    constexpr int IW = AW::IN, IH = AH::IN, ID = AD::IN;
+    constexpr int RW = row_f4<K, S>();
+    constexpr int NQ = C::NQ, NITEM = C::NITEM, PLANE = C::PLANE;
+    constexpr int K3 = K * K * K;
+    float4* xs = reinterpret_cast<float4*>(smem_raw);                                  // [NQ][ID][IH][RW]
+    float4* gs = reinterpret_cast<float4*>(smem_raw + (size_t)NQ * PLANE * 16);        // [WVOX][4]
 
     const int c0 = (blockIdx.y / n_co_pass) * CK;
     const int co0 = (blockIdx.y % n_co_pass) * COT;
-    const int sg = threadIdx.x >> 6;            // depth plane of the tile handled by this 64-thread sub-group
-    const int item = threadIdx.x & 63;
+    const int sg = threadIdx.x / C::SGT;        // sub-group: depth plane sg % 4, h slice sg / 4
+    const int item = threadIdx.x % C::SGT;
     const bool active = item < NITEM;
     const int tap = active ? item / NQ : 0;
     const int q = active ? item % NQ : 0;
-    const int kw = tap % 3, kh = (tap / 3) % 3, kd = tap / 9;
+    const int kw = tap % K, kh = (tap / K) % K, kd = tap / (K * K);
+    const int plane = sg % WTD, h0 = (sg / WTD) * C::HROWS;
 
     float2 acc[4][COT / 2];
 #pragma unroll
@@ -299,44 +357,19 @@ wgrad3_tiled_kernel(SpConvDesc d, int nPerG, int tiles_w, int tiles_h, int tiles
         const int td_ = t % tiles_d;
         const int n = t / tiles_d;
         const int ow0 = tw * TW, oh0 = th_ * TH, od0 = td_ * WTD;
-        const int id0 = od0 - d.pd, ih0 = oh0 - d.ph, iw0 = ow0 - d.pw;
+        const int id0 = od0 * S - d.pd, ih0 = oh0 * S - d.ph, iw0 = ow0 * S - d.pw;
         const int g = n / nPerG;
         const float* srcn = iside + (int64_t)n * d.Di * d.Hi * d.Wi * d.ldi;
         const float* gzn = oside + (int64_t)n * d.Do * d.Ho * d.Wo * d.ldo;
         __syncthreads();   // previous tile fully consumed
-        for (int i = threadIdx.x; i < WID * IH * IW * NQ; i += 256) {
+        for (int i = threadIdx.x; i < ID * IH * IW * NQ; i += 256) {
             const int qq = i % NQ;
             int r = i / NQ;
             const int iw = r % IW; r /= IW;
             const int ih = r % IH;
             const int idd = r / IH;
-            const int gd = id0 + idd, gh = ih0 + ih, gw = iw0 + iw;
-            const int c = c0 + qq * 4;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (gd >= 0 && gd < d.Di && gh >= 0 && gh < d.Hi && gw >= 0 && gw < d.Wi && c < d.Ci) {
-                const float* p = srcn + (((int64_t)gd * d.Hi + gh) * d.Wi + gw) * d.ldi + c;
-                if (vec_i) {
-                    v = *reinterpret_cast<const float4*>(p);
-                    if (scale) {
-                        const float4 sc = *reinterpret_cast<const float4*>(scale + (int64_t)g * d.Ci + c);
-                        const float4 sh = *reinterpret_cast<const float4*>(shift + (int64_t)g * d.Ci + c);
-                        v.x = fmaf(v.x, sc.x, sh.x); v.y = fmaf(v.y, sc.y, sh.y);
-                        v.z = fmaf(v.z, sc.z, sh.z); v.w = fmaf(v.w, sc.w, sh.w);
-                    }
-                } else {
-                    float e[4];
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        e[u] = 0.f;
-                        if (c + u < d.Ci) {
-                            e[u] = p[u];
-                            if (scale) e[u] = fmaf(e[u], scale[(int64_t)g * d.Ci + c + u], shift[(int64_t)g * d.Ci + c + u]);
-                        }
-                    }
-                    v = make_float4(e[0], e[1], e[2], e[3]);
-                }
-            }
-            xs[qq * WPLANE + (idd * IH + ih) * RW + iw] = v;
+            const float4 v = stage_quad(srcn, d, id0 + idd, ih0 + ih, iw0 + iw, c0 + qq * 4, vec_i, scale, shift, g);
+            xs[qq * PLANE + (AD::slot(idd) * IH + AH::slot(ih)) * RW + AW::slot(iw)] = v;
         }
         for (int i = threadIdx.x; i < WVOX * (COT / 4); i += 256) {
             const int j4 = i % (COT / 4);
@@ -347,24 +380,31 @@ wgrad3_tiled_kernel(SpConvDesc d, int nPerG, int tiles_w, int tiles_h, int tiles
             const int od = od0 + dd, oh = oh0 + h, ow = ow0 + w;
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
             if (od < d.Do && oh < d.Ho && ow < d.Wo) {
-                const float* p = gzn + (((int64_t)od * d.Ho + oh) * d.Wo + ow) * d.ldo + co0 + j4 * 4;
+                const int cc = co0 + j4 * 4;
+                const float* p = gzn + (((int64_t)od * d.Ho + oh) * d.Wo + ow) * d.ldo + cc;
+                float e[4];
                 if (vec_o) {
-                    v = *reinterpret_cast<const float4*>(p);
+                    const float4 a = *reinterpret_cast<const float4*>(p);
+                    e[0] = a.x; e[1] = a.y; e[2] = a.z; e[3] = a.w;
                 } else {
-                    float e[4];
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) e[u] = (co0 + j4 * 4 + u < d.Co) ? p[u] : 0.f;
-                    v = make_float4(e[0], e[1], e[2], e[3]);
+                    for (int u = 0; u < 4; ++u) e[u] = (cc + u < d.Co) ? p[u] : 0.f;
                 }
+                if (o_scale) {
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        if (cc + u < d.Co) e[u] = fmaf(e[u], o_scale[(int64_t)g * d.Co + cc + u], o_shift[(int64_t)g * d.Co + cc + u]);
+                }
+                v = make_float4(e[0], e[1], e[2], e[3]);
             }
             gs[i] = v;    // i == ((dd*TH + h)*TW + w)*4 + j4
         }
         __syncthreads();
         if (active) {
-            const float4* xrow = xs + q * WPLANE + ((sg + kd) * IH + kh) * RW + kw;
-            const float4* grow = gs + (sg * TH * TW) * (COT / 4);
+            const float4* xrow = xs + q * PLANE + ((plane + AD::tap(kd)) * IH + (h0 + AH::tap(kh))) * RW + AW::tap(kw);
+            const float4* grow = gs + ((plane * TH + h0) * TW) * (COT / 4);
 #pragma unroll 1
-            for (int h = 0; h < TH; ++h) {
+            for (int h = 0; h < C::HROWS; ++h) {
 #pragma unroll 4
                 for (int w = 0; w < TW; ++w) {
                     const float4 xv = xrow[h * RW + w];
@@ -388,9 +428,9 @@ wgrad3_tiled_kernel(SpConvDesc d, int nPerG, int tiles_w, int tiles_h, int tiles
         }
     }
 
-    // ---- reduce the four sub-groups through shared memory (fixed order) and emit this CTA's partial slab
+    // ---- reduce the sub-groups through shared memory (fixed order) and emit this CTA's partial slab
     __syncthreads();
-    float* red = reinterpret_cast<float*>(smem_raw);     // [4][NITEM][4][COT]
+    float* red = reinterpret_cast<float*>(smem_raw);     // [NSG][NITEM][4][COT]
     if (active) {
         float* r = red + ((size_t)sg * NITEM + item) * 64;
 #pragma unroll
@@ -402,7 +442,7 @@ wgrad3_tiled_kernel(SpConvDesc d, int nPerG, int tiles_w, int tiles_h, int tiles
             }
     }
     __syncthreads();
-    const int64_t wn = (int64_t)d.Co * d.Ci * 27;
+    const int64_t wn = (int64_t)d.Co * d.Ci * K3;
     float* wsp = ws + (int64_t)blockIdx.x * wn;
     for (int i = threadIdx.x; i < NITEM * 64; i += 256) {
         const int b = i % COT;
@@ -411,9 +451,10 @@ wgrad3_tiled_kernel(SpConvDesc d, int nPerG, int tiles_w, int tiles_h, int tiles
         const int tp = it / NQ, qq = it % NQ;
         const int ci = c0 + qq * 4 + a, co = co0 + b;
         if (ci < d.Ci && co < d.Co) {
-            const float v = ((red[(0 * NITEM + it) * 64 + a * COT + b] + red[(1 * NITEM + it) * 64 + a * COT + b]) +
-                             red[(2 * NITEM + it) * 64 + a * COT + b]) + red[(3 * NITEM + it) * 64 + a * COT + b];
-            wsp[((int64_t)co * d.Ci + ci) * 27 + tp] = v;
+            float v = red[(size_t)it * 64 + a * COT + b];
+#pragma unroll
+            for (int s = 1; s < C::NSG; ++s) v += red[((size_t)s * NITEM + it) * 64 + a * COT + b];
+            wsp[((int64_t)co * d.Ci + ci) * K3 + tp] = v;
         }
     }
 }
@@ -424,7 +465,7 @@ struct WgradTiledPlan {
 
 static inline WgradTiledPlan wgrad_tiled_plan(const SpConvDesc* d) {
     WgradTiledPlan p;
-    p.ck = d->Ci > 4 ? 8 : 4;
+    p.ck = (d->s == 2 && d->k == 3) ? 4 : (d->Ci > 4 ? 8 : 4);
     p.n_chunks = (d->Ci + p.ck - 1) / p.ck;
     p.n_co_pass = (d->Co + COT - 1) / COT;
     p.tiles_w = (d->Wo + TW - 1) / TW;
@@ -443,7 +484,7 @@ static inline WgradTiledPlan wgrad_tiled_plan(const SpConvDesc* d) {
 __global__ void wgrad_reduce_kernel(const float* __restrict__ ws, int chunks, int64_t wn, float* __restrict__ dw, float beta);
 
 static inline bool sp_tiled_wgrad_supported(const SpConvDesc* d) {
-    if (d->k != 3 || d->s != 1 || sp_tiled_disabled()) return false;
+    if (!sp_tiled_geometry(d) || sp_tiled_disabled()) return false;
     const int64_t ov = (int64_t)d->Do * d->Ho * d->Wo;
     return ov >= 2048 && d->Wo >= 8 && d->Ho >= 4;
 }
@@ -451,33 +492,40 @@ static inline bool sp_tiled_wgrad_supported(const SpConvDesc* d) {
 static inline size_t sp_tiled_wgrad_workspace_bytes(const SpConvDesc* d) {
     if (!sp_tiled_wgrad_supported(d)) return 0;
     const sp_tiled::WgradTiledPlan p = sp_tiled::wgrad_tiled_plan(d);
-    return (size_t)p.grid_x * d->Co * d->Ci * 27 * sizeof(float);
+    return (size_t)p.grid_x * d->Co * d->Ci * d->k * d->k * d->k * sizeof(float);
+}
+
+template <int CK, int K, int S>
+static inline int sp_tiled_wgrad_launch_t(const SpConvDesc* d, const sp_tiled::WgradTiledPlan& p, int nPerG, const float* iside,
+                                          const float* scale, const float* shift, const float* oside, const float* o_scale,
+                                          const float* o_shift, float* ws, cudaStream_t st) {
+    using namespace sp_tiled;
+    constexpr size_t smem = WgradCfg<CK, K, S>::smem;
+    static bool attr = false;
+    if (!attr) {
+        SP_CUDA(cudaFuncSetAttribute(wgrad_tiled_kernel<CK, K, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr = true;
+    }
+    dim3 grid(p.grid_x, p.n_chunks * p.n_co_pass);
+    wgrad_tiled_kernel<CK, K, S><<<grid, 256, smem, st>>>(*d, nPerG, p.tiles_w, p.tiles_h, p.tiles_d, p.total_tiles, p.n_co_pass,
+                                                         iside, scale, shift, oside, o_scale, o_shift, ws);
+    SP_LAUNCH_OK("wgrad_tiled_kernel");
+    return 0;
 }
 
 static inline int sp_tiled_wgrad_launch(const SpConvDesc* d, int nPerG, const float* iside, const float* scale,
-                                        const float* shift, const float* oside, float* dw, float beta, float* ws,
-                                        cudaStream_t st) {
+                                        const float* shift, const float* oside, const float* o_scale, const float* o_shift,
+                                        float* dw, float beta, float* ws, cudaStream_t st) {
     using namespace sp_tiled;
     const WgradTiledPlan p = wgrad_tiled_plan(d);
-    dim3 grid(p.grid_x, p.n_chunks * p.n_co_pass);
-    static bool attr8 = false, attr4 = false;
-    if (p.ck == 8) {
-        if (!attr8) {
-            SP_CUDA(cudaFuncSetAttribute(wgrad3_tiled_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wgrad_smem_bytes<8>()));
-            attr8 = true;
-        }
-        wgrad3_tiled_kernel<8><<<grid, 256, wgrad_smem_bytes<8>(), st>>>(*d, nPerG, p.tiles_w, p.tiles_h, p.tiles_d, p.total_tiles,
-                                                                        p.n_co_pass, iside, scale, shift, oside, ws);
-    } else {
-        if (!attr4) {
-            SP_CUDA(cudaFuncSetAttribute(wgrad3_tiled_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wgrad_smem_bytes<4>()));
-            attr4 = true;
-        }
-        wgrad3_tiled_kernel<4><<<grid, 256, wgrad_smem_bytes<4>(), st>>>(*d, nPerG, p.tiles_w, p.tiles_h, p.tiles_d, p.total_tiles,
-                                                                        p.n_co_pass, iside, scale, shift, oside, ws);
-    }
-    SP_LAUNCH_OK("wgrad3_tiled_kernel");
-    const int64_t wn = (int64_t)d->Co * d->Ci * 27;
+    int e;
+    if (d->s == 2 && d->k == 3) e = sp_tiled_wgrad_launch_t<4, 3, 2>(d, p, nPerG, iside, scale, shift, oside, o_scale, o_shift, ws, st);
+    else if (d->s == 2 && p.ck == 8) e = sp_tiled_wgrad_launch_t<8, 2, 2>(d, p, nPerG, iside, scale, shift, oside, o_scale, o_shift, ws, st);
+    else if (d->s == 2) e = sp_tiled_wgrad_launch_t<4, 2, 2>(d, p, nPerG, iside, scale, shift, oside, o_scale, o_shift, ws, st);
+    else if (p.ck == 8) e = sp_tiled_wgrad_launch_t<8, 3, 1>(d, p, nPerG, iside, scale, shift, oside, o_scale, o_shift, ws, st);
+    else e = sp_tiled_wgrad_launch_t<4, 3, 1>(d, p, nPerG, iside, scale, shift, oside, o_scale, o_shift, ws, st);
+    if (e) return e;
+    const int64_t wn = (int64_t)d->Co * d->Ci * d->k * d->k * d->k;
     int64_t rb = (wn + 255) / 256;
     if (rb > 148 * 16) rb = 148 * 16;
     wgrad_reduce_kernel<<<(int)rb, 256, 0, st>>>(ws, p.grid_x, wn, dw, beta);

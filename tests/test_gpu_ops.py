@@ -150,6 +150,29 @@ def test_tiled_corr_paths(case):
     _check_sequential(nn.Sequential(nn.BatchNorm3d(cin), conv, _act(act)), x)
 
 
+STRIDED_TILED_CASES = [
+    # stride-2 layers big enough for the parity-split tiled tier (sp_conv_tiled.cuh, S = 2) and the parity-class transposed
+    # kernel (sp_conv_tiledT.cuh): forward, dgrad and wgrad of each, ragged tiles on every axis
+    ("C", 16, 24, 3, 2, 1, "elu", (12, 40, 44)),               # Cae3D.py:48   16 -> 24, pad 1
+    ("C", 24, 32, 3, 2, 1, "elu", (13, 37, 41)),               # Cae3D.py:59   odd extents, two I-side channel passes in dgrad
+    ("C", 32, 40, 3, 2, 0, "elu", (13, 37, 41)),               # Cae3D.py:70   pad 0; Cout = 40 > 32: dgrad stays generic
+    ("C", 6, 10, 3, 2, 1, "elu", (12, 36, 40)),                # channel counts that are not multiples of 4
+    ("T", 24, 24, 2, 2, 0, "elu", (7, 20, 22)),                # Cae3D.py:193  convT k2 s2
+    ("T", 16, 16, 2, 2, 0, "elu", (6, 19, 23)),                # Cae3D.py:204  odd extents
+    ("T", 12, 10, 3, 2, 0, "elu", (5, 14, 18)),                # Cae3D.py:182  convT k3 s2 (small channel counts)
+    ("T", 5, 7, 2, 2, 0, "leaky", (6, 17, 21)),                # k2 s2, ragged channels
+]
+
+
+@pytest.mark.parametrize("case", STRIDED_TILED_CASES, ids=lambda c: "%s%d-%d_k%dp%s" % (c[0], c[1], c[2], c[3], str(c[5]).replace(" ", "")))
+def test_strided_tiled_paths(case):
+    kind, cin, cout, k, s, p, act, size = case
+    torch.manual_seed(400 + STRIDED_TILED_CASES.index(case))
+    conv = nn.ConvTranspose3d(cin, cout, k, stride=s, padding=p) if kind == "T" else nn.Conv3d(cin, cout, k, stride=s, padding=p)
+    x = torch.randn(2, cin, *size) * 1.5 + 0.3
+    _check_sequential(nn.Sequential(nn.BatchNorm3d(cin), conv, _act(act)), x, G=2)
+
+
 TC_CASES = [
     # >= 8192 output voxels, 8..16 channels on both sides, Ho >= 16: the tcgen05 / TMEM tier (sp_conv_tc.cuh) serves the
     # forward and — through flipped taps — the dgrad; ragged tiles in w, h and d
