@@ -134,7 +134,10 @@ int sp_bn_bwd_finalize(const double* bsums, int64_t count_per_group, int C, int 
  * `accumulate` != 0: out += ...  */
 int sp_bn_act_bwd_apply(const float* gxh, int ldg, const float* x, int ldx, const float* coef, int N,
                         int64_t vox, int C, int G, int act, float alpha, float* out, int ldout, int accumulate,
-                        void* stream);
+                        double* colsum, void* stream);
+/* colsum (optional, C doubles): receives the per-channel column sums of the values written to `out`, i.e. the bias
+ * gradient of the convolution whose output gradient `out` is; sp_bias_from_colsum turns it into db = beta*db + colsum */
+int sp_bias_from_colsum(const double* colsum, int C, float* db, float beta, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Resampling ops of the U-Net (Unet3D.py:39,41 MaxPool3d(2,2); :44,46 Upsample(x2, trilinear); :6-11,66-67,71-72

@@ -62,6 +62,73 @@ channel_sums_kernel(const float* __restrict__ a, int lda, const float* __restric
     }
 }
 
+// float4 variant (C, lda, ldb multiples of 4): thread = (channel quad, row lane); four rows in flight per thread so that
+// enough bytes are outstanding per SM to reach the HBM roof (the scalar kernel above keeps ~8 KB/SM in flight).
+template <int MODE>
+__global__ void __launch_bounds__(256)
+channel_sums_vec_kernel(const float* __restrict__ a, int lda, const float* __restrict__ b, int ldb, int64_t rows_per_group,
+                        int C4, int64_t rows_per_block, int blocks_per_group, double* __restrict__ sums) {
+    __shared__ double sm[256][8];
+    const int g = blockIdx.x / blocks_per_group;
+    const int bg = blockIdx.x % blocks_per_group;
+    const int lanesQ = C4 < 256 ? C4 : 256;
+    const int R = 256 / lanesQ;
+    const int c_l = threadIdx.x % lanesQ, r_l = threadIdx.x / lanesQ;
+    const int64_t r0 = (int64_t)bg * rows_per_block;
+    const int64_t r1 = (r0 + rows_per_block < rows_per_group) ? r0 + rows_per_block : rows_per_group;
+    const float* ag = a + (int64_t)g * rows_per_group * lda;
+    const float* bgp = (MODE == 2) ? b + (int64_t)g * rows_per_group * ldb : nullptr;
+    for (int cb = 0; cb < C4; cb += lanesQ) {   // uniform trip count: every thread reaches the barriers below
+        const int q = cb + c_l;
+        const bool live = (q < C4) && (r_l < R);
+        double s0[4] = {0.0, 0.0, 0.0, 0.0}, s1[4] = {0.0, 0.0, 0.0, 0.0};
+        if (live) {
+            auto add = [&](const float4& va, const float4& vb) {
+                const double a0 = va.x, a1 = va.y, a2 = va.z, a3 = va.w;
+                s0[0] += a0; s0[1] += a1; s0[2] += a2; s0[3] += a3;
+                s1[0] = fma(a0, (double)vb.x, s1[0]); s1[1] = fma(a1, (double)vb.y, s1[1]);
+                s1[2] = fma(a2, (double)vb.z, s1[2]); s1[3] = fma(a3, (double)vb.w, s1[3]);
+            };
+            int64_t r = r0 + r_l;
+            for (; r + 3 * (int64_t)R < r1; r += 4 * (int64_t)R) {
+                float4 va[4], vb[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    va[u] = *reinterpret_cast<const float4*>(ag + (r + (int64_t)u * R) * lda + q * 4);
+                    vb[u] = (MODE == 1) ? va[u] : *reinterpret_cast<const float4*>(bgp + (r + (int64_t)u * R) * ldb + q * 4);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) add(va[u], vb[u]);
+            }
+            for (; r < r1; r += R) {
+                const float4 va = *reinterpret_cast<const float4*>(ag + r * lda + q * 4);
+                const float4 vb = (MODE == 1) ? va : *reinterpret_cast<const float4*>(bgp + r * ldb + q * 4);
+                add(va, vb);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            sm[threadIdx.x][j] = s0[j];
+            sm[threadIdx.x][4 + j] = s1[j];
+        }
+        __syncthreads();
+        if (r_l == 0 && q < C4) {
+            for (int k = 1; k < R; ++k)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    s0[j] += sm[k * lanesQ + c_l][j];
+                    s1[j] += sm[k * lanesQ + c_l][4 + j];
+                }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                atomicAdd(&sums[((int64_t)g * C4 * 4 + q * 4 + j) * 2 + 0], s0[j]);
+                atomicAdd(&sums[((int64_t)g * C4 * 4 + q * 4 + j) * 2 + 1], s1[j]);
+            }
+        }
+        __syncthreads();
+    }
+}
+
 // One thread per channel; groups are visited in order so the running statistics see G sequential momentum updates
 // exactly like G separate nn.BatchNorm3d calls (Cae3D.py:105-108: core, penu, lesion[, interpolation]).
 __global__ void bn_finalize_kernel(const double* __restrict__ sums, double count, int C, int G, const float* __restrict__ gamma,
@@ -163,6 +230,118 @@ bn_act_bwd_apply_kernel(const float* __restrict__ gxh, int ldg, const float* __r
     }
 }
 
+// float4 variant of the apply kernel (C and all lds multiples of 4).  Thread = (channel quad, row lane), groups are walked
+// one after the other so the four coefficients of the thread's channels sit in registers.  colsum != NULL: also
+// accumulate the per-channel column sums of the values written (fp64; = bias gradient of the convolution whose output
+// gradient this kernel produces, Learner.py:121 loss.backward()).
+__global__ void __launch_bounds__(256)
+bn_act_bwd_apply_vec_kernel(const float* __restrict__ gxh, int ldg, const float* __restrict__ x, int ldx,
+                            const float* __restrict__ coef, int64_t rows_per_group, int C4, int G, int act, float alpha,
+                            float* __restrict__ out, int ldout, int accumulate, double* __restrict__ colsum) {
+    __shared__ double sm[256][4];
+    const int C = C4 * 4;
+    const int lanesQ = C4 < 256 ? C4 : 256;
+    const int R = 256 / lanesQ;
+    const int c_l = threadIdx.x % lanesQ, r_l = threadIdx.x / lanesQ;
+    const bool need_x = (coef != nullptr) || (act != SP_ACT_NONE);
+    for (int cb = 0; cb < C4; cb += lanesQ) {
+        const int q = cb + c_l;
+        const bool live = (q < C4) && (r_l < R);
+        double cs[4] = {0.0, 0.0, 0.0, 0.0};
+        if (live) {
+            for (int g = 0; g < G; ++g) {
+                float4 A = make_float4(1.f, 1.f, 1.f, 1.f), m1 = make_float4(0.f, 0.f, 0.f, 0.f), mu = m1, k = m1;
+                if (coef) {
+                    A = *reinterpret_cast<const float4*>(coef + (0 * G + g) * C + q * 4);
+                    m1 = *reinterpret_cast<const float4*>(coef + (1 * G + g) * C + q * 4);
+                    mu = *reinterpret_cast<const float4*>(coef + (2 * G + g) * C + q * 4);
+                    k = *reinterpret_cast<const float4*>(coef + (3 * G + g) * C + q * 4);
+                }
+                const int64_t rbeg = (int64_t)g * rows_per_group, rend = rbeg + rows_per_group;
+                const int64_t step = (int64_t)gridDim.x * R;
+                auto one = [&](int64_t r, const float4& gv, const float4& xv) {
+                    float4 res = gv;
+                    if (coef) {
+                        res.x = A.x * ((gv.x - m1.x) - (xv.x - mu.x) * k.x);
+                        res.y = A.y * ((gv.y - m1.y) - (xv.y - mu.y) * k.y);
+                        res.z = A.z * ((gv.z - m1.z) - (xv.z - mu.z) * k.z);
+                        res.w = A.w * ((gv.w - m1.w) - (xv.w - mu.w) * k.w);
+                    }
+                    res.x *= sp_act_bwd(xv.x, act, alpha); res.y *= sp_act_bwd(xv.y, act, alpha);
+                    res.z *= sp_act_bwd(xv.z, act, alpha); res.w *= sp_act_bwd(xv.w, act, alpha);
+                    float4* o = reinterpret_cast<float4*>(out + r * ldout + q * 4);
+                    if (accumulate) {
+                        const float4 prev = *o;
+                        res.x += prev.x; res.y += prev.y; res.z += prev.z; res.w += prev.w;
+                    }
+                    *o = res;
+                    cs[0] += (double)res.x; cs[1] += (double)res.y; cs[2] += (double)res.z; cs[3] += (double)res.w;
+                };
+                int64_t r = rbeg + (int64_t)blockIdx.x * R + r_l;
+                for (; r + step < rend; r += 2 * step) {
+                    const float4 g0 = sp_ldg_stream(reinterpret_cast<const float4*>(gxh + r * ldg + q * 4));
+                    const float4 g1 = sp_ldg_stream(reinterpret_cast<const float4*>(gxh + (r + step) * ldg + q * 4));
+                    float4 x0 = make_float4(0.f, 0.f, 0.f, 0.f), x1 = x0;
+                    if (need_x) {
+                        x0 = sp_ldg_stream(reinterpret_cast<const float4*>(x + r * ldx + q * 4));
+                        x1 = sp_ldg_stream(reinterpret_cast<const float4*>(x + (r + step) * ldx + q * 4));
+                    }
+                    one(r, g0, x0);
+                    one(r + step, g1, x1);
+                }
+                for (; r < rend; r += step) {
+                    const float4 g0 = sp_ldg_stream(reinterpret_cast<const float4*>(gxh + r * ldg + q * 4));
+                    float4 x0 = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (need_x) x0 = sp_ldg_stream(reinterpret_cast<const float4*>(x + r * ldx + q * 4));
+                    one(r, g0, x0);
+                }
+            }
+        }
+        if (colsum) {     // uniform branch
+#pragma unroll
+            for (int j = 0; j < 4; ++j) sm[threadIdx.x][j] = cs[j];
+            __syncthreads();
+            if (r_l == 0 && q < C4) {
+                for (int kk = 1; kk < R; ++kk)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) cs[j] += sm[kk * lanesQ + c_l][j];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) atomicAdd(&colsum[q * 4 + j], cs[j]);
+            }
+            __syncthreads();
+        }
+    }
+}
+
+__global__ void colsum_to_bias_kernel(const double* __restrict__ acc, int C, float* __restrict__ db, float beta) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < C) db[c] = (beta == 0.f) ? (float)acc[c] : fmaf(beta, db[c], (float)acc[c]);
+}
+
+// column sums of a [rows][ld] matrix (scalar layout fallback of the fused bias gradient)
+__global__ void __launch_bounds__(256)
+channel_sums_colonly_kernel(const float* __restrict__ a, int lda, int64_t rows, int C, int64_t rows_per_block, double* __restrict__ colsum) {
+    __shared__ double sm[256];
+    const int lanesC = C < 256 ? C : 256;
+    const int R = 256 / lanesC;
+    const int c_l = threadIdx.x % lanesC, r_l = threadIdx.x / lanesC;
+    const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
+    const int64_t r1 = (r0 + rows_per_block < rows) ? r0 + rows_per_block : rows;
+    for (int cb = 0; cb < C; cb += lanesC) {
+        const int c = cb + c_l;
+        double s = 0.0;
+        if (r_l < R && c < C)
+            for (int64_t r = r0 + r_l; r < r1; r += R) s += (double)a[r * lda + c];
+        sm[threadIdx.x] = s;
+        __syncthreads();
+        if (r_l == 0 && c < C) {
+            for (int q = 1; q < R; ++q) s += sm[q * lanesC + c_l];
+            atomicAdd(&colsum[c], s);
+        }
+        __syncthreads();
+    }
+}
+
 int launch_sums(int mode, const float* a, int lda, const float* b, int ldb, int N, int64_t vox, int C, int G,
                 double* sums, cudaStream_t st) {
     const int64_t rows_per_group = (int64_t)(N / G) * vox;
@@ -174,7 +353,12 @@ int launch_sums(int mode, const float* a, int lda, const float* b, int ldb, int 
     if (bpg < 1) bpg = 1;
     const int64_t rpb = sp_cdiv(rows_per_group, bpg);
     bpg = sp_cdiv(rows_per_group, rpb);
-    if (mode == 1)
+    const bool vec = (C % 4 == 0) && (lda % 4 == 0) && (mode == 1 || ldb % 4 == 0);
+    if (vec && mode == 1)
+        channel_sums_vec_kernel<1><<<(int)(bpg * G), 256, 0, st>>>(a, lda, nullptr, 0, rows_per_group, C / 4, rpb, (int)bpg, sums);
+    else if (vec)
+        channel_sums_vec_kernel<2><<<(int)(bpg * G), 256, 0, st>>>(a, lda, b, ldb, rows_per_group, C / 4, rpb, (int)bpg, sums);
+    else if (mode == 1)
         channel_sums_kernel<1><<<(int)(bpg * G), 256, 0, st>>>(a, lda, nullptr, 0, rows_per_group, C, rpb, (int)bpg, sums);
     else
         channel_sums_kernel<2><<<(int)(bpg * G), 256, 0, st>>>(a, lda, b, ldb, rows_per_group, C, rpb, (int)bpg, sums);
@@ -225,11 +409,27 @@ int sp_bn_bwd_finalize(const double* bsums, int64_t count_per_group, int C, int 
 }
 
 int sp_bn_act_bwd_apply(const float* gxh, int ldg, const float* x, int ldx, const float* coef, int N, int64_t vox, int C,
-                        int G, int act, float alpha, float* out, int ldout, int accumulate, void* stream) {
+                        int G, int act, float alpha, float* out, int ldout, int accumulate, double* colsum, void* stream) {
     SP_REQUIRE(gxh && out, "sp_bn_act_bwd_apply: NULL pointer");
     SP_REQUIRE(x || (!coef && act == SP_ACT_NONE), "sp_bn_act_bwd_apply: x required");
     SP_REQUIRE(N > 0 && vox > 0 && C > 0 && ldg >= C && ldout >= C && G >= 1 && N % G == 0, "sp_bn_act_bwd_apply: bad shape");
     const int64_t rows = (int64_t)N * vox;
+    const bool vec = (C % 4 == 0) && (ldg % 4 == 0) && (ldout % 4 == 0) && (!x || ldx % 4 == 0);
+    if (colsum) SP_CUDA(cudaMemsetAsync(colsum, 0, sizeof(double) * C, sp_stream(stream)));
+    if (vec) {
+        const int C4 = C / 4;
+        const int lanesQ = C4 < 256 ? C4 : 256;
+        const int R = 256 / lanesQ;
+        const int64_t rpg = (int64_t)(N / G) * vox;
+        int64_t blocks = sp_cdiv(rpg, (int64_t)R * 4);       // ~4 rows per thread and group at least
+        const int64_t cap = (int64_t)sp_num_sms() * 8;
+        if (blocks > cap) blocks = cap;
+        if (blocks < 1) blocks = 1;
+        bn_act_bwd_apply_vec_kernel<<<(int)blocks, 256, 0, sp_stream(stream)>>>(gxh, ldg, x, ldx, coef, rpg, C4, G, act, alpha, out,
+                                                                             ldout, accumulate, colsum);
+        SP_LAUNCH_OK("bn_act_bwd_apply_vec_kernel");
+        return 0;
+    }
     int64_t blocks = sp_cdiv(rows * C, 256 * 4);
     const int64_t cap = (int64_t)sp_num_sms() * 16;
     if (blocks > cap) blocks = cap;
@@ -237,6 +437,18 @@ int sp_bn_act_bwd_apply(const float* gxh, int ldg, const float* x, int ldx, cons
     bn_act_bwd_apply_kernel<<<(int)blocks, 256, 0, sp_stream(stream)>>>(gxh, ldg, x, ldx, coef, rows, (int64_t)(N / G) * vox, C, G,
                                                                      act, alpha, out, ldout, accumulate);
     SP_LAUNCH_OK("bn_act_bwd_apply_kernel");
+    if (colsum) {   // scalar layout: column sums by the generic reduction over the tensor just written
+        const int64_t rpb = sp_cdiv(rows, (int64_t)sp_num_sms() * 8);
+        channel_sums_colonly_kernel<<<(int)sp_cdiv(rows, rpb), 256, 0, sp_stream(stream)>>>(out, ldout, rows, C, rpb, colsum);
+        SP_LAUNCH_OK("channel_sums_colonly_kernel");
+    }
+    return 0;
+}
+
+int sp_bias_from_colsum(const double* colsum, int C, float* db, float beta, void* stream) {
+    SP_REQUIRE(colsum && db && C > 0, "sp_bias_from_colsum: bad arguments");
+    colsum_to_bias_kernel<<<(C + 255) / 256, 256, 0, sp_stream(stream)>>>(colsum, C, db, beta);
+    SP_LAUNCH_OK("colsum_to_bias_kernel");
     return 0;
 }
 

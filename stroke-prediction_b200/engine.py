@@ -7,7 +7,7 @@ reference) into fused units and runs them through the C-ABI:
 
 forward per unit   : bn_stats -> bn_finalize (scale/shift)  ->  corr / corrT with BN applied while staging the
                      source and bias + activation fused in the epilogue.  Only the activation output is stored.
-backward per unit  : wgrad (BN re-applied on the fly) + bias_grad, corrT / corr for the gradient w.r.t. the BN output,
+backward per unit  : wgrad (BN re-applied on the fly), bias gradient (column sums fused into the kernel that wrote gz), corrT / corr for the gradient w.r.t. the BN output,
                      bn_bwd_reduce -> bn_bwd_finalize (dgamma, dbeta, coefficients) -> bn_act_bwd_apply, which fuses
                      the BN backward with the derivative of the *previous* unit's activation.
 
@@ -248,8 +248,16 @@ def seq_backward(plan, saved, gy, need_input_grad, want):
     units = plan.units
     last = units[-1]
     # gradient w.r.t. the last conv output: gy * act'(y)
+    def colsum_for(unit, like):
+        """fp64 scratch for the bias gradient of `unit`, filled by the kernel that writes its output gradient."""
+        if unit.conv.bias is not None and want(unit.conv.bias):
+            return torch.empty(unit.cout, device=like.device, dtype=torch.float64)
+        return None
+
+    gz_colsum = None
     if last.act != ACT_NONE:
-        gz = ops.bn_act_bwd_apply(gy, saved.acts[-1], None, G, last.act, last.alpha)
+        gz_colsum = colsum_for(last, gy)
+        gz = ops.bn_act_bwd_apply(gy, saved.acts[-1], None, G, last.act, last.alpha, colsum=gz_colsum)
     else:
         gz = gy if ops.is_ndhwc(gy) else ops.as_vol(gy)
     for i in range(len(units) - 1, -1, -1):
@@ -279,8 +287,11 @@ def seq_backward(plan, saved, gy, need_input_grad, want):
             if db is None:
                 db, beta = torch.empty_like(conv.bias), 0.0
                 grads[conv.bias] = db
-            gC = gz.shape[1]
-            ops.bias_grad(gz, gz.numel() // gC, gC, gC, db, beta)
+            if gz_colsum is not None:
+                ops.bias_from_colsum(gz_colsum, db, beta)
+            else:
+                gC = gz.shape[1]
+                ops.bias_grad(gz, gz.numel() // gC, gC, gC, db, beta)
         bn_grads = u.bn is not None and u.bn.affine and (want(u.bn.weight) or want(u.bn.bias))
         need_dx = need_input_grad if i == 0 else True
         if not (need_dx or bn_grads):
@@ -309,9 +320,10 @@ def seq_backward(plan, saved, gy, need_input_grad, want):
             break
         prev_act, prev_alpha = (units[i - 1].act, units[i - 1].alpha) if i > 0 else (ACT_NONE, 0.0)
         if coef is None and prev_act == ACT_NONE:
-            gz = gxh
+            gz, gz_colsum = gxh, None
         else:
-            gz = ops.bn_act_bwd_apply(gxh, x, coef, G, prev_act, prev_alpha)
+            gz_colsum = colsum_for(units[i - 1], gxh) if i > 0 else None
+            gz = ops.bn_act_bwd_apply(gxh, x, coef, G, prev_act, prev_alpha, colsum=gz_colsum)
     else:
         return gz, grads
     return None, grads

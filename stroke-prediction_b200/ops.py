@@ -275,15 +275,21 @@ def bn_backward_coef(gxh, x, G, gamma, mean, invstd, training, dgamma, dbeta, be
     return coef
 
 
-def bn_act_bwd_apply(gxh, x, coef, G, act, alpha, out=None, accumulate=False):
-    """out (+)= A*((gxh - m1) - (x - mu)*k) * act'(x); coef None -> gxh * act'(x)."""
+def bn_act_bwd_apply(gxh, x, coef, G, act, alpha, out=None, accumulate=False, colsum=None):
+    """out (+)= A*((gxh - m1) - (x - mu)*k) * act'(x); coef None -> gxh * act'(x).  colsum: optional fp64 [C] tensor
+    receiving the column sums of `out` (fused bias gradient, see bias_from_colsum)."""
     N, C, D, H, W = gxh.shape
     if out is None:
         out = new_vol(N, C, D, H, W, gxh.device)
         accumulate = False
     check(_L().sp_bn_act_bwd_apply(_p(gxh), C, _p(x), C, _p(coef), N, D * H * W, C, G, act, float(alpha), _p(out), C,
-                                   int(accumulate), _stream()), "sp_bn_act_bwd_apply")
+                                   int(accumulate), _p(colsum), _stream()), "sp_bn_act_bwd_apply")
     return out
+
+
+def bias_from_colsum(colsum, db, beta=0.0):
+    check(_L().sp_bias_from_colsum(_p(colsum), db.numel(), _p(db), beta, _stream()), "sp_bias_from_colsum")
+    return db
 
 
 # ---------------------------------------------------------------------------------------------------- resampling
