@@ -143,7 +143,7 @@ def run_reference(args):
                                    "%d timed step(s) after %d warm-up" % (torch.__version__, sample_b, steps, warmup)},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(args, per_gpu_batch):
@@ -269,11 +269,14 @@ def run_b200(args):
         ms_e2e = timed(step_e2e, args.steps)
 
         # per-kernel attribution with CUDA events on the launching stream (one extra step, not part of `value`)
+        # (every rank runs the step — it contains the gradient all-reduce — but only rank 0 records events)
         prof = None
         if rank == 0:
             ops.start_profile()
-            step_resident()
+        step_resident()
+        if rank == 0:
             prof = ops.stop_profile()
+        barrier()
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -328,12 +331,33 @@ def run_b200(args):
                     "ms_per_step": ms_e2e / args.steps, "api": "CaeReconstructionLearner.train_batch(host_batch, epoch)"},
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "kernel_breakdown": breakdown, "op_breakdown": op_breakdown,
             "cpu_baseline": cpu}
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """Keep stdout for the ONE JSON line: everything else that writes to fd 1 (NCCL's version banner, library prints,
+    loss_step-style prints) is routed to stderr."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+        sys.stdout = sys.stderr
+
+
+def emit(line):
+    out = _REAL_STDOUT if _REAL_STDOUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
