@@ -12,6 +12,7 @@
 #include "sp_common.cuh"
 #include "sp_conv_tiled.cuh"
 #include "sp_conv_tiledT.cuh"
+#include "sp_conv_pw.cuh"
 #include "sp_conv_tc.cuh"
 
 // fixed-order sum of per-CTA partial weight-gradient slabs (fp64 accumulation: the partials carry the rounding of long
@@ -491,6 +492,11 @@ int sp_corr(const SpConvDesc* d, const float* src, const float* wp, const float*
     SP_REQUIRE(G >= 1 && d->N % G == 0, "sp_corr: N=%d not divisible by G=%d", d->N, G);
     const int coP = round_up(d->Co, kPad);
     const int nPerG = d->N / G;
+    if (sp_pw_fwd_supported(d, d->Ci)) {
+        const int64_t vox = (int64_t)d->Do * d->Ho * d->Wo;
+        return sp_pw_fwd_launch(src, d->ldi, d->Ci, dst, d->ldo, d->Co, (int64_t)d->N * vox, (int64_t)nPerG * vox, wp, bias, scale, shift,
+                                d->act, d->alpha, sp_stream(stream));
+    }
     SpTcCfg cfg;
     if (tc_serves(d, 0, &cfg))
         return tc_corr_launch(d, cfg, nPerG, src, wp + ffma_packed_floats(d, 0), bias, scale, shift, dst, sp_stream(stream));
@@ -509,6 +515,11 @@ int sp_corrT(const SpConvDesc* d, const float* src, const float* wp, const float
     SP_REQUIRE(G >= 1 && d->N % G == 0, "sp_corrT: N=%d not divisible by G=%d", d->N, G);
     const int ciP = round_up(d->Ci, kPad);
     const int nPerG = d->N / G;
+    if (sp_pw_fwd_supported(d, d->Co)) {   // 1x1x1: the transposed correlation is the same channel mix on Wt[0][co][ciP]
+        const int64_t vox = (int64_t)d->Do * d->Ho * d->Wo;
+        return sp_pw_fwd_launch(src, d->ldo, d->Co, dst, d->ldi, d->Ci, (int64_t)d->N * vox, (int64_t)nPerG * vox, wp, bias, scale, shift,
+                                d->act, d->alpha, sp_stream(stream));
+    }
     if (d->s == 1) {
         // stride 1: the transposed correlation is a correlation with flipped taps, swapped channel roles and
         // padding k-1-p; Wt[tap][co][ciP] read with flipped tap index is exactly that correlation's Wc.
@@ -534,6 +545,8 @@ size_t sp_wgrad_workspace_bytes(const SpConvDesc* d) {
         generic = (size_t)p.chunks * p.wn * sizeof(float);
     }
     tiled = sp_tiled_wgrad_workspace_bytes(d);
+    const size_t pw = sp_pw_wgrad_workspace_bytes(d);
+    if (pw > tiled) tiled = pw;
     return (generic > tiled ? generic : tiled) + 256;
 }
 
@@ -548,6 +561,8 @@ int sp_wgrad(const SpConvDesc* d, const float* iside, const float* i_scale, cons
     SP_REQUIRE(ws_bytes >= sp_wgrad_workspace_bytes(d), "sp_wgrad: workspace too small (%zu < %zu)", ws_bytes,
                sp_wgrad_workspace_bytes(d));
     const int nPerG = d->N / G;
+    if (sp_pw_wgrad_supported(d))
+        return sp_pw_wgrad_launch(d, nPerG, iside, i_scale, i_shift, oside, o_scale, o_shift, dw, beta, (float*)ws, sp_stream(stream));
     if (sp_tiled_wgrad_supported(d))
         return sp_tiled_wgrad_launch(d, nPerG, iside, i_scale, i_shift, oside, o_scale, o_shift, dw, beta, (float*)ws, sp_stream(stream));
     const WgradPlan p = wgrad_plan(d);
