@@ -25,7 +25,7 @@
 namespace sp_tiled {
 
 constexpr int TW = 16, TH = 8;                   // output tile in w, h; depth TD is a template parameter
-constexpr int COT = 16;                          // output channels per thread / per CTA pass
+constexpr int COT = 16;                          // output channels per thread / per CTA pass (wgrad; forward: template COTF)
 constexpr int VT = 4;                            // voxels per thread along w
 
 // one axis of the (parity-split) input tile of an output tile of extent T
@@ -46,8 +46,8 @@ __host__ __device__ constexpr int row_f4() {      // padded row length (float4 u
 template <int K, int S, int TD>
 __host__ __device__ constexpr int plane_f4() { return Axis<K, S, TD>::IN * Axis<K, S, TH>::IN * row_f4<K, S>(); }
 
-template <int CK, int TD, int K, int S>
-constexpr size_t smem_bytes() { return (size_t)(CK / 4) * plane_f4<K, S, TD>() * 16 + (size_t)K * K * K * CK * COT * 4; }
+template <int CK, int TD, int K, int S, int COTF>
+constexpr size_t smem_bytes() { return (size_t)(CK / 4) * plane_f4<K, S, TD>() * 16 + (size_t)K * K * K * CK * COTF * 4; }
 
 // stage one channel-quad of one input voxel: BN applied, zeros outside the volume / beyond Ci
 __device__ __forceinline__ float4 stage_quad(const float* __restrict__ srcn, const SpConvDesc& d, int gd, int gh, int gw, int c,
@@ -80,9 +80,12 @@ __device__ __forceinline__ float4 stage_quad(const float* __restrict__ srcn, con
 }
 
 // d: correlation geometry (k = K, s = S).  wp: packed [tap][src channel][dstP]; flip != 0 reads tap K^3 - 1 - t.
-template <int CK, int TD, int K, int S>
+// COTF = output channels per CTA pass (16, 8 or 2): pass blockIdx.y covers channels [co_base + y*COTF, +COTF) — the ragged
+// tail of a 24-channel layer runs as one 8-wide pass and a single-channel layer (dgrad into the 1-channel input volume,
+// Cae3D.py:41) as a 2-wide pass instead of burning a full 16-wide one.
+template <int CK, int TD, int K, int S, int COTF>
 __global__ void __launch_bounds__(32 * TD, (S == 1 ? 512 : 256) / (32 * TD))
-corr_tiled_kernel(SpConvDesc d, int nPerG, int dstP, int tiles_w, int tiles_h, int tiles_d, const float* __restrict__ src,
+corr_tiled_kernel(SpConvDesc d, int nPerG, int dstP, int co_base, int tiles_w, int tiles_h, int tiles_d, const float* __restrict__ src,
                   const float* __restrict__ wp, int flip, const float* __restrict__ bias, const float* __restrict__ scale,
                   const float* __restrict__ shift, float* __restrict__ dst) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -104,7 +107,9 @@ corr_tiled_kernel(SpConvDesc d, int nPerG, int dstP, int tiles_w, int tiles_h, i
     const int td_ = t % tiles_d;
     const int n = t / tiles_d;
     const int ow0 = tw * TW, oh0 = th_ * TH, od0 = td_ * TD;
-    const int co0 = blockIdx.y * COT;
+    const int co0 = co_base + blockIdx.y * COTF;
+    constexpr int COT = COTF;            // shadows the namespace constant inside this kernel
+    constexpr int WV = (COT >= 4) ? 4 : 2;   // floats per weight staging / load element
     const int g = n / nPerG;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -133,15 +138,22 @@ corr_tiled_kernel(SpConvDesc d, int nPerG, int dstP, int tiles_w, int tiles_h, i
             xs[q * PLANE + (AD::slot(idd) * IH + AH::slot(ih)) * RW + AW::slot(iw)] = v;
         }
         // ---- stage the weight slab [K3][CK][COT] of this chunk / output-channel pass
-        for (int i = threadIdx.x; i < K3 * CK * (COT / 4); i += NT) {
-            const int j4 = i % (COT / 4);
-            int r = i / (COT / 4);
+        for (int i = threadIdx.x; i < K3 * CK * (COT / WV); i += NT) {
+            const int j4 = i % (COT / WV);
+            int r = i / (COT / WV);
             const int cl = r % CK;
             const int tap = r / CK;
             const int st = flip ? K3 - 1 - tap : tap;
-            float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (c0 + cl < d.Ci) w = *reinterpret_cast<const float4*>(wp + ((int64_t)st * d.Ci + c0 + cl) * dstP + co0 + j4 * 4);
-            reinterpret_cast<float4*>(wsm)[(tap * CK + cl) * (COT / 4) + j4] = w;
+            const float* wsrc = wp + ((int64_t)st * d.Ci + c0 + cl) * dstP + co0 + j4 * WV;
+            if (WV == 4) {
+                float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (c0 + cl < d.Ci) w = *reinterpret_cast<const float4*>(wsrc);
+                reinterpret_cast<float4*>(wsm)[(tap * CK + cl) * (COT / 4) + j4] = w;
+            } else {
+                float2 w = make_float2(0.f, 0.f);
+                if (c0 + cl < d.Ci) w = *reinterpret_cast<const float2*>(wsrc);
+                reinterpret_cast<float2*>(wsm)[(tap * CK + cl) * (COT / 2) + j4] = w;
+            }
         }
         __syncthreads();
 
@@ -168,13 +180,17 @@ corr_tiled_kernel(SpConvDesc d, int nPerG, int dstP, int tiles_w, int tiles_h, i
                     for (int kw = 0; kw < K; ++kw) {
 #pragma unroll
                         for (int c = 0; c < 4; ++c) {
-                            const float4* wv = reinterpret_cast<const float4*>(wtap + (kw * CK + q * 4 + c) * COT);
                             float2 w[COT / 2];
+                            if (WV == 4) {
+                                const float4* wv = reinterpret_cast<const float4*>(wtap + (kw * CK + q * 4 + c) * COT);
 #pragma unroll
-                            for (int j4 = 0; j4 < COT / 4; ++j4) {
-                                const float4 t4 = wv[j4];
-                                w[j4 * 2 + 0] = make_float2(t4.x, t4.y);
-                                w[j4 * 2 + 1] = make_float2(t4.z, t4.w);
+                                for (int j4 = 0; j4 < COT / 4; ++j4) {
+                                    const float4 t4 = wv[j4];
+                                    w[j4 * 2 + 0] = make_float2(t4.x, t4.y);
+                                    w[j4 * 2 + 1] = make_float2(t4.z, t4.w);
+                                }
+                            } else {
+                                w[0] = *reinterpret_cast<const float2*>(wtap + (kw * CK + q * 4 + c) * COT);
                             }
 #pragma unroll
                             for (int v = 0; v < VT; ++v) {
@@ -193,7 +209,7 @@ corr_tiled_kernel(SpConvDesc d, int nPerG, int dstP, int tiles_w, int tiles_h, i
     // ---- epilogue: bias + activation, masked stores
     const int od = od0 + ltd, oh = oh0 + lth;
     if (od >= d.Do || oh >= d.Ho) return;
-    const bool vst = (d.ldo % 4 == 0) && (co0 + COT <= d.Co);
+    const bool vst = (COT % 4 == 0) && (d.ldo % 4 == 0) && (co0 + COT <= d.Co);
     float b[COT];
 #pragma unroll
     for (int j = 0; j < COT; ++j) b[j] = (bias && co0 + j < d.Co) ? bias[co0 + j] : 0.f;
@@ -206,10 +222,10 @@ corr_tiled_kernel(SpConvDesc d, int nPerG, int dstP, int tiles_w, int tiles_h, i
 #pragma unroll
             for (int j4 = 0; j4 < COT / 4; ++j4) {
                 float4 o;
-                o.x = sp_act_fwd(acc[v][j4 * 2 + 0].x + b[j4 * 4 + 0], d.act, d.alpha);
-                o.y = sp_act_fwd(acc[v][j4 * 2 + 0].y + b[j4 * 4 + 1], d.act, d.alpha);
-                o.z = sp_act_fwd(acc[v][j4 * 2 + 1].x + b[j4 * 4 + 2], d.act, d.alpha);
-                o.w = sp_act_fwd(acc[v][j4 * 2 + 1].y + b[j4 * 4 + 3], d.act, d.alpha);
+                o.x = sp_act_fwd(acc[v][(j4 * 2 + 0) % (COT / 2)].x + b[(j4 * 4 + 0) % COT], d.act, d.alpha);
+                o.y = sp_act_fwd(acc[v][(j4 * 2 + 0) % (COT / 2)].y + b[(j4 * 4 + 1) % COT], d.act, d.alpha);
+                o.z = sp_act_fwd(acc[v][(j4 * 2 + 1) % (COT / 2)].x + b[(j4 * 4 + 2) % COT], d.act, d.alpha);
+                o.w = sp_act_fwd(acc[v][(j4 * 2 + 1) % (COT / 2)].y + b[(j4 * 4 + 3) % COT], d.act, d.alpha);
                 reinterpret_cast<float4*>(yp)[j4] = o;
             }
         } else {
@@ -243,26 +259,40 @@ static inline bool sp_tiled_corr_supported(const SpConvDesc* d) {
     return ov >= 2048 && d->Wo >= 8 && d->Ho >= 4;
 }
 
-template <int CK, int TD, int K, int S>
-static inline int sp_tiled_corr_launch_t(const SpConvDesc* d, int nPerG, const float* src, const float* wp, int flip,
-                                         const float* bias, const float* scale, const float* shift, float* dst,
+template <int CK, int TD, int K, int S, int COTF>
+static inline int sp_tiled_corr_launch_c(const SpConvDesc* d, int nPerG, int co_base, int passes, const float* src, const float* wp,
+                                         int flip, const float* bias, const float* scale, const float* shift, float* dst,
                                          cudaStream_t st) {
     using namespace sp_tiled;
     const int tiles_w = (d->Wo + TW - 1) / TW, tiles_h = (d->Ho + TH - 1) / TH, tiles_d = (d->Do + TD - 1) / TD;
     const int64_t nblk = (int64_t)tiles_w * tiles_h * tiles_d * d->N;
     SP_REQUIRE(nblk < (1LL << 31), "tiled corr: too many tiles");
     const int dstP = (d->Co + 15) / 16 * 16;
-    dim3 grid((unsigned)nblk, (unsigned)(dstP / COT));
+    dim3 grid((unsigned)nblk, (unsigned)passes);
+    constexpr size_t smem = smem_bytes<CK, TD, K, S, COTF>();
     static bool attr = false;
     if (!attr) {
-        SP_CUDA(cudaFuncSetAttribute(corr_tiled_kernel<CK, TD, K, S>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)smem_bytes<CK, TD, K, S>()));
+        SP_CUDA(cudaFuncSetAttribute(corr_tiled_kernel<CK, TD, K, S, COTF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr = true;
     }
-    corr_tiled_kernel<CK, TD, K, S><<<grid, 32 * TD, smem_bytes<CK, TD, K, S>(), st>>>(*d, nPerG, dstP, tiles_w, tiles_h, tiles_d,
-                                                                                     src, wp, flip, bias, scale, shift, dst);
+    corr_tiled_kernel<CK, TD, K, S, COTF><<<grid, 32 * TD, smem, st>>>(*d, nPerG, dstP, co_base, tiles_w, tiles_h, tiles_d, src, wp, flip,
+                                                                       bias, scale, shift, dst);
     SP_LAUNCH_OK("corr_tiled_kernel");
     return 0;
+}
+
+// full 16-wide passes, then the ragged tail as one 2-, 8- or 16-wide pass
+template <int CK, int TD, int K, int S>
+static inline int sp_tiled_corr_launch_t(const SpConvDesc* d, int nPerG, const float* src, const float* wp, int flip,
+                                         const float* bias, const float* scale, const float* shift, float* dst,
+                                         cudaStream_t st) {
+    const int full = d->Co / 16, rem = d->Co % 16;
+    if (full > 0)
+        if (int e = sp_tiled_corr_launch_c<CK, TD, K, S, 16>(d, nPerG, 0, full, src, wp, flip, bias, scale, shift, dst, st)) return e;
+    if (rem == 0) return 0;
+    if (rem <= 2) return sp_tiled_corr_launch_c<CK, TD, K, S, 2>(d, nPerG, full * 16, 1, src, wp, flip, bias, scale, shift, dst, st);
+    if (rem <= 8) return sp_tiled_corr_launch_c<CK, TD, K, S, 8>(d, nPerG, full * 16, 1, src, wp, flip, bias, scale, shift, dst, st);
+    return sp_tiled_corr_launch_c<CK, TD, K, S, 16>(d, nPerG, full * 16, 1, src, wp, flip, bias, scale, shift, dst, st);
 }
 
 static inline int sp_tiled_corr_launch(const SpConvDesc* d, int nPerG, const float* src, const float* wp, int flip,
