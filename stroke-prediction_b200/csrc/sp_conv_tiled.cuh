@@ -489,20 +489,262 @@ wgrad_tiled_kernel(SpConvDesc d, int nPerG, int tiles_w, int tiles_h, int tiles_
     }
 }
 
+// ---- pipelined variant -------------------------------------------------------------------------------------------------
+// Same decomposition, but the tile loop is software-pipelined with cp.async: while the CTA accumulates tile i out of
+// buffer b, the raw I-side halo and O-side block of tile i+1 stream into buffer b^1 (zero-filled outside the volume by the
+// copy itself).  BatchNorm is applied in place after arrival (a shared-memory read-modify-write, ~30-cycle latency instead
+// of a global round trip in front of every tile).  One CTA per SM owns the whole shared memory: two buffers.
+// Needs 16-byte-aligned channel quads on both sides (Ci, ldi, ldo multiples of 4).
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, int src_bytes) {
+    const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(s), "l"(gsrc), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+template <int CK, int K, int S, int WD>
+struct WgradPipeCfg {
+    static constexpr int NQ = CK / 4;
+    static constexpr int NITEM = K * K * K * NQ;
+    static constexpr int SGT = NITEM <= 32 ? 32 : (NITEM <= 64 ? 64 : 128);   // threads per sub-group
+    static constexpr int NSG = 256 / SGT;
+    static constexpr int ROWS = WD * TH;                        // (plane, h) rows of 16 voxels per tile
+    static constexpr int RPS = ROWS / NSG;                      // rows per sub-group
+    static constexpr int PLANE = plane_f4<K, S, WD>();
+    static constexpr int VOX = TW * TH * WD;
+    static constexpr size_t buf_bytes = (size_t)NQ * PLANE * 16 + (size_t)VOX * COT * 4;
+    static constexpr size_t red_bytes = (size_t)NSG * NITEM * 64 * 4;
+    static constexpr size_t smem = 2 * buf_bytes > red_bytes ? 2 * buf_bytes : red_bytes;
+    static_assert(NITEM <= 128 && ROWS % NSG == 0, "bad wgrad pipe configuration");
+};
+
+template <int CK, int K, int S, int WD>
+__global__ void __launch_bounds__(256, 1)
+wgrad_tiled_pipe_kernel(SpConvDesc d, int nPerG, int tiles_w, int tiles_h, int tiles_d, int total_tiles, int n_co_pass,
+                        const float* __restrict__ iside, const float* __restrict__ scale, const float* __restrict__ shift,
+                        const float* __restrict__ oside, const float* __restrict__ o_scale, const float* __restrict__ o_shift,
+                        float* __restrict__ ws) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    using C = WgradPipeCfg<CK, K, S, WD>;
+    using AW = Axis<K, S, TW>;
+    using AH = Axis<K, S, TH>;
+    using AD = Axis<K, S, WD>;
+    constexpr int IW = AW::IN, IH = AH::IN, ID = AD::IN;
+    constexpr int RW = row_f4<K, S>();
+    constexpr int NQ = C::NQ, NITEM = C::NITEM, PLANE = C::PLANE;
+    constexpr int K3 = K * K * K;
+
+    const int c0 = (blockIdx.y / n_co_pass) * CK;
+    const int co0 = (blockIdx.y % n_co_pass) * COT;
+    const int sg = threadIdx.x / C::SGT;
+    const int item = threadIdx.x % C::SGT;
+    const bool active = item < NITEM;
+    const int tap = active ? item / NQ : 0;
+    const int q = active ? item % NQ : 0;
+    const int kw = tap % K, kh = (tap / K) % K, kd = tap / (K * K);
+
+    float2 acc[4][COT / 2];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < COT / 2; ++b) acc[a][b] = make_float2(0.f, 0.f);
+
+    auto xs_of = [&](int b) { return reinterpret_cast<float4*>(smem_raw + (size_t)b * C::buf_bytes); };
+    auto gs_of = [&](int b) { return reinterpret_cast<float4*>(smem_raw + (size_t)b * C::buf_bytes + (size_t)NQ * PLANE * 16); };
+
+    // decode a tile index
+    auto tile_origin = [&](int tile, int& n, int& od0, int& oh0, int& ow0) {
+        int t = tile;
+        const int tw = t % tiles_w; t /= tiles_w;
+        const int th_ = t % tiles_h; t /= tiles_h;
+        const int td_ = t % tiles_d;
+        n = t / tiles_d;
+        ow0 = tw * TW; oh0 = th_ * TH; od0 = td_ * WD;
+    };
+    // raw copies of one tile into buffer b (zero fill outside the volume / beyond the channel counts)
+    auto issue = [&](int tile, int b) {
+        int n, od0, oh0, ow0;
+        tile_origin(tile, n, od0, oh0, ow0);
+        const int id0 = od0 * S - d.pd, ih0 = oh0 * S - d.ph, iw0 = ow0 * S - d.pw;
+        const float* srcn = iside + (int64_t)n * d.Di * d.Hi * d.Wi * d.ldi;
+        const float* gzn = oside + (int64_t)n * d.Do * d.Ho * d.Wo * d.ldo;
+        float4* xs = xs_of(b);
+        float4* gs = gs_of(b);
+        for (int i = threadIdx.x; i < ID * IH * IW * NQ; i += 256) {
+            const int qq = i % NQ;
+            int r = i / NQ;
+            const int iw = r % IW; r /= IW;
+            const int ih = r % IH;
+            const int idd = r / IH;
+            const int gd = id0 + idd, gh = ih0 + ih, gw = iw0 + iw, c = c0 + qq * 4;
+            const bool in = gd >= 0 && gd < d.Di && gh >= 0 && gh < d.Hi && gw >= 0 && gw < d.Wi && c < d.Ci;
+            const float* p = in ? srcn + (((int64_t)gd * d.Hi + gh) * d.Wi + gw) * d.ldi + c : iside;
+            cp_async16(&xs[qq * PLANE + (AD::slot(idd) * IH + AH::slot(ih)) * RW + AW::slot(iw)], p, in ? 16 : 0);
+        }
+        for (int i = threadIdx.x; i < C::VOX * (COT / 4); i += 256) {
+            const int j4 = i % (COT / 4);
+            int r = i / (COT / 4);
+            const int w = r % TW; r /= TW;
+            const int h = r % TH;
+            const int dd = r / TH;
+            const int od = od0 + dd, oh = oh0 + h, ow = ow0 + w, cc = co0 + j4 * 4;
+            int nbytes = (od < d.Do && oh < d.Ho && ow < d.Wo) ? (d.Co - cc) * 4 : 0;
+            nbytes = nbytes < 0 ? 0 : (nbytes > 16 ? 16 : nbytes);
+            const float* p = nbytes ? gzn + (((int64_t)od * d.Ho + oh) * d.Wo + ow) * d.ldo + cc : oside;
+            cp_async16(&gs[i], p, nbytes);
+        }
+        cp_async_commit();
+    };
+    // BatchNorm in place (padding stays zero: only in-volume voxels are touched)
+    auto transform = [&](int tile, int b) {
+        int n, od0, oh0, ow0;
+        tile_origin(tile, n, od0, oh0, ow0);
+        const int g = n / nPerG;
+        if (scale) {
+            const int id0 = od0 * S - d.pd, ih0 = oh0 * S - d.ph, iw0 = ow0 * S - d.pw;
+            float4* xs = xs_of(b);
+            for (int i = threadIdx.x; i < ID * IH * IW * NQ; i += 256) {
+                const int qq = i % NQ;
+                int r = i / NQ;
+                const int iw = r % IW; r /= IW;
+                const int ih = r % IH;
+                const int idd = r / IH;
+                const int gd = id0 + idd, gh = ih0 + ih, gw = iw0 + iw, c = c0 + qq * 4;
+                if (gd >= 0 && gd < d.Di && gh >= 0 && gh < d.Hi && gw >= 0 && gw < d.Wi && c < d.Ci) {
+                    float4* e = &xs[qq * PLANE + (AD::slot(idd) * IH + AH::slot(ih)) * RW + AW::slot(iw)];
+                    float4 v = *e;
+                    const float4 sc = *reinterpret_cast<const float4*>(scale + (int64_t)g * d.Ci + c);
+                    const float4 sh = *reinterpret_cast<const float4*>(shift + (int64_t)g * d.Ci + c);
+                    v.x = fmaf(v.x, sc.x, sh.x); v.y = fmaf(v.y, sc.y, sh.y);
+                    v.z = fmaf(v.z, sc.z, sh.z); v.w = fmaf(v.w, sc.w, sh.w);
+                    *e = v;
+                }
+            }
+        }
+        if (o_scale) {
+            float4* gs = gs_of(b);
+            for (int i = threadIdx.x; i < C::VOX * (COT / 4); i += 256) {
+                const int j4 = i % (COT / 4);
+                int r = i / (COT / 4);
+                const int w = r % TW; r /= TW;
+                const int h = r % TH;
+                const int dd = r / TH;
+                const int cc = co0 + j4 * 4;
+                if (od0 + dd < d.Do && oh0 + h < d.Ho && ow0 + w < d.Wo) {
+                    float4 v = gs[i];
+                    float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        if (cc + u < d.Co) e[u] = fmaf(e[u], o_scale[(int64_t)g * d.Co + cc + u], o_shift[(int64_t)g * d.Co + cc + u]);
+                    gs[i] = make_float4(e[0], e[1], e[2], e[3]);
+                }
+            }
+        }
+    };
+
+    int buf = 0;
+    if ((int)blockIdx.x < total_tiles) issue(blockIdx.x, 0);
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        cp_async_wait_all();
+        __syncthreads();                       // buffer `buf` has landed; every thread is done with buffer buf^1
+        const int next = tile + gridDim.x;
+        if (next < total_tiles) issue(next, buf ^ 1);
+        if (scale || o_scale) {
+            transform(tile, buf);
+            __syncthreads();
+        }
+        if (active) {
+            const float4* xs = xs_of(buf);
+            const float4* gs = gs_of(buf);
+#pragma unroll 1
+            for (int rr = 0; rr < C::RPS; ++rr) {
+                const int r = sg * C::RPS + rr;
+                const int plane = r / TH, h = r % TH;
+                const float4* xrow = xs + q * PLANE + ((plane + AD::tap(kd)) * IH + (h + AH::tap(kh))) * RW + AW::tap(kw);
+                const float4* grow = gs + ((plane * TH + h) * TW) * (COT / 4);
+#pragma unroll 4
+                for (int w = 0; w < TW; ++w) {
+                    const float4 xv = xrow[w];
+                    const float4* gp = grow + w * (COT / 4);
+                    float2 gzv[COT / 2];
+#pragma unroll
+                    for (int j4 = 0; j4 < COT / 4; ++j4) {
+                        const float4 t4 = gp[j4];
+                        gzv[j4 * 2 + 0] = make_float2(t4.x, t4.y);
+                        gzv[j4 * 2 + 1] = make_float2(t4.z, t4.w);
+                    }
+#pragma unroll
+                    for (int b = 0; b < COT / 2; ++b) {
+                        acc[0][b] = sp_ffma2(xv.x, gzv[b], acc[0][b]);
+                        acc[1][b] = sp_ffma2(xv.y, gzv[b], acc[1][b]);
+                        acc[2][b] = sp_ffma2(xv.z, gzv[b], acc[2][b]);
+                        acc[3][b] = sp_ffma2(xv.w, gzv[b], acc[3][b]);
+                    }
+                }
+            }
+        }
+        buf ^= 1;
+    }
+
+    // ---- reduce the sub-groups through shared memory (fixed order) and emit this CTA's partial slab
+    cp_async_wait_all();
+    __syncthreads();
+    float* red = reinterpret_cast<float*>(smem_raw);     // [NSG][NITEM][4][COT]
+    if (active) {
+        float* r = red + ((size_t)sg * NITEM + item) * 64;
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < COT / 2; ++b) {
+                r[a * COT + 2 * b] = acc[a][b].x;
+                r[a * COT + 2 * b + 1] = acc[a][b].y;
+            }
+    }
+    __syncthreads();
+    const int64_t wn = (int64_t)d.Co * d.Ci * K3;
+    float* wsp = ws + (int64_t)blockIdx.x * wn;
+    for (int i = threadIdx.x; i < NITEM * 64; i += 256) {
+        const int b = i % COT;
+        const int a = (i / COT) % 4;
+        const int it = i / 64;
+        const int tp = it / NQ, qq = it % NQ;
+        const int ci = c0 + qq * 4 + a, co = co0 + b;
+        if (ci < d.Ci && co < d.Co) {
+            float v = red[(size_t)it * 64 + a * COT + b];
+#pragma unroll
+            for (int s2 = 1; s2 < C::NSG; ++s2) v += red[((size_t)s2 * NITEM + it) * 64 + a * COT + b];
+            wsp[((int64_t)co * d.Ci + ci) * K3 + tp] = v;
+        }
+    }
+}
+
 struct WgradTiledPlan {
     int ck, n_chunks, n_co_pass, tiles_w, tiles_h, tiles_d, total_tiles, grid_x;
+    int pipe;     // 1: wgrad_tiled_pipe_kernel (cp.async double buffering, one CTA per SM)
 };
+
+static inline bool wgrad_pipe_disabled() {
+    static int v = -1;   // SP_DISABLE_WGRAD_PIPE=1 forces the non-pipelined kernel (A/B checks)
+    if (v < 0) {
+        const char* e = getenv("SP_DISABLE_WGRAD_PIPE");
+        v = (e && e[0] == '1') ? 1 : 0;
+    }
+    return v == 1;
+}
 
 static inline WgradTiledPlan wgrad_tiled_plan(const SpConvDesc* d) {
     WgradTiledPlan p;
-    p.ck = (d->s == 2 && d->k == 3) ? 4 : (d->Ci > 4 ? 8 : 4);
+    // pipelined variant: 3x3x3 layers whose channel quads are 16-byte aligned on both sides
+    p.pipe = (d->k == 3 && d->Ci % 4 == 0 && d->ldi % 4 == 0 && d->ldo % 4 == 0 && !wgrad_pipe_disabled()) ? 1 : 0;
+    if (p.pipe) p.ck = (d->s == 2) ? 4 : (d->Ci % 16 == 0 ? 16 : (d->Ci > 4 ? 8 : 4));
+    else p.ck = (d->s == 2 && d->k == 3) ? 4 : (d->Ci > 4 ? 8 : 4);
     p.n_chunks = (d->Ci + p.ck - 1) / p.ck;
     p.n_co_pass = (d->Co + COT - 1) / COT;
     p.tiles_w = (d->Wo + TW - 1) / TW;
     p.tiles_h = (d->Ho + TH - 1) / TH;
     p.tiles_d = (d->Do + WTD - 1) / WTD;
     p.total_tiles = p.tiles_w * p.tiles_h * p.tiles_d * d->N;
-    int gx = (2 * 148) / (p.n_chunks * p.n_co_pass);     // ~2 resident CTAs per SM over all slabs
+    int gx = ((p.pipe ? 1 : 2) * 148) / (p.n_chunks * p.n_co_pass);     // resident CTAs per SM over all slabs
     if (gx < 1) gx = 1;
     if (gx > p.total_tiles) gx = p.total_tiles;
     p.grid_x = gx;
@@ -543,13 +785,36 @@ static inline int sp_tiled_wgrad_launch_t(const SpConvDesc* d, const sp_tiled::W
     return 0;
 }
 
+template <int CK, int K, int S>
+static inline int sp_tiled_wgrad_pipe_launch_t(const SpConvDesc* d, const sp_tiled::WgradTiledPlan& p, int nPerG, const float* iside,
+                                               const float* scale, const float* shift, const float* oside, const float* o_scale,
+                                               const float* o_shift, float* ws, cudaStream_t st) {
+    using namespace sp_tiled;
+    constexpr size_t smem = WgradPipeCfg<CK, K, S, WTD>::smem;
+    static_assert(smem <= 227 * 1024, "wgrad pipe buffers exceed shared memory");
+    static bool attr = false;
+    if (!attr) {
+        SP_CUDA(cudaFuncSetAttribute(wgrad_tiled_pipe_kernel<CK, K, S, WTD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr = true;
+    }
+    dim3 grid(p.grid_x, p.n_chunks * p.n_co_pass);
+    wgrad_tiled_pipe_kernel<CK, K, S, WTD><<<grid, 256, smem, st>>>(*d, nPerG, p.tiles_w, p.tiles_h, p.tiles_d, p.total_tiles,
+                                                                    p.n_co_pass, iside, scale, shift, oside, o_scale, o_shift, ws);
+    SP_LAUNCH_OK("wgrad_tiled_pipe_kernel");
+    return 0;
+}
+
 static inline int sp_tiled_wgrad_launch(const SpConvDesc* d, int nPerG, const float* iside, const float* scale,
                                         const float* shift, const float* oside, const float* o_scale, const float* o_shift,
                                         float* dw, float beta, float* ws, cudaStream_t st) {
     using namespace sp_tiled;
     const WgradTiledPlan p = wgrad_tiled_plan(d);
     int e;
-    if (d->s == 2 && d->k == 3) e = sp_tiled_wgrad_launch_t<4, 3, 2>(d, p, nPerG, iside, scale, shift, oside, o_scale, o_shift, ws, st);
+    if (p.pipe && d->s == 2) e = sp_tiled_wgrad_pipe_launch_t<4, 3, 2>(d, p, nPerG, iside, scale, shift, oside, o_scale, o_shift, ws, st);
+    else if (p.pipe && p.ck == 16) e = sp_tiled_wgrad_pipe_launch_t<16, 3, 1>(d, p, nPerG, iside, scale, shift, oside, o_scale, o_shift, ws, st);
+    else if (p.pipe && p.ck == 8) e = sp_tiled_wgrad_pipe_launch_t<8, 3, 1>(d, p, nPerG, iside, scale, shift, oside, o_scale, o_shift, ws, st);
+    else if (p.pipe) e = sp_tiled_wgrad_pipe_launch_t<4, 3, 1>(d, p, nPerG, iside, scale, shift, oside, o_scale, o_shift, ws, st);
+    else if (d->s == 2 && d->k == 3) e = sp_tiled_wgrad_launch_t<4, 3, 2>(d, p, nPerG, iside, scale, shift, oside, o_scale, o_shift, ws, st);
     else if (d->s == 2 && p.ck == 8) e = sp_tiled_wgrad_launch_t<8, 2, 2>(d, p, nPerG, iside, scale, shift, oside, o_scale, o_shift, ws, st);
     else if (d->s == 2) e = sp_tiled_wgrad_launch_t<4, 2, 2>(d, p, nPerG, iside, scale, shift, oside, o_scale, o_shift, ws, st);
     else if (p.ck == 8) e = sp_tiled_wgrad_launch_t<8, 3, 1>(d, p, nPerG, iside, scale, shift, oside, o_scale, o_shift, ws, st);
