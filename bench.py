@@ -28,11 +28,20 @@ for _p in (ROOT, os.path.join(ROOT, "oracle")):
 
 import torch  # noqa: E402
 
-CHANNELS = {"cae200": [1, 16, 24, 32, 100, 200, 1], "cae800": [1, 16, 24, 32, 100, 800, 1]}
+CHANNELS = {"cae200": [1, 16, 24, 32, 100, 200, 1], "cae800": [1, 16, 24, 32, 100, 800, 1],
+            "unet": [2, 16, 32, 64, 32, 16, 32, 2]}
 SIZE = (28, 128, 128)
 EPOCH = 60            # ramp factor f = 1 (CaeReconstructionLearner.py:53)
-METRIC = "cae_train_volumes_per_s"
 UNIT = "volumes/s"
+FFMA_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12     # 148 SMs x 128 FP32 lanes x 2 flop x max SM clock (no measured figure)
+
+
+def metric_name(workload):
+    return "unet_train_volumes_per_s" if workload == "unet" else "cae_train_volumes_per_s"
+
+
+def default_batch(workload):
+    return 4 if workload == "unet" else 8     # BASELINE.json configs[0] / configs[1]
 
 
 def peaks():
@@ -124,34 +133,81 @@ def cpu_reference_step_time(channels, batch, steps, warmup):
     return sum(times) / len(times), threads
 
 
+def cpu_reference_unet_step_time(batch, steps, warmup):
+    """Oracle port of the U-Net train step (UnetInference + UnetSegmentationLearner.loss_step + backward + Adam)."""
+    import stroke_oracle as O
+    from stroke_prediction_b200.common import data
+    from stroke_prediction_b200.common.model.Unet3D import Unet3D
+    torch.manual_seed(4)
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    sd = O.clone_state(Unet3D(CHANNELS["unet"]).state_dict(), requires_grad=True)
+    names = [k for k, v in sd.items() if v.requires_grad]
+    m = {k: torch.zeros_like(sd[k]) for k in names}
+    v = {k: torch.zeros_like(sd[k]) for k in names}
+    b = data.synthetic_unet_batch(batch, out_size=SIZE, seed=4)
+    x, labels = b[data.KEY_IMAGES], b[data.KEY_LABELS]
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        c, p_ = O.unet_forward(sd, x, True)
+        loss = O.unet_loss(c, p_, labels[:, 0:1], labels[:, 1:2])
+        grads = O.grads_of(loss, sd)
+        with torch.no_grad():
+            for k in names:
+                newp, m[k], v[k] = O.adam_step(sd[k], grads[k], m[k], v[k], it + 1, beta1=0.99)
+                sd[k].copy_(newp)
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    return sum(times) / len(times), threads
+
+
+def cpu_step_time(workload, batch, steps, warmup):
+    if workload == "unet":
+        return cpu_reference_unet_step_time(batch, steps, warmup)
+    return cpu_reference_step_time(CHANNELS[workload], batch, steps, warmup)
+
+
+def cpu_sample_text(workload, batch, steps, warmup):
+    what = ("U-Net train step, batch %d x 2x68x168x168" % batch) if workload == "unet" else \
+           ("CAE train step, batch %d x 1x28x128x128" % batch)
+    return "oracle port of the reference %s (torch %s CPU), %d timed step(s) after %d warm-up" % (what, torch.__version__, steps, warmup)
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    channels = CHANNELS[args.workload]
     sample_b = 2
     steps, warmup = max(1, min(args.steps, 2)), 1 if args.warmup > 0 else 0
-    sec, threads = cpu_reference_step_time(channels, sample_b, steps, warmup)
+    sec, threads = cpu_step_time(args.workload, sample_b, steps, warmup)
     val = sample_b / sec
     line = {
-        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "impl": "reference", "metric": metric_name(args.workload), "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
         "warmup": warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": workload_config(args, per_gpu_batch=sample_b),
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": "oracle port of the reference CAE train step (torch %s CPU), batch %d x 1x28x128x128, "
-                                   "%d timed step(s) after %d warm-up" % (torch.__version__, sample_b, steps, warmup)},
+                         "sample": cpu_sample_text(args.workload, sample_b, steps, warmup)},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     emit(line)
 
 
 def workload_config(args, per_gpu_batch):
-    return {"workload": "BASELINE configs[1]: CAE channels %s, 1x28x128x128 core/penumbra/lesion masks, "
-                        "3 encoder + 4 decoder passes + loss_step + backward + Adam" % " ".join(map(str, CHANNELS[args.workload])),
-            "per_gpu_batch": per_gpu_batch, "global_batch": per_gpu_batch * args.gpus, "volume": "1x28x128x128",
+    ch = " ".join(map(str, CHANNELS[args.workload]))
+    if args.workload == "unet":
+        wl = ("BASELINE configs[0]: Unet3D segmentation, channels %s, synthetic CBV/TTD 2x68x168x168 (28x128x128 padded by 20) "
+              "-> 2 x 1x28x128x128, UnetSegmentationLearner forward + loss_step + backward + Adam" % ch)
+        vol, act = "2x68x168x168 -> 28x128x128", "~1.1 GB"
+    else:
+        wl = ("BASELINE configs[1]: CAE channels %s, 1x28x128x128 core/penumbra/lesion masks, "
+              "3 encoder + 4 decoder passes + loss_step + backward + Adam" % ch)
+        vol, act = "1x28x128x128", "~0.75 GB"
+    return {"workload": wl, "per_gpu_batch": per_gpu_batch, "global_batch": per_gpu_batch * args.gpus, "volume": vol,
             "parallelism": "dp%d (batch-sharded, gradient all-reduce, local BN/Dice statistics)" % args.gpus,
-            "l2": "per-step working set (saved activations ~0.75 GB per volume) exceeds the 126 MB L2; no explicit flush"}
+            "l2": "per-step working set (saved activations %s per volume) exceeds the 126 MB L2; no explicit flush" % act}
 
 
 # ----------------------------------------------------------------------------------------------------- GPU arm
@@ -166,6 +222,29 @@ def algorithmic_bytes(name, key):
     except (ValueError, IndexError):
         return None
     return 4.0 * (n * di * hi * wi * ci + n * do * ho * wo * co) + 4.0 * (co * ci * k ** 3)
+
+
+def algorithmic_flops(key):
+    """2 x MACs of the layer (same for forward, dgrad and wgrad)."""
+    try:
+        parts = key.split()
+        n = int(parts[0][1:])
+        ci = int(parts[1][1:].split("x")[3])
+        do, ho, wo, co = (int(v) for v in parts[2][1:].split("x"))
+        k = int(parts[3][1:])
+    except (ValueError, IndexError):
+        return None
+    return 2.0 * n * do * ho * wo * co * ci * k ** 3
+
+
+def measured_traffic(name, key):
+    """dram bytes (read + write) per launch of this kernel from the committed `ncu --set full` capture, if one exists."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        with open(path) as f:
+            return json.load(f).get("%s [%s]" % (name, key))
+    except (OSError, ValueError):
+        return None
 
 
 def run_b200(args):
@@ -192,30 +271,50 @@ def run_b200(args):
         print("warning: --gpus %d but WORLD_SIZE %d" % (args.gpus, world), file=sys.stderr)
 
     channels = CHANNELS[args.workload]
-    B = args.batch
+    B = args.batch if args.batch > 0 else default_batch(args.workload)
     torch.manual_seed(4)
-    cae = Cae3D(Enc3D(SIZE[1], SIZE[0], channels, 5, 1.0), Dec3D(SIZE[1], SIZE[0], channels, 5, 1.0)).to(dev).train()
-    broadcast_parameters(cae)
-    opt = FusedAdam([p for p in cae.parameters() if p.requires_grad], lr=1e-3, weight_decay=1e-5, betas=(0.9, 0.999))
-    learner = CaeReconstructionLearner(None, None, cae, opt, None, 1, None, "/tmp/bench", BatchDiceLoss([1.0]))
+    if args.workload == "unet":
+        from stroke_prediction_b200.common.dto import UnetDto as UnetDtoUtil
+        from stroke_prediction_b200.common.model.Unet3D import Unet3D
+        from stroke_prediction_b200.learner.UnetSegmentationLearner import UnetSegmentationLearner
+        model = Unet3D(channels).to(dev).train()
+        broadcast_parameters(model)
+        opt = FusedAdam([p for p in model.parameters() if p.requires_grad], lr=1e-3, weight_decay=1e-5, betas=(0.99, 0.999))
+        learner = UnetSegmentationLearner(None, None, model, opt, None, 1, BatchDiceLoss([1.0]), None, "/tmp/bench")
+        host = data.synthetic_unet_batch(B, out_size=SIZE, seed=4 + rank)
+        h2d = host[data.KEY_IMAGES].numel() * 4 + host[data.KEY_LABELS].numel() * 4
+    else:
+        model = Cae3D(Enc3D(SIZE[1], SIZE[0], channels, 5, 1.0), Dec3D(SIZE[1], SIZE[0], channels, 5, 1.0)).to(dev).train()
+        broadcast_parameters(model)
+        opt = FusedAdam([p for p in model.parameters() if p.requires_grad], lr=1e-3, weight_decay=1e-5, betas=(0.9, 0.999))
+        learner = CaeReconstructionLearner(None, None, model, opt, None, 1, None, "/tmp/bench", BatchDiceLoss([1.0]))
+        host = data.synthetic_cae_batch(B, size=SIZE, seed=4 + rank)
+        h2d = host[data.KEY_LABELS].numel() * 4 + host[data.KEY_GLOBAL].numel() * 4 + 3 * B * 4
     if world > 1:
         learner.enable_data_parallel()
-
-    host = data.synthetic_cae_batch(B, size=SIZE, seed=4 + rank)
     host = {k: (v.pin_memory() if torch.is_tensor(v) else v) for k, v in host.items()}
-    h2d = host[data.KEY_LABELS].numel() * 4 + host[data.KEY_GLOBAL].numel() * 4 + 3 * B * 4
     d2h = 4
 
     # device-resident inputs for `value`
-    with torch.no_grad():
-        dto0 = learner.init_clinical_variables(host, None)
-        dto0 = learner.init_gtruth_segm_variables(host, dto0)
-    res = dto0.given_variables
+    if args.workload == "unet":
+        x_dev = ops.as_vol(host[data.KEY_IMAGES].to(dev))
+        lab = ops.as_vol(host[data.KEY_LABELS].to(dev))
+        core_gt, penu_gt = ops.extract_channel(lab, 0), ops.extract_channel(lab, 1)
+
+        def make_dto():
+            return UnetDtoUtil.init_dto(x_dev, core_gt, penu_gt)
+    else:
+        with torch.no_grad():
+            dto0 = learner.init_clinical_variables(host, None)
+            dto0 = learner.init_gtruth_segm_variables(host, dto0)
+        res = dto0.given_variables
+
+        def make_dto():
+            return CaeDtoUtil.init_dto(res.globals, res.time_to_treatment, res.scalar_types.core, res.scalar_types.penu,
+                                       None, None, res.gtruth.core, res.gtruth.penu, res.gtruth.lesion)
 
     def step_resident():
-        dto = CaeDtoUtil.init_dto(res.globals, res.time_to_treatment, res.scalar_types.core, res.scalar_types.penu,
-                                  None, None, res.gtruth.core, res.gtruth.penu, res.gtruth.lesion)
-        dto = cae(dto)
+        dto = model(make_dto())
         loss = learner.loss_step(dto, EPOCH)
         opt.zero_grad()
         loss.backward()
@@ -295,11 +394,16 @@ def run_b200(args):
     total_prof = sum(v[0] for v in fam.values())
     (top_name, top_key), (top_ms, top_n) = max(fam.items(), key=lambda kv: kv[1][0])
     abytes = algorithmic_bytes(top_name, top_key)
+    aflops = algorithmic_flops(top_key)
     avg_ms = top_ms / top_n
     achieved = (abytes / (avg_ms * 1e-3) / 1e9) if abytes else None
+    tflops = (aflops / (avg_ms * 1e-3) / 1e12) if aflops else None
+    traffic = measured_traffic(top_name, top_key)
     roofline = {"bound": "hbm", "kernel": "%s [%s]" % (top_name, top_key), "achieved": achieved, "peak": hbm_peak,
                 "peak_source": peak_src, "unit": "GB/s", "frac": (achieved / hbm_peak) if achieved else None,
-                "traffic": None, "avg_launch_ms": avg_ms, "launches_per_step": top_n,
+                "traffic": traffic, "avg_launch_ms": avg_ms, "launches_per_step": top_n,
+                "fp32_tflops": tflops, "ffma_peak_tflops": FFMA_PEAK_TFLOPS,
+                "ffma_frac": (tflops / FFMA_PEAK_TFLOPS) if tflops else None,
                 "share_of_step": top_ms / total_prof if total_prof else None,
                 "algorithmic_bytes_per_launch": abytes,
                 "note": "fp32 FFMA direct convolution: arithmetic intensity of this layer is above the FFMA ridge, so the "
@@ -319,16 +423,14 @@ def run_b200(args):
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        sec, threads = cpu_reference_step_time(channels, 2, 1, 1)
-        cpu = {"value": 2 / sec, "unit": UNIT, "cores": threads, "kind": "port",
-               "sample": "oracle port of the reference CAE train step (torch %s CPU), batch 2 x 1x28x128x128, 1 timed step "
-                         "after 1 warm-up" % torch.__version__}
+        sec, threads = cpu_step_time(args.workload, 2, 1, 1)
+        cpu = {"value": 2 / sec, "unit": UNIT, "cores": threads, "kind": "port", "sample": cpu_sample_text(args.workload, 2, 1, 1)}
 
-    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+    line = {"metric": metric_name(args.workload), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": workload_config(args, B),
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": ms_e2e / args.steps, "api": "CaeReconstructionLearner.train_batch(host_batch, epoch)"},
+                    "ms_per_step": ms_e2e / args.steps, "api": "%s.train_batch(host_batch, epoch)" % type(learner).__name__},
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "kernel_breakdown": breakdown, "op_breakdown": op_breakdown,
             "cpu_baseline": cpu}
     emit(line)
@@ -364,7 +466,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="cae200", choices=sorted(CHANNELS))
-    ap.add_argument("--batch", type=int, default=8, help="per-GPU batch")
+    ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: 8 for the CAE, 4 for the U-Net)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--dump-breakdown", default=None, help="write the full per-kernel CUDA-event attribution to this file")
     ap.add_argument("--quick", action="store_true", help="profiling aid: resident-input steps only (no e2e / attribution / CPU legs)")

@@ -89,10 +89,13 @@ int         sp_set_tc_terms(int terms);
 size_t sp_packed_weight_floats(const SpConvDesc* d, int which);
 int    sp_pack_weights(const SpConvDesc* d, int which, const float* w_torch, float* w_packed, void* stream);
 
+/* Scratch the correlation needs for this geometry (0 for the spatially tiled tiers; the wide, spatially tiny bottleneck
+ * layers Cae3D.py:70,74,178,182 run as im2col / col2im + GEMM through a caller-provided workspace). */
+size_t sp_conv_workspace_bytes(const SpConvDesc* d, int which);
 int sp_corr (const SpConvDesc* d, const float* src_iside, const float* w_packed, const float* bias,
-             const float* scale, const float* shift, int G, float* dst_oside, void* stream);
+             const float* scale, const float* shift, int G, float* dst_oside, void* ws, size_t ws_bytes, void* stream);
 int sp_corrT(const SpConvDesc* d, const float* src_oside, const float* w_packed, const float* bias,
-             const float* scale, const float* shift, int G, float* dst_iside, void* stream);
+             const float* scale, const float* shift, int G, float* dst_iside, void* ws, size_t ws_bytes, void* stream);
 
 /* dW[co][ci][tap] (torch layout) = beta*dW + sum_{n,o} O'[n,o,co] * I'[n,o*s-p+tap,ci], where I' / O' are the
  * I-side / O-side tensors after their optional per-(group,channel) affine prologue (BatchNorm of the layer

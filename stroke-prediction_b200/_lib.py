@@ -55,8 +55,9 @@ SIGNATURES = {
     "sp_set_tc_terms": (c_int, [c_int]),
     "sp_packed_weight_floats": (c_size, [_D, c_int]),
     "sp_pack_weights": (c_int, [_D, c_int, c_vp, c_vp, c_vp]),
-    "sp_corr": (c_int, [_D, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_vp, c_vp]),
-    "sp_corrT": (c_int, [_D, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_vp, c_vp]),
+    "sp_conv_workspace_bytes": (c_size, [_D, c_int]),
+    "sp_corr": (c_int, [_D, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_vp, c_vp, c_size, c_vp]),
+    "sp_corrT": (c_int, [_D, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_vp, c_vp, c_size, c_vp]),
     "sp_wgrad_workspace_bytes": (c_size, [_D]),
     "sp_wgrad": (c_int, [_D, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_vp, c_float, c_vp, c_size, c_vp]),
     "sp_bias_grad": (c_int, [c_vp, c_i64, c_int, c_int, c_vp, c_float, c_vp, c_vp]),

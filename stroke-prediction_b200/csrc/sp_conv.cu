@@ -13,6 +13,7 @@
 #include "sp_conv_tiled.cuh"
 #include "sp_conv_tiledT.cuh"
 #include "sp_conv_pw.cuh"
+#include "sp_conv_gemm.cuh"
 #include "sp_conv_tc.cuh"
 
 // fixed-order sum of per-CTA partial weight-gradient slabs (fp64 accumulation: the partials carry the rounding of long
@@ -441,6 +442,22 @@ bool tc_serves(const SpConvDesc* d, int which, SpTcCfg* cfg) {
     return f.pd >= 0 && f.ph >= 0 && f.pw >= 0 && sp_tc_corr_supported(&f, cfg);
 }
 
+// which op of a layer the GEMM tier (sp_conv_gemm.cuh) serves: everything wide enough that no spatial tier takes
+bool gemm_corr(const SpConvDesc* d) { return !sp_pw_fwd_supported(d, d->Ci) && sp_gemm_serves(d); }
+bool gemm_corrT(const SpConvDesc* d) {
+    if (sp_gemm_disabled() || d->k < 2) return false;
+    if (d->s == 1) {
+        const SpConvDesc f = flipped_desc(d);
+        if (f.pd >= 0 && f.ph >= 0 && f.pw >= 0 && sp_tiled_corr_supported(&f)) return false;
+    }
+    if (sp_tiledT_supported(d)) return false;
+    return d->Ci * d->k * d->k * d->k >= 256 && d->Co >= 16 && d->Ci >= 8;
+}
+bool gemm_wgrad(const SpConvDesc* d) {
+    if (sp_gemm_disabled() || d->k < 2 || sp_tiled_wgrad_supported(d)) return false;
+    return d->Ci * d->k * d->k * d->k >= 256 && d->Co >= 16 && d->Ci >= 8;
+}
+
 int tc_corr_launch(const SpConvDesc* d, const SpTcCfg& cfg, int nPerG, const float* src, const float* wimg, const float* bias,
                    const float* scale, const float* shift, float* dst, cudaStream_t st) {
     const uint4* img = reinterpret_cast<const uint4*>(wimg);
@@ -476,6 +493,11 @@ int sp_pack_weights(const SpConvDesc* d, int which, const float* w_torch, float*
     const int k3 = d->k * d->k * d->k;
     const int dP = round_up(which == 0 ? d->Co : d->Ci, kPad);
     const int64_t total = (int64_t)ffma_packed_floats(d, which);
+    if (which == 1 && gemm_corrT(d)) {   // GEMM tier: Wt[co][tap][ciP] (same size as the [tap][co][ciP] layout)
+        sp_gemm::pack_wt_gemm_kernel<<<grid_for(total), 256, 0, sp_stream(stream)>>>(w_torch, w_packed, d->Co, d->Ci, k3, dP);
+        SP_LAUNCH_OK("pack_wt_gemm_kernel");
+        return 0;
+    }
     pack_weights_kernel<<<grid_for(total), 256, 0, sp_stream(stream)>>>(w_torch, w_packed, d->Co, d->Ci, k3, which, dP);
     SP_LAUNCH_OK("pack_weights_kernel");
     SpTcCfg cfg;
@@ -484,8 +506,14 @@ int sp_pack_weights(const SpConvDesc* d, int which, const float* w_torch, float*
     return 0;
 }
 
+size_t sp_conv_workspace_bytes(const SpConvDesc* d, int which) {
+    if (!d || d->N <= 0) return 0;
+    if (which == 0) return gemm_corr(d) ? sp_gemm_corr_ws_bytes(d) + 256 : 0;
+    return gemm_corrT(d) ? sp_gemm_corrT_ws_bytes(d) + 256 : 0;
+}
+
 int sp_corr(const SpConvDesc* d, const float* src, const float* wp, const float* bias, const float* scale,
-            const float* shift, int G, float* dst, void* stream) {
+            const float* shift, int G, float* dst, void* ws, size_t ws_bytes, void* stream) {
     if (int e = check_desc(d)) return e;
     SP_REQUIRE(src && wp && dst, "sp_corr: NULL pointer");
     SP_REQUIRE((scale == nullptr) == (shift == nullptr), "sp_corr: scale and shift must be given together");
@@ -501,6 +529,11 @@ int sp_corr(const SpConvDesc* d, const float* src, const float* wp, const float*
     if (tc_serves(d, 0, &cfg))
         return tc_corr_launch(d, cfg, nPerG, src, wp + ffma_packed_floats(d, 0), bias, scale, shift, dst, sp_stream(stream));
     if (sp_tiled_corr_supported(d)) return sp_tiled_corr_launch(d, nPerG, src, wp, /*flip=*/0, bias, scale, shift, dst, sp_stream(stream));
+    if (gemm_corr(d)) {
+        SP_REQUIRE(ws && ws_bytes >= sp_conv_workspace_bytes(d, 0), "sp_corr: workspace too small (%zu < %zu)", ws_bytes,
+                   sp_conv_workspace_bytes(d, 0));
+        return sp_gemm_corr_launch(d, nPerG, src, wp, bias, scale, shift, dst, (float*)ws, sp_stream(stream));
+    }
     const int64_t work = (int64_t)d->N * d->Do * d->Ho * d->Wo * (coP / 8);
     corr_generic_kernel<8><<<grid_for(work), 256, 0, sp_stream(stream)>>>(*d, nPerG, coP, src, wp, bias, scale, shift, dst);
     SP_LAUNCH_OK("corr_generic_kernel");
@@ -508,7 +541,7 @@ int sp_corr(const SpConvDesc* d, const float* src, const float* wp, const float*
 }
 
 int sp_corrT(const SpConvDesc* d, const float* src, const float* wp, const float* bias, const float* scale,
-             const float* shift, int G, float* dst, void* stream) {
+             const float* shift, int G, float* dst, void* ws, size_t ws_bytes, void* stream) {
     if (int e = check_desc(d)) return e;
     SP_REQUIRE(src && wp && dst, "sp_corrT: NULL pointer");
     SP_REQUIRE((scale == nullptr) == (shift == nullptr), "sp_corrT: scale and shift must be given together");
@@ -531,6 +564,11 @@ int sp_corrT(const SpConvDesc* d, const float* src, const float* wp, const float
             return sp_tiled_corr_launch(&f, nPerG, src, wp, /*flip=*/1, bias, scale, shift, dst, sp_stream(stream));
     }
     if (sp_tiledT_supported(d)) return sp_tiledT_launch(d, nPerG, src, wp, bias, scale, shift, dst, sp_stream(stream));
+    if (gemm_corrT(d)) {
+        SP_REQUIRE(ws && ws_bytes >= sp_conv_workspace_bytes(d, 1), "sp_corrT: workspace too small (%zu < %zu)", ws_bytes,
+                   sp_conv_workspace_bytes(d, 1));
+        return sp_gemm_corrT_launch(d, nPerG, src, wp, bias, scale, shift, dst, (float*)ws, sp_stream(stream));
+    }
     const int64_t work = (int64_t)d->N * d->Di * d->Hi * d->Wi * (ciP / 8);
     corrT_generic_kernel<8><<<grid_for(work), 256, 0, sp_stream(stream)>>>(*d, nPerG, ciP, src, wp, bias, scale, shift, dst);
     SP_LAUNCH_OK("corrT_generic_kernel");
@@ -547,6 +585,7 @@ size_t sp_wgrad_workspace_bytes(const SpConvDesc* d) {
     tiled = sp_tiled_wgrad_workspace_bytes(d);
     const size_t pw = sp_pw_wgrad_workspace_bytes(d);
     if (pw > tiled) tiled = pw;
+    if (gemm_wgrad(d) && sp_gemm_wgrad_ws_bytes(d) > tiled) tiled = sp_gemm_wgrad_ws_bytes(d);
     return (generic > tiled ? generic : tiled) + 256;
 }
 
@@ -565,6 +604,8 @@ int sp_wgrad(const SpConvDesc* d, const float* iside, const float* i_scale, cons
         return sp_pw_wgrad_launch(d, nPerG, iside, i_scale, i_shift, oside, o_scale, o_shift, dw, beta, (float*)ws, sp_stream(stream));
     if (sp_tiled_wgrad_supported(d))
         return sp_tiled_wgrad_launch(d, nPerG, iside, i_scale, i_shift, oside, o_scale, o_shift, dw, beta, (float*)ws, sp_stream(stream));
+    if (gemm_wgrad(d) && !sp_pw_wgrad_supported(d))
+        return sp_gemm_wgrad_launch(d, nPerG, iside, i_scale, i_shift, oside, o_scale, o_shift, dw, beta, (float*)ws, sp_stream(stream));
     const WgradPlan p = wgrad_plan(d);
     const bool vi = (d->Ci % 4 == 0) && (d->ldi % 4 == 0);
     const bool vo = (d->Co % 4 == 0) && (d->ldo % 4 == 0);

@@ -510,7 +510,9 @@ struct WgradPipeCfg {
     static constexpr int NSG = 256 / SGT;
     static constexpr int ROWS = WD * TH;                        // (plane, h) rows of 16 voxels per tile
     static constexpr int RPS = ROWS / NSG;                      // rows per sub-group
-    static constexpr int PLANE = plane_f4<K, S, WD>();
+    // plane stride (float4 units) == 2 (mod 4) for four quads: lanes (tap, q) of one LDS.128 phase then land in 8
+    // different 16-byte bank groups (q * PLANE + {tap, tap + 1}); two quads are conflict-free with PLANE == 4 (mod 8).
+    static constexpr int PLANE = plane_f4<K, S, WD>() + ((NQ == 4 && plane_f4<K, S, WD>() % 4 == 0) ? 2 : 0);
     static constexpr int VOX = TW * TH * WD;
     static constexpr size_t buf_bytes = (size_t)NQ * PLANE * 16 + (size_t)VOX * COT * 4;
     static constexpr size_t red_bytes = (size_t)NSG * NITEM * 64 * 4;

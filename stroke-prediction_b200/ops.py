@@ -205,15 +205,25 @@ def get_tc_terms():
     return int(_L().sp_get_tc_terms())
 
 
+def _conv_ws(d, which, device):
+    nbytes = _L().sp_conv_workspace_bytes(ctypes.byref(d), which)
+    if nbytes == 0:
+        return None, 0
+    ws = workspace(nbytes, device, "conv")
+    return ws, ws.numel()
+
+
 def corr(d, src, wp, bias, scale, shift, G, dst):
     _req_cuda(src, wp, dst)
-    check(_L().sp_corr(ctypes.byref(d), _p(src), _p(wp), _p(bias), _p(scale), _p(shift), G, _p(dst), _stream()), "sp_corr")
+    ws, n = _conv_ws(d, 0, dst.device)
+    check(_L().sp_corr(ctypes.byref(d), _p(src), _p(wp), _p(bias), _p(scale), _p(shift), G, _p(dst), _p(ws), n, _stream()), "sp_corr")
     return dst
 
 
 def corrT(d, src, wp, bias, scale, shift, G, dst):
     _req_cuda(src, wp, dst)
-    check(_L().sp_corrT(ctypes.byref(d), _p(src), _p(wp), _p(bias), _p(scale), _p(shift), G, _p(dst), _stream()), "sp_corrT")
+    ws, n = _conv_ws(d, 1, dst.device)
+    check(_L().sp_corrT(ctypes.byref(d), _p(src), _p(wp), _p(bias), _p(scale), _p(shift), G, _p(dst), _p(ws), n, _stream()), "sp_corrT")
     return dst
 
 

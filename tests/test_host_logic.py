@@ -150,7 +150,7 @@ def test_argument_errors_do_not_launch():
     """Negative return + message for bad descriptors; nothing touches a GPU."""
     lib = _lib.load()
     d = _lib.SpConvDesc()
-    rc = lib.sp_corr(ctypes.byref(d), None, None, None, None, None, 1, None, None)
+    rc = lib.sp_corr(ctypes.byref(d), None, None, None, None, None, 1, None, None, 0, None)
     assert rc < 0 and b"conv" in lib.sp_last_error()
     rc = lib.sp_adam_multi(None, 0, 0, 1e-3, 0.9, 0.999, 1e-8, 0.0, 1, 1.0, 0, None)
     assert rc < 0
