@@ -65,10 +65,12 @@ int         sp_version(void);
 const char* sp_last_error(void);
 
 /*
- * Numeric mode of the 3x3x3 stride-1 correlations with 8..16 channels (Cae3D.py:44,208,211; Unet3D.py:22):
- *   0 (default)  exact fp32: FFMA tier, IEEE round-to-nearest accumulation (what the parity tests are calibrated on)
- *   2 / 3        split-precision tcgen05 tier: every fp32 operand is staged as 2 / 3 bf16 terms, products of order < terms
- *                are accumulated in fp32 in TMEM (per-layer forward rel-L2 ~5e-6 / ~1.4e-6).
+ * Tensor-core tier of the 3x3x3 stride-1 correlations with 8..16 channels (Cae3D.py:44,208,211; Unet3D.py:22) and of their
+ * dgrads.  Every fp32 operand is staged as three bf16 terms, the products of order <= 2 are accumulated by tcgen05.mma in TMEM:
+ *   4 (default)  pipelined kernel, leading products in one accumulator per kd and corrections in separate columns: per-layer
+ *                forward rel-L2 1.3e-7 (an IEEE fp32 FFMA chain: 2.6e-7 on the same data)
+ *   0            tier off (exact-fp32 FFMA tier everywhere)
+ *   2 / 3        first-generation kernels with one accumulator per output (rel-L2 ~5e-6 / ~1.4e-6), for A/B measurements
  * Packed weights depend on the mode: re-pack (sp_packed_weight_floats / sp_pack_weights) after changing it.
  */
 int         sp_get_tc_terms(void);

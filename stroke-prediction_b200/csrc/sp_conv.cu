@@ -15,6 +15,7 @@
 #include "sp_conv_pw.cuh"
 #include "sp_conv_gemm.cuh"
 #include "sp_conv_tc.cuh"
+#include "sp_conv_tc2.cuh"
 
 // fixed-order sum of per-CTA partial weight-gradient slabs (fp64 accumulation: the partials carry the rounding of long
 // fp32 chains already, the cross-CTA sum should not add to it)
@@ -461,6 +462,7 @@ bool gemm_wgrad(const SpConvDesc* d) {
 int tc_corr_launch(const SpConvDesc* d, const SpTcCfg& cfg, int nPerG, const float* src, const float* wimg, const float* bias,
                    const float* scale, const float* shift, float* dst, cudaStream_t st) {
     const uint4* img = reinterpret_cast<const uint4*>(wimg);
+    if (sp_tc_terms() == 4) return sp_tc2_corr_launch(d, nPerG, src, img, bias, scale, shift, dst, st);
     if (sp_tc_terms() == 2) return sp_tc_corr_launch_t<16, 16, 2, 4>(d, nPerG, src, img, bias, scale, shift, dst, st);
     return sp_tc_corr_launch_t<16, 16, 3, 2>(d, nPerG, src, img, bias, scale, shift, dst, st);
 }
@@ -473,7 +475,7 @@ extern "C" {
 int sp_get_tc_terms(void) { return sp_tc_terms(); }
 
 int sp_set_tc_terms(int terms) {
-    SP_REQUIRE(terms == 0 || terms == 2 || terms == 3, "sp_set_tc_terms: terms must be 0 (off), 2 or 3, got %d", terms);
+    SP_REQUIRE(terms == 0 || terms == 2 || terms == 3 || terms == 4, "sp_set_tc_terms: mode must be 0 (off), 2, 3 or 4, got %d", terms);
     sp_tc_terms_ref() = terms;
     return 0;
 }
@@ -482,7 +484,7 @@ size_t sp_packed_weight_floats(const SpConvDesc* d, int which) {
     if (!d) return 0;
     size_t n = ffma_packed_floats(d, which);
     SpTcCfg cfg;
-    if (tc_serves(d, which, &cfg)) n += sp_tc_wimg_bytes(cfg.cip, cfg.cop, sp_tc_terms()) / sizeof(float);
+    if (tc_serves(d, which, &cfg)) n += sp_tc_wimg_bytes(cfg.cip, cfg.cop, sp_tc_image_terms()) / sizeof(float);
     return n;
 }
 
@@ -502,7 +504,7 @@ int sp_pack_weights(const SpConvDesc* d, int which, const float* w_torch, float*
     SP_LAUNCH_OK("pack_weights_kernel");
     SpTcCfg cfg;
     if (tc_serves(d, which, &cfg))
-        return sp_tc_pack_launch(d, which, sp_tc_terms(), cfg.cip, cfg.cop, w_torch, w_packed + total, sp_stream(stream));
+        return sp_tc_pack_launch(d, which, sp_tc_image_terms(), cfg.cip, cfg.cop, w_torch, w_packed + total, sp_stream(stream));
     return 0;
 }
 

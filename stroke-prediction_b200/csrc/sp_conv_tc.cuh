@@ -346,20 +346,24 @@ corr3_tc_kernel(SpConvDesc d, int nPerG, int tiles_w, int tiles_h, int tiles_d, 
 }  // namespace sp_tc
 
 // ---- host side --------------------------------------------------------------------------------------------------------
-// Numeric mode of the tensor-core tier: number of bf16 terms per fp32 operand.  0 (default) = tier off: the exact-fp32
-// FFMA tier serves every layer.  2 / 3 = split-precision tcgen05 (measured forward rel-L2 4.8e-6 / 1.4e-6 per layer against
-// 1-2e-7 for IEEE fp32 FFMA chains: the tensor core's fp32 accumulator truncates).  Set at run time through
-// sp_set_tc_terms(); the initial value may be given in the environment (SP_TC_TERMS=0|2|3).
+// Mode of the tensor-core tier for the 8..16-channel 3x3x3 stride-1 correlations:
+//   4 (default)  pipelined three-term kernel with split accumulators (sp_conv_tc2.cuh): per-layer forward rel-L2 1.3e-7 against
+//                2.6e-7 for an IEEE fp32 FFMA chain on the same data — fp32-grade, 2.6x the FFMA tier's speed
+//   0            tier off: the exact-fp32 FFMA tier serves every layer
+//   2 / 3        first-generation kernels (one accumulator per output, 2 / 3 bf16 terms: rel-L2 4.8e-6 / 1.4e-6 because the tensor
+//                core's fp32 accumulator truncates); kept for A/B measurements
+// Set at run time through sp_set_tc_terms(); the initial value may be given in the environment (SP_TC_TERMS=0|2|3|4).
 static inline int& sp_tc_terms_ref() {
     static int v = -1;
     if (v < 0) {
-        v = 0;
+        v = 4;
         const char* e = getenv("SP_TC_TERMS");
-        if (e && (e[0] == '2' || e[0] == '3')) v = e[0] - '0';
+        if (e && (e[0] == '0' || e[0] == '2' || e[0] == '3' || e[0] == '4')) v = e[0] - '0';
     }
     return v;
 }
 static inline int sp_tc_terms() { return sp_tc_terms_ref(); }
+static inline int sp_tc_image_terms() { return sp_tc_terms() == 4 ? 3 : sp_tc_terms(); }   // bf16 terms of the weight image
 
 struct SpTcCfg { int cip, cop, td; };
 

@@ -194,8 +194,9 @@ def pack_weights(d, which, w):
 
 
 def set_tc_terms(terms):
-    """Numeric mode of the 16-channel 3x3x3 stride-1 correlations (include/stroke_b200.h): 0 = exact fp32 FFMA tier
-    (default), 2 / 3 = split-precision tcgen05 tier.  Packed weights depend on the mode, so cached packs are dropped."""
+    """Mode of the tensor-core tier of the 16-channel 3x3x3 stride-1 correlations (include/stroke_b200.h): 4 = pipelined
+    split-accumulator tcgen05 kernel (default, fp32-grade), 0 = exact fp32 FFMA tier, 2 / 3 = first-generation kernels.
+    Packed weights depend on the mode, so cached packs are dropped."""
     check(_L().sp_set_tc_terms(int(terms)), "sp_set_tc_terms")
     from . import engine
     engine.bump_weights_epoch()

@@ -7,7 +7,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <vector>
-#include "../../stroke-prediction_b200/csrc/sp_conv_tc.cuh"
+#include "../../stroke-prediction_b200/csrc/sp_conv_tc2.cuh"
 
 void sp_set_error(const char* fmt, ...) {
     va_list ap;
@@ -61,6 +61,7 @@ static void cpu_corr(const SpConvDesc& d, const std::vector<float>& x, const std
 }
 
 static long long* g_prof = nullptr;
+static int g_terms = 7;
 template <int NS, int TD>
 static int run_gpu(const SpConvDesc& d, const float* dx, const float* dw, const float* dsc, const float* dsh, float* dy, void* dimg) {
     if (sp_tc_pack_launch(&d, 0, NS, 16, 16, dw, dimg, 0)) return 1;
@@ -68,12 +69,17 @@ static int run_gpu(const SpConvDesc& d, const float* dx, const float* dw, const 
 }
 
 static int launch(int ns, const SpConvDesc& d, const float* dx, const float* dw, const float* dsc, const float* dsh, float* dy, void* dimg) {
+    if (ns == 32) {   // pipelined kernel (three terms, split accumulators)
+        if (sp_tc_pack_launch(&d, 0, 3, 16, 16, dw, dimg, 0)) return 1;
+        return sp_tc2_corr_launch(&d, d.N, dx, (const uint4*)dimg, nullptr, dsc, dsh, dy, 0, g_prof, g_terms);
+    }
     return ns == 2 ? run_gpu<2, 4>(d, dx, dw, dsc, dsh, dy, dimg) : run_gpu<3, 2>(d, dx, dw, dsc, dsh, dy, dimg);
 }
 
 int main(int argc, char** argv) {
     const char* mode = argc > 1 ? argv[1] : "random";
     const int ns = argc > 2 ? atoi(argv[2]) : 2;
+    if (argc > 3) g_terms = atoi(argv[3]);
     if (!strcmp(mode, "time")) {
         SpConvDesc d = make_desc(32, 28, 124, 124, 16, 16, 1, 2, 2);
         const size_t nx = (size_t)d.N * d.Di * d.Hi * d.Wi * d.Ci, ny = (size_t)d.N * d.Do * d.Ho * d.Wo * d.Co;
@@ -97,6 +103,16 @@ int main(int argc, char** argv) {
         const double flop = 2.0 * ny * 27 * 16, bytes = 4.0 * (nx + ny);
         printf("time ns=%d: %.3f ms  %.1f TFLOP/s (fp32-equivalent)  %.0f GB/s algorithmic\n", ns, ms, flop / ms * 1e-9, bytes / ms * 1e-6);
         CK(cudaMalloc(&g_prof, 64)); CK(cudaMemset(g_prof, 0, 64));
+        if (ns == 32) {
+            launch(ns, d, dx, dw, nullptr, nullptr, dy, dimg);
+            CK(cudaDeviceSynchronize());
+            long long hp[8];
+            CK(cudaMemcpy(hp, g_prof, 64, cudaMemcpyDeviceToHost));
+            const long long t = hp[3] ? hp[3] : 1;
+            printf("  CTA0 cycles per tile (%lld tiles): MMA thread: wait a_full %lld, wait t_empty %lld, issue %lld | stager: wait a_empty %lld, work %lld | "
+                   "epilogue: wait t_full %lld, work %lld\n", t, hp[0] / t, hp[1] / t, hp[2] / t, hp[4] / t, hp[5] / t, hp[6] / t, hp[7] / t);
+            return 0;
+        }
         launch(ns, d, dx, dw, nullptr, nullptr, dy, dimg);
         CK(cudaDeviceSynchronize());
         long long hp[5];
@@ -151,6 +167,29 @@ int main(int argc, char** argv) {
             num += e2 * e2; den += ref[i] * ref[i];
             if (fabs(e2) > maxabs) maxabs = fabs(e2);
             if (!(fabs(e2) <= 1e-3 * (1.0 + fabs(ref[i])))) { if (nbad == 0) first_bad = i; ++nbad; }
+        }
+        if (!onehot) {   // what an IEEE fp32 FFMA chain (the exact tier) gives on the same data
+            double n32 = 0;
+            for (int nn = 0; nn < d.N; ++nn)
+                for (int od = 0; od < d.Do; ++od)
+                    for (int oh = 0; oh < d.Ho; ++oh)
+                        for (int ow = 0; ow < d.Wo; ++ow)
+                            for (int co = 0; co < d.Co; ++co) {
+                                float acc = 0.f;
+                                for (int ci = 0; ci < d.Ci; ++ci)
+                                    for (int kd = 0; kd < 3; ++kd)
+                                        for (int kh = 0; kh < 3; ++kh)
+                                            for (int kw = 0; kw < 3; ++kw) {
+                                                const int id = od - d.pd + kd, ih = oh - d.ph + kh, iw = ow - d.pw + kw;
+                                                if (id < 0 || id >= d.Di || ih < 0 || ih >= d.Hi || iw < 0 || iw >= d.Wi) continue;
+                                                float xv = x[((((size_t)nn * d.Di + id) * d.Hi + ih) * d.Wi + iw) * d.Ci + ci];
+                                                if (!sc.empty()) xv = fmaf(xv, sc[ci], sh[ci]);
+                                                acc = fmaf(xv, w[((size_t)co * d.Ci + ci) * 27 + (kd * 3 + kh) * 3 + kw], acc);
+                                            }
+                                const double e3 = (double)acc - ref[((((size_t)nn * d.Do + od) * d.Ho + oh) * d.Wo + ow) * d.Co + co];
+                                n32 += e3 * e3;
+                            }
+            printf("fp32 FFMA chain (CPU) rel-L2 %.3e\n", sqrt(n32 / (den > 0 ? den : 1)));
         }
         if (onehot) printf("onehot tap %2d ci %2d co %2d: ", cases[cs][0], cases[cs][1], cases[cs][2]);
         printf("ns=%d rel-L2 %.3e max-abs %.3e mismatches %zu / %zu\n", ns, sqrt(num / (den > 0 ? den : 1)), maxabs, nbad, ny);
