@@ -370,7 +370,7 @@ struct SpTcCfg { int cip, cop, td; };
 // layers served: 3x3x3 stride-1, <= 16 channels on both sides (the 28-deep 16->16 layers hold ~75 % of the conv FLOPs)
 static inline bool sp_tc_corr_supported(const SpConvDesc* d, SpTcCfg* cfg) {
     if (d->k != 3 || d->s != 1 || sp_tc_terms() == 0) return false;
-    if (d->Ci > 16 || d->Co > 16 || d->Ci < 8) return false;
+    if (d->Ci > 16 || d->Co > 16 || d->Ci < 8 || d->Co < 8) return false;   // narrower layers: FFMA tier (2- / 8-wide passes)
     const int64_t ov = (int64_t)d->Do * d->Ho * d->Wo;
     if (ov < 8192 || d->Wo < 8 || d->Ho < 16) return false;
     if (cfg) { cfg->cip = 16; cfg->cop = 16; cfg->td = 4; }

@@ -169,6 +169,8 @@ corr3_tc_pipe_kernel(SpConvDesc d, int nPerG, int tiles_w, int tiles_h, int tile
         const int st = tid - 128;
         const bool vec = (d.ldi % 4 == 0);
         static_assert(KCH2 == 2, "staging packs (slot, chunk) assuming two chunks");
+        static_assert(NSTAGE % 32 == 0, "a staging thread must keep one channel chunk");
+        const int my_chunk = (st >> 4) % KCH2;
         int it = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
             const int buf = it & 1, use = it >> 1;
@@ -182,6 +184,17 @@ corr3_tc_pipe_kernel(SpConvDesc d, int nPerG, int tiles_w, int tiles_h, int tile
             const int g = n / nPerG;
             const float* srcn = src + (int64_t)n * d.Di * d.Hi * d.Wi * d.ldi;
             uint4* Ab = As + (size_t)buf * ABUF_U4;
+            // BatchNorm coefficients of this thread's channel chunk (fixed per thread: NSTAGE is a multiple of 32)
+            float bsc[8], bsh[8];
+            {
+                const int c = my_chunk * 8;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const bool okc = scale && (c + j < d.Ci);
+                    bsc[j] = okc ? scale[(int64_t)g * d.Ci + c + j] : 1.f;
+                    bsh[j] = okc ? shift[(int64_t)g * d.Ci + c + j] : 0.f;
+                }
+            }
             constexpr int SLOT_GROUPS = (SLOTS2 + 15) / 16;
             constexpr int NITEMS = SLOT_GROUPS * KCH2 * 16;
             constexpr int PER_R = 4;                                        // loads in flight per thread and round
@@ -232,12 +245,10 @@ corr3_tc_pipe_kernel(SpConvDesc d, int nPerG, int tiles_w, int tiles_h, int tile
                     const int c = chunk * 8;
                     float v[8] = {ra[u].x, ra[u].y, ra[u].z, ra[u].w, rb[u].x, rb[u].y, rb[u].z, rb[u].w};
                     if (inside && scale) {
-                        const float* sc = scale + (int64_t)g * d.Ci + c;
-                        const float* sh = shift + (int64_t)g * d.Ci + c;
 #pragma unroll
-                        for (int j = 0; j < 8; ++j)
-                            if (c + j < d.Ci) v[j] = fmaf(v[j], sc[j], sh[j]);
+                        for (int j = 0; j < 8; ++j) v[j] = fmaf(v[j], bsc[j], bsh[j]);      // channels >= Ci: 0 * 1 + 0
                     }
+                    (void)c;
                     uint4 o[NS2];
                     split8_trunc3(v, o);
 #pragma unroll
