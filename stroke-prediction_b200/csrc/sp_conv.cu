@@ -16,6 +16,7 @@
 #include "sp_conv_gemm.cuh"
 #include "sp_conv_tc.cuh"
 #include "sp_conv_tc2.cuh"
+#include "sp_wgrad_tc.cuh"
 
 // fixed-order sum of per-CTA partial weight-gradient slabs (fp64 accumulation: the partials carry the rounding of long
 // fp32 chains already, the cross-CTA sum should not add to it)
@@ -587,6 +588,7 @@ size_t sp_wgrad_workspace_bytes(const SpConvDesc* d) {
     tiled = sp_tiled_wgrad_workspace_bytes(d);
     const size_t pw = sp_pw_wgrad_workspace_bytes(d);
     if (pw > tiled) tiled = pw;
+    if (sp_tc_wgrad_workspace_bytes(d) > tiled) tiled = sp_tc_wgrad_workspace_bytes(d);
     if (gemm_wgrad(d) && sp_gemm_wgrad_ws_bytes(d) > tiled) tiled = sp_gemm_wgrad_ws_bytes(d);
     return (generic > tiled ? generic : tiled) + 256;
 }
@@ -604,6 +606,8 @@ int sp_wgrad(const SpConvDesc* d, const float* iside, const float* i_scale, cons
     const int nPerG = d->N / G;
     if (sp_pw_wgrad_supported(d))
         return sp_pw_wgrad_launch(d, nPerG, iside, i_scale, i_shift, oside, o_scale, o_shift, dw, beta, (float*)ws, sp_stream(stream));
+    if (sp_tc_wgrad_supported(d))
+        return sp_tc_wgrad_launch(d, nPerG, iside, i_scale, i_shift, oside, o_scale, o_shift, dw, beta, (float*)ws, sp_stream(stream));
     if (sp_tiled_wgrad_supported(d))
         return sp_tiled_wgrad_launch(d, nPerG, iside, i_scale, i_shift, oside, o_scale, o_shift, dw, beta, (float*)ws, sp_stream(stream));
     if (gemm_wgrad(d) && !sp_pw_wgrad_supported(d))
