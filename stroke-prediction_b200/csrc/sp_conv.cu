@@ -17,6 +17,7 @@
 #include "sp_conv_tc.cuh"
 #include "sp_conv_tc2.cuh"
 #include "sp_wgrad_tc.cuh"
+#include "sp_conv_thin.cuh"
 
 // fixed-order sum of per-CTA partial weight-gradient slabs (fp64 accumulation: the partials carry the rounding of long
 // fp32 chains already, the cross-CTA sum should not add to it)
@@ -450,6 +451,7 @@ bool gemm_corrT(const SpConvDesc* d) {
     if (sp_gemm_disabled() || d->k < 2) return false;
     if (d->s == 1) {
         const SpConvDesc f = flipped_desc(d);
+        if (sp_thin_bwd_supported(&f)) return false;
         if (f.pd >= 0 && f.ph >= 0 && f.pw >= 0 && sp_tiled_corr_supported(&f)) return false;
     }
     if (sp_tiledT_supported(d)) return false;
@@ -531,6 +533,7 @@ int sp_corr(const SpConvDesc* d, const float* src, const float* wp, const float*
     SpTcCfg cfg;
     if (tc_serves(d, 0, &cfg))
         return tc_corr_launch(d, cfg, nPerG, src, wp + ffma_packed_floats(d, 0), bias, scale, shift, dst, sp_stream(stream));
+    if (sp_thin_fwd_supported(d)) return sp_thin_fwd_launch(d, nPerG, src, wp, /*flip=*/0, bias, scale, shift, dst, sp_stream(stream));
     if (sp_tiled_corr_supported(d)) return sp_tiled_corr_launch(d, nPerG, src, wp, /*flip=*/0, bias, scale, shift, dst, sp_stream(stream));
     if (gemm_corr(d)) {
         SP_REQUIRE(ws && ws_bytes >= sp_conv_workspace_bytes(d, 0), "sp_corr: workspace too small (%zu < %zu)", ws_bytes,
@@ -563,6 +566,7 @@ int sp_corrT(const SpConvDesc* d, const float* src, const float* wp, const float
         SpTcCfg cfg;
         if (tc_serves(d, 1, &cfg))
             return tc_corr_launch(&f, cfg, nPerG, src, wp + ffma_packed_floats(d, 1), bias, scale, shift, dst, sp_stream(stream));
+        if (sp_thin_bwd_supported(&f)) return sp_thin_bwd_launch(&f, nPerG, src, wp, bias, scale, shift, dst, sp_stream(stream));
         if (f.pd >= 0 && f.ph >= 0 && f.pw >= 0 && sp_tiled_corr_supported(&f))
             return sp_tiled_corr_launch(&f, nPerG, src, wp, /*flip=*/1, bias, scale, shift, dst, sp_stream(stream));
     }
@@ -589,6 +593,7 @@ size_t sp_wgrad_workspace_bytes(const SpConvDesc* d) {
     const size_t pw = sp_pw_wgrad_workspace_bytes(d);
     if (pw > tiled) tiled = pw;
     if (sp_tc_wgrad_workspace_bytes(d) > tiled) tiled = sp_tc_wgrad_workspace_bytes(d);
+    if (sp_thin_wgrad_workspace_bytes(d) > tiled) tiled = sp_thin_wgrad_workspace_bytes(d);
     if (gemm_wgrad(d) && sp_gemm_wgrad_ws_bytes(d) > tiled) tiled = sp_gemm_wgrad_ws_bytes(d);
     return (generic > tiled ? generic : tiled) + 256;
 }
@@ -606,6 +611,8 @@ int sp_wgrad(const SpConvDesc* d, const float* iside, const float* i_scale, cons
     const int nPerG = d->N / G;
     if (sp_pw_wgrad_supported(d))
         return sp_pw_wgrad_launch(d, nPerG, iside, i_scale, i_shift, oside, o_scale, o_shift, dw, beta, (float*)ws, sp_stream(stream));
+    if (sp_thin_wgrad_supported(d))
+        return sp_thin_wgrad_launch(d, nPerG, iside, i_scale, i_shift, oside, o_scale, o_shift, dw, beta, (float*)ws, sp_stream(stream));
     if (sp_tc_wgrad_supported(d))
         return sp_tc_wgrad_launch(d, nPerG, iside, i_scale, i_shift, oside, o_scale, o_shift, dw, beta, (float*)ws, sp_stream(stream));
     if (sp_tiled_wgrad_supported(d))
