@@ -237,6 +237,32 @@ def algorithmic_flops(key):
     return 2.0 * n * do * ho * wo * co * ci * k ** 3
 
 
+def tensor_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["bf16_tflops_sustained"])
+    except (OSError, ValueError, KeyError):
+        return 1405.0
+
+
+def tensor_core_issue_factor(name, key):
+    """bf16 MACs the tcgen05 tier executes per algorithmic fp32 MAC, or None when the layer runs on the FFMA tiers
+    (mirrors sp_tc_corr_supported / sp_tc_wgrad_supported: 3x3x3 stride-1 layers with 9..16 channels on both sides)."""
+    import re
+    m = re.match(r"N(\d+) I(\d+)x(\d+)x(\d+)x(\d+) O(\d+)x(\d+)x(\d+)x(\d+) k(\d+) s(\d+)", key or "")
+    if not m:
+        return None
+    ci, co, k, st = int(m.group(5)), int(m.group(9)), int(m.group(10)), int(m.group(11))
+    if k != 3 or st != 1 or not (8 < ci <= 16 and 8 < co <= 16):
+        return None
+    if name == "sp_wgrad":
+        return 12.0
+    if name in ("sp_corr", "sp_corrT"):
+        return 6.0
+    return None
+
+
 def measured_traffic(name, key):
     """dram bytes (read + write) per launch of this kernel from the committed `ncu --set full` capture, if one exists."""
     path = os.path.join(ROOT, "profiles", "traffic.json")
@@ -405,9 +431,21 @@ def run_b200(args):
                 "fp32_tflops": tflops, "ffma_peak_tflops": FFMA_PEAK_TFLOPS,
                 "ffma_frac": (tflops / FFMA_PEAK_TFLOPS) if tflops else None,
                 "share_of_step": top_ms / total_prof if total_prof else None,
-                "algorithmic_bytes_per_launch": abytes,
-                "note": "fp32 FFMA direct convolution: arithmetic intensity of this layer is above the FFMA ridge, so the "
-                        "HBM fraction is reported for the contract while the binding roof is FP32 FFMA (see DESIGN.md)"}
+                "algorithmic_bytes_per_launch": abytes}
+    tc_factor = tensor_core_issue_factor(top_name, top_key)
+    if tc_factor and tflops:
+        # exact-fp32 emulation on tcgen05: every operand is three bf16 terms, so the tensor pipe executes `tc_factor` bf16
+        # MACs per algorithmic fp32 MAC (9 products x 64/48 padded rows for wgrad, 6 products for forward / dgrad)
+        tc_peak = tensor_peak()
+        roofline.update({"tier": "tcgen05 split-bf16 (3 terms per fp32 operand)", "tensor_issue_factor": tc_factor,
+                         "tensor_executed_tflops": tflops * tc_factor, "tensor_peak_tflops": tc_peak,
+                         "tensor_frac": tflops * tc_factor / tc_peak,
+                         "note": "algorithmic HBM fraction reported for the contract; the kernel is bound by the tensor pipe / "
+                                 "shared-memory operand fetch of the split-bf16 MMAs it issues (M = 64 single-CTA MMAs cap "
+                                 "at half the dense bf16 peak), see DESIGN.md 3.2"})
+    else:
+        roofline["note"] = ("fp32 FFMA direct convolution: arithmetic intensity of this layer is above the FFMA ridge, so the "
+                            "HBM fraction is reported for the contract while the binding roof is FP32 FFMA (see DESIGN.md)")
     if args.dump_breakdown:
         with open(args.dump_breakdown, "w") as f:
             for k, v in sorted(fam.items(), key=lambda kv: -kv[1][0]):

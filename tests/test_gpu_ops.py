@@ -197,6 +197,43 @@ def test_tensor_core_corr_paths(case):
     _check_sequential(nn.Sequential(nn.BatchNorm3d(cin), conv, _act(act)), x, G=2)
 
 
+WGRAD_TC_CASES = [
+    # the tcgen05 weight-gradient tier (sp_wgrad_tc.cuh): 3x3x3 stride 1, 9..16 channels on both sides, Do >= 8, Wo >= 24;
+    # several 32-wide column tiles with a ragged last one, ragged 4-row tiles, zero padding on every axis
+    ("C", 16, 16, 3, 1, (1, 2, 2), "elu", (8, 17, 67)),        # Cae3D.py:208  Wo = 69: three column tiles
+    ("C", 16, 16, 3, 1, (1, 0, 0), "elu", (10, 23, 44)),       # Cae3D.py:44   Wo = 42, Ho = 21
+    ("C", 10, 14, 3, 1, 1, "leaky", (9, 18, 40)),              # ragged channel halves on both sides
+]
+
+
+@pytest.mark.parametrize("case", WGRAD_TC_CASES, ids=lambda c: "%s%d-%d_p%s" % (c[0], c[1], c[2], str(c[5]).replace(" ", "")))
+def test_tensor_core_wgrad_paths(case):
+    """dW from tcgen05 MMAs with MN-major operands (voxels = contraction index), walked along the depth axis through a
+    ring of input planes; G = 2 stacked statistics groups.  Same bars as the FFMA tier."""
+    kind, cin, cout, k, s, p, act, size = case
+    torch.manual_seed(500 + WGRAD_TC_CASES.index(case))
+    conv = nn.Conv3d(cin, cout, k, stride=s, padding=p)
+    x = torch.randn(4, cin, *size) * 1.5 + 0.3
+    _check_sequential(nn.Sequential(nn.BatchNorm3d(cin), conv, _act(act)), x, G=2)
+
+
+POINTWISE_CASES = [
+    # 1x1x1 mixes on enough rows for several CTAs / grid-stride passes with a ragged tail (sp_conv_pw.cuh)
+    (16, 16, "elu", (7, 33, 35)),          # Cae3D.py:215  pw16_fwd<16>, pw_wgrad16<16>
+    (16, 1, "sigmoid", (7, 33, 35)),       # Cae3D.py:218  pw16_fwd<1>, pw_wgrad16<1>; dgrad 1 -> 16
+    (16, 32, "leaky", (5, 21, 30)),        # Unet3D.py:50  two 16-wide output passes
+    (32, 2, "sigmoid", (5, 21, 30)),       # Unet3D.py:52  runtime-Cs kernels
+]
+
+
+@pytest.mark.parametrize("case", POINTWISE_CASES, ids=lambda c: "%d-%d" % (c[0], c[1]))
+def test_pointwise_paths(case):
+    cin, cout, act, size = case
+    torch.manual_seed(600 + POINTWISE_CASES.index(case))
+    x = torch.randn(3, cin, *size) * 1.5 + 0.3
+    _check_sequential(nn.Sequential(nn.BatchNorm3d(cin), nn.Conv3d(cin, cout, 1), _act(act)), x)
+
+
 @pytest.mark.parametrize("terms", [3, 2, 0])
 @pytest.mark.parametrize("case", TC_CASES[:2], ids=lambda c: "%s%d-%d_p%s" % (c[0], c[1], c[2], str(c[5]).replace(" ", "")))
 def test_tensor_core_legacy_modes(case, terms):
@@ -272,10 +309,11 @@ def test_raw_perfusion_statistics_do_not_cancel():
 
 # ---------------------------------------------------------------------------------------------------- resampling
 @pytest.mark.parametrize("size", [(4, 6, 8), (5, 7, 9), (2, 2, 2)])
-def test_maxpool_with_ties(size):
+@pytest.mark.parametrize("C", [5, 8])            # 8: the 128-bit kernels
+def test_maxpool_with_ties(size, C):
     _, _, ops = _mods()
     torch.manual_seed(3)
-    x = torch.randn(2, 5, *size)
+    x = torch.randn(2, C, *size)
     x[:, :, :, : size[1] // 2] = 0.25            # constant region -> every window there is an 8-way tie
     x[0, 0] = torch.round(x[0, 0])               # many partial ties
     xr = x.clone().requires_grad_(True)
@@ -291,10 +329,10 @@ def test_maxpool_with_ties(size):
 
 @pytest.mark.parametrize("align", [False, True])
 @pytest.mark.parametrize("size", [(3, 4, 5), (1, 2, 7), (10, 35, 35)])
-def test_trilinear_upsample(align, size):
+@pytest.mark.parametrize("C,off,extra", [(6, 2, 3), (8, 4, 8)])       # (8, 4, 8): 16-byte aligned slice -> the 128-bit kernels
+def test_trilinear_upsample(align, size, C, off, extra):
     _, _, ops = _mods()
     torch.manual_seed(5)
-    C = 6
     x = torch.randn(2, C, *size)
     xr = x.clone().requires_grad_(True)
     yr = F.interpolate(xr, scale_factor=2, mode="trilinear", align_corners=align)
@@ -302,13 +340,13 @@ def test_trilinear_upsample(align, size):
     yr.backward(gy)
     xv = ops.as_vol(x.cuda())
     N, _, D, H, W = x.shape
-    cat = ops.zeros_vol(N, C + 3, 2 * D, 2 * H, 2 * W, "cuda")     # write into a channel slice of a wider buffer
-    ops.upsample2_fwd(xv, cat, 2, align)
-    assert rel_l2(cat[:, 2:2 + C], yr) < 1e-6
-    assert float(cat[:, :2].abs().max()) == 0.0 and float(cat[:, 2 + C:].abs().max()) == 0.0
-    gcat = ops.zeros_vol(N, C + 3, 2 * D, 2 * H, 2 * W, "cuda")
-    gcat[:, 2:2 + C] = gy.cuda()
-    gx = ops.upsample2_bwd(gcat, 2, C, align)
+    cat = ops.zeros_vol(N, C + extra, 2 * D, 2 * H, 2 * W, "cuda")     # write into a channel slice of a wider buffer
+    ops.upsample2_fwd(xv, cat, off, align)
+    assert rel_l2(cat[:, off:off + C], yr) < 1e-6
+    assert float(cat[:, :off].abs().max()) == 0.0 and float(cat[:, off + C:].abs().max()) == 0.0
+    gcat = ops.zeros_vol(N, C + extra, 2 * D, 2 * H, 2 * W, "cuda")
+    gcat[:, off:off + C] = gy.cuda()
+    gx = ops.upsample2_bwd(gcat, off, C, align)
     assert rel_l2(gx, xr.grad) < 1e-5
 
 
