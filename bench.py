@@ -180,7 +180,7 @@ def run_reference(args):
     if rank != 0:
         return
     sample_b = 2
-    steps, warmup = max(1, min(args.steps, 2)), 1 if args.warmup > 0 else 0
+    steps, warmup = max(1, min(args.steps, 5)), 1 if args.warmup > 0 else 0
     sec, threads = cpu_step_time(args.workload, sample_b, steps, warmup)
     val = sample_b / sec
     line = {
@@ -461,8 +461,8 @@ def run_b200(args):
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        sec, threads = cpu_step_time(args.workload, 2, 1, 1)
-        cpu = {"value": 2 / sec, "unit": UNIT, "cores": threads, "kind": "port", "sample": cpu_sample_text(args.workload, 2, 1, 1)}
+        sec, threads = cpu_step_time(args.workload, 2, 4, 1)
+        cpu = {"value": 2 / sec, "unit": UNIT, "cores": threads, "kind": "port", "sample": cpu_sample_text(args.workload, 2, 4, 1)}
 
     line = {"metric": metric_name(args.workload), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",

@@ -185,6 +185,12 @@ int sp_absdiff_mean(const float* a, const float* b, int64_t n, int mode, double*
 int sp_absdiff_bwd(const float* a, const float* b, int64_t n, int mode, const float* gscale, float gmul,
                    float* ga, int acc_a, float* gb, int acc_b, void* stream);
 
+/* Evaluation counts of the thresholded masks (replaces the host round trip + medpy dc / precision / sensitivity /
+ * specificity of metrics.py:31-47,49-62): counts[0..3] = TP, FP, FN, TN of (result > threshold) against
+ * (target > threshold) over n contiguous floats.  The surface distances (hd, assd) are not computed on the device. */
+int sp_binary_counts(const float* result, const float* target, int64_t n, float threshold, double* counts,
+                     void* stream);
+
 /* ------------------------------------------------------------------------------------------------------------
  * Latent interpolation z_c + s*(z_p - z_c), s per sample (Cae3D.py:78-89).
  * ---------------------------------------------------------------------------------------------------------- */

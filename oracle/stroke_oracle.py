@@ -201,6 +201,21 @@ def unet_loss(core_out, penu_out, core, penu):
 
 
 # ------------------------------------------------------------------------------------------------ optimizer
+def binary_measures(result, target, threshold=0.5):
+    """metrics.py:31-47 without the surface distances: medpy.metric.binary (MedPy==0.3.0, requirements.txt:2, not
+    vendored) dc / precision / sensitivity / specificity restated from their published definitions on boolean masks."""
+    r = (result > threshold).reshape(-1)
+    t = (target > threshold).reshape(-1)
+    tp = int((r & t).sum()); fp = int((r & ~t).sum()); fn = int((~r & t).sum()); tn = int((~r & ~t).sum())
+    size_r, size_t = int(r.sum()), int(t.sum())
+    dc = 2.0 * tp / float(size_r + size_t) if size_r + size_t > 0 else 0.0
+    precision = tp / float(tp + fp) if tp + fp > 0 else 0.0
+    sensitivity = tp / float(tp + fn) if tp + fn > 0 else 0.0
+    specificity = tn / float(tn + fp) if tn + fp > 0 else 0.0
+    return {"dc": dc, "precision": precision, "sensitivity": sensitivity, "specificity": specificity,
+            "counts": (tp, fp, fn, tn)}
+
+
 def adam_step(p, g, m, v, step, lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=1e-5):
     """One torch.optim.Adam update on tensors, installed-torch form.  Returns (p, m, v)."""
     g = g + weight_decay * p

@@ -84,6 +84,7 @@ SIGNATURES = {
     "sp_dice_bwd": (c_int, [c_vp, c_vp, c_i64, c_vp, c_float, c_float, c_vp, c_float, c_vp, c_int, c_vp]),
     "sp_absdiff_mean": (c_int, [c_vp, c_vp, c_i64, c_int, c_vp, c_vp, c_vp]),
     "sp_absdiff_bwd": (c_int, [c_vp, c_vp, c_i64, c_int, c_vp, c_float, c_vp, c_int, c_vp, c_int, c_vp]),
+    "sp_binary_counts": (c_int, [c_vp, c_vp, c_i64, c_float, c_vp, c_vp]),
     "sp_latent_interp_fwd": (c_int, [c_vp, c_vp, c_vp, c_int, c_i64, c_vp, c_vp]),
     "sp_latent_interp_bwd": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_i64, c_vp, c_int, c_vp, c_int, c_vp, c_vp, c_vp]),
     "sp_adam_multi": (c_int, [c_vp, c_int, c_i64, c_double, c_double, c_double, c_double, c_double, c_i64, c_double,

@@ -1,10 +1,51 @@
-"""Loss of the hot path: whole-batch soft Dice (API of the reference's common/metrics.py:8-28).
+"""Loss and per-batch evaluation metrics of the hot path (API of the reference's common/metrics.py).
 
-The medpy-based evaluation metrics of metrics.py:31-62 are a "next" row and not part of this module.
+* ``BatchDiceLoss`` — whole-batch soft Dice (metrics.py:8-28).
+* ``binary_measures_torch`` / ``binary_measures_many`` — the thresholded overlap metrics every train / validation batch
+  reports (metrics.py:31-62).  The reference copies both volumes to the host and calls the un-vendored
+  ``MedPy==0.3.0`` (``requirements.txt:2``); here ONE reduction kernel per pair counts TP / FP / FN / TN on the device and
+  the four count-based measures follow medpy's published definitions (dc = 2 TP / (|A| + |B|), precision = TP / (TP + FP),
+  sensitivity = TP / (TP + FN), specificity = TN / (TN + FP); each 0.0 when its denominator is 0).  The surface
+  distances ``hd`` / ``assd`` (Euclidean distance transforms) are NOT computed on the device: they keep the reference's
+  initial value ``numpy.inf`` (metrics.py:36-37).
 """
+import numpy
+import torch
 from torch.nn.modules.loss import _Loss as LossModule
 
-from .. import functions
+from .. import functions, ops
+from .dto.MetricMeasuresDto import BinaryMeasuresDto
+
+
+def measures_from_counts(tp, fp, fn, tn):
+    """medpy.metric.binary dc / precision / sensitivity / specificity from the confusion counts."""
+    tp, fp, fn, tn = float(tp), float(fp), float(fn), float(tn)
+    size_r, size_t = tp + fp, tp + fn
+    dc = 2.0 * tp / (size_r + size_t) if (size_r + size_t) > 0 else 0.0
+    precision = tp / (tp + fp) if (tp + fp) > 0 else 0.0
+    sensitivity = tp / (tp + fn) if (tp + fn) > 0 else 0.0
+    specificity = tn / (tn + fp) if (tn + fp) > 0 else 0.0
+    return BinaryMeasuresDto(dc, numpy.inf, numpy.inf, precision, sensitivity, specificity)
+
+
+def binary_measures_many(pairs, binary_threshold=0.5):
+    """[(result, target), ...] (CUDA tensors) -> [BinaryMeasuresDto, ...] with ONE device-to-host read for all pairs."""
+    pairs = list(pairs)
+    if not pairs:
+        return []
+    dev = pairs[0][0].device
+    counts = torch.empty((len(pairs), 4), device=dev, dtype=torch.float64)
+    for i, (r, t) in enumerate(pairs):
+        ops.binary_counts(r.detach(), t.detach(), binary_threshold, out=counts[i])
+    host = counts.cpu().tolist()
+    return [measures_from_counts(*row) for row in host]
+
+
+def binary_measures_torch(result, target, cuda=True, binary_threshold=0.5):
+    """Signature of metrics.py:49; ``cuda`` is kept for source compatibility — there is no CPU path."""
+    if not result.is_cuda:
+        raise RuntimeError("binary_measures_torch: CUDA tensors only — there is no CPU path")
+    return binary_measures_many([(result, target)], binary_threshold)[0]
 
 
 class BatchDiceLoss(LossModule):

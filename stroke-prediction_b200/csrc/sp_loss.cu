@@ -164,6 +164,30 @@ interp_bwd_kernel(const float* __restrict__ g, const float* __restrict__ zc, con
     acc[0] = (double)f;
     if (dstep_acc) block_reduce_atomic<1>(acc, dstep_acc + b);
 }
+// ---- thresholded evaluation counts (metrics.py:31-47: result > 0.5 vs target > 0.5) ---------------------------------
+// counts[0..3] = TP, FP, FN, TN as exact integers in doubles (a 28x128x128 batch is < 2^53 voxels by far)
+__global__ void __launch_bounds__(256)
+binary_counts_kernel(const float* __restrict__ r, const float* __restrict__ t, int64_t n, float thr, double* __restrict__ counts) {
+    unsigned int c[4] = {0u, 0u, 0u, 0u};
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    int iter = 0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const bool a = r[i] > thr, b = t[i] > thr;
+        c[0] += (a && b) ? 1u : 0u;
+        c[1] += (a && !b) ? 1u : 0u;
+        c[2] += (!a && b) ? 1u : 0u;
+        c[3] += (!a && !b) ? 1u : 0u;
+        if (++iter == (1 << 20)) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { acc[q] += (double)c[q]; c[q] = 0u; }
+            iter = 0;
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) acc[q] += (double)c[q];
+    block_reduce_atomic<4>(acc, counts);
+}
+
 __global__ void cast_d2f_kernel(const double* __restrict__ src, float* __restrict__ dst, int n) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) dst[i] = (float)src[i];
@@ -205,6 +229,14 @@ int sp_absdiff_mean(const float* a, const float* b, int64_t n, int mode, double*
     SP_LAUNCH_OK("absdiff_sum_kernel");
     mean_from_sum_kernel<<<1, 1, 0, sp_stream(stream)>>>(sum_ws, (double)n, out);
     SP_LAUNCH_OK("mean_from_sum_kernel");
+    return 0;
+}
+
+int sp_binary_counts(const float* result, const float* target, int64_t n, float threshold, double* counts, void* stream) {
+    SP_REQUIRE(result && target && counts && n > 0, "sp_binary_counts: bad arguments");
+    SP_CUDA(cudaMemsetAsync(counts, 0, 4 * sizeof(double), sp_stream(stream)));
+    binary_counts_kernel<<<red_grid(n), 256, 0, sp_stream(stream)>>>(result, target, n, threshold, counts);
+    SP_LAUNCH_OK("binary_counts_kernel");
     return 0;
 }
 

@@ -2,6 +2,8 @@
 import torch
 
 from .. import functions
+from ..common import metrics
+from ..common.dto import MetricMeasuresDto as MetricMeasuresDtoInit
 from ..common.dto.CaeDto import CaeDto
 from ..common.inference.CaeEncInference import CaeEncInference
 from .Learner import Learner
@@ -43,6 +45,15 @@ class CaePredictionLearner(Learner, CaeEncInference):
         loss = loss + functions.l1_mean(lat_gt.core, lat_in.core)
         loss = loss + functions.l1_mean(lat_gt.penu, lat_in.penu)
         return loss / 6
+
+    def batch_metrics_step(self, dto: CaeDto, epoch):
+        """CaePredictionLearner.py:59-67 (metrics on the frozen CAE's ground-truth branch), one D2H for all."""
+        batch_metrics = MetricMeasuresDtoInit.init_dto()
+        batch_metrics.lesion, batch_metrics.core, batch_metrics.penu = metrics.binary_measures_many([
+            (dto.reconstructions.gtruth.interpolation, dto.given_variables.gtruth.lesion),
+            (dto.reconstructions.gtruth.core, dto.given_variables.gtruth.core),
+            (dto.reconstructions.gtruth.penu, dto.given_variables.gtruth.penu)])
+        return batch_metrics
 
     def print_epoch(self, epoch, phase, epoch_metrics):
         print('\nEpoch {}/{} {} loss: {:.3}'.format(epoch + 1, self._n_epochs, phase, epoch_metrics.loss), end=' ')

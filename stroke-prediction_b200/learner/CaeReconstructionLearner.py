@@ -6,6 +6,8 @@ every term is a fused reduction kernel with a closed-form gradient kernel (funct
 import numpy
 
 from .. import functions
+from ..common import metrics
+from ..common.dto import MetricMeasuresDto as MetricMeasuresDtoInit
 from ..common.dto.CaeDto import CaeDto
 from ..common.inference.CaeInference import CaeInference
 from .Learner import Learner
@@ -52,6 +54,15 @@ class CaeReconstructionLearner(Learner, CaeInference):
         loss = loss + self._criterion(rec.lesion, given.lesion)
         loss = loss + factor * functions.l1_mean(lat.interpolation, lat.lesion)
         return loss / (5 + factor)
+
+    def batch_metrics_step(self, dto: CaeDto, epoch):
+        """CaeReconstructionLearner.py:72-80: thresholded overlap of the three reconstructions, one D2H for all."""
+        batch_metrics = MetricMeasuresDtoInit.init_dto()
+        batch_metrics.lesion, batch_metrics.core, batch_metrics.penu = metrics.binary_measures_many([
+            (dto.reconstructions.gtruth.interpolation, dto.given_variables.gtruth.lesion),
+            (dto.reconstructions.gtruth.core, dto.given_variables.gtruth.core),
+            (dto.reconstructions.gtruth.penu, dto.given_variables.gtruth.penu)])
+        return batch_metrics
 
     def print_epoch(self, epoch, phase, epoch_metrics):
         print('\nEpoch {}/{} {} loss: {:.3}'.format(epoch + 1, self._n_epochs, phase, epoch_metrics.loss), end=' ')

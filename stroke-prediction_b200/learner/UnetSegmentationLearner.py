@@ -2,6 +2,8 @@
 ``self`` in the base-class call — defect D2, SURVEY App. B — is not reproduced)."""
 import numpy
 
+from ..common import metrics
+from ..common.dto import MetricMeasuresDto as MetricMeasuresDtoInit
 from ..common.dto.UnetDto import UnetDto
 from ..common.inference.UnetInference import UnetInference
 from .Learner import Learner
@@ -20,6 +22,13 @@ class UnetSegmentationLearner(Learner, UnetInference):
         loss = self._criterion(dto.outputs.core, dto.given_variables.core)
         loss = loss + self._criterion(dto.outputs.penu, dto.given_variables.penu)
         return loss / 2
+
+    def batch_metrics_step(self, dto: UnetDto, epoch):
+        """UnetSegmentationLearner.py:30-36: thresholded overlap of both outputs, one D2H."""
+        batch_metrics = MetricMeasuresDtoInit.init_dto()
+        batch_metrics.core, batch_metrics.penu = metrics.binary_measures_many([
+            (dto.outputs.core, dto.given_variables.core), (dto.outputs.penu, dto.given_variables.penu)])
+        return batch_metrics
 
     def get_start_epoch(self):
         return len(self._metric_dtos['training'])

@@ -21,7 +21,7 @@ _KERNELS_PER_CALL = {
     "sp_bn_finalize": 1, "sp_bn_bwd_reduce": 1, "sp_bn_bwd_finalize": 1, "sp_bn_act_bwd_apply": 1,
     "sp_maxpool2_fwd": 1, "sp_maxpool2_bwd": 1, "sp_upsample2_fwd": 1, "sp_upsample2_bwd": 1, "sp_crop_copy": 1,
     "sp_crop_add": 1, "sp_ncdhw_to_ndhwc": 1, "sp_ndhwc_to_ncdhw": 1, "sp_dice_sums": 1, "sp_dice_loss": 1,
-    "sp_dice_bwd": 1, "sp_absdiff_mean": 2, "sp_absdiff_bwd": 1, "sp_latent_interp_fwd": 1,
+    "sp_dice_bwd": 1, "sp_absdiff_mean": 2, "sp_absdiff_bwd": 1, "sp_binary_counts": 1, "sp_latent_interp_fwd": 1,
     "sp_latent_interp_bwd": 1, "sp_adam_multi": 1,
 }
 
@@ -411,6 +411,17 @@ def absdiff_mean(a, b, mode):
 def absdiff_bwd(a, b, mode, gscale, gmul, ga, acc_a, gb, acc_b):
     check(_L().sp_absdiff_bwd(_p(a), _p(b), a.numel(), mode, _p(gscale), float(gmul), _p(ga), int(acc_a), _p(gb),
                               int(acc_b), _stream()), "sp_absdiff_bwd")
+
+
+def binary_counts(result, target, threshold, out=None):
+    """TP, FP, FN, TN of (result > threshold) vs (target > threshold) as 4 doubles on the device (metrics.py:31-47)."""
+    _req_cuda(result, target)
+    assert result.numel() == target.numel()
+    result, target = result.contiguous(), target.contiguous()
+    if out is None:
+        out = torch.empty(4, device=result.device, dtype=torch.float64)
+    check(_L().sp_binary_counts(_p(result), _p(target), result.numel(), float(threshold), _p(out), _stream()), "sp_binary_counts")
+    return out
 
 
 # ---------------------------------------------------------------------------------------------------- interpolation

@@ -398,6 +398,32 @@ def test_dice_all_zero_prediction_and_target():
     assert abs(l.item() - 0.0) < 1e-6 and torch.isfinite(o.grad).all()   # (0 + eps) / (0 + eps) = 1 -> loss 0
 
 
+def test_binary_measures_match_oracle():
+    """Thresholded overlap metrics (metrics.py:31-47) from the device confusion counts vs the oracle's restatement of medpy's
+    definitions: counts are exact integers, the derived measures agree to the last bit; empty masks give 0.0."""
+    _, _, ops = _mods()
+    import stroke_oracle as O
+    from stroke_prediction_b200.common import metrics
+    torch.manual_seed(11)
+    shape = (3, 1, 9, 31, 33)            # odd element count: tail handling
+    res = torch.rand(shape)
+    tgt = (torch.rand(shape) > 0.7).float()
+    res[0, 0, 0, 0, :5] = 0.5            # exactly the threshold: '>' is strict (metrics.py:32)
+    cases = [(res, tgt), (torch.zeros(shape), tgt), (res, torch.zeros(shape)), (torch.zeros(shape), torch.zeros(shape)),
+             (torch.ones(shape), torch.ones(shape))]
+    got = metrics.binary_measures_many([(r.cuda(), t.cuda()) for r, t in cases])
+    for (r, t), g in zip(cases, got):
+        ref = O.binary_measures(r, t)
+        cnt = ops.binary_counts(r.cuda(), t.cuda(), 0.5).cpu().tolist()
+        assert tuple(int(c) for c in cnt) == ref["counts"]
+        assert sum(ref["counts"]) == r.numel()
+        for k in ("dc", "precision", "sensitivity", "specificity"):
+            assert getattr(g, k) == ref[k], (k, getattr(g, k), ref[k])
+        assert g.hd == float("inf") and g.assd == float("inf")
+    single = metrics.binary_measures_torch(res.cuda(), tgt.cuda(), True)
+    assert single.dc == O.binary_measures(res, tgt)["dc"]
+
+
 def test_hinge_and_l1_including_exact_zeros():
     _, functions, _ = _mods()
     torch.manual_seed(13)

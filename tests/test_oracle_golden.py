@@ -115,3 +115,17 @@ def test_adam_restatement_matches_torch():
         opt.step()
         p, m, v = O.adam_step(p, g, m, v, t)
         assert rel_max(p, ref) < 1e-6
+
+
+def test_oracle_binary_measures_definitions():
+    """medpy.metric.binary dc / precision / sensitivity / specificity on a hand-computed case (metrics.py:31-47)."""
+    import torch
+    import stroke_oracle as O
+    r = torch.tensor([0.9, 0.8, 0.2, 0.6, 0.1, 0.5])      # > 0.5 -> 1 1 0 1 0 0
+    t = torch.tensor([1.0, 0.0, 1.0, 1.0, 0.0, 0.0])
+    m = O.binary_measures(r, t)
+    assert m["counts"] == (2, 1, 1, 2)
+    assert m["dc"] == 2 * 2 / (3 + 3) and m["precision"] == 2 / 3 and m["sensitivity"] == 2 / 3 and m["specificity"] == 2 / 3
+    z = torch.zeros(4)
+    e = O.binary_measures(z, z)
+    assert e["dc"] == 0.0 and e["precision"] == 0.0 and e["sensitivity"] == 0.0 and e["specificity"] == 1.0
