@@ -17,6 +17,7 @@
 #include "sp_conv_tc.cuh"
 #include "sp_conv_tc2.cuh"
 #include "sp_wgrad_tc.cuh"
+#include "sp_wgrad_tc24.cuh"
 #include "sp_conv_thin.cuh"
 
 // fixed-order sum of per-CTA partial weight-gradient slabs (fp64 accumulation: the partials carry the rounding of long
@@ -593,6 +594,7 @@ size_t sp_wgrad_workspace_bytes(const SpConvDesc* d) {
     const size_t pw = sp_pw_wgrad_workspace_bytes(d);
     if (pw > tiled) tiled = pw;
     if (sp_tc_wgrad_workspace_bytes(d) > tiled) tiled = sp_tc_wgrad_workspace_bytes(d);
+    if (sp_tc24_wgrad_workspace_bytes(d) > tiled) tiled = sp_tc24_wgrad_workspace_bytes(d);
     if (sp_thin_wgrad_workspace_bytes(d) > tiled) tiled = sp_thin_wgrad_workspace_bytes(d);
     if (gemm_wgrad(d) && sp_gemm_wgrad_ws_bytes(d) > tiled) tiled = sp_gemm_wgrad_ws_bytes(d);
     return (generic > tiled ? generic : tiled) + 256;
@@ -615,6 +617,8 @@ int sp_wgrad(const SpConvDesc* d, const float* iside, const float* i_scale, cons
         return sp_thin_wgrad_launch(d, nPerG, iside, i_scale, i_shift, oside, o_scale, o_shift, dw, beta, (float*)ws, sp_stream(stream));
     if (sp_tc_wgrad_supported(d))
         return sp_tc_wgrad_launch(d, nPerG, iside, i_scale, i_shift, oside, o_scale, o_shift, dw, beta, (float*)ws, sp_stream(stream));
+    if (sp_tc24_wgrad_supported(d))
+        return sp_tc24_wgrad_launch(d, nPerG, iside, i_scale, i_shift, oside, o_scale, o_shift, dw, beta, (float*)ws, sp_stream(stream));
     if (sp_tiled_wgrad_supported(d))
         return sp_tiled_wgrad_launch(d, nPerG, iside, i_scale, i_shift, oside, o_scale, o_shift, dw, beta, (float*)ws, sp_stream(stream));
     if (gemm_wgrad(d) && !sp_pw_wgrad_supported(d))

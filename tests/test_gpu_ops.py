@@ -203,6 +203,10 @@ WGRAD_TC_CASES = [
     ("C", 16, 16, 3, 1, (1, 2, 2), "elu", (8, 17, 67)),        # Cae3D.py:208  Wo = 69: three column tiles
     ("C", 16, 16, 3, 1, (1, 0, 0), "elu", (10, 23, 44)),       # Cae3D.py:44   Wo = 42, Ho = 21
     ("C", 10, 14, 3, 1, 1, "leaky", (9, 18, 40)),              # ragged channel halves on both sides
+    # 17..24 channels on either side: three 8-channel groups, two accumulator passes (sp_wgrad_tc24.cuh)
+    ("C", 24, 24, 3, 1, (1, 0, 0), "elu", (9, 19, 44)),        # Cae3D.py:52,55
+    ("C", 24, 16, 3, 1, (1, 2, 2), "elu", (8, 14, 35)),        # Cae3D.py:200  24 -> 16: the third O-side group is empty
+    ("C", 12, 20, 3, 1, 1, "leaky", (10, 17, 33)),             # ragged groups on both sides
 ]
 
 

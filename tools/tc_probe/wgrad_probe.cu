@@ -6,7 +6,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <vector>
-#include "../../stroke-prediction_b200/csrc/sp_wgrad_tc.cuh"
+#include "../../stroke-prediction_b200/csrc/sp_wgrad_tc24.cuh"
 
 void sp_set_error(const char* fmt, ...) {
     va_list ap;
@@ -42,49 +42,59 @@ static SpConvDesc make_desc(int N, int Di, int Hi, int Wi, int Ci, int Co, int p
     return d;
 }
 
+static bool g_wide = false;
+static int launch_wgrad(const SpConvDesc* d, const float* dx, const float* dsc, const float* dsh, const float* dz, float* ddw, float* dws,
+                        long long* prof, int drain_every, int mrows) {
+    if (g_wide) return sp_tc24_wgrad_launch(d, d->N, dx, dsc, dsh, dz, nullptr, nullptr, ddw, 0.f, dws, 0, prof, drain_every);
+    return sp_tc_wgrad_launch(d, d->N, dx, dsc, dsh, dz, nullptr, nullptr, ddw, 0.f, dws, 0, prof, drain_every, mrows);
+}
+
 int main(int argc, char** argv) {
     const char* mode = argc > 1 ? argv[1] : "check";
     const int drain_every = argc > 2 ? atoi(argv[2]) : 2;
     const int mrows = argc > 3 ? atoi(argv[3]) : 128;
-    const bool timing = !strcmp(mode, "time");
-    SpConvDesc d = timing ? make_desc(32, 28, 126, 126, 16, 16, 1, 2, 2) : make_desc(2, 9, 21, 45, 16, 16, 1, 0, 2);
+    const bool timing = !strncmp(mode, "time", 4);
+    const bool wide = strlen(mode) > 2 && !strcmp(mode + strlen(mode) - 2, "24");      // check24 / time24: the 24-channel tier
+    SpConvDesc d = wide ? (timing ? make_desc(32, 14, 58, 58, 24, 24, 1, 2, 2) : make_desc(2, 9, 21, 45, 24, 20, 1, 0, 2))
+                        : (timing ? make_desc(32, 28, 126, 126, 16, 16, 1, 2, 2) : make_desc(2, 9, 21, 45, 16, 16, 1, 0, 2));
+    g_wide = wide;
     const size_t nx = (size_t)d.N * d.Di * d.Hi * d.Wi * d.Ci, nz = (size_t)d.N * d.Do * d.Ho * d.Wo * d.Co;
     const int wn = d.Co * d.Ci * 27;
     const sp_wtc::WtcPlan p = sp_wtc::plan(&d);
     printf("geometry N %d I %dx%dx%d O %dx%dx%d pad %d,%d,%d  tiles %lld grid %d smem %zu\n", d.N, d.Di, d.Hi, d.Wi, d.Do, d.Ho, d.Wo,
            d.pd, d.ph, d.pw, (long long)p.total, p.grid, (size_t)sp_wtc::SMEM_W);
-    std::vector<float> x(nx), z(nz), sc(16), sh(16);
+    std::vector<float> x(nx), z(nz), sc(24), sh(24);
     srand(4321);
     for (size_t i = 0; i < nx; ++i) x[i] = (float)rand() / RAND_MAX * 2.f - 0.7f;
     for (size_t i = 0; i < nz; ++i) z[i] = ((float)rand() / RAND_MAX - 0.45f) * 0.01f;
-    for (int c = 0; c < 16; ++c) { sc[c] = 0.5f + 0.1f * c; sh[c] = -0.3f + 0.05f * c; }
+    for (int c = 0; c < 24; ++c) { sc[c] = 0.5f + 0.1f * c; sh[c] = -0.3f + 0.05f * c; }
     float *dx, *dz, *dsc, *dsh, *dws, *ddw;
     long long* dprof;
-    CK(cudaMalloc(&dx, nx * 4)); CK(cudaMalloc(&dz, nz * 4)); CK(cudaMalloc(&dsc, 64)); CK(cudaMalloc(&dsh, 64));
+    CK(cudaMalloc(&dx, nx * 4)); CK(cudaMalloc(&dz, nz * 4)); CK(cudaMalloc(&dsc, 96)); CK(cudaMalloc(&dsh, 96));
     CK(cudaMalloc(&dws, (size_t)p.grid * wn * 4)); CK(cudaMalloc(&ddw, wn * 4)); CK(cudaMalloc(&dprof, 64));
     CK(cudaMemcpy(dx, x.data(), nx * 4, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(dz, z.data(), nz * 4, cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(dsc, sc.data(), 64, cudaMemcpyHostToDevice)); CK(cudaMemcpy(dsh, sh.data(), 64, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dsc, sc.data(), 96, cudaMemcpyHostToDevice)); CK(cudaMemcpy(dsh, sh.data(), 96, cudaMemcpyHostToDevice));
     CK(cudaMemset(dprof, 0, 64));
 
     if (timing) {
         cudaEvent_t e0, e1;
         CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
         for (int it = 0; it < 2; ++it)
-            if (sp_tc_wgrad_launch(&d, d.N, dx, dsc, dsh, dz, nullptr, nullptr, ddw, 0.f, dws, 0, nullptr, drain_every, mrows)) return 3;
+            if (launch_wgrad(&d, dx, dsc, dsh, dz, ddw, dws, nullptr, drain_every, mrows)) return 3;
         CK(cudaDeviceSynchronize());
         const int reps = 5;
         CK(cudaEventRecord(e0));
-        for (int it = 0; it < reps; ++it) sp_tc_wgrad_launch(&d, d.N, dx, dsc, dsh, dz, nullptr, nullptr, ddw, 0.f, dws, 0, nullptr, drain_every, mrows);
+        for (int it = 0; it < reps; ++it) launch_wgrad(&d, dx, dsc, dsh, dz, ddw, dws, nullptr, drain_every, mrows);
         CK(cudaEventRecord(e1));
         CK(cudaDeviceSynchronize());
         float ms;
         CK(cudaEventElapsedTime(&ms, e0, e1));
         ms /= reps;
-        const double flop = 2.0 * nz * 27 * 16, bytes = 4.0 * (nx + nz);
+        const double flop = 2.0 * nz * 27 * d.Ci, bytes = 4.0 * (nx + nz);
         printf("time drain_every=%d mrows=%d: %.3f ms  %.1f TFLOP/s (fp32-equivalent)  %.0f GB/s algorithmic\n", drain_every, mrows, ms, flop / ms * 1e-9,
                bytes / ms * 1e-6);
-        sp_tc_wgrad_launch(&d, d.N, dx, dsc, dsh, dz, nullptr, nullptr, ddw, 0.f, dws, 0, dprof, drain_every, mrows);
+        launch_wgrad(&d, dx, dsc, dsh, dz, ddw, dws, dprof, drain_every, mrows);
         CK(cudaDeviceSynchronize());
         long long hp[8];
         CK(cudaMemcpy(hp, dprof, 64, cudaMemcpyDeviceToHost));
@@ -94,7 +104,7 @@ int main(int argc, char** argv) {
         return 0;
     }
 
-    if (sp_tc_wgrad_launch(&d, d.N, dx, dsc, dsh, dz, nullptr, nullptr, ddw, 0.f, dws, 0, nullptr, drain_every, mrows)) return 3;
+    if (launch_wgrad(&d, dx, dsc, dsh, dz, ddw, dws, nullptr, drain_every, mrows)) return 3;
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) { printf("kernel failed: %s\n", cudaGetErrorString(e)); return 4; }
     std::vector<float> dw(wn);
