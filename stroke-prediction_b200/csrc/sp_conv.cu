@@ -19,6 +19,7 @@
 #include "sp_wgrad_tc.cuh"
 #include "sp_wgrad_tc24.cuh"
 #include "sp_conv_thin.cuh"
+#include "sp_conv_k2s2.cuh"
 
 // fixed-order sum of per-CTA partial weight-gradient slabs (fp64 accumulation: the partials carry the rounding of long
 // fp32 chains already, the cross-CTA sum should not add to it)
@@ -455,11 +456,11 @@ bool gemm_corrT(const SpConvDesc* d) {
         if (sp_thin_bwd_supported(&f)) return false;
         if (f.pd >= 0 && f.ph >= 0 && f.pw >= 0 && sp_tiled_corr_supported(&f)) return false;
     }
-    if (sp_tiledT_supported(d)) return false;
+    if (sp_tiledT_supported(d) || sp_k2s2_supported(d)) return false;
     return d->Ci * d->k * d->k * d->k >= 256 && d->Co >= 16 && d->Ci >= 8;
 }
 bool gemm_wgrad(const SpConvDesc* d) {
-    if (sp_gemm_disabled() || d->k < 2 || sp_tiled_wgrad_supported(d)) return false;
+    if (sp_gemm_disabled() || d->k < 2 || sp_tiled_wgrad_supported(d) || sp_k2s2_supported(d)) return false;
     return d->Ci * d->k * d->k * d->k >= 256 && d->Co >= 16 && d->Ci >= 8;
 }
 
@@ -534,6 +535,8 @@ int sp_corr(const SpConvDesc* d, const float* src, const float* wp, const float*
     SpTcCfg cfg;
     if (tc_serves(d, 0, &cfg))
         return tc_corr_launch(d, cfg, nPerG, src, wp + ffma_packed_floats(d, 0), bias, scale, shift, dst, sp_stream(stream));
+    if (sp_k2s2_supported(d) && sp_k2s2_aligned(src, dst) && (!bias || sp_k2s2_aligned(bias, wp)))
+        return sp_k2s2_down_launch(d, nPerG, src, wp, bias, scale, shift, dst, sp_stream(stream));
     if (sp_thin_fwd_supported(d)) return sp_thin_fwd_launch(d, nPerG, src, wp, /*flip=*/0, bias, scale, shift, dst, sp_stream(stream));
     if (sp_tiled_corr_supported(d)) return sp_tiled_corr_launch(d, nPerG, src, wp, /*flip=*/0, bias, scale, shift, dst, sp_stream(stream));
     if (gemm_corr(d)) {
@@ -571,6 +574,8 @@ int sp_corrT(const SpConvDesc* d, const float* src, const float* wp, const float
         if (f.pd >= 0 && f.ph >= 0 && f.pw >= 0 && sp_tiled_corr_supported(&f))
             return sp_tiled_corr_launch(&f, nPerG, src, wp, /*flip=*/1, bias, scale, shift, dst, sp_stream(stream));
     }
+    if (sp_k2s2_supported(d) && sp_k2s2_aligned(src, dst) && (!bias || sp_k2s2_aligned(bias, wp)))
+        return sp_k2s2_up_launch(d, nPerG, src, wp, bias, scale, shift, dst, sp_stream(stream));
     if (sp_tiledT_supported(d)) return sp_tiledT_launch(d, nPerG, src, wp, bias, scale, shift, dst, sp_stream(stream));
     if (gemm_corrT(d)) {
         SP_REQUIRE(ws && ws_bytes >= sp_conv_workspace_bytes(d, 1), "sp_corrT: workspace too small (%zu < %zu)", ws_bytes,
@@ -596,6 +601,7 @@ size_t sp_wgrad_workspace_bytes(const SpConvDesc* d) {
     if (sp_tc_wgrad_workspace_bytes(d) > tiled) tiled = sp_tc_wgrad_workspace_bytes(d);
     if (sp_tc24_wgrad_workspace_bytes(d) > tiled) tiled = sp_tc24_wgrad_workspace_bytes(d);
     if (sp_thin_wgrad_workspace_bytes(d) > tiled) tiled = sp_thin_wgrad_workspace_bytes(d);
+    if (sp_k2s2_wgrad_workspace_bytes(d) > tiled) tiled = sp_k2s2_wgrad_workspace_bytes(d);
     if (gemm_wgrad(d) && sp_gemm_wgrad_ws_bytes(d) > tiled) tiled = sp_gemm_wgrad_ws_bytes(d);
     return (generic > tiled ? generic : tiled) + 256;
 }
@@ -613,6 +619,8 @@ int sp_wgrad(const SpConvDesc* d, const float* iside, const float* i_scale, cons
     const int nPerG = d->N / G;
     if (sp_pw_wgrad_supported(d))
         return sp_pw_wgrad_launch(d, nPerG, iside, i_scale, i_shift, oside, o_scale, o_shift, dw, beta, (float*)ws, sp_stream(stream));
+    if (sp_k2s2_supported(d) && sp_k2s2_aligned(iside, oside))
+        return sp_k2s2_wgrad_launch(d, nPerG, iside, i_scale, i_shift, oside, o_scale, o_shift, dw, beta, (float*)ws, sp_stream(stream));
     if (sp_thin_wgrad_supported(d))
         return sp_thin_wgrad_launch(d, nPerG, iside, i_scale, i_shift, oside, o_scale, o_shift, dw, beta, (float*)ws, sp_stream(stream));
     if (sp_tc_wgrad_supported(d))
