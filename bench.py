@@ -319,7 +319,8 @@ def run_b200(args):
     if world > 1:
         learner.enable_data_parallel()
     host = {k: (v.pin_memory() if torch.is_tensor(v) else v) for k, v in host.items()}
-    d2h = 4
+    # the loss (4 bytes) + the evaluation counts of batch_metrics_step (4 doubles per compared pair) come back every step
+    d2h = 4 + 32 * (2 if args.workload == "unet" else 3)
 
     # device-resident inputs for `value`
     if args.workload == "unet":

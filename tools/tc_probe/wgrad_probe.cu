@@ -1,12 +1,13 @@
 // wgrad_probe.cu — standalone mapping / numerics / timing probe of the tcgen05 weight-gradient tier (sp_wgrad_tc.cuh).
 // Diagnostic only: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -o wgrad_probe wgrad_probe.cu
 //   ./wgrad_probe check [drain_every]  : small ragged geometry (padding in d / w, partial tiles) vs a double-precision CPU sum
+//   modes: check | time (16 channels), check24 | time24 (24 channels); suffix 'a' (checka, time24a) = experimental A-in-TMEM kernel
 //   ./wgrad_probe time  [drain_every]  : the 16->16 layer of the CAE decoder at batch 32 (28x126x126 -> 28x128x128, pad 1,2,2)
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
 #include <vector>
-#include "../../stroke-prediction_b200/csrc/sp_wgrad_tc24.cuh"
+#include "sp_wgrad_tca.cuh"
 
 void sp_set_error(const char* fmt, ...) {
     va_list ap;
@@ -42,15 +43,19 @@ static SpConvDesc make_desc(int N, int Di, int Hi, int Wi, int Ci, int Co, int p
     return d;
 }
 
-static bool g_wide = false;
+static bool g_wide = false, g_tca = false;
 static int launch_wgrad(const SpConvDesc* d, const float* dx, const float* dsc, const float* dsh, const float* dz, float* ddw, float* dws,
                         long long* prof, int drain_every, int mrows) {
+    if (g_tca) return sp_tca_wgrad_launch(d, d->N, dx, dsc, dsh, dz, nullptr, nullptr, ddw, 0.f, dws, 0, prof, drain_every);
     if (g_wide) return sp_tc24_wgrad_launch(d, d->N, dx, dsc, dsh, dz, nullptr, nullptr, ddw, 0.f, dws, 0, prof, drain_every);
     return sp_tc_wgrad_launch(d, d->N, dx, dsc, dsh, dz, nullptr, nullptr, ddw, 0.f, dws, 0, prof, drain_every, mrows);
 }
 
 int main(int argc, char** argv) {
-    const char* mode = argc > 1 ? argv[1] : "check";
+    char modebuf[32];
+    strncpy(modebuf, argc > 1 ? argv[1] : "check", 31); modebuf[31] = 0;
+    if (strlen(modebuf) > 1 && modebuf[strlen(modebuf) - 1] == 'a') { g_tca = true; modebuf[strlen(modebuf) - 1] = 0; }   // checka / time24a: A in TMEM
+    const char* mode = modebuf;
     const int drain_every = argc > 2 ? atoi(argv[2]) : 2;
     const int mrows = argc > 3 ? atoi(argv[3]) : 128;
     const bool timing = !strncmp(mode, "time", 4);
@@ -71,11 +76,11 @@ int main(int argc, char** argv) {
     float *dx, *dz, *dsc, *dsh, *dws, *ddw;
     long long* dprof;
     CK(cudaMalloc(&dx, nx * 4)); CK(cudaMalloc(&dz, nz * 4)); CK(cudaMalloc(&dsc, 96)); CK(cudaMalloc(&dsh, 96));
-    CK(cudaMalloc(&dws, (size_t)p.grid * wn * 4)); CK(cudaMalloc(&ddw, wn * 4)); CK(cudaMalloc(&dprof, 64));
+    CK(cudaMalloc(&dws, (size_t)p.grid * wn * 4)); CK(cudaMalloc(&ddw, wn * 4)); CK(cudaMalloc(&dprof, 128));
     CK(cudaMemcpy(dx, x.data(), nx * 4, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(dz, z.data(), nz * 4, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(dsc, sc.data(), 96, cudaMemcpyHostToDevice)); CK(cudaMemcpy(dsh, sh.data(), 96, cudaMemcpyHostToDevice));
-    CK(cudaMemset(dprof, 0, 64));
+    CK(cudaMemset(dprof, 0, 128));
 
     if (timing) {
         cudaEvent_t e0, e1;
@@ -96,11 +101,11 @@ int main(int argc, char** argv) {
                bytes / ms * 1e-6);
         launch_wgrad(&d, dx, dsc, dsh, dz, ddw, dws, dprof, drain_every, mrows);
         CK(cudaDeviceSynchronize());
-        long long hp[8];
-        CK(cudaMemcpy(hp, dprof, 64, cudaMemcpyDeviceToHost));
+        long long hp[16];
+        CK(cudaMemcpy(hp, dprof, 128, cudaMemcpyDeviceToHost));
         const long long t = hp[3] ? hp[3] : 1;
         printf("  CTA0 cycles per step (%lld steps): issuer 0: wait a_full %lld, wait t_empty %lld, issue %lld | stager: wait a_empty %lld, work %lld | "
-               "drain warp 0: wait t_full %lld, work %lld\n", t, hp[0] / t, hp[1] / t, hp[2] / t, hp[4] / t, hp[5] / t, hp[6] / t, hp[7] / t);
+               "drain warp 0: wait t_full %lld, work %lld | issuer s_full wait %lld | producer: wait s_free %lld, work %lld\n", t, hp[0] / t, hp[1] / t, hp[2] / t, hp[4] / t, hp[5] / t, hp[6] / t, hp[7] / t, hp[8] / t, hp[9] / t, hp[10] / t);
         return 0;
     }
 
