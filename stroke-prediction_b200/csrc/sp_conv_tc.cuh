@@ -133,7 +133,7 @@ __device__ __forceinline__ void split8(const float* v, uint4* out) {
 // transposed == 0 (sp_corr):  Wsrc(co, ci, tap) = w[(co*Ci + ci)*27 + tap]            GEMM N = co, K = ci
 // transposed == 1 (sp_corrT): GEMM N = conv-ci, K = conv-co, taps flipped: Wsrc(n, k, tap) = w[(k*Ci + n)*27 + 26 - tap]
 template <int NS>
-__global__ void pack_wimg_kernel(const float* __restrict__ w, int Co, int Ci, int transposed, int CIP, int COP, uint4* __restrict__ img) {
+__global__ void pack_wimg_kernel(const float* __restrict__ w, int Co, int Ci, int transposed, int CIP, int COP, int k0, uint4* __restrict__ img) {
     const int KCH = CIP / 8, NTOT = NS * COP;
     const int total = 27 * KCH * COP;
     const int Nn = transposed ? Ci : Co, Kk = transposed ? Co : Ci;
@@ -144,7 +144,7 @@ __global__ void pack_wimg_kernel(const float* __restrict__ w, int Co, int Ci, in
         float v[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            const int k = chunk * 8 + j;
+            const int k = k0 + chunk * 8 + j;          // k0: first GEMM-K channel of this input-channel pass
             float x = 0.f;
             if (n < Nn && k < Kk)
                 x = transposed ? w[((int64_t)k * Ci + n) * 27 + (26 - tap)] : w[((int64_t)n * Ci + k) * 27 + tap];
@@ -365,15 +365,16 @@ static inline int& sp_tc_terms_ref() {
 static inline int sp_tc_terms() { return sp_tc_terms_ref(); }
 static inline int sp_tc_image_terms() { return sp_tc_terms() == 4 ? 3 : sp_tc_terms(); }   // bf16 terms of the weight image
 
-struct SpTcCfg { int cip, cop, td; };
+struct SpTcCfg { int cip, cop, td, passes; };     // passes: input-channel passes of 16 (pipelined kernel, 17..24 channels)
 
 // layers served: 3x3x3 stride-1, <= 16 channels on both sides (the 28-deep 16->16 layers hold ~75 % of the conv FLOPs)
 static inline bool sp_tc_corr_supported(const SpConvDesc* d, SpTcCfg* cfg) {
     if (d->k != 3 || d->s != 1 || sp_tc_terms() == 0) return false;
-    if (d->Ci > 16 || d->Co > 16 || d->Ci < 8 || d->Co < 8) return false;   // narrower layers: FFMA tier (2- / 8-wide passes)
+    const int cmax = (sp_tc_terms() == 4) ? 24 : 16;                        // the pipelined kernel also serves the 24-channel level
+    if (d->Ci > cmax || d->Co > cmax || d->Ci < 8 || d->Co < 8) return false;   // narrower layers: FFMA tier (2- / 8-wide passes)
     const int64_t ov = (int64_t)d->Do * d->Ho * d->Wo;
     if (ov < 8192 || d->Wo < 8 || d->Ho < 16) return false;
-    if (cfg) { cfg->cip = 16; cfg->cop = 16; cfg->td = 4; }
+    if (cfg) { cfg->cip = 16; cfg->cop = d->Co > 16 ? 24 : 16; cfg->td = 4; cfg->passes = (d->Ci + 15) / 16; }
     return true;
 }
 
@@ -401,12 +402,17 @@ static inline int sp_tc_corr_launch_t(const SpConvDesc* d, int nPerG, const floa
     return 0;
 }
 
+// one image per input-channel pass (GEMM-K channels [16 p, 16 p + 16)), one after the other
 static inline int sp_tc_pack_launch(const SpConvDesc* d, int transposed, int ns, int cip, int cop, const float* w, void* img,
-                                    cudaStream_t st) {
+                                    cudaStream_t st, int passes = 1) {
     const int total = 27 * (cip / 8) * cop;
     const int blocks = (total + 255) / 256;
-    if (ns == 2) sp_tc::pack_wimg_kernel<2><<<blocks, 256, 0, st>>>(w, d->Co, d->Ci, transposed, cip, cop, (uint4*)img);
-    else sp_tc::pack_wimg_kernel<3><<<blocks, 256, 0, st>>>(w, d->Co, d->Ci, transposed, cip, cop, (uint4*)img);
-    SP_LAUNCH_OK("pack_wimg_kernel");
+    const size_t img_u4 = (size_t)27 * (cip / 8) * ns * cop;
+    for (int p = 0; p < passes; ++p) {
+        uint4* ip = (uint4*)img + p * img_u4;
+        if (ns == 2) sp_tc::pack_wimg_kernel<2><<<blocks, 256, 0, st>>>(w, d->Co, d->Ci, transposed, cip, cop, 16 * p, ip);
+        else sp_tc::pack_wimg_kernel<3><<<blocks, 256, 0, st>>>(w, d->Co, d->Ci, transposed, cip, cop, 16 * p, ip);
+        SP_LAUNCH_OK("pack_wimg_kernel");
+    }
     return 0;
 }

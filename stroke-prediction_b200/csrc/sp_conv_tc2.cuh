@@ -23,23 +23,30 @@ using namespace sp_tc;
 
 constexpr int TD2 = 2;                               // output planes per tile
 constexpr int NS2 = 3;
-constexpr int CIP2 = 16, COP2 = 16;
+constexpr int CIP2 = 16;
 constexpr int KCH2 = CIP2 / 8;
 constexpr int SLOTS2 = slots<TD2>();                 // 720
 // The two 16-byte K chunks of one operand row are fetched together: their planes must not be a multiple of 128 bytes apart
 // (same banks -> the operand fetch serialises, measured 64 cycles per MMA).  Pad every chunk plane to an odd multiple of 64 B.
 constexpr int PSLOTS2 = SLOTS2 + 4;                  // 724 slots -> 11584 B = 90.5 x 128
 constexpr int PLANE_B2 = PSLOTS2 * 16;
-constexpr int NTOT2 = NS2 * COP2;                    // 48 rows of the weight image per (tap, chunk)
-constexpr int BROWS2 = NTOT2 + 4;                    // padded chunk stride of the weight image in shared memory (832 B)
-constexpr int WIMG2 = wimg_u4<CIP2, COP2, NS2>();    // global (unpadded) image
-constexpr int WIMG2S = 27 * KCH2 * BROWS2;           // shared-memory image
 constexpr int ABUF_U4 = NS2 * KCH2 * PSLOTS2;        // uint4 per A buffer
-constexpr int KDCOLS = 48;                           // TMEM columns per (plane, kd): [main | cA | cB]
-constexpr int PCOLS = 3 * KDCOLS;                    // TMEM columns per plane (144)
 constexpr int NSTAGE = 192;                          // staging threads (warps 4..9)
 constexpr int NTHREADS2 = 16 * 32;                   // 4 epilogue warps + 6 staging warps + 6 MMA warps
-constexpr size_t SMEM2 = (size_t)2 * ABUF_U4 * 16 + (size_t)WIMG2S * 16 + 128;
+
+// COP = padded output channels of the GEMM: 16 (the 16-channel layers) or 24 (the 24-channel level of the CAE, whose
+// 17..24 input channels run as TWO passes of 16 + 8 input channels, the second accumulating onto the first's raw sums)
+template <int COP>
+struct Tc2 {
+    static constexpr int NTOT = NS2 * COP;                       // rows of the weight image per (tap, chunk)
+    static constexpr int BROWS = NTOT + 4;                       // padded chunk stride in shared memory (832 / 1216 B)
+    static constexpr int WIMG = wimg_u4<CIP2, COP, NS2>();       // global (unpadded) image
+    static constexpr int WIMGS = 27 * KCH2 * BROWS;              // shared-memory image
+    static constexpr int KDCOLS = 3 * COP;                       // TMEM columns per (plane, kd): [main | cA | cB]
+    static constexpr int PCOLS = 3 * KDCOLS;                     // TMEM columns per plane (144 / 216)
+    static constexpr size_t SMEM = (size_t)2 * ABUF_U4 * 16 + (size_t)WIMGS * 16 + 128;
+};
+static_assert(Tc2<24>::SMEM <= 227 * 1024 && 2 * Tc2<24>::PCOLS <= 512, "tc2: shared / tensor memory");
 
 // Exact three-term bf16 split by TRUNCATION: t1 = v & 0xffff0000, r = v - t1, ... (24 significand bits = 3 x 8, every
 // subtraction is exact).  Integer / FADD work only — the cvt-based split (sp_tc::split8) is bound by the 16-lane conversion
@@ -121,15 +128,35 @@ __device__ __forceinline__ void tmem_ld16x3(uint32_t a0, uint32_t a1, uint32_t a
     }
 }
 
+// NCOL consecutive columns in 8-column pieces, one wait
+template <int NCOL>
+__device__ __forceinline__ void tmem_ld_n(uint32_t taddr, float* v) {
+    uint32_t r[NCOL];
+#pragma unroll
+    for (int c = 0; c < NCOL; c += 8)
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=r"(r[c]), "=r"(r[c + 1]), "=r"(r[c + 2]), "=r"(r[c + 3]), "=r"(r[c + 4]), "=r"(r[c + 5]), "=r"(r[c + 6]), "=r"(r[c + 7])
+                     : "r"(taddr + c) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < NCOL; ++i) v[i] = __uint_as_float(r[i]);
+}
+
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory");
 }
 
+// sstride: floats between the scale / shift rows of two statistics groups (the layer's full channel count when `src` is a
+// channel slice); accum != 0: add the raw sums already in dst (second input-channel pass); fin == 0: store raw sums (no bias,
+// no activation: first pass of two).
+template <int COP>
 __global__ void __launch_bounds__(NTHREADS2, 1)
 corr3_tc_pipe_kernel(SpConvDesc d, int nPerG, int tiles_w, int tiles_h, int tiles_d, int total_tiles,
                      const float* __restrict__ src, const uint4* __restrict__ wimg, const float* __restrict__ bias,
-                     const float* __restrict__ scale, const float* __restrict__ shift, float* __restrict__ dst,
-                     long long* __restrict__ prof, int dbg_terms) {
+                     const float* __restrict__ scale, const float* __restrict__ shift, int sstride, int accum, int fin,
+                     float* __restrict__ dst, long long* __restrict__ prof, int dbg_terms) {
+    using T = Tc2<COP>;
+    constexpr int NTOT2 = T::NTOT, BROWS2 = T::BROWS, WIMG2 = T::WIMG, WIMG2S = T::WIMGS, KDCOLS = T::KDCOLS, PCOLS = T::PCOLS;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const bool pr = (prof != nullptr) && (blockIdx.x == 0);
     long long pw0 = 0, pw1 = 0, pwk = 0;
@@ -191,8 +218,8 @@ corr3_tc_pipe_kernel(SpConvDesc d, int nPerG, int tiles_w, int tiles_h, int tile
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     const bool okc = scale && (c + j < d.Ci);
-                    bsc[j] = okc ? scale[(int64_t)g * d.Ci + c + j] : 1.f;
-                    bsh[j] = okc ? shift[(int64_t)g * d.Ci + c + j] : 0.f;
+                    bsc[j] = okc ? scale[(int64_t)g * sstride + c + j] : 1.f;
+                    bsh[j] = okc ? shift[(int64_t)g * sstride + c + j] : 0.f;
                 }
             }
             constexpr int SLOT_GROUPS = (SLOTS2 + 15) / 16;
@@ -295,9 +322,9 @@ corr3_tc_pipe_kernel(SpConvDesc d, int nPerG, int tiles_w, int tiles_h, int tile
                         //   a1 x [w1|w2|w3] -> [main | cA | cB];  a2 x [w1|w2] -> [cA | cB];  a3 x [w1] -> cA
                         // (main holds only the nine leading products a1*w1 of this kd; every correction term, 2^-8 .. 2^-16 of
                         // the result, goes to the two correction blocks)
-                        if (dbg_terms & 1) umma_bf16(dk, da, db, umma_idesc_bf16(48), first);
-                        if (dbg_terms & 2) umma_bf16(dk + 16u, da + (uint64_t)(1 * KCH2 * PSLOTS2), db, umma_idesc_bf16(32), 1u);
-                        if (dbg_terms & 4) umma_bf16(dk + 16u, da + (uint64_t)(2 * KCH2 * PSLOTS2), db, umma_idesc_bf16(16), 1u);
+                        if (dbg_terms & 1) umma_bf16(dk, da, db, umma_idesc_bf16(3 * COP), first);
+                        if (dbg_terms & 2) umma_bf16(dk + (uint32_t)COP, da + (uint64_t)(1 * KCH2 * PSLOTS2), db, umma_idesc_bf16(2 * COP), 1u);
+                        if (dbg_terms & 4) umma_bf16(dk + (uint32_t)COP, da + (uint64_t)(2 * KCH2 * PSLOTS2), db, umma_idesc_bf16(COP), 1u);
                     }
                 }
                 umma_commit(t_full + 8 * p);                      // this lane's share of plane p is complete
@@ -310,9 +337,9 @@ corr3_tc_pipe_kernel(SpConvDesc d, int nPerG, int tiles_w, int tiles_h, int tile
         // =================================================================== epilogue warps 0..3 (TMEM lane quarter = warp)
         const int q = warp;
         const int r = q * 32 + lane;                              // GEMM row = output voxel within the plane
-        float b16[16];
+        float b16[COP];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) b16[j] = (bias && j < d.Co) ? bias[j] : 0.f;
+        for (int j = 0; j < COP; ++j) b16[j] = (bias && fin && j < d.Co) ? bias[j] : 0.f;
         int it = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
             int n, od0, oh0, ow0;
@@ -327,33 +354,49 @@ corr3_tc_pipe_kernel(SpConvDesc d, int nPerG, int tiles_w, int tiles_h, int tile
                 tc_fence_after();
                 const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(p * PCOLS);
                 // per kd: (cB + cA) + main — corrections first, then the leading sum; then the three kd
-                float acc[16];
+                float acc[COP];
 #pragma unroll
                 for (int kd = 0; kd < 3; ++kd) {
-                    float v[48];
-                    tmem_ld48(ta + kd * KDCOLS, v);               // [main | cA | cB]
+                    float v[KDCOLS];
+                    tmem_ld_n<KDCOLS>(ta + kd * KDCOLS, v);       // [main | cA | cB]
                     if (kd == 2) {
                         tc_fence_before();
                         mbar_arrive(t_empty + 8 * p);             // TMEM of this plane may be overwritten
                     }
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const float s_kd = (v[32 + j] + v[16 + j]) + v[j];
+                    for (int j = 0; j < COP; ++j) {
+                        const float s_kd = (v[2 * COP + j] + v[COP + j]) + v[j];
                         acc[j] = (kd == 0) ? s_kd : acc[j] + s_kd;
                     }
                 }
                 const int od = od0 + p;
                 if (od < d.Do && oh < d.Ho && ow < d.Wo) {
                     float* yp = dst + ((((int64_t)n * d.Do + od) * d.Ho + oh) * d.Wo + ow) * d.ldo;
+                    const bool vecy = (d.ldo % 4 == 0) && d.Co == COP;
+                    if (accum) {                                  // raw sums of the first input-channel pass
+                        if (vecy) {
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) acc[j] = sp_act_fwd(acc[j] + b16[j], d.act, d.alpha);
-                    if ((d.ldo % 4 == 0) && d.Co == 16) {
+                            for (int j4 = 0; j4 < COP / 4; ++j4) {
+                                const float4 o = reinterpret_cast<const float4*>(yp)[j4];
+                                acc[4 * j4] += o.x; acc[4 * j4 + 1] += o.y; acc[4 * j4 + 2] += o.z; acc[4 * j4 + 3] += o.w;
+                            }
+                        } else {
 #pragma unroll
-                        for (int j4 = 0; j4 < 4; ++j4)
+                            for (int j = 0; j < COP; ++j)
+                                if (j < d.Co) acc[j] += yp[j];
+                        }
+                    }
+                    if (fin) {
+#pragma unroll
+                        for (int j = 0; j < COP; ++j) acc[j] = sp_act_fwd(acc[j] + b16[j], d.act, d.alpha);
+                    }
+                    if (vecy) {
+#pragma unroll
+                        for (int j4 = 0; j4 < COP / 4; ++j4)
                             reinterpret_cast<float4*>(yp)[j4] = make_float4(acc[4 * j4], acc[4 * j4 + 1], acc[4 * j4 + 2], acc[4 * j4 + 3]);
                     } else {
 #pragma unroll
-                        for (int j = 0; j < 16; ++j)
+                        for (int j = 0; j < COP; ++j)
                             if (j < d.Co) yp[j] = acc[j];
                     }
                 }
@@ -371,20 +414,47 @@ corr3_tc_pipe_kernel(SpConvDesc d, int nPerG, int tiles_w, int tiles_h, int tile
 
 }  // namespace sp_tc2
 
-static inline int sp_tc2_corr_launch(const SpConvDesc* d, int nPerG, const float* src, const uint4* wimg, const float* bias,
-                                     const float* scale, const float* shift, float* dst, cudaStream_t st, long long* prof = nullptr, int dbg_terms = 7) {
+template <int COP>
+static inline int sp_tc2_corr_launch_t(const SpConvDesc* d, int nPerG, const float* src, const uint4* wimg, const float* bias,
+                                       const float* scale, const float* shift, int sstride, int accum, int fin, float* dst,
+                                       cudaStream_t st, long long* prof, int dbg_terms) {
     using namespace sp_tc2;
     const int tiles_w = (d->Wo + TWO - 1) / TWO, tiles_h = (d->Ho + THO - 1) / THO, tiles_d = (d->Do + TD2 - 1) / TD2;
     const int64_t total = (int64_t)tiles_w * tiles_h * tiles_d * d->N;
     SP_REQUIRE(total < (1LL << 31), "tc corr: too many tiles");
     static bool attr = false;
     if (!attr) {
-        SP_CUDA(cudaFuncSetAttribute(corr3_tc_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM2));
+        SP_CUDA(cudaFuncSetAttribute(corr3_tc_pipe_kernel<COP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Tc2<COP>::SMEM));
         attr = true;
     }
     int grid = sp_num_sms();
     if (grid > total) grid = (int)total;
-    corr3_tc_pipe_kernel<<<grid, NTHREADS2, SMEM2, st>>>(*d, nPerG, tiles_w, tiles_h, tiles_d, (int)total, src, wimg, bias, scale, shift, dst, prof, dbg_terms);
+    corr3_tc_pipe_kernel<COP><<<grid, NTHREADS2, Tc2<COP>::SMEM, st>>>(*d, nPerG, tiles_w, tiles_h, tiles_d, (int)total, src, wimg, bias, scale,
+                                                                        shift, sstride, accum, fin, dst, prof, dbg_terms);
     SP_LAUNCH_OK("corr3_tc_pipe_kernel");
+    return 0;
+}
+
+// d->Ci <= 16, d->Co <= 16: one pass.  Wider layers (<= 24 channels): output width 24, input channels in passes of 16 whose
+// weight images lie one after the other in `wimg` (pass p covers input channels [16 p, 16 p + 16)).
+static inline int sp_tc2_corr_launch(const SpConvDesc* d, int nPerG, const float* src, const uint4* wimg, const float* bias,
+                                     const float* scale, const float* shift, float* dst, cudaStream_t st, long long* prof = nullptr, int dbg_terms = 7) {
+    using namespace sp_tc2;
+    if (d->Ci <= 16 && d->Co <= 16)
+        return sp_tc2_corr_launch_t<16>(d, nPerG, src, wimg, bias, scale, shift, d->Ci, 0, 1, dst, st, prof, dbg_terms);
+    const int cop = d->Co > 16 ? 24 : 16;
+    const int npass = (d->Ci + 15) / 16;
+    const size_t img_u4 = (size_t)27 * KCH2 * NS2 * cop;
+    for (int p = 0; p < npass; ++p) {
+        SpConvDesc s = *d;
+        s.Ci = (d->Ci - 16 * p < 16) ? d->Ci - 16 * p : 16;
+        const float* sp = src + 16 * p;
+        const float* scp = scale ? scale + 16 * p : nullptr;
+        const float* shp = shift ? shift + 16 * p : nullptr;
+        const int e = (cop == 24)
+            ? sp_tc2_corr_launch_t<24>(&s, nPerG, sp, wimg + p * img_u4, bias, scp, shp, d->Ci, p > 0, p == npass - 1, dst, st, prof, dbg_terms)
+            : sp_tc2_corr_launch_t<16>(&s, nPerG, sp, wimg + p * img_u4, bias, scp, shp, d->Ci, p > 0, p == npass - 1, dst, st, prof, dbg_terms);
+        if (e) return e;
+    }
     return 0;
 }

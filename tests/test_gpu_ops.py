@@ -181,6 +181,11 @@ TC_CASES = [
     ("C", 16, 16, 3, 1, 0, "leaky", (12, 34, 30)),             # Unet3D.py:22  valid conv (dgrad has pad 2)
     ("C", 12, 10, 3, 1, (1, 1, 1), "elu", (10, 33, 31)),       # channel counts that are not multiples of 8
     ("T", 16, 16, 3, 1, 0, "elu", (8, 30, 36)),                # convT k3 s1 forward = flipped correlation
+    # 17..24 channels: output width 24 and / or two input-channel passes (16 + 8) of the pipelined kernel
+    ("C", 24, 24, 3, 1, (1, 0, 0), "elu", (9, 40, 29)),        # Cae3D.py:52,55
+    ("C", 24, 16, 3, 1, (1, 2, 2), "elu", (9, 30, 30)),        # Cae3D.py:200  two passes in, 16 out (dgrad: 16 in, 24 out)
+    ("C", 20, 18, 3, 1, (1, 1, 1), "leaky", (10, 33, 31)),     # ragged second pass (4 channels), ragged 24-wide output
+    ("T", 24, 24, 3, 1, 0, "elu", (8, 30, 36)),                # convT k3 s1 with 24 channels
 ]
 
 
