@@ -370,8 +370,10 @@ struct SpTcCfg { int cip, cop, td, passes; };     // passes: input-channel passe
 // layers served: 3x3x3 stride-1, <= 16 channels on both sides (the 28-deep 16->16 layers hold ~75 % of the conv FLOPs)
 static inline bool sp_tc_corr_supported(const SpConvDesc* d, SpTcCfg* cfg) {
     if (d->k != 3 || d->s != 1 || sp_tc_terms() == 0) return false;
-    const int cmax = (sp_tc_terms() == 4) ? 24 : 16;                        // the pipelined kernel also serves the 24-channel level
-    if (d->Ci > cmax || d->Co > cmax || d->Ci < 8 || d->Co < 8) return false;   // narrower layers: FFMA tier (2- / 8-wide passes)
+    // the pipelined kernel also serves 24-wide outputs and up to three input-channel passes of 16 (the 24-channel level of the
+    // CAE, Unet3D.py:19 block5's 48 -> 16 convolution on the concatenated skip)
+    const int comax = (sp_tc_terms() == 4) ? 24 : 16, cimax = (sp_tc_terms() == 4) ? 48 : 16;
+    if (d->Ci > cimax || d->Co > comax || d->Ci < 8 || d->Co < 8) return false;   // narrower layers: FFMA tier (2- / 8-wide passes)
     const int64_t ov = (int64_t)d->Do * d->Ho * d->Wo;
     if (ov < 8192 || d->Wo < 8 || d->Ho < 16) return false;
     if (cfg) { cfg->cip = 16; cfg->cop = d->Co > 16 ? 24 : 16; cfg->td = 4; cfg->passes = (d->Ci + 15) / 16; }

@@ -186,6 +186,7 @@ TC_CASES = [
     ("C", 24, 16, 3, 1, (1, 2, 2), "elu", (9, 30, 30)),        # Cae3D.py:200  two passes in, 16 out (dgrad: 16 in, 24 out)
     ("C", 20, 18, 3, 1, (1, 1, 1), "leaky", (10, 33, 31)),     # ragged second pass (4 channels), ragged 24-wide output
     ("T", 24, 24, 3, 1, 0, "elu", (8, 30, 36)),                # convT k3 s1 with 24 channels
+    ("C", 48, 16, 3, 1, 0, "leaky", (10, 30, 34)),             # Unet3D.py:19 block5 on the concat: three input passes (dgrad: FFMA tier)
 ]
 
 
