@@ -38,16 +38,17 @@ class CaeInference(Inference):
     def init_clinical_variables(self, batch: dict, step):
         globals_incl_time = batch[data.KEY_GLOBAL].float()
         n = globals_incl_time.size()[0]
-        type_core = torch.zeros(n, 1, 1, 1, 1)
-        type_penumbra = torch.ones(n, 1, 1, 1, 1)
         time_to_treatment = self.get_time_to_treatment(batch, globals_incl_time, step)
 
         if self.is_cuda:
             if time_to_treatment is not None:
                 time_to_treatment = self._to_device(time_to_treatment)
             globals_incl_time = self._to_device(globals_incl_time)
-            type_core = self._to_device(type_core)
-            type_penumbra = self._to_device(type_penumbra)
+            type_core = torch.zeros(n, 1, 1, 1, 1, device=self.device)        # constants: created where they are used
+            type_penumbra = torch.ones(n, 1, 1, 1, 1, device=self.device)
+        else:
+            type_core = torch.zeros(n, 1, 1, 1, 1)
+            type_penumbra = torch.ones(n, 1, 1, 1, 1)
 
         return CaeDtoUtil.init_dto(globals_incl_time, time_to_treatment, type_core, type_penumbra,
                                    None, None, None, None, None)
@@ -59,12 +60,15 @@ class CaeInference(Inference):
         if labels.dtype != torch.float32:
             labels = labels.float()
         B, C, D, H, W = labels.shape
-        # The three masks land in ONE [3B, 1, D, H, W] buffer, channel-major, as three strided copies (for a pinned
-        # host batch that is three 2-D DMA transfers, no kernel).  The encoder recognises the adjacent slices and runs
-        # core / penumbra / lesion as one stacked pass.
+        # The three masks land in ONE [3B, 1, D, H, W] buffer, channel-major: the encoder recognises the adjacent slices and
+        # runs core / penumbra / lesion as one stacked pass.  The host batch crosses PCIe as ONE contiguous (pinned: asynchronous)
+        # transfer; the (sample, channel) -> (channel, sample) reorder is a device-side strided copy.  (Copying the three channel
+        # slices separately makes torch gather each of them into a pageable temporary on the host first.)
+        if not labels.is_contiguous():
+            labels = labels.contiguous()
+        dev = labels.to(self.device, non_blocking=labels.is_pinned()) if not labels.is_cuda else labels
         buf = torch.empty((3 * B, 1, D, H, W), device=self.device, dtype=torch.float32)
-        for c in range(3):
-            buf[c * B:(c + 1) * B].copy_(labels[:, c:c + 1], non_blocking=True)
+        buf.view(3, B, D * H * W).copy_(dev.view(B, C, D * H * W)[:, :3].transpose(0, 1))
         dto.given_variables.gtruth.core = buf[0:B]
         dto.given_variables.gtruth.penu = buf[B:2 * B]
         dto.given_variables.gtruth.lesion = buf[2 * B:3 * B]
