@@ -90,15 +90,16 @@ channel_sums_vec_kernel(const float* __restrict__ a, int lda, const float* __res
                 s1[2] = fma(a2, (double)vb.z, s1[2]); s1[3] = fma(a3, (double)vb.w, s1[3]);
             };
             int64_t r = r0 + r_l;
-            for (; r + 3 * (int64_t)R < r1; r += 4 * (int64_t)R) {
-                float4 va[4], vb[4];
+            constexpr int U = (MODE == 1) ? 8 : 4;          // eight 128-bit loads in flight per thread in both modes
+            for (; r + (U - 1) * (int64_t)R < r1; r += U * (int64_t)R) {
+                float4 va[U], vb[U];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    va[u] = *reinterpret_cast<const float4*>(ag + (r + (int64_t)u * R) * lda + q * 4);
-                    vb[u] = (MODE == 1) ? va[u] : *reinterpret_cast<const float4*>(bgp + (r + (int64_t)u * R) * ldb + q * 4);
+                for (int u = 0; u < U; ++u) {
+                    va[u] = sp_ldg_stream(reinterpret_cast<const float4*>(ag + (r + (int64_t)u * R) * lda + q * 4));
+                    vb[u] = (MODE == 1) ? va[u] : sp_ldg_stream(reinterpret_cast<const float4*>(bgp + (r + (int64_t)u * R) * ldb + q * 4));
                 }
 #pragma unroll
-                for (int u = 0; u < 4; ++u) add(va[u], vb[u]);
+                for (int u = 0; u < U; ++u) add(va[u], vb[u]);
             }
             for (; r < r1; r += R) {
                 const float4 va = *reinterpret_cast<const float4*>(ag + r * lda + q * 4);
