@@ -600,6 +600,7 @@ size_t sp_wgrad_workspace_bytes(const SpConvDesc* d) {
     if (pw > tiled) tiled = pw;
     if (sp_tc_wgrad_workspace_bytes(d) > tiled) tiled = sp_tc_wgrad_workspace_bytes(d);
     if (sp_tc24_wgrad_workspace_bytes(d) > tiled) tiled = sp_tc24_wgrad_workspace_bytes(d);
+    if (sp_tc_wgrad_sliced_workspace_bytes(d) > tiled) tiled = sp_tc_wgrad_sliced_workspace_bytes(d);
     if (sp_thin_wgrad_workspace_bytes(d) > tiled) tiled = sp_thin_wgrad_workspace_bytes(d);
     if (sp_k2s2_wgrad_workspace_bytes(d) > tiled) tiled = sp_k2s2_wgrad_workspace_bytes(d);
     if (gemm_wgrad(d) && sp_gemm_wgrad_ws_bytes(d) > tiled) tiled = sp_gemm_wgrad_ws_bytes(d);
@@ -625,6 +626,8 @@ int sp_wgrad(const SpConvDesc* d, const float* iside, const float* i_scale, cons
         return sp_thin_wgrad_launch(d, nPerG, iside, i_scale, i_shift, oside, o_scale, o_shift, dw, beta, (float*)ws, sp_stream(stream));
     if (sp_tc_wgrad_supported(d))
         return sp_tc_wgrad_launch(d, nPerG, iside, i_scale, i_shift, oside, o_scale, o_shift, dw, beta, (float*)ws, sp_stream(stream));
+    if (sp_tc_wgrad_sliced_supported(d) && (reinterpret_cast<uintptr_t>(iside) & 15) == 0)
+        return sp_tc_wgrad_sliced_launch(d, nPerG, iside, i_scale, i_shift, oside, o_scale, o_shift, dw, beta, (float*)ws, sp_stream(stream));
     if (sp_tc24_wgrad_supported(d))
         return sp_tc24_wgrad_launch(d, nPerG, iside, i_scale, i_shift, oside, o_scale, o_shift, dw, beta, (float*)ws, sp_stream(stream));
     if (sp_tiled_wgrad_supported(d))

@@ -69,7 +69,7 @@ __host__ __device__ constexpr int a_off(int term, int buf, int half) {
 
 template <int MROWS>
 __global__ void __launch_bounds__(NTHREADS_W, 1)
-wgrad3_tc_kernel(SpConvDesc d, int nPerG, int tiles_w, int tiles_h, int total_cols, int drain_every,
+wgrad3_tc_kernel(SpConvDesc d, int nPerG, int tiles_w, int tiles_h, int total_cols, int drain_every, int isstride,
                  const float* __restrict__ X, const float* __restrict__ i_scale, const float* __restrict__ i_shift,
                  const float* __restrict__ dZ, const float* __restrict__ o_scale, const float* __restrict__ o_shift,
                  float* __restrict__ ws, long long* __restrict__ prof) {
@@ -127,8 +127,8 @@ wgrad3_tc_kernel(SpConvDesc d, int nPerG, int tiles_w, int tiles_h, int total_co
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 const bool okc = i_scale && (half * 8 + j < d.Ci);
-                bsc[j] = okc ? i_scale[(int64_t)g * d.Ci + half * 8 + j] : 1.f;
-                bsh[j] = okc ? i_shift[(int64_t)g * d.Ci + half * 8 + j] : 0.f;
+                bsc[j] = okc ? i_scale[(int64_t)g * isstride + half * 8 + j] : 1.f;      // isstride: channels of the whole layer
+                bsh[j] = okc ? i_shift[(int64_t)g * isstride + half * 8 + j] : 0.f;      // when X is a 16-channel slice of it
             }
             for (int od = 0; od < d.Do; ++od, ++it) {
                 const int buf = it & 1, use = it >> 1;
@@ -379,15 +379,69 @@ static inline int sp_tc_wgrad_launch(const SpConvDesc* d, int nPerG, const float
         attr = true;
     }
     if (mrows == 64)
-        wgrad3_tc_kernel<64><<<p.grid, NTHREADS_W, SMEM_W, st>>>(*d, nPerG, p.tiles_w, p.tiles_h, (int)p.total, drain_every, iside,
+        wgrad3_tc_kernel<64><<<p.grid, NTHREADS_W, SMEM_W, st>>>(*d, nPerG, p.tiles_w, p.tiles_h, (int)p.total, drain_every, d->Ci, iside,
                                                                  i_scale, i_shift, oside, o_scale, o_shift, ws, prof);
     else
-        wgrad3_tc_kernel<128><<<p.grid, NTHREADS_W, SMEM_W, st>>>(*d, nPerG, p.tiles_w, p.tiles_h, (int)p.total, drain_every, iside,
+        wgrad3_tc_kernel<128><<<p.grid, NTHREADS_W, SMEM_W, st>>>(*d, nPerG, p.tiles_w, p.tiles_h, (int)p.total, drain_every, d->Ci, iside,
                                                                   i_scale, i_shift, oside, o_scale, o_shift, ws, prof);
     SP_LAUNCH_OK("wgrad3_tc_kernel");
     const int64_t wn = (int64_t)d->Co * d->Ci * 27;
     int64_t rb = (wn + 255) / 256;
     wgrad_reduce_kernel<<<(int)rb, 256, 0, st>>>(ws, p.grid, wn, dw, beta);
     SP_LAUNCH_OK("wgrad_reduce_kernel");
+    return 0;
+}
+
+// ---- 25..48 input channels, 9..16 output channels (Unet3D.py:19 block5 on the 48-channel concat): the I-side runs as slices of
+// 16 channels through the kernel above (X + 16 c with the layer's row stride, its slice of the BN coefficients); every slice
+// has its own per-CTA partials, which a scatter-reduce folds into dW[co][16 c + ci][tap].
+__global__ void wgrad_reduce_slice_kernel(const float* __restrict__ ws, int chunks, int Co, int cs, int Ci, int ci0,
+                                          float* __restrict__ dw, float beta) {
+    const int wn = Co * cs * 27;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= wn) return;
+    float s = 0.f;
+    for (int c = 0; c < chunks; ++c) s += ws[(int64_t)c * wn + i];
+    const int tap = i % 27, ci = (i / 27) % cs, co = i / (27 * cs);
+    float* o = dw + ((int64_t)co * Ci + ci0 + ci) * 27 + tap;
+    *o = (beta != 0.f ? beta * *o : 0.f) + s;
+}
+
+static inline bool sp_tc_wgrad_sliced_supported(const SpConvDesc* d) {
+    if (d->k != 3 || d->s != 1 || sp_tc_terms() == 0 || sp_tc_wgrad_disabled()) return false;
+    if (d->Ci <= 24 || d->Ci > 48 || d->Co <= 8 || d->Co > 16 || d->ldi % 4 != 0) return false;
+    if (d->pd > 2 || d->ph > 2 || d->pw > 2) return false;
+    const sp_wtc::WtcPlan p = sp_wtc::plan(d);
+    return p.total >= 16 && p.total < (1LL << 31) && d->Wo >= 24 && d->Do >= 8;
+}
+
+static inline size_t sp_tc_wgrad_sliced_workspace_bytes(const SpConvDesc* d) {
+    if (!sp_tc_wgrad_sliced_supported(d)) return 0;
+    return (size_t)((d->Ci + 15) / 16) * sp_wtc::plan(d).grid * d->Co * 16 * 27 * sizeof(float);
+}
+
+static inline int sp_tc_wgrad_sliced_launch(const SpConvDesc* d, int nPerG, const float* iside, const float* i_scale,
+                                            const float* i_shift, const float* oside, const float* o_scale, const float* o_shift,
+                                            float* dw, float beta, float* ws, cudaStream_t st, int drain_every = 2) {
+    using namespace sp_wtc;
+    const WtcPlan p = plan(d);
+    static bool attr = false;
+    if (!attr) {
+        SP_CUDA(cudaFuncSetAttribute(wgrad3_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_W));
+        attr = true;
+    }
+    const int nsl = (d->Ci + 15) / 16;
+    for (int c = 0; c < nsl; ++c) {
+        SpConvDesc s = *d;
+        s.Ci = (d->Ci - 16 * c < 16) ? d->Ci - 16 * c : 16;
+        float* wsc = ws + (size_t)c * p.grid * d->Co * 16 * 27;
+        wgrad3_tc_kernel<64><<<p.grid, NTHREADS_W, SMEM_W, st>>>(s, nPerG, p.tiles_w, p.tiles_h, (int)p.total, drain_every, d->Ci,
+                                                                 iside + 16 * c, i_scale ? i_scale + 16 * c : nullptr,
+                                                                 i_shift ? i_shift + 16 * c : nullptr, oside, o_scale, o_shift, wsc, nullptr);
+        SP_LAUNCH_OK("wgrad3_tc_kernel");
+        const int wn = d->Co * s.Ci * 27;
+        wgrad_reduce_slice_kernel<<<(wn + 255) / 256, 256, 0, st>>>(wsc, p.grid, d->Co, s.Ci, d->Ci, 16 * c, dw, beta);
+        SP_LAUNCH_OK("wgrad_reduce_slice_kernel");
+    }
     return 0;
 }

@@ -213,6 +213,8 @@ WGRAD_TC_CASES = [
     ("C", 24, 24, 3, 1, (1, 0, 0), "elu", (9, 19, 44)),        # Cae3D.py:52,55
     ("C", 24, 16, 3, 1, (1, 2, 2), "elu", (8, 14, 35)),        # Cae3D.py:200  24 -> 16: the third O-side group is empty
     ("C", 12, 20, 3, 1, 1, "leaky", (10, 17, 33)),             # ragged groups on both sides
+    ("C", 48, 16, 3, 1, 0, "leaky", (10, 18, 40)),             # Unet3D.py:19 block5: three 16-channel I-side slices, scatter-reduce
+    ("C", 40, 12, 3, 1, (1, 1, 1), "elu", (8, 16, 30)),        # ragged last slice (8 channels)
 ]
 
 
