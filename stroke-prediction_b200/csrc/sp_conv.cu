@@ -489,7 +489,7 @@ size_t sp_packed_weight_floats(const SpConvDesc* d, int which) {
     if (!d) return 0;
     size_t n = ffma_packed_floats(d, which);
     SpTcCfg cfg;
-    if (tc_serves(d, which, &cfg)) n += cfg.passes * sp_tc_wimg_bytes(cfg.cip, cfg.cop, sp_tc_image_terms()) / sizeof(float);
+    if (tc_serves(d, which, &cfg)) n += (size_t)cfg.passes * cfg.nslices * sp_tc_wimg_bytes(cfg.cip, cfg.cop, sp_tc_image_terms()) / sizeof(float);
     return n;
 }
 
@@ -509,7 +509,7 @@ int sp_pack_weights(const SpConvDesc* d, int which, const float* w_torch, float*
     SP_LAUNCH_OK("pack_weights_kernel");
     SpTcCfg cfg;
     if (tc_serves(d, which, &cfg))
-        return sp_tc_pack_launch(d, which, sp_tc_image_terms(), cfg.cip, cfg.cop, w_torch, w_packed + total, sp_stream(stream), cfg.passes);
+        return sp_tc_pack_launch(d, which, sp_tc_image_terms(), cfg.cip, cfg.cop, w_torch, w_packed + total, sp_stream(stream), cfg.passes, cfg.nslices);
     return 0;
 }
 
@@ -626,7 +626,7 @@ int sp_wgrad(const SpConvDesc* d, const float* iside, const float* i_scale, cons
         return sp_thin_wgrad_launch(d, nPerG, iside, i_scale, i_shift, oside, o_scale, o_shift, dw, beta, (float*)ws, sp_stream(stream));
     if (sp_tc_wgrad_supported(d))
         return sp_tc_wgrad_launch(d, nPerG, iside, i_scale, i_shift, oside, o_scale, o_shift, dw, beta, (float*)ws, sp_stream(stream));
-    if (sp_tc_wgrad_sliced_supported(d) && (reinterpret_cast<uintptr_t>(iside) & 15) == 0)
+    if (sp_tc_wgrad_sliced_supported(d) && ((reinterpret_cast<uintptr_t>(iside) | reinterpret_cast<uintptr_t>(oside)) & 15) == 0)
         return sp_tc_wgrad_sliced_launch(d, nPerG, iside, i_scale, i_shift, oside, o_scale, o_shift, dw, beta, (float*)ws, sp_stream(stream));
     if (sp_tc24_wgrad_supported(d))
         return sp_tc24_wgrad_launch(d, nPerG, iside, i_scale, i_shift, oside, o_scale, o_shift, dw, beta, (float*)ws, sp_stream(stream));

@@ -133,12 +133,13 @@ __device__ __forceinline__ void split8(const float* v, uint4* out) {
 // transposed == 0 (sp_corr):  Wsrc(co, ci, tap) = w[(co*Ci + ci)*27 + tap]            GEMM N = co, K = ci
 // transposed == 1 (sp_corrT): GEMM N = conv-ci, K = conv-co, taps flipped: Wsrc(n, k, tap) = w[(k*Ci + n)*27 + 26 - tap]
 template <int NS>
-__global__ void pack_wimg_kernel(const float* __restrict__ w, int Co, int Ci, int transposed, int CIP, int COP, int k0, uint4* __restrict__ img) {
+__global__ void pack_wimg_kernel(const float* __restrict__ w, int Co, int Ci, int transposed, int CIP, int COP, int k0, int n0, uint4* __restrict__ img) {
     const int KCH = CIP / 8, NTOT = NS * COP;
     const int total = 27 * KCH * COP;
     const int Nn = transposed ? Ci : Co, Kk = transposed ? Co : Ci;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-        const int n = i % COP;
+        const int nl = i % COP;
+        const int n = n0 + nl;                        // n0: first GEMM-N channel of this output slice
         const int chunk = (i / COP) % KCH;
         const int tap = i / (COP * KCH);
         float v[8];
@@ -153,7 +154,7 @@ __global__ void pack_wimg_kernel(const float* __restrict__ w, int Co, int Ci, in
         uint4 o[NS];
         split8<NS>(v, o);
 #pragma unroll
-        for (int s = 0; s < NS; ++s) img[(tap * KCH + chunk) * NTOT + s * COP + n] = o[s];
+        for (int s = 0; s < NS; ++s) img[(tap * KCH + chunk) * NTOT + s * COP + nl] = o[s];
     }
 }
 
@@ -365,18 +366,25 @@ static inline int& sp_tc_terms_ref() {
 static inline int sp_tc_terms() { return sp_tc_terms_ref(); }
 static inline int sp_tc_image_terms() { return sp_tc_terms() == 4 ? 3 : sp_tc_terms(); }   // bf16 terms of the weight image
 
-struct SpTcCfg { int cip, cop, td, passes; };     // passes: input-channel passes of 16 (pipelined kernel, 17..24 channels)
+struct SpTcCfg { int cip, cop, td, passes, nslices; };   // pipelined kernel: input-channel passes of 16, output slices of 16 (Co > 24)
 
 // layers served: 3x3x3 stride-1, <= 16 channels on both sides (the 28-deep 16->16 layers hold ~75 % of the conv FLOPs)
 static inline bool sp_tc_corr_supported(const SpConvDesc* d, SpTcCfg* cfg) {
     if (d->k != 3 || d->s != 1 || sp_tc_terms() == 0) return false;
-    // the pipelined kernel also serves 24-wide outputs and up to three input-channel passes of 16 (the 24-channel level of the
-    // CAE, Unet3D.py:19 block5's 48 -> 16 convolution on the concatenated skip)
-    const int comax = (sp_tc_terms() == 4) ? 24 : 16, cimax = (sp_tc_terms() == 4) ? 48 : 16;
+    // the pipelined kernel also serves wider layers: 17..24 output channels as one 24-wide pass, more as slices of 16 (each its
+    // own launch into a channel slice of dst), and up to six input-channel passes of 16 whose raw sums accumulate in dst
+    // (the 24-channel level of the CAE, every Block3x3x3 of the U-Net: Unet3D.py:19,22)
+    const int comax = (sp_tc_terms() == 4) ? 96 : 16, cimax = (sp_tc_terms() == 4) ? 96 : 16;
     if (d->Ci > cimax || d->Co > comax || d->Ci < 8 || d->Co < 8) return false;   // narrower layers: FFMA tier (2- / 8-wide passes)
     const int64_t ov = (int64_t)d->Do * d->Ho * d->Wo;
     if (ov < 8192 || d->Wo < 8 || d->Ho < 16) return false;
-    if (cfg) { cfg->cip = 16; cfg->cop = d->Co > 16 ? 24 : 16; cfg->td = 4; cfg->passes = (d->Ci + 15) / 16; }
+    if (d->Co > 24 && d->ldo % 4 != 0) return false;
+    if (cfg) {
+        cfg->cip = 16; cfg->td = 4;
+        cfg->cop = (d->Co > 16 && d->Co <= 24) ? 24 : 16;
+        cfg->nslices = (d->Co <= 24) ? 1 : (d->Co + 15) / 16;
+        cfg->passes = (d->Ci + 15) / 16;
+    }
     return true;
 }
 
@@ -404,17 +412,19 @@ static inline int sp_tc_corr_launch_t(const SpConvDesc* d, int nPerG, const floa
     return 0;
 }
 
-// one image per input-channel pass (GEMM-K channels [16 p, 16 p + 16)), one after the other
+// one image per (output slice, input-channel pass): GEMM-N channels [16 s, ..), GEMM-K channels [16 p, 16 p + 16); image
+// (s, p) lies at index s * passes + p
 static inline int sp_tc_pack_launch(const SpConvDesc* d, int transposed, int ns, int cip, int cop, const float* w, void* img,
-                                    cudaStream_t st, int passes = 1) {
+                                    cudaStream_t st, int passes = 1, int nslices = 1) {
     const int total = 27 * (cip / 8) * cop;
     const int blocks = (total + 255) / 256;
     const size_t img_u4 = (size_t)27 * (cip / 8) * ns * cop;
-    for (int p = 0; p < passes; ++p) {
-        uint4* ip = (uint4*)img + p * img_u4;
-        if (ns == 2) sp_tc::pack_wimg_kernel<2><<<blocks, 256, 0, st>>>(w, d->Co, d->Ci, transposed, cip, cop, 16 * p, ip);
-        else sp_tc::pack_wimg_kernel<3><<<blocks, 256, 0, st>>>(w, d->Co, d->Ci, transposed, cip, cop, 16 * p, ip);
-        SP_LAUNCH_OK("pack_wimg_kernel");
-    }
+    for (int sl = 0; sl < nslices; ++sl)
+        for (int p = 0; p < passes; ++p) {
+            uint4* ip = (uint4*)img + (size_t)(sl * passes + p) * img_u4;
+            if (ns == 2) sp_tc::pack_wimg_kernel<2><<<blocks, 256, 0, st>>>(w, d->Co, d->Ci, transposed, cip, cop, 16 * p, 16 * sl, ip);
+            else sp_tc::pack_wimg_kernel<3><<<blocks, 256, 0, st>>>(w, d->Co, d->Ci, transposed, cip, cop, 16 * p, 16 * sl, ip);
+            SP_LAUNCH_OK("pack_wimg_kernel");
+        }
     return 0;
 }

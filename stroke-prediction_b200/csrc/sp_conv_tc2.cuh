@@ -435,26 +435,32 @@ static inline int sp_tc2_corr_launch_t(const SpConvDesc* d, int nPerG, const flo
     return 0;
 }
 
-// d->Ci <= 16, d->Co <= 16: one pass.  Wider layers (<= 24 channels): output width 24, input channels in passes of 16 whose
-// weight images lie one after the other in `wimg` (pass p covers input channels [16 p, 16 p + 16)).
+// d->Ci <= 16, d->Co <= 16: one launch.  Wider layers: output width 24 (17..24 channels) or slices of 16 output channels (more),
+// input channels in passes of 16; the weight image of (slice s, pass p) is image s * npass + p of `wimg`.
 static inline int sp_tc2_corr_launch(const SpConvDesc* d, int nPerG, const float* src, const uint4* wimg, const float* bias,
                                      const float* scale, const float* shift, float* dst, cudaStream_t st, long long* prof = nullptr, int dbg_terms = 7) {
     using namespace sp_tc2;
     if (d->Ci <= 16 && d->Co <= 16)
         return sp_tc2_corr_launch_t<16>(d, nPerG, src, wimg, bias, scale, shift, d->Ci, 0, 1, dst, st, prof, dbg_terms);
-    const int cop = d->Co > 16 ? 24 : 16;
+    const int cop = (d->Co > 16 && d->Co <= 24) ? 24 : 16;
+    const int nsl = (d->Co <= 24) ? 1 : (d->Co + 15) / 16;
     const int npass = (d->Ci + 15) / 16;
     const size_t img_u4 = (size_t)27 * KCH2 * NS2 * cop;
-    for (int p = 0; p < npass; ++p) {
-        SpConvDesc s = *d;
-        s.Ci = (d->Ci - 16 * p < 16) ? d->Ci - 16 * p : 16;
-        const float* sp = src + 16 * p;
-        const float* scp = scale ? scale + 16 * p : nullptr;
-        const float* shp = shift ? shift + 16 * p : nullptr;
-        const int e = (cop == 24)
-            ? sp_tc2_corr_launch_t<24>(&s, nPerG, sp, wimg + p * img_u4, bias, scp, shp, d->Ci, p > 0, p == npass - 1, dst, st, prof, dbg_terms)
-            : sp_tc2_corr_launch_t<16>(&s, nPerG, sp, wimg + p * img_u4, bias, scp, shp, d->Ci, p > 0, p == npass - 1, dst, st, prof, dbg_terms);
-        if (e) return e;
-    }
+    for (int sl = 0; sl < nsl; ++sl)
+        for (int p = 0; p < npass; ++p) {
+            SpConvDesc s = *d;
+            s.Ci = (d->Ci - 16 * p < 16) ? d->Ci - 16 * p : 16;
+            if (nsl > 1) s.Co = (d->Co - 16 * sl < 16) ? d->Co - 16 * sl : 16;
+            const float* sp = src + 16 * p;
+            const float* scp = scale ? scale + 16 * p : nullptr;
+            const float* shp = shift ? shift + 16 * p : nullptr;
+            const float* bp = bias ? bias + 16 * sl : nullptr;
+            float* dp = dst + 16 * sl;
+            const uint4* ip = wimg + (size_t)(sl * npass + p) * img_u4;
+            const int e = (cop == 24)
+                ? sp_tc2_corr_launch_t<24>(&s, nPerG, sp, ip, bp, scp, shp, d->Ci, p > 0, p == npass - 1, dp, st, prof, dbg_terms)
+                : sp_tc2_corr_launch_t<16>(&s, nPerG, sp, ip, bp, scp, shp, d->Ci, p > 0, p == npass - 1, dp, st, prof, dbg_terms);
+            if (e) return e;
+        }
     return 0;
 }

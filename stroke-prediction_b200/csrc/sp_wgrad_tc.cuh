@@ -69,7 +69,7 @@ __host__ __device__ constexpr int a_off(int term, int buf, int half) {
 
 template <int MROWS>
 __global__ void __launch_bounds__(NTHREADS_W, 1)
-wgrad3_tc_kernel(SpConvDesc d, int nPerG, int tiles_w, int tiles_h, int total_cols, int drain_every, int isstride,
+wgrad3_tc_kernel(SpConvDesc d, int nPerG, int tiles_w, int tiles_h, int total_cols, int drain_every, int isstride, int osstride,
                  const float* __restrict__ X, const float* __restrict__ i_scale, const float* __restrict__ i_shift,
                  const float* __restrict__ dZ, const float* __restrict__ o_scale, const float* __restrict__ o_shift,
                  float* __restrict__ ws, long long* __restrict__ prof) {
@@ -212,7 +212,7 @@ wgrad3_tc_kernel(SpConvDesc d, int nPerG, int tiles_w, int tiles_h, int total_co
 #pragma unroll
                                 for (int j = 0; j < 8; ++j)
                                     if (half * 8 + j < d.Co)
-                                        v[j] = fmaf(v[j], o_scale[(int64_t)g * d.Co + half * 8 + j], o_shift[(int64_t)g * d.Co + half * 8 + j]);
+                                        v[j] = fmaf(v[j], o_scale[(int64_t)g * osstride + half * 8 + j], o_shift[(int64_t)g * osstride + half * 8 + j]);
                             }
                         }
                         uint4 o[3];
@@ -379,10 +379,10 @@ static inline int sp_tc_wgrad_launch(const SpConvDesc* d, int nPerG, const float
         attr = true;
     }
     if (mrows == 64)
-        wgrad3_tc_kernel<64><<<p.grid, NTHREADS_W, SMEM_W, st>>>(*d, nPerG, p.tiles_w, p.tiles_h, (int)p.total, drain_every, d->Ci, iside,
+        wgrad3_tc_kernel<64><<<p.grid, NTHREADS_W, SMEM_W, st>>>(*d, nPerG, p.tiles_w, p.tiles_h, (int)p.total, drain_every, d->Ci, d->Co, iside,
                                                                  i_scale, i_shift, oside, o_scale, o_shift, ws, prof);
     else
-        wgrad3_tc_kernel<128><<<p.grid, NTHREADS_W, SMEM_W, st>>>(*d, nPerG, p.tiles_w, p.tiles_h, (int)p.total, drain_every, d->Ci, iside,
+        wgrad3_tc_kernel<128><<<p.grid, NTHREADS_W, SMEM_W, st>>>(*d, nPerG, p.tiles_w, p.tiles_h, (int)p.total, drain_every, d->Ci, d->Co, iside,
                                                                   i_scale, i_shift, oside, o_scale, o_shift, ws, prof);
     SP_LAUNCH_OK("wgrad3_tc_kernel");
     const int64_t wn = (int64_t)d->Co * d->Ci * 27;
@@ -392,24 +392,29 @@ static inline int sp_tc_wgrad_launch(const SpConvDesc* d, int nPerG, const float
     return 0;
 }
 
-// ---- 25..48 input channels, 9..16 output channels (Unet3D.py:19 block5 on the 48-channel concat): the I-side runs as slices of
-// 16 channels through the kernel above (X + 16 c with the layer's row stride, its slice of the BN coefficients); every slice
-// has its own per-CTA partials, which a scatter-reduce folds into dW[co][16 c + ci][tap].
-__global__ void wgrad_reduce_slice_kernel(const float* __restrict__ ws, int chunks, int Co, int cs, int Ci, int ci0,
+// ---- wider layers (Unet3D.py:19,22: 48 -> 16, 32 -> 32, 96 -> 32, ...): both sides run as slices of 16 channels through the
+// kernel above (X + 16 c / dZ + 16 c' with the layer's row strides and its slices of the affine coefficients); every slice
+// pair has its own per-CTA partials, which a scatter-reduce folds into dW[16 c' + co][16 c + ci][tap].
+__global__ void wgrad_reduce_slice_kernel(const float* __restrict__ ws, int chunks, int cos, int cs, int Ci, int co0, int ci0,
                                           float* __restrict__ dw, float beta) {
-    const int wn = Co * cs * 27;
+    const int wn = cos * cs * 27;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= wn) return;
     float s = 0.f;
     for (int c = 0; c < chunks; ++c) s += ws[(int64_t)c * wn + i];
     const int tap = i % 27, ci = (i / 27) % cs, co = i / (27 * cs);
-    float* o = dw + ((int64_t)co * Ci + ci0 + ci) * 27 + tap;
+    float* o = dw + ((int64_t)(co0 + co) * Ci + ci0 + ci) * 27 + tap;
     *o = (beta != 0.f ? beta * *o : 0.f) + s;
 }
 
 static inline bool sp_tc_wgrad_sliced_supported(const SpConvDesc* d) {
     if (d->k != 3 || d->s != 1 || sp_tc_terms() == 0 || sp_tc_wgrad_disabled()) return false;
-    if (d->Ci <= 24 || d->Ci > 48 || d->Co <= 8 || d->Co > 16 || d->ldi % 4 != 0) return false;
+    if (d->Ci <= 24 && d->Co <= 24) return false;                    // the single-launch kernels take these
+    // Measured on the U-Net (B200): slicing pays for 48 -> 16 on 30x130x130 (2.48 -> 2.02 ms) but not for the spatially small
+    // wide layers, where every slice pair re-stages both tiles and pays the pipeline fill of 148 persistent CTAs
+    // (96 -> 32 on 18x68x68: 1.86 -> 2.46 ms, 32 -> 32 on 28x78x78: 0.97 -> 1.17 ms): at most three slice pairs are taken.
+    if (((d->Ci + 15) / 16) * ((d->Co + 15) / 16) > 3) return false;
+    if (d->Ci <= 8 || d->Ci > 96 || d->Co <= 8 || d->Co > 64 || d->ldi % 4 != 0 || d->ldo % 4 != 0) return false;
     if (d->pd > 2 || d->ph > 2 || d->pw > 2) return false;
     const sp_wtc::WtcPlan p = sp_wtc::plan(d);
     return p.total >= 16 && p.total < (1LL << 31) && d->Wo >= 24 && d->Do >= 8;
@@ -417,7 +422,7 @@ static inline bool sp_tc_wgrad_sliced_supported(const SpConvDesc* d) {
 
 static inline size_t sp_tc_wgrad_sliced_workspace_bytes(const SpConvDesc* d) {
     if (!sp_tc_wgrad_sliced_supported(d)) return 0;
-    return (size_t)((d->Ci + 15) / 16) * sp_wtc::plan(d).grid * d->Co * 16 * 27 * sizeof(float);
+    return (size_t)sp_wtc::plan(d).grid * 16 * 16 * 27 * sizeof(float);       // one slice pair at a time (stream-ordered reuse)
 }
 
 static inline int sp_tc_wgrad_sliced_launch(const SpConvDesc* d, int nPerG, const float* iside, const float* i_scale,
@@ -430,18 +435,21 @@ static inline int sp_tc_wgrad_sliced_launch(const SpConvDesc* d, int nPerG, cons
         SP_CUDA(cudaFuncSetAttribute(wgrad3_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_W));
         attr = true;
     }
-    const int nsl = (d->Ci + 15) / 16;
-    for (int c = 0; c < nsl; ++c) {
-        SpConvDesc s = *d;
-        s.Ci = (d->Ci - 16 * c < 16) ? d->Ci - 16 * c : 16;
-        float* wsc = ws + (size_t)c * p.grid * d->Co * 16 * 27;
-        wgrad3_tc_kernel<64><<<p.grid, NTHREADS_W, SMEM_W, st>>>(s, nPerG, p.tiles_w, p.tiles_h, (int)p.total, drain_every, d->Ci,
-                                                                 iside + 16 * c, i_scale ? i_scale + 16 * c : nullptr,
-                                                                 i_shift ? i_shift + 16 * c : nullptr, oside, o_scale, o_shift, wsc, nullptr);
-        SP_LAUNCH_OK("wgrad3_tc_kernel");
-        const int wn = d->Co * s.Ci * 27;
-        wgrad_reduce_slice_kernel<<<(wn + 255) / 256, 256, 0, st>>>(wsc, p.grid, d->Co, s.Ci, d->Ci, 16 * c, dw, beta);
-        SP_LAUNCH_OK("wgrad_reduce_slice_kernel");
-    }
+    const int nsi = (d->Ci + 15) / 16, nso = (d->Co + 15) / 16;
+    for (int co = 0; co < nso; ++co)
+        for (int c = 0; c < nsi; ++c) {
+            SpConvDesc s = *d;
+            s.Ci = (d->Ci - 16 * c < 16) ? d->Ci - 16 * c : 16;
+            s.Co = (d->Co - 16 * co < 16) ? d->Co - 16 * co : 16;
+            wgrad3_tc_kernel<64><<<p.grid, NTHREADS_W, SMEM_W, st>>>(s, nPerG, p.tiles_w, p.tiles_h, (int)p.total, drain_every, d->Ci, d->Co,
+                                                                     iside + 16 * c, i_scale ? i_scale + 16 * c : nullptr,
+                                                                     i_shift ? i_shift + 16 * c : nullptr, oside + 16 * co,
+                                                                     o_scale ? o_scale + 16 * co : nullptr,
+                                                                     o_shift ? o_shift + 16 * co : nullptr, ws, nullptr);
+            SP_LAUNCH_OK("wgrad3_tc_kernel");
+            const int wn = s.Co * s.Ci * 27;
+            wgrad_reduce_slice_kernel<<<(wn + 255) / 256, 256, 0, st>>>(ws, p.grid, s.Co, s.Ci, d->Ci, 16 * co, 16 * c, dw, beta);
+            SP_LAUNCH_OK("wgrad_reduce_slice_kernel");
+        }
     return 0;
 }

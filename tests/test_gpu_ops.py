@@ -186,7 +186,10 @@ TC_CASES = [
     ("C", 24, 16, 3, 1, (1, 2, 2), "elu", (9, 30, 30)),        # Cae3D.py:200  two passes in, 16 out (dgrad: 16 in, 24 out)
     ("C", 20, 18, 3, 1, (1, 1, 1), "leaky", (10, 33, 31)),     # ragged second pass (4 channels), ragged 24-wide output
     ("T", 24, 24, 3, 1, 0, "elu", (8, 30, 36)),                # convT k3 s1 with 24 channels
-    ("C", 48, 16, 3, 1, 0, "leaky", (10, 30, 34)),             # Unet3D.py:19 block5 on the concat: three input passes (dgrad: FFMA tier)
+    ("C", 48, 16, 3, 1, 0, "leaky", (10, 30, 34)),             # Unet3D.py:19 block5 on the concat: three input passes; dgrad: three output slices
+    ("C", 32, 32, 3, 1, 0, "leaky", (10, 30, 34)),             # Unet3D.py:22 block2/4: two passes x two 16-wide output slices
+    ("C", 96, 32, 3, 1, 0, "leaky", (10, 30, 26)),             # Unet3D.py:19 block4 on the concat: six passes; dgrad: 2 passes x 6 slices
+    ("C", 40, 28, 3, 1, (1, 1, 1), "elu", (9, 28, 22)),        # ragged last pass (8 channels) and ragged last slice (12 channels)
 ]
 
 
@@ -215,6 +218,8 @@ WGRAD_TC_CASES = [
     ("C", 12, 20, 3, 1, 1, "leaky", (10, 17, 33)),             # ragged groups on both sides
     ("C", 48, 16, 3, 1, 0, "leaky", (10, 18, 40)),             # Unet3D.py:19 block5: three 16-channel I-side slices, scatter-reduce
     ("C", 40, 12, 3, 1, (1, 1, 1), "elu", (8, 16, 30)),        # ragged last slice (8 channels)
+    ("C", 16, 40, 3, 1, (1, 1, 1), "elu", (8, 16, 30)),        # three O-side slices, the last one ragged
+    ("C", 32, 32, 3, 1, 0, "leaky", (10, 18, 40)),             # 2 x 2 slice pairs: more than three -> stays on the FFMA tier
 ]
 
 
