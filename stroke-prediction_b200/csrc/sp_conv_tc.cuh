@@ -377,7 +377,7 @@ static inline bool sp_tc_corr_supported(const SpConvDesc* d, SpTcCfg* cfg) {
     const int comax = (sp_tc_terms() == 4) ? 96 : 16, cimax = (sp_tc_terms() == 4) ? 96 : 16;
     if (d->Ci > cimax || d->Co > comax || d->Ci < 8 || d->Co < 8) return false;   // narrower layers: FFMA tier (2- / 8-wide passes)
     const int64_t ov = (int64_t)d->Do * d->Ho * d->Wo;
-    if (ov < 8192 || d->Wo < 8 || d->Ho < 16) return false;
+    if (ov < 4096 || d->Wo < 8 || d->Ho < 16) return false;      // (the CAE's 32-channel level: 7x27x27 per sample)
     if (d->Co > 24 && d->ldo % 4 != 0) return false;
     if (cfg) {
         cfg->cip = 16; cfg->td = 4;
