@@ -505,10 +505,13 @@ int sp_pack_weights(const SpConvDesc* d, int which, const float* w_torch, float*
         SP_LAUNCH_OK("pack_wt_gemm_kernel");
         return 0;
     }
-    pack_weights_kernel<<<grid_for(total), 256, 0, sp_stream(stream)>>>(w_torch, w_packed, d->Co, d->Ci, k3, which, dP);
-    SP_LAUNCH_OK("pack_weights_kernel");
     SpTcCfg cfg;
-    if (tc_serves(d, which, &cfg))
+    const bool tc = tc_serves(d, which, &cfg);
+    if (!tc) {      // a layer the tensor-core tier serves never reads the FFMA layout (same predicate at pack and at run time)
+        pack_weights_kernel<<<grid_for(total), 256, 0, sp_stream(stream)>>>(w_torch, w_packed, d->Co, d->Ci, k3, which, dP);
+        SP_LAUNCH_OK("pack_weights_kernel");
+    }
+    if (tc)
         return sp_tc_pack_launch(d, which, sp_tc_image_terms(), cfg.cip, cfg.cop, w_torch, w_packed + total, sp_stream(stream), cfg.passes, cfg.nslices);
     return 0;
 }
