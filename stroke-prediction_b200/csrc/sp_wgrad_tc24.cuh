@@ -35,7 +35,7 @@ constexpr int ACC_LD = MAXBLK * BCOLS + 4;         // 364 = 4 * 91
 constexpr int ACC_B = 24 * ACC_LD * 4;
 constexpr int SCR_LD = BCOLS + 4;                  // 76 = 4 * 19
 constexpr int SCR_B = 24 * SCR_LD * 4;
-constexpr int W_EPI = 4, W_MMA = MAXBLK, W_STG = 8;
+constexpr int W_EPI = 4, W_MMA = MAXBLK, W_STG = 10;
 constexpr int NSTG = W_STG * 32;
 constexpr int NTHREADS_W = (W_EPI + W_MMA + W_STG) * 32;      // 544
 constexpr int XP_ITEMS = XH * XW * NG, NZ_ITEMS = TWW * THW * NG;
