@@ -70,7 +70,10 @@ __device__ __forceinline__ void tmem_ld72(uint32_t taddr, float* v) {
 
 __device__ __forceinline__ void drain_bar() { asm volatile("bar.sync 1, 96;" ::: "memory"); }
 
-// blocks [b0, b0 + nblk) of the nine (kd, kw) accumulator blocks (b = kd * 3 + kw)
+// blocks [b0, b0 + nblk) of the nine (kd, kw) accumulator blocks (b = kd * 3 + kw).
+// MROWS = 64: at most 16 output channels (24 -> 16, Cae3D.py:200): two O-side groups per term, M groups 2 t + g, rows 16 t + co
+// = TMEM lanes 32 t + co as well, and half the A-operand fetch of the M = 128 form.
+template <int MROWS>
 __global__ void __launch_bounds__(NTHREADS_W, 1)
 wgrad3_tc24_kernel(SpConvDesc d, int nPerG, int tiles_w, int tiles_h, int total_cols, int drain_every, int b0, int nblk,
                    const float* __restrict__ X, const float* __restrict__ i_scale, const float* __restrict__ i_shift,
@@ -178,6 +181,7 @@ wgrad3_tc24_kernel(SpConvDesc d, int nPerG, int tiles_w, int tiles_h, int total_
                         } else if (item < n_items) {
                             const int j = item - nx_items;
                             const int grp = j % NG, v = j / NG;                // voxel of the output tile, row-major
+                            if (MROWS == 64 && grp == 2) continue;             // no third O-side group in the M = 64 layout
                             dsto[u] = buf * A_BUF_B + grp * PS + v * 16;
                             meta[u] = grp | 8;
                             const int gh = oh0 + v / TWW, gw = ow0 + v % TWW;
@@ -228,7 +232,7 @@ wgrad3_tc24_kernel(SpConvDesc d, int nPerG, int tiles_w, int tiles_h, int total_
                         uint4 o[3];
                         split8_trunc3(v, o);
                         unsigned char* dstp = (isz ? a_reg : x_reg) + dsto[u];
-                        const int tstride = isz ? 4 * PS : X_TERM_B;
+                        const int tstride = isz ? (MROWS == 128 ? 4 : 2) * PS : X_TERM_B;
 #pragma unroll
                         for (int s2 = 0; s2 < 3; ++s2) *reinterpret_cast<uint4*>(dstp + s2 * tstride) = o[s2];
                     }
@@ -247,7 +251,7 @@ wgrad3_tc24_kernel(SpConvDesc d, int nPerG, int tiles_w, int tiles_h, int total_
             const int b = b0 + bi, kd = b / 3, kw = b % 3;
             const uint32_t a_base = smem_u32(a_reg), x_base = smem_u32(x_reg);
             const uint32_t dcol = tmem_base + (uint32_t)(bi * BCOLS);
-            constexpr uint32_t IDESC = sp_wtc::idesc_mn(128, BCOLS);
+            constexpr uint32_t IDESC = sp_wtc::idesc_mn(MROWS, BCOLS);
             bool fresh = true;
             int drains = 0, pc = 0;
             for (int it = 0; it < nsteps; ++it) {
@@ -375,13 +379,20 @@ static inline int sp_tc24_wgrad_launch(const SpConvDesc* d, int nPerG, const flo
     const sp_wtc::WtcPlan p = sp_wtc::plan(d);
     static bool attr = false;
     if (!attr) {
-        SP_CUDA(cudaFuncSetAttribute(wgrad3_tc24_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_W));
+        SP_CUDA(cudaFuncSetAttribute(wgrad3_tc24_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_W));
+        SP_CUDA(cudaFuncSetAttribute(wgrad3_tc24_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_W));
         attr = true;
     }
     for (int pass = 0; pass < 2; ++pass) {
         const int b0 = pass == 0 ? 0 : MAXBLK, nblk = pass == 0 ? MAXBLK : 9 - MAXBLK;
-        wgrad3_tc24_kernel<<<p.grid, NTHREADS_W, SMEM_W, st>>>(*d, nPerG, p.tiles_w, p.tiles_h, (int)p.total, drain_every, b0, nblk, iside,
-                                                               i_scale, i_shift, oside, o_scale, o_shift, ws, pass == 0 ? prof : nullptr);
+        if (d->Co <= 16)
+            wgrad3_tc24_kernel<64><<<p.grid, NTHREADS_W, SMEM_W, st>>>(*d, nPerG, p.tiles_w, p.tiles_h, (int)p.total, drain_every, b0, nblk,
+                                                                       iside, i_scale, i_shift, oside, o_scale, o_shift, ws,
+                                                                       pass == 0 ? prof : nullptr);
+        else
+            wgrad3_tc24_kernel<128><<<p.grid, NTHREADS_W, SMEM_W, st>>>(*d, nPerG, p.tiles_w, p.tiles_h, (int)p.total, drain_every, b0, nblk,
+                                                                        iside, i_scale, i_shift, oside, o_scale, o_shift, ws,
+                                                                        pass == 0 ? prof : nullptr);
         SP_LAUNCH_OK("wgrad3_tc24_kernel");
     }
     const int64_t wn = (int64_t)d->Co * d->Ci * 27;
