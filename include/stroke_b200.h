@@ -65,12 +65,15 @@ int         sp_version(void);
 const char* sp_last_error(void);
 
 /*
- * Tensor-core tier of the 3x3x3 stride-1 correlations with 8..16 channels (Cae3D.py:44,208,211; Unet3D.py:22) and of their
- * dgrads.  Every fp32 operand is staged as three bf16 terms, the products of order <= 2 are accumulated by tcgen05.mma in TMEM:
- *   4 (default)  pipelined kernel, leading products in one accumulator per kd and corrections in separate columns: per-layer
- *                forward rel-L2 1.3e-7 (an IEEE fp32 FFMA chain: 2.6e-7 on the same data)
- *   0            tier off (exact-fp32 FFMA tier everywhere)
- *   2 / 3        first-generation kernels with one accumulator per output (rel-L2 ~5e-6 / ~1.4e-6), for A/B measurements
+ * Tensor-core tiers of the 3x3x3 stride-1 layers (Cae3D.py:44,52,55,63,66,186-211; Unet3D.py:19,22): forward and dgrad with
+ * 8..96 channels on either side (mode 4), weight gradients with 9..24 channels (wider I-sides as 16-channel slices).  Every
+ * fp32 operand is staged as three bf16 terms (exact split), the products of order <= 2 (forward / dgrad) or all nine
+ * products (weight gradient) are accumulated by tcgen05.mma in TMEM:
+ *   4 (default)  pipelined kernels, leading products in one accumulator per kd and corrections in separate columns: per-layer
+ *                forward rel-L2 1.3e-7, weight gradient 5.7e-7 (an IEEE fp32 FFMA chain: 2.6e-7 / 1.7e-6 on the same data)
+ *   0            tiers off (exact-fp32 FFMA tiers everywhere, weight gradients included)
+ *   2 / 3        first-generation forward kernels, 8..16 channels only, one accumulator per output (rel-L2 ~5e-6 / ~1.4e-6),
+ *                for A/B measurements
  * Packed weights depend on the mode: re-pack (sp_packed_weight_floats / sp_pack_weights) after changing it.
  */
 int         sp_get_tc_terms(void);
