@@ -29,19 +29,26 @@ for _p in (ROOT, os.path.join(ROOT, "oracle")):
 import torch  # noqa: E402
 
 CHANNELS = {"cae200": [1, 16, 24, 32, 100, 200, 1], "cae800": [1, 16, 24, 32, 100, 800, 1],
-            "unet": [2, 16, 32, 64, 32, 16, 32, 2]}
+            "unet": [2, 16, 32, 64, 32, 16, 32, 2],
+            "cae800step": [1, 16, 24, 32, 100, 800, 1], "pred": [1, 16, 24, 32, 100, 200, 1],
+            "cae_scaled": [1, 16, 24, 32, 100, 200, 1], "unet_scaled": [2, 16, 32, 64, 32, 16, 32, 2]}
 SIZE = (28, 128, 128)
+SCALED_CAE = (60, 256, 256)       # BASELINE configs[4]; D = 64 does not round-trip
+SCALED_UNET_OUT = (64, 256, 256)  # input 2 x 104 x 296 x 296
 EPOCH = 60            # ramp factor f = 1 (CaeReconstructionLearner.py:53)
 UNIT = "volumes/s"
 FFMA_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12     # 148 SMs x 128 FP32 lanes x 2 flop x max SM clock (no measured figure)
 
 
 def metric_name(workload):
-    return "unet_train_volumes_per_s" if workload == "unet" else "cae_train_volumes_per_s"
+    return {"unet": "unet_train_volumes_per_s", "unet_scaled": "unet_train_volumes_per_s",
+            "cae800step": "cae_step_train_volumes_per_s", "pred": "cae_prediction_train_volumes_per_s"}.get(workload, "cae_train_volumes_per_s")
 
 
 def default_batch(workload):
-    return 4 if workload == "unet" else 8     # BASELINE.json configs[0] / configs[1]
+    # BASELINE.json configs[0] batch 4, configs[1] batch 8, configs[2] reference default batch 4 (util.py:64),
+    # configs[3] global batch 32 over 8 GPUs = 4 per GPU, configs[4] global 64-256 over 8 GPUs = 8..32 per GPU
+    return {"unet": 4, "cae200": 8, "cae800": 8, "cae800step": 4, "pred": 4, "cae_scaled": 8, "unet_scaled": 4}[workload]
 
 
 def peaks():
@@ -164,6 +171,8 @@ def cpu_reference_unet_step_time(batch, steps, warmup):
 
 
 def cpu_step_time(workload, batch, steps, warmup):
+    if workload not in ("unet", "cae200", "cae800"):
+        raise SystemExit("bench.py --impl reference: the CPU arm covers the workloads cae200, cae800 and unet")
     if workload == "unet":
         return cpu_reference_unet_step_time(batch, steps, warmup)
     return cpu_reference_step_time(CHANNELS[workload], batch, steps, warmup)
@@ -176,37 +185,63 @@ def cpu_sample_text(workload, batch, steps, warmup):
 
 
 def run_reference(args):
+    """CPU arm: the reference algorithm (oracle port, bit-identical to the reference modules in forward — see DESIGN.md §4)
+    on all host cores, on the SAME workload, per-GPU batch, step and warm-up counts as the GPU arm, so the driver's ratio
+    compares like with like.  Only a time budget (SP_REF_BUDGET_S, default 900 s) can shorten it, and the line then says so."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sample_b = 2
-    steps, warmup = max(1, min(args.steps, 5)), 1 if args.warmup > 0 else 0
-    sec, threads = cpu_step_time(args.workload, sample_b, steps, warmup)
-    val = sample_b / sec
+    B = args.batch if args.batch > 0 else default_batch(args.workload)
+    budget = float(os.environ.get("SP_REF_BUDGET_S", "900"))
+    steps, warmup = max(1, args.steps), max(0, args.warmup)
+    t0 = time.perf_counter()
+    sec1, threads = cpu_step_time(args.workload, B, 1, 0)                 # one untimed probe step = first warm-up step
+    probe = time.perf_counter() - t0
+    truncated = None
+    if probe * (steps + warmup) > budget:
+        fit = max(1, int(budget / probe) - 1)
+        new_warm = min(warmup, 1)
+        new_steps = max(1, min(steps, fit - new_warm))
+        truncated = "time budget %.0f s: %d+%d steps requested, %d+%d run (%.1f s per step)" % (budget, warmup, steps, new_warm, new_steps, probe)
+        steps, warmup = new_steps, new_warm
+    sec, threads = cpu_step_time(args.workload, B, steps, max(0, warmup - 1))
+    val = B / sec
     line = {
         "impl": "reference", "metric": metric_name(args.workload), "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
         "warmup": warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args, per_gpu_batch=sample_b),
+        "config": workload_config(args.workload, B, args.gpus),
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": cpu_sample_text(args.workload, sample_b, steps, warmup)},
+                         "sample": cpu_sample_text(args.workload, B, steps, warmup)},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
+    if truncated:
+        line["truncated"] = truncated
     emit(line)
 
 
-def workload_config(args, per_gpu_batch):
-    ch = " ".join(map(str, CHANNELS[args.workload]))
-    if args.workload == "unet":
-        wl = ("BASELINE configs[0]: Unet3D segmentation, channels %s, synthetic CBV/TTD 2x68x168x168 (28x128x128 padded by 20) "
-              "-> 2 x 1x28x128x128, UnetSegmentationLearner forward + loss_step + backward + Adam" % ch)
-        vol, act = "2x68x168x168 -> 28x128x128", "~1.1 GB"
-    else:
-        wl = ("BASELINE configs[1]: CAE channels %s, 1x28x128x128 core/penumbra/lesion masks, "
-              "3 encoder + 4 decoder passes + loss_step + backward + Adam" % ch)
-        vol, act = "1x28x128x128", "~0.75 GB"
-    return {"workload": wl, "per_gpu_batch": per_gpu_batch, "global_batch": per_gpu_batch * args.gpus, "volume": vol,
-            "parallelism": "dp%d (batch-sharded, gradient all-reduce, local BN/Dice statistics)" % args.gpus,
+WORKLOAD_TEXT = {
+    "unet": ("BASELINE configs[0]: Unet3D segmentation, channels %s, synthetic CBV/TTD 2x68x168x168 (28x128x128 padded by 20) "
+             "-> 2 x 1x28x128x128, UnetSegmentationLearner forward + loss_step + backward + Adam", "2x68x168x168 -> 28x128x128", "~1.1 GB"),
+    "cae200": ("BASELINE configs[1]: CAE channels %s, 1x28x128x128 core/penumbra/lesion masks, "
+               "3 encoder + 4 decoder passes + loss_step + backward + Adam", "1x28x128x128", "~0.75 GB"),
+    "cae800": ("CAE channels %s (paper width, README.md:57), 1x28x128x128 masks, full reconstruction training step",
+               "1x28x128x128", "~0.75 GB"),
+    "cae800step": ("BASELINE configs[2]: CAE channels %s, frozen, Enc3DStep trainable (train_interpolationstep_after_reconstruction), "
+                   "CaeStepLearner forward + loss_step + backward + Adam", "1x28x128x128", "~0.75 GB"),
+    "pred": ("BASELINE configs[3]: shape prediction, new Enc3D (trainable) on 2x28x128x128 soft segmentations + frozen CAE, channels %s, "
+             "CaePredictionLearner two-pass inference + loss_step + backward + Adam", "2x28x128x128 + 3x28x128x128", "~1 GB"),
+    "cae_scaled": ("BASELINE configs[4]: CAE channels %s on 1x60x256x256 masks (64 does not round-trip the strided stages), "
+                   "full reconstruction training step", "1x60x256x256", "~6.6 GB"),
+    "unet_scaled": ("BASELINE configs[4]: Unet3D channels %s, 2x104x296x296 -> 64x256x256, training step", "2x104x296x296 -> 64x256x256", "~7.5 GB"),
+}
+
+
+def workload_config(workload, per_gpu_batch, gpus):
+    ch = " ".join(map(str, CHANNELS[workload]))
+    text, vol, act = WORKLOAD_TEXT[workload]
+    return {"workload": text % ch, "per_gpu_batch": per_gpu_batch, "global_batch": per_gpu_batch * gpus, "volume": vol,
+            "parallelism": "dp%d (batch-sharded, gradient all-reduce, local BN/Dice statistics)" % gpus,
             "l2": "per-step working set (saved activations %s per volume) exceeds the 126 MB L2; no explicit flush" % act}
 
 
@@ -273,96 +308,164 @@ def measured_traffic(name, key):
         return None
 
 
-def run_b200(args):
-    import torch.distributed as dist
-    from stroke_prediction_b200 import ops
-    from stroke_prediction_b200.common import data
-    from stroke_prediction_b200.common.dto import CaeDto as CaeDtoUtil
-    from stroke_prediction_b200.common.metrics import BatchDiceLoss
-    from stroke_prediction_b200.common.model.Cae3D import Cae3D, Dec3D, Enc3D
-    from stroke_prediction_b200.learner.CaeReconstructionLearner import CaeReconstructionLearner
-    from stroke_prediction_b200.optim import FusedAdam
-    from stroke_prediction_b200.parallel import broadcast_parameters
+class Workload:
+    """One benchmarked training step: model + learner + host batch + the two step functions (resident / end to end)."""
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device — the hot path has no CPU fallback (use --impl reference for the CPU arm)")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    if world != args.gpus and rank == 0:
-        print("warning: --gpus %d but WORLD_SIZE %d" % (args.gpus, world), file=sys.stderr)
+    def __init__(self, name, B, dev, rank, world):
+        from stroke_prediction_b200 import ops
+        from stroke_prediction_b200.common import data
+        from stroke_prediction_b200.common.dto import CaeDto as CaeDtoUtil
+        from stroke_prediction_b200.common.metrics import BatchDiceLoss
+        from stroke_prediction_b200.common.model.Cae3D import Cae3D, Dec3D, Enc3D, Enc3DStep
+        from stroke_prediction_b200.optim import FusedAdam
+        from stroke_prediction_b200.parallel import broadcast_parameters
+        self.name, self.B, self.dev = name, B, dev
+        channels = CHANNELS[name]
+        torch.manual_seed(4)
+        crit = BatchDiceLoss([1.0])
+        if name in ("unet", "unet_scaled"):
+            from stroke_prediction_b200.common.dto import UnetDto as UnetDtoUtil
+            from stroke_prediction_b200.common.model.Unet3D import Unet3D
+            from stroke_prediction_b200.learner.UnetSegmentationLearner import UnetSegmentationLearner
+            out_size = SIZE if name == "unet" else SCALED_UNET_OUT
+            model = Unet3D(channels).to(dev).train()
+            broadcast_parameters(model)
+            opt = FusedAdam([p for p in model.parameters() if p.requires_grad], lr=1e-3, weight_decay=1e-5, betas=(0.99, 0.999))
+            learner = UnetSegmentationLearner(None, None, model, opt, None, 1, crit, None, "/tmp/bench")
+            host = data.synthetic_unet_batch(B, out_size=out_size, seed=4 + rank)
+            self.h2d = host[data.KEY_IMAGES].numel() * 4 + host[data.KEY_LABELS].numel() * 4
+            self.d2h = 4 + 32 * 2
+            x_dev = ops.as_vol(host[data.KEY_IMAGES].to(dev))
+            lab = ops.as_vol(host[data.KEY_LABELS].to(dev))
+            core_gt, penu_gt = ops.extract_channel(lab, 0), ops.extract_channel(lab, 1)
+            self.make_dto = lambda: UnetDtoUtil.init_dto(x_dev, core_gt, penu_gt)
+            self.forward = lambda dto: model(dto)
+            self.trainable = model
+        else:
+            size = SCALED_CAE if name == "cae_scaled" else SIZE
+            enc_cls = Enc3DStep if name == "cae800step" else Enc3D
+            model = Cae3D(enc_cls(size[1], size[0], channels, 5, 1.0), Dec3D(size[1], size[0], channels, 5, 1.0)).to(dev).train()
+            self.trainable = model
+            host = data.synthetic_cae_batch(B, size=size, seed=4 + rank)
+            self.h2d = host[data.KEY_LABELS].numel() * 4 + host[data.KEY_GLOBAL].numel() * 4 + 3 * B * 4
+            self.d2h = 4 + 32 * 3
+            if name == "cae800step":
+                from stroke_prediction_b200.learner.CaeStepLearner import CaeStepLearner
+                model.freeze(True)                         # train_interpolationstep_after_reconstruction.py:27-30
+                for p in list(model.enc.reduce.parameters()) + list(model.enc.step.parameters()):
+                    p.requires_grad = True
+                broadcast_parameters(model)
+                opt = FusedAdam([p for p in model.parameters() if p.requires_grad], lr=1e-3, weight_decay=1e-5)
+                learner = CaeStepLearner(None, None, model, opt, None, 1, None, "/tmp/bench", crit)
+            elif name == "pred":
+                from stroke_prediction_b200.learner.CaePredictionLearner import CaePredictionLearner
+                new_enc = Enc3D(size[1], size[0], channels, 5, 1.0).to(dev).train()
+                broadcast_parameters(model)
+                broadcast_parameters(new_enc)
+                opt = FusedAdam([p for p in new_enc.parameters() if p.requires_grad], lr=1e-3, weight_decay=1e-5)
+                learner = CaePredictionLearner(None, None, model, new_enc, opt, None, 1, None, "/tmp/bench", crit)
+                g = torch.Generator().manual_seed(14 + rank)
+                soft = torch.rand(B, 2, *size, generator=g)        # U-Net soft segmentations in [0, 1] (train_shape_prediction.py:53)
+                host[data.KEY_IMAGES] = (0.5 * soft + 0.5 * host[data.KEY_LABELS][:, 0:2]).contiguous()
+                self.h2d += host[data.KEY_IMAGES].numel() * 4
+                self.trainable = new_enc
+            else:
+                broadcast_parameters(model)
+                opt = FusedAdam([p for p in model.parameters() if p.requires_grad], lr=1e-3, weight_decay=1e-5, betas=(0.9, 0.999))
+                learner = CaeReconstructionLearner_(None, None, model, opt, None, 1, None, "/tmp/bench", crit)
+            if name == "pred":
+                # resident form: the device copy of the batch dict; inference_step's H2D copies become no-ops
+                dev_batch = {k: (v.to(dev) if torch.is_tensor(v) and k != data.KEY_GLOBAL else v) for k, v in host.items()}
+                self.make_dto = None
+                self.forward = lambda _dto: learner.inference_step(dev_batch)
+            else:
+                with torch.no_grad():
+                    step0 = None
+                    dto0 = learner.init_clinical_variables(host, step0)
+                    dto0 = learner.init_gtruth_segm_variables(host, dto0)
+                res = dto0.given_variables
+                self.make_dto = lambda: CaeDtoUtil.init_dto(res.globals, res.time_to_treatment, res.scalar_types.core,
+                                                            res.scalar_types.penu, None, None, res.gtruth.core, res.gtruth.penu,
+                                                            res.gtruth.lesion)
+                self.forward = lambda dto: model(dto)
+        if world > 1:
+            learner.enable_data_parallel()
+        self.model, self.opt, self.learner = model, opt, learner
+        self.host = {k: (v.pin_memory() if torch.is_tensor(v) else v) for k, v in host.items()}
 
-    channels = CHANNELS[args.workload]
-    B = args.batch if args.batch > 0 else default_batch(args.workload)
-    torch.manual_seed(4)
-    if args.workload == "unet":
-        from stroke_prediction_b200.common.dto import UnetDto as UnetDtoUtil
-        from stroke_prediction_b200.common.model.Unet3D import Unet3D
-        from stroke_prediction_b200.learner.UnetSegmentationLearner import UnetSegmentationLearner
-        model = Unet3D(channels).to(dev).train()
-        broadcast_parameters(model)
-        opt = FusedAdam([p for p in model.parameters() if p.requires_grad], lr=1e-3, weight_decay=1e-5, betas=(0.99, 0.999))
-        learner = UnetSegmentationLearner(None, None, model, opt, None, 1, BatchDiceLoss([1.0]), None, "/tmp/bench")
-        host = data.synthetic_unet_batch(B, out_size=SIZE, seed=4 + rank)
-        h2d = host[data.KEY_IMAGES].numel() * 4 + host[data.KEY_LABELS].numel() * 4
-    else:
-        model = Cae3D(Enc3D(SIZE[1], SIZE[0], channels, 5, 1.0), Dec3D(SIZE[1], SIZE[0], channels, 5, 1.0)).to(dev).train()
-        broadcast_parameters(model)
-        opt = FusedAdam([p for p in model.parameters() if p.requires_grad], lr=1e-3, weight_decay=1e-5, betas=(0.9, 0.999))
-        learner = CaeReconstructionLearner(None, None, model, opt, None, 1, None, "/tmp/bench", BatchDiceLoss([1.0]))
-        host = data.synthetic_cae_batch(B, size=SIZE, seed=4 + rank)
-        h2d = host[data.KEY_LABELS].numel() * 4 + host[data.KEY_GLOBAL].numel() * 4 + 3 * B * 4
-    if world > 1:
-        learner.enable_data_parallel()
-    host = {k: (v.pin_memory() if torch.is_tensor(v) else v) for k, v in host.items()}
-    # the loss (4 bytes) + the evaluation counts of batch_metrics_step (4 doubles per compared pair) come back every step
-    d2h = 4 + 32 * (2 if args.workload == "unet" else 3)
-
-    # device-resident inputs for `value`
-    if args.workload == "unet":
-        x_dev = ops.as_vol(host[data.KEY_IMAGES].to(dev))
-        lab = ops.as_vol(host[data.KEY_LABELS].to(dev))
-        core_gt, penu_gt = ops.extract_channel(lab, 0), ops.extract_channel(lab, 1)
-
-        def make_dto():
-            return UnetDtoUtil.init_dto(x_dev, core_gt, penu_gt)
-    else:
-        with torch.no_grad():
-            dto0 = learner.init_clinical_variables(host, None)
-            dto0 = learner.init_gtruth_segm_variables(host, dto0)
-        res = dto0.given_variables
-
-        def make_dto():
-            return CaeDtoUtil.init_dto(res.globals, res.time_to_treatment, res.scalar_types.core, res.scalar_types.penu,
-                                       None, None, res.gtruth.core, res.gtruth.penu, res.gtruth.lesion)
-
-    def step_resident():
-        dto = model(make_dto())
-        loss = learner.loss_step(dto, EPOCH)
-        opt.zero_grad()
+    def step_resident(self):
+        dto = self.forward(self.make_dto() if self.make_dto is not None else None)
+        loss = self.learner.loss_step(dto, EPOCH)
+        self.opt.zero_grad()
         loss.backward()
-        if learner._grad_sync is not None:
-            learner._grad_sync()
-        opt.step()
+        if self.learner._grad_sync is not None:
+            self.learner._grad_sync()
+        self.opt.step()
         return loss
 
-    def step_e2e():
-        return learner.train_batch(host, EPOCH).loss
+    def step_e2e(self):
+        return self.learner.train_batch(self.host, EPOCH).loss
+
+    def close(self):
+        self.opt.detach_grad_sink()
+
+
+def CaeReconstructionLearner_(*a, **k):
+    from stroke_prediction_b200.learner.CaeReconstructionLearner import CaeReconstructionLearner
+    return CaeReconstructionLearner(*a, **k)
+
+
+def dp_check(w, world, dev):
+    """N > 1 correctness evidence on the CUDA path (one extra step, not timed): (1) the all-reduced flat gradient equals the
+    sum of the per-rank local gradients gathered separately; (2) after the optimizer step every rank holds bit-identical
+    parameters (64-bit checksum + max |difference| against rank 0)."""
+    import torch.distributed as dist
+    sink = w.opt._sink
+    dto = w.forward(w.make_dto() if w.make_dto is not None else None)
+    loss = w.learner.loss_step(dto, EPOCH)
+    w.opt.zero_grad()
+    loss.backward()
+    local = sink.flat.clone()
+    gathered = [torch.empty_like(local) for _ in range(world)]
+    dist.all_gather(gathered, local)
+    want = torch.stack(gathered).double().sum(0)
+    w.learner._grad_sync()
+    got = sink.flat.double()
+    err = float((got - want).abs().max())
+    ref = float(want.abs().max())
+    views_ok = all(p.grad is not None and p.grad.data_ptr() >= sink.flat.data_ptr() and
+                   p.grad.data_ptr() < sink.flat.data_ptr() + 4 * sink.flat.numel() for p in sink.params)
+    w.opt.step()
+    flat_p = torch.cat([p.detach().reshape(-1) for p in w.trainable.parameters()])
+    root = flat_p.clone()
+    dist.broadcast(root, 0)
+    pdiff = torch.tensor([float((flat_p - root).abs().max())], device=dev)
+    dist.all_reduce(pdiff, op=dist.ReduceOp.MAX)
+    chk = flat_p.view(torch.int32).long().sum().reshape(1)
+    chks = [torch.empty_like(chk) for _ in range(world)]
+    dist.all_gather(chks, chk)
+    return {"ranks": world, "allreduce_max_abs_err": err, "grad_max_abs": ref, "allreduce_rel_err": err / ref if ref else None,
+            "grad_views_alias_flat_buffer": bool(views_ok), "param_max_abs_diff_vs_rank0": float(pdiff.item()),
+            "param_checksums_equal": len({int(c.item()) for c in chks}) == 1, "grad_scale": w.opt.grad_scale}
+
+
+def measure(args, name, B, world, rank, local, dev, steps, headline):
+    """Time one workload; returns the record dict on rank 0 (None elsewhere)."""
+    import torch.distributed as dist
+    from stroke_prediction_b200 import ops
+    torch.cuda.reset_peak_memory_stats(dev)
+    w = Workload(name, B, dev, rank, world)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps):
+    def timed(fn, n):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for _ in range(steps):
+        for _ in range(n):
             fn()
         e1.record()
         barrier()
@@ -373,45 +476,55 @@ def run_b200(args):
             ms = float(t.item())
         return ms
 
-    import contextlib
-    with contextlib.redirect_stdout(open(os.devnull, "w")):   # loss_step-style prints must not pollute the JSON line
-        for _ in range(args.warmup if args.quick else max(args.warmup, 3)):
-            step_resident()
-        sampler = ClockSampler(local)
-        if rank == 0:
-            sampler.start()
-        ops.reset_launch_count()
-        ms_total = timed(step_resident, args.steps)
-        launches = ops.launch_count()
-        clocks = sampler.stop() if rank == 0 else None
-        if args.quick:
-            if rank == 0:
-                sys.stderr.write("quick: %.3f ms/step, %.2f volumes/s\n" % (ms_total / args.steps, world * B / (ms_total / args.steps * 1e-3)))
-            if world > 1:
-                dist.destroy_process_group()
-            return
-        for _ in range(2):
-            step_e2e()
-        ms_e2e = timed(step_e2e, args.steps)
-
-        # per-kernel attribution with CUDA events on the launching stream (one extra step, not part of `value`)
-        # (every rank runs the step — it contains the gradient all-reduce — but only rank 0 records events)
-        prof = None
-        if rank == 0:
-            ops.start_profile()
-        step_resident()
-        if rank == 0:
-            prof = ops.stop_profile()
-        barrier()
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
-
-    ms_step = ms_total / args.steps
+    warm = args.warmup if args.quick else max(args.warmup, 3)
+    for _ in range(warm):
+        w.step_resident()
+    sampler = ClockSampler(local)
+    if rank == 0 and headline:
+        sampler.start()
+    ops.reset_launch_count()
+    ms_total = timed(w.step_resident, steps)
+    launches = ops.launch_count()
+    clocks = sampler.stop() if (rank == 0 and headline) else None
+    ms_step = ms_total / steps
     value = world * B / (ms_step * 1e-3)
-    e2e_val = world * B / (ms_e2e / args.steps * 1e-3)
+    if args.quick:
+        if rank == 0:
+            sys.stderr.write("quick[%s]: %.3f ms/step, %.2f volumes/s\n" % (name, ms_step, value))
+        w.close()
+        return None
+    for _ in range(2):
+        w.step_e2e()
+    ms_e2e = timed(w.step_e2e, steps)
 
+    # per-kernel attribution with CUDA events on the launching stream (one extra step, not part of `value`)
+    # (every rank runs the step — it contains the gradient all-reduce — but only rank 0 records events)
+    prof = None
+    if rank == 0:
+        ops.start_profile()
+    w.step_resident()
+    if rank == 0:
+        prof = ops.stop_profile()
+    barrier()
+    check = dp_check(w, world, dev) if (world > 1 and headline) else None
+    peak_mem = torch.cuda.max_memory_allocated(dev)
+    h2d, d2h, api = w.h2d, w.d2h, "%s.train_batch(host_batch, epoch)" % type(w.learner).__name__
+    w.close()
+    del w
+    torch.cuda.empty_cache()
+    if rank != 0:
+        return None
+
+    e2e_val = world * B / (ms_e2e / steps * 1e-3)
+    rec = {"metric": metric_name(name), "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warm,
+           "ms_per_step": ms_step, "config": workload_config(name, B, world),
+           "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                   "ms_per_step": ms_e2e / steps, "api": api},
+           "gpu_launches": launches, "peak_memory_bytes": int(peak_mem)}
+    return rec, prof, clocks, check
+
+
+def roofline_of(prof, dump=None):
     hbm_peak, peak_src = peaks()
     fam = {}
     for (name, key), ts in prof.items():
@@ -436,42 +549,101 @@ def run_b200(args):
     tc_factor = tensor_core_issue_factor(top_name, top_key)
     if tc_factor and tflops:
         # exact-fp32 emulation on tcgen05: every operand is three bf16 terms, so the tensor pipe executes `tc_factor` bf16
-        # MACs per algorithmic fp32 MAC (9 products x 64/48 padded rows for wgrad, 6 products for forward / dgrad)
+        # MACs per algorithmic fp32 MAC
         tc_peak = tensor_peak()
         roofline.update({"tier": "tcgen05 split-bf16 (3 terms per fp32 operand)", "tensor_issue_factor": tc_factor,
                          "tensor_executed_tflops": tflops * tc_factor, "tensor_peak_tflops": tc_peak,
                          "tensor_frac": tflops * tc_factor / tc_peak,
                          "note": "algorithmic HBM fraction reported for the contract; the kernel is bound by the tensor pipe / "
-                                 "shared-memory operand fetch of the split-bf16 MMAs it issues (M = 64 single-CTA MMAs cap "
-                                 "at half the dense bf16 peak), see DESIGN.md 3.2"})
+                                 "shared-memory operand fetch of the split-bf16 MMAs it issues, see DESIGN.md 3.2"})
     else:
         roofline["note"] = ("fp32 FFMA direct convolution: arithmetic intensity of this layer is above the FFMA ridge, so the "
                             "HBM fraction is reported for the contract while the binding roof is FP32 FFMA (see DESIGN.md)")
-    if args.dump_breakdown:
-        with open(args.dump_breakdown, "w") as f:
+    if dump:
+        with open(dump, "w") as f:
             for k, v in sorted(fam.items(), key=lambda kv: -kv[1][0]):
                 f.write("%9.3f ms  x%-3d %s [%s]\n" % (v[0], v[1], k[0], k[1]))
-    top5 = sorted(fam.items(), key=lambda kv: -kv[1][0])[:12]
-    breakdown = [{"kernel": "%s [%s]" % k, "ms_per_step": round(v[0], 3), "launches": v[1]} for k, v in top5]
+    top = sorted(fam.items(), key=lambda kv: -kv[1][0])[:12]
+    breakdown = [{"kernel": "%s [%s]" % k, "ms_per_step": round(v[0], 3), "launches": v[1]} for k, v in top]
     by_op = {}
     for (name, key), v in fam.items():
         o = by_op.setdefault(name, [0.0, 0])
         o[0] += v[0]
         o[1] += v[1]
     op_breakdown = {k: {"ms_per_step": round(v[0], 3), "launches": v[1]} for k, v in sorted(by_op.items(), key=lambda kv: -kv[1][0])}
+    return roofline, breakdown, op_breakdown
+
+
+def run_b200(args):
+    import contextlib
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the hot path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    if world != args.gpus and rank == 0:
+        print("warning: --gpus %d but WORLD_SIZE %d" % (args.gpus, world), file=sys.stderr)
+
+    B = args.batch if args.batch > 0 else default_batch(args.workload)
+    with contextlib.redirect_stdout(open(os.devnull, "w")):   # loss_step-style prints must not pollute the JSON line
+        out = measure(args, args.workload, B, world, rank, local, dev, args.steps, headline=True)
+        extras = {}
+        if not args.quick and args.extras != "none":
+            # the other BASELINE configs as sub-records of the same line (so BENCH / SCALE carry them): the U-Net half of the
+            # metric (configs[0]), the paper-width step learner (configs[2]), shape prediction (configs[3]), the scaled volumes
+            # (configs[4]) and a small-per-GPU-batch point of the headline workload (launch / collective-latency regime)
+            wanted = [("unet", "unet", None), ("cae800step", "cae800step", None), ("pred", "pred", None),
+                      ("cae200_batch2", "cae200", 2), ("cae_scaled", "cae_scaled", None), ("unet_scaled", "unet_scaled", None)]
+            if args.extras != "all":
+                keep = set(args.extras.split(","))
+                wanted = [x for x in wanted if x[0] in keep]
+            for key, wl, b_over in wanted:
+                if wl == args.workload and b_over is None:
+                    continue
+                try:
+                    r = measure(args, wl, b_over or default_batch(wl), world, rank, local, dev, max(3, min(args.steps, 8)), headline=False)
+                    if r is not None:
+                        rec, prof, _, _ = r
+                        rl, bd, _ = roofline_of(prof)
+                        rec["roofline"] = rl
+                        rec["kernel_breakdown"] = bd[:6]
+                        extras[key] = rec
+                except Exception as exc:    # an extra must never cost the headline line
+                    torch.cuda.empty_cache()
+                    if world > 1:
+                        raise
+                    extras[key] = {"error": "%s: %s" % (type(exc).__name__, str(exc)[:200])}
+    if rank != 0 or out is None:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    rec, prof, clocks, check = out
+    roofline, breakdown, op_breakdown = roofline_of(prof, args.dump_breakdown)
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         sec, threads = cpu_step_time(args.workload, 2, 4, 1)
         cpu = {"value": 2 / sec, "unit": UNIT, "cores": threads, "kind": "port", "sample": cpu_sample_text(args.workload, 2, 4, 1)}
+        if "unet" in extras and "error" not in extras["unet"]:
+            sec, threads = cpu_step_time("unet", 2, 2, 1)
+            extras["unet"]["cpu_baseline"] = {"value": 2 / sec, "unit": UNIT, "cores": threads, "kind": "port",
+                                              "sample": cpu_sample_text("unet", 2, 2, 1)}
 
-    line = {"metric": metric_name(args.workload), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic", "config": workload_config(args, B),
-            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": ms_e2e / args.steps, "api": "%s.train_batch(host_batch, epoch)" % type(learner).__name__},
-            "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "kernel_breakdown": breakdown, "op_breakdown": op_breakdown,
-            "cpu_baseline": cpu}
+    line = {"metric": rec["metric"], "value": rec["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": rec["warmup"],
+            "ms_per_step": rec["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": rec["config"], "e2e": rec["e2e"],
+            "gpu_launches": rec["gpu_launches"], "clocks": clocks, "roofline": roofline, "kernel_breakdown": breakdown,
+            "op_breakdown": op_breakdown, "cpu_baseline": cpu, "peak_memory_bytes": rec["peak_memory_bytes"]}
+    if check is not None:
+        line["dp_check"] = check
+    for k, v in extras.items():
+        line[k] = v
     emit(line)
     if world > 1:
         dist.destroy_process_group()
@@ -505,7 +677,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="cae200", choices=sorted(CHANNELS))
-    ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: 8 for the CAE, 4 for the U-Net)")
+    ap.add_argument("--extras", default="all", help="sub-records: all | none | comma list of unet,cae800step,pred,cae200_batch2,cae_scaled,unet_scaled")
+    ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: see default_batch)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--dump-breakdown", default=None, help="write the full per-kernel CUDA-event attribution to this file")
     ap.add_argument("--quick", action="store_true", help="profiling aid: resident-input steps only (no e2e / attribution / CPU legs)")

@@ -51,6 +51,9 @@ class Unet3D(nn.Module):
 
         self.channel_dim = channel_dim
         self.channels_crop = channels_crop
+        # None: each nn.Upsample decides (installed-torch default False; legacy torch-0.3.1 pickles -> True, see
+        # engine._align); True / False: explicit switch for both upsampling steps
+        self.align_corners = None
 
         self.block1 = Block3x3x3(n_ch_in, ch_b1)
         self.pool12 = nn.MaxPool3d(2, 2)

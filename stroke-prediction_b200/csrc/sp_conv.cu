@@ -464,6 +464,34 @@ bool gemm_wgrad(const SpConvDesc* d) {
     return d->Ci * d->k * d->k * d->k >= 256 && d->Co >= 16 && d->Ci >= 8;
 }
 
+// ONE tier choice per (geometry, direction), shared by sp_packed_weight_floats / sp_pack_weights (which layout to write) and
+// sp_corr / sp_corrT (which kernel reads it), so the two can never disagree — whatever tiers are switched off.
+enum SpTier { TIER_PW, TIER_TC, TIER_K2S2, TIER_THIN, TIER_TILED, TIER_TILEDT, TIER_GEMM, TIER_GENERIC };
+
+SpTier corr_tier(const SpConvDesc* d, SpTcCfg* cfg) {
+    if (sp_pw_fwd_supported(d, d->Ci)) return TIER_PW;
+    if (tc_serves(d, 0, cfg)) return TIER_TC;
+    if (sp_k2s2_supported(d)) return TIER_K2S2;          // (falls to the tiers below at run time if a pointer is misaligned)
+    if (sp_thin_fwd_supported(d)) return TIER_THIN;
+    if (sp_tiled_corr_supported(d)) return TIER_TILED;
+    if (gemm_corr(d)) return TIER_GEMM;
+    return TIER_GENERIC;
+}
+
+SpTier corrT_tier(const SpConvDesc* d, SpTcCfg* cfg) {
+    if (sp_pw_fwd_supported(d, d->Co)) return TIER_PW;
+    if (d->s == 1) {
+        const SpConvDesc f = flipped_desc(d);
+        if (tc_serves(d, 1, cfg)) return TIER_TC;
+        if (sp_thin_bwd_supported(&f)) return TIER_THIN;
+        if (f.pd >= 0 && f.ph >= 0 && f.pw >= 0 && sp_tiled_corr_supported(&f)) return TIER_TILED;
+    }
+    if (sp_k2s2_supported(d)) return TIER_K2S2;
+    if (sp_tiledT_supported(d)) return TIER_TILEDT;
+    if (gemm_corrT(d)) return TIER_GEMM;
+    return TIER_GENERIC;
+}
+
 int tc_corr_launch(const SpConvDesc* d, const SpTcCfg& cfg, int nPerG, const float* src, const float* wimg, const float* bias,
                    const float* scale, const float* shift, float* dst, cudaStream_t st) {
     const uint4* img = reinterpret_cast<const uint4*>(wimg);
@@ -489,7 +517,7 @@ size_t sp_packed_weight_floats(const SpConvDesc* d, int which) {
     if (!d) return 0;
     size_t n = ffma_packed_floats(d, which);
     SpTcCfg cfg;
-    if (tc_serves(d, which, &cfg)) n += (size_t)cfg.passes * cfg.nslices * sp_tc_wimg_bytes(cfg.cip, cfg.cop, sp_tc_image_terms()) / sizeof(float);
+    if ((which == 0 ? corr_tier(d, &cfg) : corrT_tier(d, &cfg)) == TIER_TC) n += (size_t)cfg.passes * cfg.nslices * sp_tc_wimg_bytes(cfg.cip, cfg.cop, sp_tc_image_terms()) / sizeof(float);
     return n;
 }
 
@@ -500,13 +528,14 @@ int sp_pack_weights(const SpConvDesc* d, int which, const float* w_torch, float*
     const int k3 = d->k * d->k * d->k;
     const int dP = round_up(which == 0 ? d->Co : d->Ci, kPad);
     const int64_t total = (int64_t)ffma_packed_floats(d, which);
-    if (which == 1 && gemm_corrT(d)) {   // GEMM tier: Wt[co][tap][ciP] (same size as the [tap][co][ciP] layout)
+    SpTcCfg cfg;
+    const SpTier tier = which == 0 ? corr_tier(d, &cfg) : corrT_tier(d, &cfg);
+    if (which == 1 && tier == TIER_GEMM) {   // GEMM tier: Wt[co][tap][ciP] (same size as the [tap][co][ciP] layout)
         sp_gemm::pack_wt_gemm_kernel<<<grid_for(total), 256, 0, sp_stream(stream)>>>(w_torch, w_packed, d->Co, d->Ci, k3, dP);
         SP_LAUNCH_OK("pack_wt_gemm_kernel");
         return 0;
     }
-    SpTcCfg cfg;
-    const bool tc = tc_serves(d, which, &cfg);
+    const bool tc = tier == TIER_TC;
     if (!tc) {      // a layer the tensor-core tier serves never reads the FFMA layout (same predicate at pack and at run time)
         pack_weights_kernel<<<grid_for(total), 256, 0, sp_stream(stream)>>>(w_torch, w_packed, d->Co, d->Ci, k3, which, dP);
         SP_LAUNCH_OK("pack_weights_kernel");
@@ -518,8 +547,9 @@ int sp_pack_weights(const SpConvDesc* d, int which, const float* w_torch, float*
 
 size_t sp_conv_workspace_bytes(const SpConvDesc* d, int which) {
     if (!d || d->N <= 0) return 0;
-    if (which == 0) return gemm_corr(d) ? sp_gemm_corr_ws_bytes(d) + 256 : 0;
-    return gemm_corrT(d) ? sp_gemm_corrT_ws_bytes(d) + 256 : 0;
+    SpTcCfg cfg;
+    if (which == 0) return corr_tier(d, &cfg) == TIER_GEMM ? sp_gemm_corr_ws_bytes(d) + 256 : 0;
+    return corrT_tier(d, &cfg) == TIER_GEMM ? sp_gemm_corrT_ws_bytes(d) + 256 : 0;
 }
 
 int sp_corr(const SpConvDesc* d, const float* src, const float* wp, const float* bias, const float* scale,
@@ -536,13 +566,14 @@ int sp_corr(const SpConvDesc* d, const float* src, const float* wp, const float*
                                 d->act, d->alpha, sp_stream(stream));
     }
     SpTcCfg cfg;
-    if (tc_serves(d, 0, &cfg))
+    const SpTier tier = corr_tier(d, &cfg);
+    if (tier == TIER_TC)
         return tc_corr_launch(d, cfg, nPerG, src, wp + ffma_packed_floats(d, 0), bias, scale, shift, dst, sp_stream(stream));
     if (sp_k2s2_supported(d) && sp_k2s2_aligned(src, dst) && (!bias || sp_k2s2_aligned(bias, wp)))
         return sp_k2s2_down_launch(d, nPerG, src, wp, bias, scale, shift, dst, sp_stream(stream));
     if (sp_thin_fwd_supported(d)) return sp_thin_fwd_launch(d, nPerG, src, wp, /*flip=*/0, bias, scale, shift, dst, sp_stream(stream));
     if (sp_tiled_corr_supported(d)) return sp_tiled_corr_launch(d, nPerG, src, wp, /*flip=*/0, bias, scale, shift, dst, sp_stream(stream));
-    if (gemm_corr(d)) {
+    if (tier == TIER_GEMM) {
         SP_REQUIRE(ws && ws_bytes >= sp_conv_workspace_bytes(d, 0), "sp_corr: workspace too small (%zu < %zu)", ws_bytes,
                    sp_conv_workspace_bytes(d, 0));
         return sp_gemm_corr_launch(d, nPerG, src, wp, bias, scale, shift, dst, (float*)ws, sp_stream(stream));
@@ -566,12 +597,13 @@ int sp_corrT(const SpConvDesc* d, const float* src, const float* wp, const float
         return sp_pw_fwd_launch(src, d->ldo, d->Co, dst, d->ldi, d->Ci, (int64_t)d->N * vox, (int64_t)nPerG * vox, wp, bias, scale, shift,
                                 d->act, d->alpha, sp_stream(stream));
     }
+    SpTcCfg cfg;
+    const SpTier tier = corrT_tier(d, &cfg);
     if (d->s == 1) {
         // stride 1: the transposed correlation is a correlation with flipped taps, swapped channel roles and
         // padding k-1-p; Wt[tap][co][ciP] read with flipped tap index is exactly that correlation's Wc.
         const SpConvDesc f = flipped_desc(d);
-        SpTcCfg cfg;
-        if (tc_serves(d, 1, &cfg))
+        if (tier == TIER_TC)
             return tc_corr_launch(&f, cfg, nPerG, src, wp + ffma_packed_floats(d, 1), bias, scale, shift, dst, sp_stream(stream));
         if (sp_thin_bwd_supported(&f)) return sp_thin_bwd_launch(&f, nPerG, src, wp, bias, scale, shift, dst, sp_stream(stream));
         if (f.pd >= 0 && f.ph >= 0 && f.pw >= 0 && sp_tiled_corr_supported(&f))
@@ -580,7 +612,7 @@ int sp_corrT(const SpConvDesc* d, const float* src, const float* wp, const float
     if (sp_k2s2_supported(d) && sp_k2s2_aligned(src, dst) && (!bias || sp_k2s2_aligned(bias, wp)))
         return sp_k2s2_up_launch(d, nPerG, src, wp, bias, scale, shift, dst, sp_stream(stream));
     if (sp_tiledT_supported(d)) return sp_tiledT_launch(d, nPerG, src, wp, bias, scale, shift, dst, sp_stream(stream));
-    if (gemm_corrT(d)) {
+    if (tier == TIER_GEMM) {
         SP_REQUIRE(ws && ws_bytes >= sp_conv_workspace_bytes(d, 1), "sp_corrT: workspace too small (%zu < %zu)", ws_bytes,
                    sp_conv_workspace_bytes(d, 1));
         return sp_gemm_corrT_launch(d, nPerG, src, wp, bias, scale, shift, dst, (float*)ws, sp_stream(stream));

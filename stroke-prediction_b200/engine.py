@@ -13,6 +13,8 @@ backward per unit  : wgrad (BN re-applied on the fly), bias gradient (column sum
 
 ``SeqFunction`` / ``UnetFunction`` expose the chains to autograd as single nodes.
 """
+import weakref
+
 import torch
 import torch.nn as nn
 
@@ -54,43 +56,95 @@ class GradSink:
         self.flat = torch.zeros(total, device=dev, dtype=torch.float32)
         self.params = params
         self._views = {}
-        for p, o in zip(params, offs):
-            v = self.flat[o:o + p.numel()].view(p.shape)
-            p.grad = v
-            self._views[id(p)] = v
+        self._offsets = {id(p): o for p, o in zip(params, offs)}
+        for p in params:
+            self._attach(p)
         self.dirty = False
 
-    def view(self, p):
-        v = self._views.get(id(p))
-        if v is not None and p.grad is not v:
-            p.grad = v        # somebody set .grad = None (zero_grad(set_to_none=True)): re-attach
+    def _attach(self, p):
+        o = self._offsets[id(p)]
+        v = self.flat[o:o + p.numel()].view(p.shape)
+        p.grad = v
+        self._views[id(p)] = v
         return v
+
+    def owns(self, p):
+        return id(p) in self._offsets
+
+    def view(self, p):
+        """The gradient view of `p` inside ``flat`` (None if `p` is not ours).  Self-healing: ``zero_grad(set_to_none=
+        True)`` drops ``p.grad``, and ``Module._apply`` (``model.cpu()`` / ``.to(device)``) re-binds the STORAGE of the
+        very tensor object we handed out (``param.grad.data = fn(grad)``), so identity alone proves nothing — the
+        view's address is compared with its slot of the flat buffer and the view is rebuilt when they differ."""
+        o = self._offsets.get(id(p))
+        if o is None:
+            return None
+        v = self._views[id(p)]
+        if (p.grad is not v or v.device != self.flat.device
+                or v.data_ptr() != self.flat.data_ptr() + 4 * o):
+            v = self._attach(p)
+        return v
+
+    def reattach(self):
+        """Re-validate every view (after anything that may have moved the module)."""
+        for p in self.params:
+            self.view(p)
+
+    def release(self):
+        """Detach: parameters get ordinary (None) gradients again."""
+        for p in self.params:
+            if p.grad is self._views.get(id(p)):
+                p.grad = None
+        self._views.clear()
+        self._offsets.clear()
+        self.params = []
 
     def zero(self):
         self.flat.zero_()
         self.dirty = False
 
 
-_sinks = []
+# id(parameter) -> (weak reference to the parameter, the sink that owns its gradient).  Keyed by id because tensors
+# compare element-wise; the weak reference's callback drops the entry with the parameter (and with it the last reference
+# to the sink's flat buffer).  The LATEST sink attached to a parameter wins, e.g. when a second Learner / optimizer is
+# built over a model a first one trained (the reference trains the CAE, then CaeStepLearner or CaePredictionLearner on
+# the same modules).
+_sink_of = {}
+
+
+def _owner(p):
+    hit = _sink_of.get(id(p))
+    if hit is None or hit[0]() is not p:
+        return None
+    return hit[1]
 
 
 def register_grad_sink(sink):
-    _sinks.append(sink)
+    for p in sink.params:
+        old = _owner(p)
+        if old is not None and old is not sink:
+            old._offsets.pop(id(p), None)      # the previous owner no longer serves this parameter
+            old._views.pop(id(p), None)
+            old.params = [q for q in old.params if q is not p]
+        key = id(p)
+        _sink_of[key] = (weakref.ref(p, lambda _r, key=key: _sink_of.pop(key, None)), sink)
     return sink
 
 
 def unregister_grad_sink(sink):
-    if sink in _sinks:
-        _sinks.remove(sink)
+    for p in list(sink.params):
+        if _owner(p) is sink:
+            del _sink_of[id(p)]
 
 
 def _sink_view(p):
-    for s in _sinks:
-        v = s.view(p)
-        if v is not None:
-            s.dirty = True
-            return v
-    return None
+    s = _owner(p)
+    if s is None:
+        return None
+    v = s.view(p)
+    if v is not None:
+        s.dirty = True
+    return v
 
 
 def _triple(v):
@@ -143,13 +197,23 @@ class FusedUnit:
         return ops.conv_desc(N, in_size, self.cin, out_size, self.cout, self.k, self.s, self.pad, a, al)
 
     def packed(self, d, which):
+        """Packed weights for direction `which` under geometry `d`.  The layout sp_pack_weights writes (FFMA / GEMM /
+        tensor-core image, and the buffer size) depends on the tier the GEOMETRY selects, so the cache is keyed on the
+        geometry as well as on the parameter version: the same unchanged weights at another volume size (validation,
+        Tester, visualisation) get their own pack."""
         w = self.conv.weight
+        geom = (which, d.N, d.Di, d.Hi, d.Wi, d.Ci, d.ldi, d.Do, d.Ho, d.Wo, d.Co, d.ldo, d.k, d.s, d.pd, d.ph, d.pw)
         key = (w._version, w.data_ptr(), _weights_epoch)
-        hit = self._packed.get(which)
+        hit = self._packed.get(geom)
         if hit is not None and hit[0] == key:
             return hit[1]
+        if len(self._packed) >= 8:          # bounded: drop packs of geometries / versions no longer in use
+            for g in [g for g, h in self._packed.items() if h[0] != key]:
+                del self._packed[g]
+            if len(self._packed) >= 8:
+                self._packed.clear()
         wp = ops.pack_weights(d, which, w)
-        self._packed[which] = (key, wp)
+        self._packed[geom] = (key, wp)
         return wp
 
     def params(self):
@@ -430,9 +494,30 @@ class UnetPlan:
         return ps + self.classify.params()
 
 
+_warned_legacy_upsample = False
+
+
 def _align(unet, name):
-    ac = getattr(getattr(unet, name), "align_corners", None)
-    return bool(ac)  # None (installed default) == False
+    """align_corners of the trilinear x2 upsampling `unet.<name>` (Unet3D.py:44,46).
+
+    ``unet.align_corners`` (None | bool), when set, overrides everything.  Otherwise the module's own attribute decides:
+    None = the installed torch's default (False).  A module WITHOUT the attribute is a pickle written by the reference's
+    pinned torch 0.3.1 (``nn.Upsample`` had no such field and interpolated with corner alignment): it keeps the
+    behaviour it was trained with (True), with a one-time warning."""
+    global _warned_legacy_upsample
+    override = getattr(unet, "align_corners", None)
+    if override is not None:
+        return bool(override)
+    mod = getattr(unet, name)
+    if "align_corners" not in vars(mod):
+        if not _warned_legacy_upsample:
+            import warnings
+            warnings.warn("Unet3D.%s has no align_corners attribute (checkpoint pickled by torch < 0.4): using "
+                          "align_corners=True, the interpolation it was trained with; set unet.align_corners to override"
+                          % name)
+            _warned_legacy_upsample = True
+        return True
+    return bool(mod.align_corners)  # None (installed default) == False
 
 
 def _crop_offsets(big, small):

@@ -25,13 +25,11 @@ class CaePredictionLearner(Learner, CaeEncInference):
     def load_model(self, cuda=True):
         Learner.load_model(self, self.is_cuda)
         enc = torch.load(self.path('load', self.FNB_MODEL, '_enc'), weights_only=False)
-        self._new_enc = enc.cuda() if cuda else enc
+        self._new_enc = self.adopt_checkpoint(getattr(self, '_new_enc', None), enc, cuda)
 
     def save_model(self, suffix=''):
         Learner.save_model(self, suffix)
-        device = next(self._new_enc.parameters()).device
-        torch.save(self._new_enc.cpu(), self.path('save', self.FNB_MODEL, '_enc' + suffix))
-        self._new_enc.to(device)
+        torch.save(self.cpu_snapshot(self._new_enc), self.path('save', self.FNB_MODEL, '_enc' + suffix))
 
     def adapt_betas(self, epoch):
         pass

@@ -6,6 +6,7 @@ subclass's ``loss_step``, ``zero_grad`` / ``backward`` / fused Adam step, one sc
 state objects).  Plotting (matplotlib) and jsonpickle history files are host-side orchestration outside the hot-path
 scope; they are used when those packages are importable and skipped otherwise.
 """
+import copy
 import json
 from abc import abstractmethod
 
@@ -93,8 +94,26 @@ class Learner(Inference):
         return numpy.inf
 
     def load_model(self, cuda=True):
+        """Learner.py:96-101.  The reference replaces ``self._model`` by the unpickled module although the optimizer it
+        was handed still holds the parameters of the script-built one, so a "continued" training never updates the loaded
+        weights (defect D11).  When the checkpoint has the structure of the model the optimizer was built on, its
+        tensors are copied INTO that model (optimizer / gradient-sink links stay valid: the resume really resumes);
+        otherwise the module is replaced like in the reference."""
         model = torch.load(self.path('load', self.FNB_MODEL), weights_only=False)
-        self._model = model.cuda() if cuda else model
+        self._model = self.adopt_checkpoint(getattr(self, '_model', None), model, cuda)
+
+    @staticmethod
+    def adopt_checkpoint(live, loaded, cuda=True):
+        if live is not None and type(live) is type(loaded):
+            have, want = live.state_dict(), loaded.state_dict()
+            if have.keys() == want.keys() and all(have[k].shape == want[k].shape for k in have):
+                with torch.no_grad():
+                    for k, t in have.items():
+                        t.copy_(want[k])
+                from .. import engine
+                engine.bump_weights_epoch()
+                return live
+        return loaded.cuda() if cuda else loaded
 
     def load_training(self):
         path_training = self.path('load', self.FNB_TRAIN)
@@ -119,10 +138,25 @@ class Learner(Inference):
         with open(self.path('save', self.FNB_TRAIN), 'w') as fp:
             fp.write(text)
 
+    @staticmethod
+    def cpu_snapshot(module):
+        """A CPU deep copy of `module` for checkpointing (the reference pickles ``model.cpu()`` and moves it back,
+        Learner.py:112-114).  The LIVE module is never moved: ``Module._apply`` re-binds the storage of every
+        ``param.grad``, which would silently cut the gradients loose from the flat gradient buffer the backward kernels,
+        the all-reduce and the fused Adam share (engine.GradSink).  Gradients are not part of a checkpoint."""
+        params = list(module.parameters())
+        grads = [p.grad for p in params]
+        for p in params:
+            p.grad = None
+        try:
+            clone = copy.deepcopy(module)
+        finally:
+            for p, g in zip(params, grads):
+                p.grad = g
+        return clone.cpu()
+
     def save_model(self, suffix=''):
-        device = self.device
-        torch.save(self._model.cpu(), self.path('save', self.FNB_MODEL, suffix))
-        self._model.to(device)
+        torch.save(self.cpu_snapshot(self._model), self.path('save', self.FNB_MODEL, suffix))
 
     # ------------------------------------------------------------------------------------------ hot path
     def train_batch(self, batch: dict, epoch) -> MetricMeasuresDto:

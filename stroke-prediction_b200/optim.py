@@ -61,9 +61,43 @@ class FusedAdam(Optimizer):
         sink = getattr(self, '_sink', None)
         if sink is not None:
             engine.unregister_grad_sink(sink)
-            for p in sink.params:
-                p.grad = None
+            sink.release()
             self._sink = None
+
+    def __del__(self):
+        # a dropped optimizer must not keep routing its parameters' gradients into a buffer nobody reads
+        try:
+            sink = self.__dict__.get('_sink')
+            if sink is not None:
+                engine.unregister_grad_sink(sink)
+        except Exception:
+            pass
+
+    def load_state_dict(self, state_dict):
+        """torch's ``load_state_dict`` REPLACES ``param_groups`` and ``state`` by new objects.  The reference loads into
+        the very optimizer its scheduler was built on (Learner.py:96-103), and ``from_torch`` shares these objects with
+        the script's ``torch.optim.Adam`` so that ``MultiStepLR`` / ``adapt_betas`` keep acting on the optimizer that
+        steps: load, then move the loaded content back INTO the original objects."""
+        groups, state = self.param_groups, self.state
+        super().load_state_dict(state_dict)
+        new_groups, new_state = self.param_groups, self.state
+        if new_groups is not groups:
+            for old, new in zip(groups, new_groups):
+                if old is not new:
+                    keep = {k: old[k] for k in ('initial_lr',) if k in old and k not in new}
+                    old.clear()
+                    old.update(new)
+                    old.update(keep)
+            self.param_groups = groups
+        if new_state is not state:
+            state.clear()
+            state.update(new_state)
+            self.state = state
+        for st in self.state.values():
+            for k in ('exp_avg', 'exp_avg_sq'):
+                if k in st and not st[k].is_contiguous():
+                    st[k] = st[k].contiguous()
+        self._tables = {}
 
     def zero_grad(self, set_to_none=True):
         sink = getattr(self, '_sink', None)
@@ -110,13 +144,16 @@ class FusedAdam(Optimizer):
                 by_step = {steps.pop(): entries}
             b1, b2 = group['betas']
             for t, ents in by_step.items():
-                key = (gi, t if len(by_step) > 1 else -1,
-                       tuple((p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel()) for p, g, m, v in ents))
-                hit = self._tables.get(key[:2])
-                if hit is None or hit[0] != key[2]:
+                # the pointer table does not depend on the step count: key it on the pointer set (bounded: one entry per
+                # distinct set of tensors that ever stepped together), never on t
+                ptrs = tuple((p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel()) for p, g, m, v in ents)
+                hit = self._tables.get((gi, ptrs))
+                if hit is None:
+                    if len(self._tables) >= 16:
+                        self._tables.clear()
                     table, blocks = ops.make_adam_table(ents, ents[0][0].device)
-                    hit = (key[2], table, blocks)
-                    self._tables[key[:2]] = hit
+                    hit = (ptrs, table, blocks)
+                    self._tables[(gi, ptrs)] = hit
                 ops.adam_multi(hit[1], len(ents), hit[2], group['lr'], b1, b2, group['eps'], group['weight_decay'],
                                t, self.grad_scale, self.fuse_zero_grad)
                 self.launches += 1

@@ -505,3 +505,371 @@ def test_stacked_passes_equal_separate_passes():
         assert rel_max(b1[k].double(), b2[k].double()) < 1e-6, k
     for n in g1:
         assert rel_l2(g1[n], g2[n]) < 2e-4, n      # fp32 reduction partition differs (one 3B-sample wgrad vs three B-sample ones)
+
+
+# ===================================================================================================== round 2 additions
+def _unet_oracle(sd0, x, labels, dtype):
+    s = O.clone_state(sd0, requires_grad=True, dtype=dtype)
+    c, p_ = O.unet_forward(s, x.to(dtype), True)
+    l = O.unet_loss(c, p_, labels[:, 0:1].to(dtype), labels[:, 1:2].to(dtype))
+    return c, p_, l, O.grads_of(l, s)
+
+
+def test_unet_named_config_full_size_against_oracle():
+    """BASELINE configs[0] at its OWN shape: channels 2 16 32 64 32 16 32 2, input 2 x 68 x 168 x 168 -> 28 x 128 x 128.
+    B = 2: forward, loss and every parameter gradient (noise-floor rule against fp64); B = 4 (the benchmarked batch, whose
+    tile / grid wrap differs): forward + loss."""
+    A = _api()
+    torch.manual_seed(35)
+    unet = A.Unet3D([2, 16, 32, 64, 32, 16, 32, 2])
+    sd = O.clone_state(unet.state_dict())
+    unet = unet.cuda().train()
+    opt = A.FusedAdam(unet.parameters(), lr=1e-3, weight_decay=1e-5, betas=(0.99, 0.999))
+    learner = A.UnetSegmentationLearner(None, None, unet, opt, None, 1, A.BatchDiceLoss([1.0]))
+    batch = A.data.synthetic_unet_batch(2, out_size=(28, 128, 128), seed=4)
+    assert tuple(batch[A.data.KEY_IMAGES].shape) == (2, 2, 68, 168, 168)
+    dto = learner.inference_step(batch)
+    assert tuple(dto.outputs.core.shape) == (2, 1, 28, 128, 128)
+    loss = learner.loss_step(dto, 0)
+    opt.zero_grad()
+    loss.backward()
+    labels, x = batch[A.data.KEY_LABELS], batch[A.data.KEY_IMAGES]
+    c32, p32, l32, g32 = _unet_oracle(sd, x, labels, torch.float32)
+    g64 = _unet_oracle(sd, x, labels, torch.float64)[3]
+    assert rel_l2(dto.outputs.core, c32) < TOL_ACT and rel_l2(dto.outputs.penu, p32) < TOL_ACT
+    assert abs(_dice_binary(dto.outputs.penu.cpu(), p32) - 1.0) < TOL_DICE or float((p32 > 0.5).sum()) == 0
+    assert abs(loss.item() - l32.item()) < 1e-5
+    names = set(g64)
+    floor = {n: rel_l2(g32[n], g64[n]) for n in names}
+    sdk = O.ulp_perturbed(sd, names, torch.Generator().manual_seed(7))      # one more draw of the fp32 floor
+    g32k, g64k = _unet_oracle(sdk, x, labels, torch.float32)[3], _unet_oracle(sdk, x, labels, torch.float64)[3]
+    for n in names:
+        floor[n] = max(floor[n], rel_l2(g32k[n], g64k[n]))
+    bad = []
+    for n, p in unet.named_parameters():
+        e_gpu = rel_l2(p.grad, g64[n])
+        print("%-36s gpu/f64 %.2e cpu32-floor/f64 %.2e" % (n, e_gpu, floor[n]))
+        if e_gpu > max(TOL_GRAD, 2 * floor[n]):
+            bad.append("%s: gpu %g cpu32 floor %g" % (n, e_gpu, floor[n]))
+    assert not bad, bad
+    # the benchmarked batch: B = 4 forward + loss, running statistics reset so both sides start from the same state
+    del dto, loss
+    unet.load_state_dict(sd)
+    batch4 = A.data.synthetic_unet_batch(4, out_size=(28, 128, 128), seed=5)
+    with torch.no_grad():
+        dto4 = learner.inference_step(batch4)
+        loss4 = learner.loss_step(dto4, 0)
+    with torch.no_grad():
+        c4, p4 = O.unet_forward(O.clone_state(sd), batch4[A.data.KEY_IMAGES], True)
+        l4 = O.unet_loss(c4, p4, batch4[A.data.KEY_LABELS][:, 0:1], batch4[A.data.KEY_LABELS][:, 1:2])
+    assert rel_l2(dto4.outputs.core, c4) < TOL_ACT and rel_l2(dto4.outputs.penu, p4) < TOL_ACT
+    assert abs(loss4.item() - l4.item()) < 1e-5
+
+
+def test_cae_named_config_benchmark_batch_forward_loss():
+    """BASELINE configs[1] at the benchmarked batch 8 (stacked passes N = 24 / 32): latents, reconstructions, loss."""
+    A = _api()
+    ch = [1, 16, 24, 32, 100, 200, 1]
+    torch.manual_seed(37)
+    cae = A.Cae3D(A.Enc3D(128, 28, ch, 5, 1.0), A.Dec3D(128, 28, ch, 5, 1.0))
+    sd = O.clone_state(cae.state_dict())
+    cae = cae.cuda().train()
+    learner = A.CaeReconstructionLearner(None, None, cae, A.FusedAdam(cae.parameters(), lr=1e-3), None, 1, None, "/tmp/x",
+                                         A.BatchDiceLoss([1.0]))
+    batch = A.data.synthetic_cae_batch(8, seed=6)
+    with torch.no_grad():
+        dto = learner.inference_step(batch)
+        loss = learner.loss_step(dto, 60)
+        labels = batch[A.data.KEY_LABELS]
+        step = O.time_to_treatment(batch[A.data.KEY_GLOBAL])
+        lat, rec = O.cae_forward(sd, ch, 1.0, True, labels[:, 0:1], labels[:, 1:2], labels[:, 2:3], step)
+        oloss = O.cae_reconstruction_loss(lat, rec, labels[:, 0:1], labels[:, 1:2], labels[:, 2:3], 60)
+    assert abs(loss.item() - oloss.item()) < 1e-5
+    for k in ("core", "penu", "lesion", "interpolation"):
+        assert rel_l2(getattr(dto.latents.gtruth, k), lat[k]) < TOL_ACT, k
+        r = getattr(dto.reconstructions.gtruth, k)
+        assert tuple(r.shape) == (8, 1, 28, 128, 128)
+        assert rel_l2(r, rec[k]) < TOL_ACT, k
+
+
+def test_enc3dctp_training_step_gradients():
+    """SURVEY a5 backward: Cae3DCtp (3-channel encoder on mask + cropped CBV / TTD, virtual concat) through
+    CaeReconstructionLearner.loss_step — every encoder / decoder gradient against the fp64 oracle of the same graph."""
+    A = _api()
+    from stroke_prediction_b200.common.dto import CaeDto as U
+    from stroke_prediction_b200.common.model.Cae3D import Cae3DCtp
+    ch = [3, 4, 6, 8, 10, 12, 1]
+    torch.manual_seed(27)
+    cae = Cae3DCtp(A.Enc3DCtp(56, 28, ch, 5, 1.0, [20, 20, 20]), A.Dec3D(56, 28, ch, 5, 1.0))
+    sd0 = O.clone_state(cae.state_dict())
+    cae = cae.cuda().train()
+    b = A.data.synthetic_cae_batch(2, size=(28, 56, 56), seed=9)
+    labels = b[A.data.KEY_LABELS]
+    g = torch.Generator().manual_seed(3)
+    cbv = torch.zeros(2, 1, 68, 96, 96)
+    ttd = torch.zeros(2, 1, 68, 96, 96)
+    cbv[:, :, 20:-20, 20:-20, 20:-20] = 12 * torch.rand(2, 1, 28, 56, 56, generator=g)
+    ttd[:, :, 20:-20, 20:-20, 20:-20] = 40 * torch.rand(2, 1, 28, 56, 56, generator=g)
+    step = O.time_to_treatment(b[A.data.KEY_GLOBAL])
+    opt = A.FusedAdam(cae.parameters(), lr=1e-3, weight_decay=1e-5)
+    learner = A.CaeReconstructionLearner(None, None, cae, opt, None, 1, None, "/tmp/x", A.BatchDiceLoss([1.0]))
+    dto = U.init_dto(None, step.float().cuda(), None, None, cbv.cuda(), ttd.cuda(), labels[:, 0:1].cuda(),
+                     labels[:, 1:2].cuda(), labels[:, 2:3].cuda())
+    dto = cae(dto)
+    loss = learner.loss_step(dto, 60)
+    opt.zero_grad()
+    loss.backward()
+
+    def oracle(dtype, signs=None):
+        sd = O.clone_state(sd0, requires_grad=True, dtype=dtype)
+        crop = lambda t: t[:, :, 20:-20, 20:-20, 20:-20]
+        cat = lambda m: torch.cat((m, crop(cbv), crop(ttd)), 1).to(dtype)
+        lat = {k: O.encoder_pass(cat(labels[:, j:j + 1]), sd, ch, 1.0, True) for j, k in enumerate(("core", "penu", "lesion"))}
+        lat["interpolation"] = O.interpolate(lat["core"], lat["penu"], step.to(dtype))
+        rec = {k: O.decoder_pass(v, sd, ch, 1.0, True) for k, v in lat.items()}
+        l = O.cae_reconstruction_loss(lat, rec, labels[:, 0:1].to(dtype), labels[:, 1:2].to(dtype), labels[:, 2:3].to(dtype), 60, signs)
+        return lat, rec, l, O.grads_of(l, sd)
+
+    lat32, rec32, l32, g32 = oracle(torch.float32)
+    assert abs(loss.item() - l32.item()) < 1e-5
+    for k in ("core", "penu", "lesion", "interpolation"):
+        assert rel_l2(getattr(dto.latents.gtruth, k), lat32[k]) < TOL_ACT, k
+    s_gpu = O.hinge_signs(dto.reconstructions.gtruth)
+    _, rec64, _, g64 = oracle(torch.float64, s_gpu)
+    _check_signs(s_gpu, rec64)
+    g64_cpu = oracle(torch.float64, O.hinge_signs(rec32))[3]
+    n = 0
+    for name, p in cae.named_parameters():
+        e_gpu, e_cpu = rel_l2(p.grad, g64[name]), rel_l2(g32[name], g64_cpu[name])
+        assert e_gpu <= max(TOL_GRAD, 4 * e_cpu), "%s: gpu-vs-fp64 %g, cpu32-vs-fp64 %g" % (name, e_gpu, e_cpu)
+        n += 1
+    assert n > 0
+    # CBV / TTD that require a gradient take the autograd (torch.cat) form of the concat: the input gradient must arrive
+    cbv_g = cbv.cuda().requires_grad_(True)
+    dto2 = U.init_dto(None, step.float().cuda(), None, None, cbv_g, ttd.cuda(), labels[:, 0:1].cuda(), labels[:, 1:2].cuda(),
+                      labels[:, 2:3].cuda())
+    dto2 = cae.enc(dto2)
+    dto2.latents.gtruth.core.sum().backward()
+    sd = O.clone_state(sd0, dtype=torch.float64)
+    cbv64 = cbv.double().requires_grad_(True)
+    crop = lambda t: t[:, :, 20:-20, 20:-20, 20:-20]
+    O.encoder_pass(torch.cat((labels[:, 0:1].double(), crop(cbv64), crop(ttd.double())), 1), sd, ch, 1.0, True).sum().backward()
+    assert rel_l2(cbv_g.grad, cbv64.grad) < 1e-4
+
+
+def _sink_aliases(opt):
+    sink = opt._sink
+    base = sink.flat.data_ptr()
+    return all(p.grad is not None and base <= p.grad.data_ptr() < base + 4 * sink.flat.numel() for p in sink.params)
+
+
+def test_save_model_keeps_the_gradient_sink_attached(tmp_path):
+    """train -> save_model -> train: the checkpoint must not move the live module (Module._apply re-binds param.grad
+    storage and would cut the gradients loose from the flat buffer that the all-reduce and the fused Adam read)."""
+    A = _api()
+    ch = [1, 4, 6, 8, 10, 12, 1]
+    torch.manual_seed(51)
+    cae = A.Cae3D(A.Enc3D(56, 28, ch, 5, 1.0), A.Dec3D(56, 28, ch, 5, 1.0)).cuda().train()
+    opt = torch.optim.Adam(cae.parameters(), lr=1e-3, weight_decay=1e-5)
+    learner = A.CaeReconstructionLearner(None, None, cae, opt, None, 1, None, str(tmp_path / "run"), A.BatchDiceLoss([1.0]))
+    learner.enable_data_parallel()            # world size 1: the sync is a no-op, the wiring is the real one
+    fused = learner._optimizer
+    batch = A.data.synthetic_cae_batch(2, size=(28, 56, 56), seed=5)
+    learner.train_batch(batch, 30)
+    assert _sink_aliases(fused)
+    learner.save_model()
+    learner.save_training()
+    assert all(p.is_cuda for p in cae.parameters()) and _sink_aliases(fused)
+    before = [p.detach().clone() for p in cae.parameters()]
+    # gradients of the next step must land in the flat buffer (seen through a fresh forward/backward without the step)
+    dto = learner.inference_step(batch)
+    loss = learner.loss_step(dto, 30)
+    fused.zero_grad()
+    loss.backward()
+    assert _sink_aliases(fused) and float(fused._sink.flat.abs().sum()) > 0
+    gsum = sum(float(p.grad.double().abs().sum()) for p in fused._sink.params)
+    assert abs(gsum - float(fused._sink.flat.double().abs().sum())) <= 1e-6 * gsum
+    learner.train_batch(batch, 30)
+    assert any((p.detach() - b).abs().max().item() > 0 for p, b in zip(cae.parameters(), before))
+    # even a caller that DOES move the module (reference-style scripts) is healed on the next backward
+    cae.cpu()
+    cae.cuda()
+    learner.train_batch(batch, 30)
+    assert _sink_aliases(fused)
+    # the checkpoint is a CPU whole-module pickle like the reference's (Learner.py:112-114)
+    m = torch.load(str(tmp_path / "run") + "_cae1.model", weights_only=False)
+    assert all(not p.is_cuda and p.grad is None for p in m.parameters())
+
+
+def test_second_learner_over_the_same_model_owns_the_gradients():
+    """The reference trains the CAE, then builds CaeStepLearner on the same modules: the newest optimizer's sink must
+    receive the gradients (and the old one must stop claiming them)."""
+    A = _api()
+    ch = [1, 4, 6, 8, 10, 12, 1]
+    torch.manual_seed(53)
+    cae = A.Cae3D(A.Enc3D(56, 28, ch, 5, 1.0), A.Dec3D(56, 28, ch, 5, 1.0)).cuda().train()
+    batch = A.data.synthetic_cae_batch(2, size=(28, 56, 56), seed=5)
+    l1 = A.CaeReconstructionLearner(None, None, cae, torch.optim.Adam(cae.parameters(), lr=1e-3), None, 1, None, "/tmp/x",
+                                    A.BatchDiceLoss([1.0]))
+    l1.train_batch(batch, 30)
+    old = l1._optimizer._sink
+    l2 = A.CaeReconstructionLearner(None, None, cae, torch.optim.Adam(cae.parameters(), lr=1e-3), None, 1, None, "/tmp/x",
+                                    A.BatchDiceLoss([1.0]))
+    new = l2._optimizer._sink
+    assert new is not old and not old.params
+    dto = l2.inference_step(batch)
+    loss = l2.loss_step(dto, 30)
+    l2._optimizer.zero_grad()
+    loss.backward()
+    assert float(new.flat.abs().sum()) > 0 and float(old.flat.abs().sum()) == 0
+    assert _sink_aliases(l2._optimizer)
+
+
+def test_reference_format_checkpoint_round_trip(tmp_path):
+    """a reference-format checkpoint — whole-module pickle whose classes are named by the REFERENCE's module
+    path (`common.model.Cae3D.*`, Learner.py:112-114), a torch.optim.Adam `.optim` state_dict and the history file —
+    resumes training in a new learner: same loss trajectory as the uninterrupted run, and the script's LR scheduler
+    still drives the optimizer that steps (its objects survive `load_state_dict`)."""
+    import contextlib
+    import stroke_prediction_b200 as pkg
+    import stroke_prediction_b200.common.model.Cae3D as M
+    A = _api()
+    pkg.install_reference_aliases()
+    ch = [1, 4, 6, 8, 10, 12, 1]
+    batches = [A.data.synthetic_cae_batch(2, size=(28, 56, 56), seed=60 + i) for i in range(4)]
+
+    @contextlib.contextmanager
+    def reference_class_paths():
+        """While active, the model classes pickle as `common.model.Cae3D.<name>` exactly like a reference-written file."""
+        classes = [c for c in vars(M).values() if isinstance(c, type) and c.__module__ == M.__name__]
+        for c in classes:
+            c.__module__ = "common.model.Cae3D"
+        try:
+            yield
+        finally:
+            for c in classes:
+                c.__module__ = M.__name__
+
+    def fresh():
+        torch.manual_seed(55)
+        cae = A.Cae3D(A.Enc3D(56, 28, ch, 5, 1.0), A.Dec3D(56, 28, ch, 5, 1.0)).cuda().train()
+        opt = torch.optim.Adam(cae.parameters(), lr=1e-3, weight_decay=1e-5)
+        sched = torch.optim.lr_scheduler.MultiStepLR(opt, [1, 3])
+        return cae, opt, sched
+
+    def learner(cae, opt, sched, prev, out):
+        return A.CaeReconstructionLearner(None, None, cae, opt, sched, 4, prev, out, A.BatchDiceLoss([1.0]))
+
+    # uninterrupted: 4 steps, one "epoch" per step so the scheduler acts (lr 1e-3, 1e-4, 1e-4, 1e-5)
+    cae, opt, sched = fresh()
+    ln = learner(cae, opt, sched, None, str(tmp_path / "a"))
+    ref_losses, ref_lrs = [], []
+    for e, b in enumerate(batches):
+        ref_lrs.append(ln._optimizer.param_groups[0]["lr"])
+        ref_losses.append(ln.train_batch(b, 30).loss)
+        ln.adapt_lr(e)
+    assert ref_lrs[0] == 1e-3 and abs(ref_lrs[1] - 1e-4) < 1e-12 and abs(ref_lrs[3] - 1e-5) < 1e-12
+
+    # interrupted after 2 steps, checkpointed in the reference's on-disk format
+    cae, opt, sched = fresh()
+    ln = learner(cae, opt, sched, None, str(tmp_path / "b"))
+    for e, b in enumerate(batches[:2]):
+        m = ln.train_batch(b, 30)
+        assert abs(m.loss - ref_losses[e]) < 1e-6
+        ln.adapt_lr(e)
+        ln._metric_dtos['training'].append(m)
+        ln._metric_dtos['validate'].append(m)
+    with reference_class_paths():
+        ln.save_model()
+    ln.save_training()
+    with open(str(tmp_path / "b") + "_cae1.model", "rb") as f:
+        raw = f.read()
+    assert b"common.model.Cae3D" in raw and b"stroke_prediction_b200" not in raw
+    sd_opt = torch.load(str(tmp_path / "b") + "_cae1.optim", weights_only=False)
+    assert set(sd_opt) == {"state", "param_groups"} and "exp_avg" in next(iter(sd_opt["state"].values()))
+
+    # resumed in a new process-like setting: new model object, new Adam, new scheduler (as the scripts build them)
+    cae2, opt2, sched2 = fresh()
+    with torch.no_grad():
+        for p in cae2.parameters():
+            p.add_(1.0)                       # prove the weights really come from the checkpoint
+    groups_before, state_before = opt2.param_groups, opt2.state
+    ln2 = learner(cae2, opt2, sched2, str(tmp_path / "b"), str(tmp_path / "c"))
+    assert ln2.get_start_epoch() == 2 and abs(ln2.get_start_min_loss() - min(ref_losses[:2])) < 1e-6
+    assert ln2._model is cae2                 # adopted in place: the optimizer still owns the live parameters
+    assert ln2._optimizer.param_groups is groups_before and ln2._optimizer.state is state_before
+    assert opt2.param_groups is groups_before and sched2.optimizer is opt2
+    assert abs(opt2.param_groups[0]["lr"] - 1e-4) < 1e-12         # the saved learning rate came back
+    sched2.last_epoch = 2                     # the reference does not persist the scheduler; position it by hand
+    for e, b in enumerate(batches[2:], start=2):
+        assert abs(ln2._optimizer.param_groups[0]["lr"] - ref_lrs[e]) < 1e-12, e
+        got = ln2.train_batch(b, 30).loss
+        assert abs(got - ref_losses[e]) < 2e-5 * max(1.0, abs(ref_losses[e])), (e, got, ref_losses[e])
+        ln2.adapt_lr(e)
+
+    # Tester path: the reference-format pickle loads by path (Tester.py:17) and runs
+    class T(A.Tester, A.CaeInference):
+        def __init__(self, path):
+            A.Tester.__init__(self, None, path, "/tmp/x")
+            A.CaeInference.__init__(self, self._model, 10)
+
+    t = T(str(tmp_path / "b") + "_cae1.model")
+    t._model.cuda()
+    _, dto = t.infer_batch(A.data.synthetic_cae_batch(1, size=(28, 56, 56), seed=3))
+    assert tuple(dto.reconstructions.gtruth.core.shape) == (1, 1, 28, 56, 56)
+
+
+def test_validate_batch_matches_oracle_eval_forward():
+    """Learner.validate_batch (Learner.py:132-142): eval-mode forward + loss + metrics, no graph, no parameter change."""
+    A = _api()
+    ch = [1, 4, 6, 8, 10, 12, 1]
+    torch.manual_seed(57)
+    cae = A.Cae3D(A.Enc3D(56, 28, ch, 5, 1.0), A.Dec3D(56, 28, ch, 5, 1.0))
+    sd = O.clone_state(cae.state_dict())
+    cae = cae.cuda().eval()
+    ln = A.CaeReconstructionLearner(None, None, cae, A.FusedAdam(cae.parameters(), lr=1e-3), None, 1, None, "/tmp/x", A.BatchDiceLoss([1.0]))
+    batch = A.data.synthetic_cae_batch(2, size=(28, 56, 56), seed=8)
+    before = {k: v.clone() for k, v in cae.state_dict().items()}
+    m = ln.validate_batch(batch, 60)
+    labels = batch[A.data.KEY_LABELS]
+    step = O.time_to_treatment(batch[A.data.KEY_GLOBAL])
+    with torch.no_grad():
+        lat, rec = O.cae_forward(sd, ch, 1.0, False, labels[:, 0:1], labels[:, 1:2], labels[:, 2:3], step)
+        oloss = O.cae_reconstruction_loss(lat, rec, labels[:, 0:1], labels[:, 1:2], labels[:, 2:3], 60)
+    assert abs(m.loss - oloss.item()) < 1e-5
+    want = O.binary_measures(rec["core"], labels[:, 0:1])
+    assert abs(m.core.dc - want["dc"]) < TOL_DICE
+    for k, v in cae.state_dict().items():
+        assert torch.equal(v, before[k]), k
+
+
+def test_packed_weight_cache_is_keyed_on_geometry():
+    """Unchanged weights, changing volume size (validation / Tester / visualisation after training): each geometry selects
+    its own tier and packed layout (FFMA pack below 4096 output voxels, tensor-core image above, GEMM layout for wide tiny
+    planes), so a pack cached for one size must never be served to another."""
+    import torch.nn as nn
+    from stroke_prediction_b200 import engine
+    torch.manual_seed(59)
+    seq = nn.Sequential(nn.BatchNorm3d(16), nn.Conv3d(16, 16, 3, padding=(1, 0, 0)), nn.ELU(1.0),
+                        nn.BatchNorm3d(16), nn.ConvTranspose3d(16, 16, 3), nn.ELU(1.0)).eval()
+    for m in seq:
+        if isinstance(m, nn.BatchNorm3d):
+            m.running_mean.uniform_(-0.5, 0.5)
+            m.running_var.uniform_(0.5, 2.0)
+    plan = engine.SeqPlan(seq.cuda())
+    for size in [(6, 10, 10), (20, 40, 40), (6, 10, 10), (8, 64, 64), (20, 40, 40)]:
+        x = torch.randn(2, 16, *size)
+        with torch.no_grad():
+            y = engine.run_sequential(plan, x.cuda())
+            want = seq.cpu()(x)
+            seq.cuda()
+        assert rel_l2(y, want) < TOL_ACT, size
+    # gradients w.r.t. the input through both directions at alternating sizes as well
+    for size in [(6, 10, 10), (20, 40, 40), (6, 10, 10)]:
+        x = torch.randn(2, 16, *size)
+        xg = x.cuda().requires_grad_(True)
+        engine.run_sequential(plan, xg).square().sum().backward()
+        xc = x.clone().requires_grad_(True)
+        seq.cpu()(xc).square().sum().backward()
+        seq.cuda()
+        assert rel_l2(xg.grad, xc.grad) < 1e-4, size

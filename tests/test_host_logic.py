@@ -154,3 +154,71 @@ def test_argument_errors_do_not_launch():
     assert rc < 0 and b"conv" in lib.sp_last_error()
     rc = lib.sp_adam_multi(None, 0, 0, 1e-3, 0.9, 0.999, 1e-8, 0.0, 1, 1.0, 0, None)
     assert rc < 0
+
+
+def test_fused_adam_load_state_dict_keeps_the_scheduler_link():
+    """torch's load_state_dict replaces param_groups / state by new objects; a scheduler built on the script's
+    torch.optim.Adam (whose groups FusedAdam.from_torch shares) must keep driving the optimizer that steps after a resume."""
+    from stroke_prediction_b200.optim import FusedAdam
+    w = [torch.nn.Parameter(torch.randn(3, 3)), torch.nn.Parameter(torch.randn(5))]
+    opt = torch.optim.Adam(w, lr=1e-3, weight_decay=1e-5)
+    sched = torch.optim.lr_scheduler.MultiStepLR(opt, [1])
+    fused = FusedAdam.from_torch(opt)
+    assert fused.param_groups is opt.param_groups and fused.state is opt.state
+    # a checkpoint written by another torch.optim.Adam run
+    src = torch.optim.Adam([torch.nn.Parameter(t.detach().clone()) for t in w], lr=5e-4, weight_decay=1e-5, betas=(0.7, 0.999))
+    for p in src.param_groups[0]['params']:
+        p.grad = torch.ones_like(p)
+    src.step()
+    groups, state = fused.param_groups, fused.state
+    fused.load_state_dict(src.state_dict())
+    assert fused.param_groups is groups and fused.state is state and opt.param_groups is groups and opt.state is state
+    assert fused.param_groups[0]['lr'] == 5e-4 and fused.param_groups[0]['betas'] == (0.7, 0.999)
+    assert fused.param_groups[0]['params'][0] is w[0]
+    assert float(fused.state[w[0]]['step']) == 1.0 and torch.equal(fused.state[w[1]]['exp_avg'], src.state[src.param_groups[0]['params'][1]]['exp_avg'])
+    sched.step()                                   # milestone 1: lr *= 0.1 on the groups the fused optimizer reads
+    assert abs(fused.param_groups[0]['lr'] - 5e-5) < 1e-15
+
+
+def test_legacy_upsample_pickle_defaults_to_align_corners_true():
+    """nn.Upsample pickled by torch 0.3.1 has no align_corners attribute and interpolated with corner alignment."""
+    import warnings
+    unet = Unet3D([2, 4, 8, 16, 8, 4, 8, 2])
+    assert engine._align(unet, "upsa34") is False                    # installed torch: None -> False
+    del unet.upsa34.__dict__["align_corners"]
+    engine._warned_legacy_upsample = False
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        assert engine._align(unet, "upsa34") is True
+    assert any("align_corners" in str(x.message) for x in w)
+    unet.align_corners = False
+    assert engine._align(unet, "upsa34") is False and engine._align(unet, "upsa45") is False
+    unet.align_corners = True
+    assert engine._align(unet, "upsa45") is True
+
+
+def test_cpu_snapshot_leaves_the_live_module_alone():
+    from stroke_prediction_b200.learner.Learner import Learner
+    m = Cae3D(Enc3D(56, 28, [1, 4, 6, 8, 10, 12, 1], 5, 1.0), Dec3D(56, 28, [1, 4, 6, 8, 10, 12, 1], 5, 1.0))
+    grads = []
+    for p in m.parameters():
+        p.grad = torch.zeros_like(p)
+        grads.append(p.grad)
+    snap = Learner.cpu_snapshot(m)
+    assert all(p.grad is g for p, g in zip(m.parameters(), grads))
+    assert all(q.grad is None for q in snap.parameters())
+    assert all(torch.equal(p, q) and p is not q for p, q in zip(m.parameters(), snap.parameters()))
+    assert '_sp_plans' not in vars(snap.enc)
+
+
+def test_adopt_checkpoint_copies_into_the_live_module():
+    from stroke_prediction_b200.learner.Learner import Learner
+    ch = [1, 4, 6, 8, 10, 12, 1]
+    live = Cae3D(Enc3D(56, 28, ch, 5, 1.0), Dec3D(56, 28, ch, 5, 1.0))
+    loaded = Cae3D(Enc3D(56, 28, ch, 5, 1.0), Dec3D(56, 28, ch, 5, 1.0))
+    params = list(live.parameters())
+    out = Learner.adopt_checkpoint(live, loaded, cuda=False)
+    assert out is live and all(p is q for p, q in zip(live.parameters(), params))
+    assert all(torch.equal(a, b) for a, b in zip(live.state_dict().values(), loaded.state_dict().values()))
+    other = Cae3D(Enc3D(56, 28, [1, 4, 6, 8, 10, 16, 1], 5, 1.0), Dec3D(56, 28, [1, 4, 6, 8, 10, 16, 1], 5, 1.0))
+    assert Learner.adopt_checkpoint(live, other, cuda=False) is other          # different structure: replaced, like the reference
