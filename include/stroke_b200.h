@@ -190,9 +190,51 @@ int sp_absdiff_bwd(const float* a, const float* b, int64_t n, int mode, const fl
 
 /* Evaluation counts of the thresholded masks (replaces the host round trip + medpy dc / precision / sensitivity /
  * specificity of metrics.py:31-47,49-62): counts[0..3] = TP, FP, FN, TN of (result > threshold) against
- * (target > threshold) over n contiguous floats.  The surface distances (hd, assd) are not computed on the device. */
+ * (target > threshold) over n contiguous floats. */
 int sp_binary_counts(const float* result, const float* target, int64_t n, float threshold, double* counts,
                      void* stream);
+
+/* Surface distances of the thresholded masks (replaces `mpm.hd` / `mpm.assd`, metrics.py:43-45; MedPy==0.3.0
+ * `__surface_distances`: border = mask XOR binary_erosion(mask, connectivity-1 cross, outside = 0); distances = exact
+ * Euclidean distance transform of the OTHER mask's border complement, read at the own border voxels, unit voxel spacing).
+ * The arrays are a dense (n0, n1, n2, n3) lattice, n3 contiguous; an extent-1 axis may be dropped by the caller, who then
+ * passes all_border != 0: with an extent-1 axis every set voxel has an outside neighbour, the erosion is empty and the whole
+ * object is "border" — exactly what MedPy computes on the reference's B x 1 x D x H x W batches (the batch axis is a lattice
+ * axis with unit spacing there, and is one here).
+ * out8: hd, assd, asd(result->target), asd(target->result), hd(result->target), hd(target->result), border voxel counts of
+ * result and target; hd = assd = +inf when either mask is empty (metrics.py:36-37,43). */
+size_t sp_surface_distances_workspace_bytes(int64_t total);
+int sp_surface_distances(const float* result, const float* target, int n0, int n1, int n2, int n3, int all_border,
+                         float threshold, double* out8, void* ws, size_t ws_bytes, void* stream);
+
+/* Signed distance map of a thresholded mask (the SDM baseline, test_sdm_resampling.py:16-33):
+ *   out = sign * ( edt(v > thr) - edt(outside) ),  outside = (v < thr) when outside_is_lt != 0 (the penumbra form, :17-18)
+ *   or !(v > thr) (the core form, :31-32, with sign = -1); edt(m) = distance of every voxel of m to the nearest voxel outside m
+ *   (scipy.ndimage.distance_transform_edt), exact, unit spacing, over the (n0, n1, n2, n3) lattice. */
+size_t sp_signed_distance_workspace_bytes(int64_t total);
+int sp_signed_distance(const float* mask, int n0, int n1, int n2, int n3, float threshold, int outside_is_lt, float sign,
+                       float* out, void* ws, size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Augmentation / resampling transforms in front of the hot path (common/data.py:215-380), on dense [n_vol][D][H][W]
+ * volumes (torch B x C x D x H x W after ToTensor, data.py:299-310: D = z, H = y, W = x).
+ * ---------------------------------------------------------------------------------------------------------- */
+/* scipy.ndimage.gaussian_filter(field, sigma, mode="constant", cval=0, truncate) of n_vol fp64 volumes (ElasticDeform's
+ * noise smoothing, data.py:336-338); out and tmp: n_vol*D*H*W doubles each */
+int sp_gauss3d(const double* in, int64_t nvol, int D, int H, int W, double sigma, double truncate, double* out, double* tmp,
+               void* stream);
+/* ElasticDeform.elastic_transform (data.py:331-341): out[d,h,w] = img( d + alpha*zscale*f3, h + alpha*f1, w + alpha*f2 ) by
+ * linear interpolation, 0 outside the volume (map_coordinates order 1, mode "constant"); f1..f3 = the smoothed noise fields in
+ * the reference's draw order */
+int sp_elastic_warp(const float* img, const double* f1, const double* f2, const double* f3, int64_t nvol, int D, int H, int W,
+                    double alpha, double zscale, float* out, void* stream);
+/* ResamplePlaneXY (data.py:354-380): scipy.ndimage.zoom of every (H, W) plane to (Ho, Wo), order 0 (nearest) or 1 (linear) */
+int sp_zoom_plane_xy(const float* in, int64_t planes, int H, int W, int Ho, int Wo, int order, float* out, void* stream);
+/* HemisphericFlip (data.py:215-245): mirror along x (= W) */
+int sp_flip_w(const float* in, int64_t rows, int W, float* out, void* stream);
+/* PadImages (data.py:280-296): constant border of (pd, ph, pw) voxels */
+int sp_pad_volume(const float* in, int64_t nvol, int D, int H, int W, int pd, int ph, int pw, float value, float* out,
+                  void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Latent interpolation z_c + s*(z_p - z_c), s per sample (Cae3D.py:78-89).

@@ -323,9 +323,78 @@ def unet_case(R, name, channels, out_size, B, seed, eval_too=True):
     print('\nwrote', name, 'loss', loss.item())
 
 
+def transforms_case(name, seed=11):
+    """The reference's own data transforms (common/data.py:215-380) on one small synthetic sample; pins
+    oracle.elastic_transform / resample_plane_xy / pad_images / hemispheric_flip / to_tensor."""
+    import random
+    import common.data as RD
+    rng = np.random.RandomState(seed)
+    X = Y = 24
+    Z = 10
+    labels = (rng.rand(X, Y, Z, 2) > 0.6).astype(np.float32)
+    images = rng.rand(X, Y, Z, 2).astype(np.float32) * 12
+    clinical = rng.rand(1, 1, 1, 5)
+    fx = {'labels': labels, 'images': images, 'clinical': clinical, 'seed': np.array(seed)}
+
+    # ElasticDeform exactly as __call__ chains it (data.py:343-351): channel 0 creates the random state, later channels and the
+    # images continue the same stream.  (The reference seeds from the wall clock; the fixture pins the seed.)
+    ed = RD.ElasticDeform(alpha=100, sigma=4, apply_to_images=True)
+    rs = np.random.RandomState(seed + 1)
+    out_l = np.zeros_like(labels)
+    out_i = np.zeros_like(images)
+    for c in range(labels.shape[3]):
+        out_l[:, :, :, c], rs = ed.elastic_transform(labels[:, :, :, c].copy(), 100, 4, random_state=rs)
+    for c in range(images.shape[3]):
+        out_i[:, :, :, c], rs = ed.elastic_transform(images[:, :, :, c].copy(), 100, 4, random_state=rs)
+    fx['elastic_labels'], fx['elastic_images'], fx['elastic_seed'] = out_l, out_i, np.array(seed + 1)
+    # restatement check: same noise stream -> same result
+    rs2 = np.random.RandomState(seed + 1)
+    for c in range(labels.shape[3]):
+        noise = [rs2.rand(X, Y, Z) for _ in range(3)]
+        mine = O.elastic_transform(labels[:, :, :, c], noise, 100, 4)
+        assert np.array_equal(mine, out_l[:, :, :, c]), 'elastic restatement differs from the reference'
+
+    class Arr(np.ndarray):
+        """`array != []` (data.py:367 etc.) was a scalar True on the reference's numpy 1.14; current numpy broadcasts and fails."""
+        def __ne__(self, other):
+            return True if isinstance(other, list) else np.ndarray.__ne__(self, other)
+
+    def fresh():
+        return {RD.KEY_IMAGES: images.copy().view(Arr), RD.KEY_LABELS: labels.copy().view(Arr),
+                RD.KEY_GLOBAL: clinical.copy().view(Arr), RD.KEY_CASE_ID: 3}
+
+    # (the reference's ResamplePlaneXY sizes its output by slicing the input, data.py:369, so it only works for factors <= 1)
+    for sf, mode in ((0.5, 'nearest'), (0.75, 'nearest'), (0.5, 'bilinear'), (0.75, 'bilinear')):
+        r = RD.ResamplePlaneXY(sf, mode)(fresh())
+        key = 'zoom_%s_%s' % (str(sf).replace('.', 'p'), mode)
+        fx[key + '_images'], fx[key + '_labels'] = np.array(r[RD.KEY_IMAGES]), np.array(r[RD.KEY_LABELS])
+        assert np.array_equal(O.resample_plane_xy(images, sf, 0 if mode == 'nearest' else 1), np.array(r[RD.KEY_IMAGES]))
+    sample = fresh()
+    p = RD.PadImages(3, 2, 1, pad_value=0.5)(fresh())
+    fx['pad_images'] = np.array(p[RD.KEY_IMAGES])
+    assert np.array_equal(O.pad_images(images, 3, 2, 1, 0.5), np.array(p[RD.KEY_IMAGES]))
+    random.seed(5)
+    flips = []
+    for _ in range(4):
+        f = RD.HemisphericFlip()(fresh())
+        flips.append(not np.array_equal(np.array(f[RD.KEY_LABELS]), labels))
+    fx['flip_decisions_seed5'] = np.array(flips)
+    fx['flipped_labels'] = np.flip(labels, RD.DIM_HORIZONTAL_NUMPY_3D).copy()
+    ff = RD.HemisphericFlipFixedToCaseId(split_id=2)(fresh())
+    assert np.array_equal(np.array(ff[RD.KEY_LABELS]), fx['flipped_labels'])
+    random.seed(9)
+    rp = RD.RandomPatch(16, 12, 6, 2, 1, 1)(fresh())
+    fx['patch_images_seed9'], fx['patch_labels_seed9'] = np.array(rp[RD.KEY_IMAGES]), np.array(rp[RD.KEY_LABELS])
+    tt = RD.ToTensor()(fresh())
+    fx['to_tensor_labels'] = tt[RD.KEY_LABELS].contiguous().numpy()
+    assert np.array_equal(O.to_tensor(labels), fx['to_tensor_labels'])
+    np.savez_compressed(os.path.join(OUT, name + '.npz'), **fx)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     R = import_reference()
+    transforms_case('transforms_tiny')
     torch.set_num_threads(max(1, (os.cpu_count() or 2) // 2))
     tiny = [1, 4, 6, 8, 10, 12, 1]
     cae_case(R, 'cae_rec_tiny', tiny, (28, 56), 2, 30, 4, 'reconstruction')

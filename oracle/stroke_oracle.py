@@ -216,6 +216,93 @@ def binary_measures(result, target, threshold=0.5):
             "counts": (tp, fp, fn, tn)}
 
 
+def surface_distances_medpy(result, reference, connectivity=1):
+    """MedPy==0.3.0 ``medpy.metric.binary.__surface_distances`` restated on scipy (requirements.txt:2,6; MedPy is not
+    vendored): border = mask XOR binary_erosion(mask, cross of `connectivity`), distances = distance_transform_edt of the
+    reference border's complement read at the result's border voxels (unit voxel spacing)."""
+    import numpy as np
+    from scipy.ndimage import binary_erosion, distance_transform_edt, generate_binary_structure
+    result = np.atleast_1d(np.asarray(result).astype(bool))
+    reference = np.atleast_1d(np.asarray(reference).astype(bool))
+    footprint = generate_binary_structure(result.ndim, connectivity)
+    if 0 == np.count_nonzero(result):
+        raise RuntimeError('The first supplied array does not contain any binary object.')
+    if 0 == np.count_nonzero(reference):
+        raise RuntimeError('The second supplied array does not contain any binary object.')
+    result_border = result ^ binary_erosion(result, structure=footprint, iterations=1)
+    reference_border = reference ^ binary_erosion(reference, structure=footprint, iterations=1)
+    dt = distance_transform_edt(~reference_border, sampling=None)
+    return dt[result_border]
+
+
+def surface_measures(result, target, threshold=0.5):
+    """hd / assd exactly as metrics.py:31-47 obtains them: thresholded uint8 arrays of the FULL shape handed in (the reference
+    hands in the B x 1 x D x H x W batch), ``mpm.hd`` = max of the two directed maxima, ``mpm.assd`` = mean of the two directed
+    means; both stay inf unless both masks have voxels."""
+    import numpy as np
+    r = (np.asarray(result) > threshold).astype(np.uint8)
+    t = (np.asarray(target) > threshold).astype(np.uint8)
+    if not (r.any() and t.any()):
+        return {"hd": float("inf"), "assd": float("inf")}
+    s1, s2 = surface_distances_medpy(r, t), surface_distances_medpy(t, r)
+    return {"hd": float(max(s1.max(), s2.max())), "assd": float(np.mean((s1.mean(), s2.mean()))),
+            "asd_rt": float(s1.mean()), "asd_tr": float(s2.mean()), "n_r": int(s1.size), "n_t": int(s2.size)}
+
+
+def signed_distance_map(volume, threshold=0.5, outside_is_lt=True, sign=1.0):
+    """test_sdm_resampling.py:16-18 (penumbra form: edt(v > thr) - edt(v < thr)) and :31-32 (core form, sign = -1:
+    edt(1 - bin) - edt(bin) = -(edt(bin) - edt(~bin)))."""
+    import numpy as np
+    from scipy.ndimage import distance_transform_edt
+    v = np.asarray(volume)
+    inside = v > threshold
+    outside = (v < threshold) if outside_is_lt else ~inside
+    return sign * (distance_transform_edt(inside) - distance_transform_edt(outside))
+
+
+# ------------------------------------------------------------------------------------------------ data transforms
+def elastic_transform(image, noise, alpha=100, sigma=4):
+    """ElasticDeform.elastic_transform (data.py:331-341) with the three uniform [0, 1) noise fields handed in (the reference
+    draws them from a numpy RandomState): numpy volume indexed [x][y][z]; np.meshgrid's default 'xy' indexing makes the
+    FIRST coordinate follow `dy` and the second `dx` (requires X == Y)."""
+    import numpy as np
+    from scipy.ndimage import gaussian_filter, map_coordinates
+    shape = image.shape
+    dx = gaussian_filter((noise[0] * 2 - 1), sigma, mode="constant", cval=0) * alpha
+    dy = gaussian_filter((noise[1] * 2 - 1), sigma, mode="constant", cval=0) * alpha
+    dz = gaussian_filter((noise[2] * 2 - 1), sigma, mode="constant", cval=0) * alpha * 0.22
+    x, y, z = np.meshgrid(np.arange(shape[0]), np.arange(shape[1]), np.arange(shape[2]))
+    indices = np.reshape(y + dy, (-1, 1)), np.reshape(x + dx, (-1, 1)), np.reshape(z + dz, (-1, 1))
+    return map_coordinates(image, indices, order=1).reshape(shape)
+
+
+def resample_plane_xy(volume, scale_factor, order=0):
+    """ResamplePlaneXY (data.py:354-380): scipy.ndimage.zoom of every [x][y] slice of a [x][y][z][c] array."""
+    import numpy as np
+    import scipy.ndimage as ndi
+    sx, sy = ndi.zoom(volume[:, :, 0, 0], scale_factor, order=0).shape[0:2]
+    out = np.zeros((sx, sy) + volume.shape[2:], dtype=volume.dtype)
+    for c in range(volume.shape[3]):
+        for z in range(volume.shape[2]):
+            out[:, :, z, c] = ndi.zoom(volume[:, :, z, c], scale_factor, order=order)
+    return out
+
+
+def pad_images(volume, px, py, pz, value=0.0):
+    """PadImages (data.py:280-296) on a [x][y][z][c] array."""
+    import numpy as np
+    sx, sy, sz, sc = volume.shape
+    out = np.ones((sx + 2 * px, sy + 2 * py, sz + 2 * pz, sc), dtype=np.float32) * float(value)
+    out[px:-px, py:-py, pz:-pz, :] = volume
+    return out
+
+
+def to_tensor(volume):
+    """ToTensor (data.py:299-310): [x][y][z][c] -> C x Z x Y x X."""
+    import numpy as np
+    return np.ascontiguousarray(np.transpose(volume, (3, 2, 1, 0)))
+
+
 def adam_step(p, g, m, v, step, lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=1e-5):
     """One torch.optim.Adam update on tensors, installed-torch form.  Returns (p, m, v)."""
     g = g + weight_decay * p

@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "libstroke_b200.so")
-SOURCES = ["sp_api.cu", "sp_conv.cu", "sp_norm.cu", "sp_resample.cu", "sp_loss.cu", "sp_optim.cu"]
+SOURCES = ["sp_api.cu", "sp_conv.cu", "sp_norm.cu", "sp_resample.cu", "sp_loss.cu", "sp_optim.cu", "sp_metrics.cu", "sp_augment.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-O2"]
 
@@ -85,6 +85,15 @@ SIGNATURES = {
     "sp_absdiff_mean": (c_int, [c_vp, c_vp, c_i64, c_int, c_vp, c_vp, c_vp]),
     "sp_absdiff_bwd": (c_int, [c_vp, c_vp, c_i64, c_int, c_vp, c_float, c_vp, c_int, c_vp, c_int, c_vp]),
     "sp_binary_counts": (c_int, [c_vp, c_vp, c_i64, c_float, c_vp, c_vp]),
+    "sp_surface_distances_workspace_bytes": (c_size, [c_i64]),
+    "sp_surface_distances": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_float, c_vp, c_vp, c_size, c_vp]),
+    "sp_signed_distance_workspace_bytes": (c_size, [c_i64]),
+    "sp_signed_distance": (c_int, [c_vp, c_int, c_int, c_int, c_int, c_float, c_int, c_float, c_vp, c_vp, c_size, c_vp]),
+    "sp_gauss3d": (c_int, [c_vp, c_i64, c_int, c_int, c_int, c_double, c_double, c_vp, c_vp, c_vp]),
+    "sp_elastic_warp": (c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_int, c_int, c_int, c_double, c_double, c_vp, c_vp]),
+    "sp_zoom_plane_xy": (c_int, [c_vp, c_i64, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp]),
+    "sp_flip_w": (c_int, [c_vp, c_i64, c_int, c_vp, c_vp]),
+    "sp_pad_volume": (c_int, [c_vp, c_i64, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_vp, c_vp]),
     "sp_latent_interp_fwd": (c_int, [c_vp, c_vp, c_vp, c_int, c_i64, c_vp, c_vp]),
     "sp_latent_interp_bwd": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_i64, c_vp, c_int, c_vp, c_int, c_vp, c_vp, c_vp]),
     "sp_adam_multi": (c_int, [c_vp, c_int, c_i64, c_double, c_double, c_double, c_double, c_double, c_i64, c_double,

@@ -1,13 +1,17 @@
 """Loss and per-batch evaluation metrics of the hot path (API of the reference's common/metrics.py).
 
 * ``BatchDiceLoss`` — whole-batch soft Dice (metrics.py:8-28).
-* ``binary_measures_torch`` / ``binary_measures_many`` — the thresholded overlap metrics every train / validation batch
-  reports (metrics.py:31-62).  The reference copies both volumes to the host and calls the un-vendored
-  ``MedPy==0.3.0`` (``requirements.txt:2``); here ONE reduction kernel per pair counts TP / FP / FN / TN on the device and
-  the four count-based measures follow medpy's published definitions (dc = 2 TP / (|A| + |B|), precision = TP / (TP + FP),
-  sensitivity = TP / (TP + FN), specificity = TN / (TN + FP); each 0.0 when its denominator is 0).  The surface
-  distances ``hd`` / ``assd`` (Euclidean distance transforms) are NOT computed on the device: they keep the reference's
-  initial value ``numpy.inf`` (metrics.py:36-37).
+* ``binary_measures_torch`` / ``binary_measures_many`` — the thresholded metrics every train / validation batch reports
+  (metrics.py:31-62).  The reference copies both volumes to the host and calls the un-vendored
+  ``MedPy==0.3.0`` (``requirements.txt:2``); here everything is computed on the device and ALL pairs of a batch come back
+  in ONE device-to-host read:
+  - dc / precision / sensitivity / specificity from the confusion counts of one reduction kernel per pair (medpy's
+    published definitions: dc = 2 TP / (|A| + |B|), precision = TP / (TP + FP), sensitivity = TP / (TP + FN),
+    specificity = TN / (TN + FP); each 0.0 when its denominator is 0);
+  - hd / assd (``mpm.hd`` / ``mpm.assd``, metrics.py:43-45) from exact Euclidean distance transforms on the device
+    (``sp_surface_distances``): like medpy they treat the WHOLE array handed in — the reference hands in the
+    B x 1 x D x H x W batch — as one lattice with unit spacing, and stay ``numpy.inf`` unless both masks have voxels.
+  ``SURFACE_DISTANCES = False`` skips the distance transforms (hd / assd stay ``inf``).
 """
 import numpy
 import torch
@@ -16,8 +20,10 @@ from torch.nn.modules.loss import _Loss as LossModule
 from .. import functions, ops
 from .dto.MetricMeasuresDto import BinaryMeasuresDto
 
+SURFACE_DISTANCES = True
 
-def measures_from_counts(tp, fp, fn, tn):
+
+def measures_from_counts(tp, fp, fn, tn, hd=numpy.inf, assd=numpy.inf):
     """medpy.metric.binary dc / precision / sensitivity / specificity from the confusion counts."""
     tp, fp, fn, tn = float(tp), float(fp), float(fn), float(tn)
     size_r, size_t = tp + fp, tp + fn
@@ -25,20 +31,27 @@ def measures_from_counts(tp, fp, fn, tn):
     precision = tp / (tp + fp) if (tp + fp) > 0 else 0.0
     sensitivity = tp / (tp + fn) if (tp + fn) > 0 else 0.0
     specificity = tn / (tn + fp) if (tn + fp) > 0 else 0.0
-    return BinaryMeasuresDto(dc, numpy.inf, numpy.inf, precision, sensitivity, specificity)
+    return BinaryMeasuresDto(dc, hd, assd, precision, sensitivity, specificity)
 
 
-def binary_measures_many(pairs, binary_threshold=0.5):
+def binary_measures_many(pairs, binary_threshold=0.5, surface_distances=None):
     """[(result, target), ...] (CUDA tensors) -> [BinaryMeasuresDto, ...] with ONE device-to-host read for all pairs."""
     pairs = list(pairs)
     if not pairs:
         return []
+    if surface_distances is None:
+        surface_distances = SURFACE_DISTANCES
     dev = pairs[0][0].device
-    counts = torch.empty((len(pairs), 4), device=dev, dtype=torch.float64)
+    out = torch.empty((len(pairs), 12), device=dev, dtype=torch.float64)
     for i, (r, t) in enumerate(pairs):
-        ops.binary_counts(r.detach(), t.detach(), binary_threshold, out=counts[i])
-    host = counts.cpu().tolist()
-    return [measures_from_counts(*row) for row in host]
+        r, t = r.detach(), t.detach()
+        ops.binary_counts(r, t, binary_threshold, out=out[i, 0:4])
+        if surface_distances:
+            ops.surface_distances(r, t, binary_threshold, out=out[i, 4:12])
+    host = out.cpu().tolist()
+    if surface_distances:
+        return [measures_from_counts(*row[0:4], hd=row[4], assd=row[5]) for row in host]
+    return [measures_from_counts(*row[0:4]) for row in host]
 
 
 def binary_measures_torch(result, target, cuda=True, binary_threshold=0.5):

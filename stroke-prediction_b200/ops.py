@@ -22,7 +22,8 @@ _KERNELS_PER_CALL = {
     "sp_maxpool2_fwd": 1, "sp_maxpool2_bwd": 1, "sp_upsample2_fwd": 1, "sp_upsample2_bwd": 1, "sp_crop_copy": 1,
     "sp_crop_add": 1, "sp_ncdhw_to_ndhwc": 1, "sp_ndhwc_to_ncdhw": 1, "sp_dice_sums": 1, "sp_dice_loss": 1,
     "sp_dice_bwd": 1, "sp_absdiff_mean": 2, "sp_absdiff_bwd": 1, "sp_binary_counts": 1, "sp_latent_interp_fwd": 1,
-    "sp_latent_interp_bwd": 1, "sp_adam_multi": 1,
+    "sp_latent_interp_bwd": 1, "sp_adam_multi": 1, "sp_surface_distances": 13, "sp_signed_distance": 11,
+    "sp_gauss3d": 3, "sp_elastic_warp": 1, "sp_zoom_plane_xy": 1, "sp_flip_w": 1, "sp_pad_volume": 1,
 }
 
 
@@ -421,6 +422,129 @@ def binary_counts(result, target, threshold, out=None):
     if out is None:
         out = torch.empty(4, device=result.device, dtype=torch.float64)
     check(_L().sp_binary_counts(_p(result), _p(target), result.numel(), float(threshold), _p(out), _stream()), "sp_binary_counts")
+    return out
+
+
+def _lattice(t):
+    """Dense tensor of any rank -> (n0, n1, n2, n3, had_singleton_axis): extent-1 axes dropped, at most 4 axes left."""
+    dims = [int(d) for d in t.shape]
+    keep = [d for d in dims if d != 1]
+    if len(keep) > 4:
+        raise RuntimeError("surface distances: at most 4 axes of extent > 1 are supported, got shape %r" % (tuple(dims),))
+    while len(keep) < 4:
+        keep.insert(0, 1)
+    return keep[0], keep[1], keep[2], keep[3], len([d for d in dims if d == 1]) > 0
+
+
+def surface_distances(result, target, threshold=0.5, out=None):
+    """hd / assd (+ the directed parts) of (result > threshold) vs (target > threshold) as 8 doubles on the device; the
+    arrays are taken as ONE lattice exactly like medpy takes the reference's whole B x 1 x D x H x W batch (metrics.py:43-45)."""
+    _req_cuda(result, target)
+    if tuple(result.shape) != tuple(target.shape):
+        raise RuntimeError("surface_distances: shape mismatch %r vs %r" % (tuple(result.shape), tuple(target.shape)))
+    result = _dense_c(result)
+    target = _dense_c(target)
+    n0, n1, n2, n3, single = _lattice(result)
+    total = n0 * n1 * n2 * n3
+    if out is None:
+        out = torch.empty(8, device=result.device, dtype=torch.float64)
+    ws = workspace(_L().sp_surface_distances_workspace_bytes(total), result.device, "metrics")
+    check(_L().sp_surface_distances(_p(result), _p(target), n0, n1, n2, n3, int(single), float(threshold), _p(out), _p(ws),
+                                    ws.numel(), _stream()), "sp_surface_distances")
+    return out
+
+
+def signed_distance(mask, threshold=0.5, outside_is_lt=True, sign=1.0):
+    """sign * (edt(mask > thr) - edt(outside)) over the dense lattice of `mask` (extent-1 axes ignored), fp32."""
+    _req_cuda(mask)
+    mask = _dense_c(mask)
+    n0, n1, n2, n3, _ = _lattice(mask)
+    total = n0 * n1 * n2 * n3
+    out = torch.empty_like(mask)
+    ws = workspace(_L().sp_signed_distance_workspace_bytes(total), mask.device, "metrics")
+    check(_L().sp_signed_distance(_p(mask), n0, n1, n2, n3, float(threshold), int(bool(outside_is_lt)), float(sign), _p(out),
+                                  _p(ws), ws.numel(), _stream()), "sp_signed_distance")
+    return out
+
+
+def _dense_c(t):
+    """fp32, C-contiguous in its LOGICAL axis order (a single-channel NDHWC volume already is)."""
+    if t.dtype != torch.float32:
+        t = t.float()
+    if t.is_contiguous():
+        return t
+    if t.dim() == 5 and t.shape[1] == 1 and is_ndhwc(t):
+        return t.permute(0, 2, 3, 4, 1).reshape(t.shape)      # same memory, contiguous strides (C = 1)
+    return t.contiguous()
+
+
+# ---------------------------------------------------------------------------------------------------- augmentation
+def _ncdhw(x):
+    _req_cuda(x)
+    if x.dim() != 5:
+        raise RuntimeError("expected a B x C x D x H x W tensor, got shape %r" % (tuple(x.shape),))
+    if x.dtype != torch.float32:
+        x = x.float()
+    return x if x.is_contiguous() else x.contiguous()
+
+
+def gauss3d(fields, sigma=4.0, truncate=4.0):
+    """scipy gaussian_filter(mode='constant', cval=0) of fp64 volumes [..., D, H, W] (any leading axes)."""
+    _req_cuda(fields)
+    f = fields.double().contiguous()
+    D, H, W = f.shape[-3:]
+    nvol = f.numel() // (D * H * W)
+    out, tmp = torch.empty_like(f), torch.empty_like(f)
+    check(_L().sp_gauss3d(_p(f), nvol, D, H, W, float(sigma), float(truncate), _p(out), _p(tmp), _stream()), "sp_gauss3d")
+    return out
+
+
+def elastic_warp(x, f1, f2, f3, alpha=100.0, zscale=0.22):
+    """x: B x C x D x H x W fp32; f1..f3: smoothed fp64 noise fields of the same shape (reference draw order)."""
+    x = _ncdhw(x)
+    B, C, D, H, W = x.shape
+    fs = [f.double().contiguous() for f in (f1, f2, f3)]
+    for f in fs:
+        if tuple(f.shape) != tuple(x.shape):
+            raise RuntimeError("elastic_warp: displacement fields must have the volume's shape")
+    out = torch.empty_like(x)
+    check(_L().sp_elastic_warp(_p(x), _p(fs[0]), _p(fs[1]), _p(fs[2]), B * C, D, H, W, float(alpha), float(zscale), _p(out),
+                               _stream()), "sp_elastic_warp")
+    return out
+
+
+def zoom_plane_xy(x, scale_factor, order=0):
+    x = _ncdhw(x)
+    B, C, D, H, W = x.shape
+    Ho, Wo = int(round(H * scale_factor)), int(round(W * scale_factor))       # scipy.ndimage.zoom: round(n * zoom)
+    out = torch.empty((B, C, D, Ho, Wo), device=x.device, dtype=torch.float32)
+    check(_L().sp_zoom_plane_xy(_p(x), B * C * D, H, W, Ho, Wo, int(order), _p(out), _stream()), "sp_zoom_plane_xy")
+    return out
+
+
+def flip_w(x):
+    x = _ncdhw(x)
+    out = torch.empty_like(x)
+    W = x.shape[-1]
+    check(_L().sp_flip_w(_p(x), x.numel() // W, W, _p(out), _stream()), "sp_flip_w")
+    return out
+
+
+def pad_volume(x, pd, ph, pw, value=0.0):
+    x = _ncdhw(x)
+    B, C, D, H, W = x.shape
+    out = torch.empty((B, C, D + 2 * pd, H + 2 * ph, W + 2 * pw), device=x.device, dtype=torch.float32)
+    check(_L().sp_pad_volume(_p(x), B * C, D, H, W, pd, ph, pw, float(value), _p(out), _stream()), "sp_pad_volume")
+    return out
+
+
+def crop_volume(x, offs, size):
+    """x[:, :, od:od+D, oh:oh+H, ow:ow+W] as a dense copy (RandomPatch, data.py:248-277)."""
+    x = _ncdhw(x)
+    B, C, Ds, Hs, Ws = x.shape
+    D, H, W = size
+    out = torch.empty((B, C, D, H, W), device=x.device, dtype=torch.float32)
+    check(_L().sp_crop_copy(_p(x), Ds, Hs, Ws, 1, _p(out), D, H, W, 1, B * C, 1, offs[0], offs[1], offs[2], _stream()), "sp_crop_copy")
     return out
 
 

@@ -873,3 +873,70 @@ def test_packed_weight_cache_is_keyed_on_geometry():
         seq.cpu()(xc).square().sum().backward()
         seq.cuda()
         assert rel_l2(xg.grad, xc.grad) < 1e-4, size
+
+
+def test_curve_tester_cached_sweep_equals_per_step_inference():
+    """CaeReconstructionTesterCurve.infer_curve (latents cached, all time points decoded as one stacked pass, one
+    D2H) against the reference's procedure — a full model run per time point (CaeReconstructionTesterCurve.py:18-42)."""
+    from stroke_prediction_b200.tester.CaeReconstructionTesterCurve import CaeReconstructionTesterCurve
+    A = _api()
+    ch = [1, 4, 6, 8, 10, 12, 1]
+    torch.manual_seed(61)
+    cae = A.Cae3D(A.Enc3D(56, 28, ch, 5, 1.0), A.Dec3D(56, 28, ch, 5, 1.0))
+    for m in cae.modules():                       # non-trivial running statistics (eval mode uses them)
+        if isinstance(m, torch.nn.BatchNorm3d):
+            m.running_mean.uniform_(-0.2, 0.2)
+            m.running_var.uniform_(0.6, 1.5)
+    sd = O.clone_state(cae.state_dict())
+    t = CaeReconstructionTesterCurve(None, cae.cuda(), "/tmp/x", 10, ta_to_tr_fixed_hours=range(4))
+    batch = A.data.synthetic_cae_batch(1, size=(28, 56, 56), seed=3)
+    sched = t.curve_steps(batch)
+    assert len(sched) == 1 + 4 + 9 + 11 and sched[0] == (None, '')
+    steps = [s for s, _ in sched]
+    fast = t.infer_curve(batch, steps)
+    assert len(fast) == len(steps)
+    labels = batch[A.data.KEY_LABELS]
+    for (m_fast, d_fast), s in zip(fast, steps):
+        m_ref, d_ref = t.infer_batch(batch, s)
+        assert rel_max(d_fast.given_variables.time_to_treatment, d_ref.given_variables.time_to_treatment) == 0
+        assert rel_l2(d_fast.reconstructions.gtruth.interpolation, d_ref.reconstructions.gtruth.interpolation) < 1e-6
+        assert rel_l2(d_fast.latents.gtruth.interpolation, d_ref.latents.gtruth.interpolation) < 1e-6
+        for part in ("lesion", "core", "penu"):
+            a, b = getattr(m_fast, part), getattr(m_ref, part)
+            for k in ("dc", "hd", "assd", "precision", "sensitivity", "specificity"):
+                va, vb = getattr(a, k), getattr(b, k)
+                assert va == vb or abs(va - vb) <= 1e-9 * abs(vb), (s, part, k, va, vb)
+    # and one time point against the oracle (eval mode, batch 1)
+    s = steps[3]
+    step = O.time_to_treatment(batch[A.data.KEY_GLOBAL], 10.0, s)
+    lat, rec = O.cae_forward(sd, ch, 1.0, False, labels[:, 0:1], labels[:, 1:2], labels[:, 2:3], step)
+    assert rel_l2(fast[3][1].reconstructions.gtruth.interpolation, rec["interpolation"]) < TOL_ACT
+    want = O.binary_measures(rec["interpolation"], labels[:, 2:3])
+    assert abs(fast[3][0].lesion.dc - want["dc"]) < TOL_DICE
+    import io, contextlib
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        batch[A.data.KEY_CASE_ID] = torch.tensor([7])
+        t._dataloader = [batch]
+        t.run_inference()
+    assert buf.getvalue().count("Case Id=7") == len(steps) and "tr_to_penumbra=1.0" in buf.getvalue()
+
+
+def test_sdm_baseline_matches_scipy_restatement():
+    """test_sdm_resampling.py:15-52 with resample=False: signed distance maps + interpolation + sign segmentation."""
+    from stroke_prediction_b200.common import sdm
+    A = _api()
+    b = A.data.synthetic_cae_batch(1, size=(28, 64, 64), seed=12)
+    lab = b[A.data.KEY_LABELS]
+    core, penu = lab[:, 0:1], lab[:, 1:2]
+    tt = 0.37
+    rc, ri, rp = sdm.sdm_interpolate(core.cuda(), penu.cuda(), tt)
+    pc = O.signed_distance_map(core[0, 0].numpy(), 0.5, False, -1.0)
+    pp = O.signed_distance_map(penu[0, 0].numpy(), 0.5, True, 1.0)
+    want = pp * tt - pc * (1 - tt)
+    assert rel_max(rc, pc) < 1e-6 and rel_max(rp, pp) < 1e-6 and rel_max(ri, want) < 1e-5
+    seg = (ri > 0).float().cpu()
+    assert abs(_dice_binary(seg, torch.from_numpy((want > 0).astype(np.float32))) - 1.0) < TOL_DICE
+    # degenerate case: empty core -> artificial core at the penumbra's centre of mass (reference :24-29)
+    rc2, _, _ = sdm.sdm_interpolate(torch.zeros_like(core).cuda(), penu.cuda(), tt)
+    assert float(rc2.min()) == 0.0 and int((rc2 == 0).sum()) == 63      # 3 dilations of one voxel by the 3-D cross: |x|+|y|+|z| <= 3 -> 63 voxels

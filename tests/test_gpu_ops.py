@@ -436,9 +436,90 @@ def test_binary_measures_match_oracle():
         assert sum(ref["counts"]) == r.numel()
         for k in ("dc", "precision", "sensitivity", "specificity"):
             assert getattr(g, k) == ref[k], (k, getattr(g, k), ref[k])
-        assert g.hd == float("inf") and g.assd == float("inf")
+        sm = O.surface_measures(r.numpy(), t.numpy())
+        assert g.hd == sm["hd"], (g.hd, sm["hd"])                       # sqrt of an exact integer squared distance
+        assert g.assd == sm["assd"] or abs(g.assd - sm["assd"]) <= 1e-12 * sm["assd"], (g.assd, sm["assd"])
     single = metrics.binary_measures_torch(res.cuda(), tgt.cuda(), True)
     assert single.dc == O.binary_measures(res, tgt)["dc"]
+    off = metrics.binary_measures_many([(res.cuda(), tgt.cuda())], surface_distances=False)[0]
+    assert off.hd == float("inf") and off.assd == float("inf") and off.dc == single.dc
+
+
+def _blobs(shape, seed, n=3):
+    """A few random ellipsoidal blobs in an array of `shape` (last three axes spatial), soft values in [0, 1]."""
+    import numpy as np
+    rng = np.random.RandomState(seed)
+    out = np.zeros(shape, dtype=np.float32)
+    sp = shape[-3:]
+    zz, yy, xx = np.meshgrid(*[np.arange(s) for s in sp], indexing="ij")
+    flat = out.reshape((-1,) + tuple(sp))
+    for i in range(flat.shape[0]):
+        for _ in range(n):
+            c = [rng.uniform(0.2, 0.8) * s for s in sp]
+            r = [max(1.0, rng.uniform(0.08, 0.3) * s) for s in sp]
+            d = ((zz - c[0]) / r[0]) ** 2 + ((yy - c[1]) / r[1]) ** 2 + ((xx - c[2]) / r[2]) ** 2
+            flat[i] = np.maximum(flat[i], np.clip(1.2 - d, 0, 1))
+    return torch.from_numpy(out)
+
+
+@pytest.mark.parametrize("shape", [(2, 1, 12, 40, 36), (1, 1, 28, 64, 64), (3, 1, 7, 33, 29), (10, 30, 28), (3, 9, 20, 24),
+                                   (4, 1, 28, 128, 128)])
+def test_surface_distances_match_medpy_restatement(shape):
+    """hd / assd (metrics.py:43-45 -> MedPy 0.3.0 `__surface_distances`) on the device against the scipy restatement, on the
+    reference's B x 1 x D x H x W batches (extent-1 channel axis: the erosion is empty, every object voxel is "border", the batch
+    axis is a lattice axis) and on arrays without extent-1 axes (true connectivity-1 erosion)."""
+    _, _, ops = _mods()
+    import stroke_oracle as O
+    r, t = _blobs(shape, 3), _blobs(shape, 5)
+    got = ops.surface_distances(r.cuda(), t.cuda(), 0.5).cpu().tolist()
+    ref = O.surface_measures(r.numpy(), t.numpy())
+    assert got[6] == ref["n_r"] and got[7] == ref["n_t"]
+    assert got[0] == ref["hd"], (got[0], ref["hd"])
+    assert abs(got[1] - ref["assd"]) <= 1e-12 * ref["assd"]
+    assert abs(got[2] - ref["asd_rt"]) <= 1e-12 * ref["asd_rt"] and abs(got[3] - ref["asd_tr"]) <= 1e-12 * ref["asd_tr"]
+    # the same volume as an NDHWC-strided single-channel tensor (what the models return)
+    if len(shape) == 5:
+        rv = ops.as_vol(r.cuda())
+        got2 = ops.surface_distances(rv, t.cuda(), 0.5).cpu().tolist()
+        assert got2 == got
+
+
+def test_surface_distances_edge_cases():
+    _, _, ops = _mods()
+    import stroke_oracle as O
+    shape = (2, 1, 6, 20, 20)
+    z = torch.zeros(shape)
+    one = torch.zeros(shape)
+    one[1, 0, 3, 4, 5] = 1.0
+    other = torch.zeros(shape)
+    other[0, 0, 1, 10, 17] = 1.0
+    full = torch.ones(shape)
+    inf = float("inf")
+    for r, t in [(z, one), (one, z), (z, z)]:
+        got = ops.surface_distances(r.cuda(), t.cuda(), 0.5).cpu().tolist()
+        assert got[0] == inf and got[1] == inf
+    for r, t in [(one, one), (one, other), (full, one), (full, full)]:
+        got = ops.surface_distances(r.cuda(), t.cuda(), 0.5).cpu().tolist()
+        ref = O.surface_measures(r.numpy(), t.numpy())
+        assert got[0] == ref["hd"] and abs(got[1] - ref["assd"]) <= 1e-12 * max(ref["assd"], 1e-300), (got, ref)
+    # two single voxels in different samples: the batch axis counts as a lattice axis, sqrt(1 + 4 + 36 + 144)
+    got = ops.surface_distances(one.cuda(), other.cuda(), 0.5).cpu().tolist()
+    assert got[0] == (1 + 2 ** 2 + 6 ** 2 + 12 ** 2) ** 0.5
+    with pytest.raises(RuntimeError):
+        ops.surface_distances(torch.zeros(2, 2, 2, 2, 2, 2).cuda(), torch.zeros(2, 2, 2, 2, 2, 2).cuda())
+
+
+@pytest.mark.parametrize("form", ["penu", "core"])
+def test_signed_distance_map_matches_scipy(form):
+    """SDM baseline (test_sdm_resampling.py:16-33): edt(inside) - edt(outside) per case volume."""
+    _, _, ops = _mods()
+    import stroke_oracle as O
+    v = _blobs((28, 64, 64), 9)
+    v[3, 10, 10:14] = 0.5                   # exactly the threshold: neither inside nor (for the '<' form) outside
+    lt, sign = (True, 1.0) if form == "penu" else (False, -1.0)
+    got = ops.signed_distance(v.cuda(), 0.5, lt, sign).cpu()
+    ref = torch.from_numpy(O.signed_distance_map(v.numpy(), 0.5, lt, sign)).float()
+    assert torch.equal(got, ref) or rel_max(got, ref) < 1e-6
 
 
 def test_hinge_and_l1_including_exact_zeros():
@@ -524,3 +605,103 @@ def test_no_cpu_fallback():
         ops.as_vol(torch.zeros(1, 1, 2, 2, 2))
     with pytest.raises(RuntimeError):
         functions.dice_term(torch.rand(10), torch.rand(10))
+
+
+# ---------------------------------------------------------------------------------------------------- data transforms (n2)
+def _np_to_batch(v):
+    """reference numpy sample [x][y][z][c] -> torch B x C x Z x Y x X on the device"""
+    return torch.from_numpy(v.copy()).permute(3, 2, 1, 0).unsqueeze(0).contiguous().cuda()
+
+
+def _batch_to_np(t):
+    return t[0].permute(3, 2, 1, 0).contiguous().cpu().numpy()
+
+
+def test_device_transforms_against_reference_fixture():
+    """common/data.py:215-380 on the device vs outputs of the reference's own transform classes (tests/golden/transforms_tiny,
+    generated by oracle/make_golden.py): elastic deformation replayed with the reference's numpy noise stream, per-slice zoom
+    (nearest / bilinear), constant padding, hemispheric flip, random patch, ToTensor."""
+    import random
+    import numpy as np
+    from util import load
+    from stroke_prediction_b200.common import data, gpu_transforms as T
+    fx = load("transforms_tiny")
+    labels, images = fx["labels"], fx["images"]
+    X, Y, Z, C = labels.shape
+    batch = {data.KEY_LABELS: _np_to_batch(labels), data.KEY_IMAGES: _np_to_batch(images), data.KEY_CASE_ID: [3]}
+    assert np.array_equal(batch[data.KEY_LABELS][0].cpu().numpy(), fx["to_tensor_labels"])
+    tt = T.ToTensor()({data.KEY_LABELS: labels, data.KEY_IMAGES: images})
+    assert torch.equal(tt[data.KEY_LABELS], batch[data.KEY_LABELS])
+    # elastic: the reference draws dx, dy, dz per channel from ONE running RandomState, labels first, then images
+    rs = np.random.RandomState(int(fx["elastic_seed"]))
+    def draw(n_ch):
+        noise = np.zeros((3, 1, n_ch, Z, Y, X))
+        for c in range(n_ch):
+            for f in range(3):
+                noise[f, 0, c] = rs.rand(X, Y, Z).transpose(2, 1, 0)
+        return torch.from_numpy(noise)
+    n_l, n_i = draw(C), draw(images.shape[3])
+    out = T.ElasticDeform(100, 4, apply_to_images=True)(batch, noise=n_l, image_noise=n_i)
+    got_l, got_i = _batch_to_np(out[data.KEY_LABELS]), _batch_to_np(out[data.KEY_IMAGES])
+    assert np.abs(got_l - fx["elastic_labels"]).max() < 2e-6, np.abs(got_l - fx["elastic_labels"]).max()
+    assert np.abs(got_i - fx["elastic_images"]).max() < 2e-5 and rel_l2(got_i, fx["elastic_images"]) < 1e-6
+    assert float(np.abs(got_l - labels).max()) > 0.5           # it really deformed something
+    # zoom
+    for sf, tag in ((0.5, "0p5"), (0.75, "0p75")):
+        for mode in ("nearest", "bilinear"):
+            z = T.ResamplePlaneXY(sf, mode)(batch)
+            for key, name in ((data.KEY_IMAGES, "images"), (data.KEY_LABELS, "labels")):
+                want = fx["zoom_%s_%s_%s" % (tag, mode, name)]
+                got = _batch_to_np(z[key])
+                assert got.shape == want.shape
+                if mode == "nearest":
+                    assert np.array_equal(got, want), (sf, mode, name)
+                else:
+                    assert np.abs(got - want).max() <= 1e-5 * max(1.0, np.abs(want).max()), (sf, mode, name)
+    up = T.ResamplePlaneXY(1.5, "bilinear")(batch)                           # factors > 1 (the reference's class cannot)
+    import stroke_oracle as O
+    assert np.abs(_batch_to_np(up[data.KEY_IMAGES]) - O.resample_plane_xy(images, 1.5, 1)).max() < 2e-5
+    # pad, flip, patch
+    p = T.PadImages(3, 2, 1, pad_value=0.5)(batch)
+    assert np.array_equal(_batch_to_np(p[data.KEY_IMAGES]), fx["pad_images"])
+    random.seed(5)
+    for want_flip in fx["flip_decisions_seed5"]:
+        f = T.HemisphericFlip()(batch)
+        assert np.array_equal(_batch_to_np(f[data.KEY_LABELS]), fx["flipped_labels"] if want_flip else labels)
+    f = T.HemisphericFlipFixedToCaseId(split_id=2)(batch)
+    assert np.array_equal(_batch_to_np(f[data.KEY_LABELS]), fx["flipped_labels"])
+    f = T.HemisphericFlipFixedToCaseId(split_id=5)(batch)
+    assert np.array_equal(_batch_to_np(f[data.KEY_LABELS]), labels)
+    random.seed(9)
+    rp = T.RandomPatch(16, 12, 6, 2, 1, 1)(batch)
+    assert np.array_equal(_batch_to_np(rp[data.KEY_IMAGES]), fx["patch_images_seed9"])
+    assert np.array_equal(_batch_to_np(rp[data.KEY_LABELS]), fx["patch_labels_seed9"])
+
+
+def test_elastic_deform_named_shape_against_scipy_restatement():
+    """ElasticDeform at the CAE's volume size (128 x 128 x 28, batch 2, 3 label channels) vs the scipy restatement."""
+    import numpy as np
+    import stroke_oracle as O
+    from stroke_prediction_b200.common import data, gpu_transforms as T
+    b = data.synthetic_cae_batch(2, seed=4)
+    lab = b[data.KEY_LABELS]
+    rs = np.random.RandomState(123)
+    B, C, D, H, W = lab.shape
+    noise = np.zeros((3, B, C, D, H, W))
+    want = np.zeros((B, C, D, H, W), np.float32)
+    for n in range(B):
+        for c in range(C):
+            fields = [rs.rand(W, H, D) for _ in range(3)]
+            for f in range(3):
+                noise[f, n, c] = fields[f].transpose(2, 1, 0)
+            vol = lab[n, c].permute(2, 1, 0).contiguous().numpy()                       # [x][y][z]
+            want[n, c] = O.elastic_transform(vol, fields, 100, 4).transpose(2, 1, 0)
+    out = T.ElasticDeform()({data.KEY_LABELS: lab.cuda()}, noise=torch.from_numpy(noise))[data.KEY_LABELS]
+    assert np.abs(out.cpu().numpy() - want).max() < 5e-6
+    # device-generated noise: same statistics (values stay in [0, 1], mass roughly preserved), deterministic per generator
+    g = torch.Generator(device="cuda").manual_seed(3)
+    o1 = T.ElasticDeform(generator=g)({data.KEY_LABELS: lab.cuda()})[data.KEY_LABELS]
+    g = torch.Generator(device="cuda").manual_seed(3)
+    o2 = T.ElasticDeform(generator=g)({data.KEY_LABELS: lab.cuda()})[data.KEY_LABELS]
+    assert torch.equal(o1, o2) and float(o1.min()) >= 0.0 and float(o1.max()) <= 1.0
+    assert abs(float(o1.sum()) / float(lab.sum()) - 1.0) < 0.2

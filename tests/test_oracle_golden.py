@@ -129,3 +129,63 @@ def test_oracle_binary_measures_definitions():
     z = torch.zeros(4)
     e = O.binary_measures(z, z)
     assert e["dc"] == 0.0 and e["precision"] == 0.0 and e["sensitivity"] == 0.0 and e["specificity"] == 1.0
+
+
+def test_oracle_surface_measures_known_answers():
+    """MedPy 0.3.0 hd / assd restatement (oracle.surface_measures) on hand-computed cases (metrics.py:31-47)."""
+    import numpy as np
+    import stroke_oracle as O
+    # two single voxels in a 3-D array: both are their own border; distance sqrt(1 + 4 + 9)
+    a = np.zeros((5, 6, 7), np.float32)
+    b = np.zeros((5, 6, 7), np.float32)
+    a[1, 1, 1] = 1
+    b[2, 3, 4] = 1
+    m = O.surface_measures(a, b)
+    assert m["hd"] == 14 ** 0.5 and m["assd"] == 14 ** 0.5
+    # a 3x3x3 cube against its centre voxel: the cube's border is its 26 shell voxels (connectivity-1 erosion leaves the centre),
+    # their distances to the centre are 6 x 1, 12 x sqrt(2), 8 x sqrt(3); the centre voxel is 1 away from the shell
+    a[:] = 0
+    b[:] = 0
+    a[1:4, 1:4, 1:4] = 1
+    b[2, 2, 2] = 1
+    m = O.surface_measures(a, b)
+    want_rt = (6 * 1 + 12 * 2 ** 0.5 + 8 * 3 ** 0.5) / 26
+    assert abs(m["asd_rt"] - want_rt) < 1e-12 and m["asd_tr"] == 1.0 and m["hd"] == 3 ** 0.5
+    assert abs(m["assd"] - 0.5 * (want_rt + 1.0)) < 1e-12
+    # the reference hands in B x 1 x D x H x W: the extent-1 channel axis empties the erosion -> every voxel is border, and the
+    # batch axis is a lattice axis (a voxel in sample 0 and the same position in sample 1 are 1 apart)
+    a5 = np.zeros((2, 1, 5, 6, 7), np.float32)
+    b5 = np.zeros((2, 1, 5, 6, 7), np.float32)
+    a5[0, 0, 1:4, 1:4, 1:4] = 1
+    b5[1, 0, 2, 2, 2] = 1
+    m = O.surface_measures(a5, b5)
+    assert m["n_r"] == 27 and m["n_t"] == 1
+    assert m["hd"] == (1 + 3) ** 0.5                      # corner voxel: sqrt(3) in-plane, 1 along the batch axis
+    assert O.surface_measures(np.zeros((2, 1, 3, 3, 3)), b5[:, :, :3, :3, :3])["hd"] == float("inf")
+    # signed distance map: 1-D-like check inside a volume
+    v = np.zeros((1, 1, 9), np.float32)
+    v[0, 0, 3:6] = 1
+    s = O.signed_distance_map(v, 0.5, True, 1.0)
+    assert list(s[0, 0]) == [-3, -2, -1, 1, 2, 1, -1, -2, -3]
+
+
+def test_oracle_transforms_against_reference_fixture():
+    """oracle.elastic_transform / resample_plane_xy / pad_images / to_tensor reproduce the reference's own transform classes
+    (tests/golden/transforms_tiny.npz, common/data.py:280-380) bit for bit."""
+    import numpy as np
+    import stroke_oracle as O
+    from util import load
+    fx = load("transforms_tiny")
+    labels, images = fx["labels"], fx["images"]
+    rs = np.random.RandomState(int(fx["elastic_seed"]))
+    for c in range(labels.shape[3]):
+        noise = [rs.rand(*labels.shape[:3]) for _ in range(3)]
+        assert np.array_equal(O.elastic_transform(labels[:, :, :, c], noise, 100, 4), fx["elastic_labels"][:, :, :, c])
+    for c in range(images.shape[3]):
+        noise = [rs.rand(*images.shape[:3]) for _ in range(3)]
+        assert np.array_equal(O.elastic_transform(images[:, :, :, c], noise, 100, 4), fx["elastic_images"][:, :, :, c])
+    for sf, tag in ((0.5, "0p5"), (0.75, "0p75")):
+        for order, mode in ((0, "nearest"), (1, "bilinear")):
+            assert np.array_equal(O.resample_plane_xy(images, sf, order), fx["zoom_%s_%s_images" % (tag, mode)])
+    assert np.array_equal(O.pad_images(images, 3, 2, 1, 0.5), fx["pad_images"])
+    assert np.array_equal(O.to_tensor(labels), fx["to_tensor_labels"])
