@@ -16,6 +16,7 @@
 #include "sp_conv_gemm.cuh"
 #include "sp_conv_tc.cuh"
 #include "sp_conv_tc2.cuh"
+#include "sp_conv_tc3.cuh"
 #include "sp_wgrad_tc.cuh"
 #include "sp_wgrad_tc24.cuh"
 #include "sp_conv_thin.cuh"
@@ -495,6 +496,7 @@ SpTier corrT_tier(const SpConvDesc* d, SpTcCfg* cfg) {
 int tc_corr_launch(const SpConvDesc* d, const SpTcCfg& cfg, int nPerG, const float* src, const float* wimg, const float* bias,
                    const float* scale, const float* shift, float* dst, cudaStream_t st) {
     const uint4* img = reinterpret_cast<const uint4*>(wimg);
+    if (sp_tc_gen3()) return sp_tc3_corr_launch(d, nPerG, sp_tc_image_terms(), src, img, bias, scale, shift, dst, st);
     if (sp_tc_terms() == 4) return sp_tc2_corr_launch(d, nPerG, src, img, bias, scale, shift, dst, st);
     if (sp_tc_terms() == 2) return sp_tc_corr_launch_t<16, 16, 2, 4>(d, nPerG, src, img, bias, scale, shift, dst, st);
     return sp_tc_corr_launch_t<16, 16, 3, 2>(d, nPerG, src, img, bias, scale, shift, dst, st);
@@ -508,7 +510,7 @@ extern "C" {
 int sp_get_tc_terms(void) { return sp_tc_terms(); }
 
 int sp_set_tc_terms(int terms) {
-    SP_REQUIRE(terms == 0 || terms == 2 || terms == 3 || terms == 4, "sp_set_tc_terms: mode must be 0 (off), 2, 3 or 4, got %d", terms);
+    SP_REQUIRE(terms >= 0 && terms <= 5, "sp_set_tc_terms: mode must be 0 (off) .. 5, got %d", terms);
     sp_tc_terms_ref() = terms;
     return 0;
 }
@@ -517,7 +519,9 @@ size_t sp_packed_weight_floats(const SpConvDesc* d, int which) {
     if (!d) return 0;
     size_t n = ffma_packed_floats(d, which);
     SpTcCfg cfg;
-    if ((which == 0 ? corr_tier(d, &cfg) : corrT_tier(d, &cfg)) == TIER_TC) n += (size_t)cfg.passes * cfg.nslices * sp_tc_wimg_bytes(cfg.cip, cfg.cop, sp_tc_image_terms()) / sizeof(float);
+    if ((which == 0 ? corr_tier(d, &cfg) : corrT_tier(d, &cfg)) == TIER_TC && sp_tc_gen3())
+        n += (size_t)cfg.passes * cfg.nslices * sp_tc3_wimg_u4(cfg.cop, sp_tc_image_terms()) * 4;
+    else if ((which == 0 ? corr_tier(d, &cfg) : corrT_tier(d, &cfg)) == TIER_TC) n += (size_t)cfg.passes * cfg.nslices * sp_tc_wimg_bytes(cfg.cip, cfg.cop, sp_tc_image_terms()) / sizeof(float);
     return n;
 }
 
@@ -540,6 +544,8 @@ int sp_pack_weights(const SpConvDesc* d, int which, const float* w_torch, float*
         pack_weights_kernel<<<grid_for(total), 256, 0, sp_stream(stream)>>>(w_torch, w_packed, d->Co, d->Ci, k3, which, dP);
         SP_LAUNCH_OK("pack_weights_kernel");
     }
+    if (tc && sp_tc_gen3())
+        return sp_tc3_pack_launch(d, which, sp_tc_image_terms(), cfg.cop, w_torch, w_packed + total, sp_stream(stream), cfg.passes, cfg.nslices);
     if (tc)
         return sp_tc_pack_launch(d, which, sp_tc_image_terms(), cfg.cip, cfg.cop, w_torch, w_packed + total, sp_stream(stream), cfg.passes, cfg.nslices);
     return 0;

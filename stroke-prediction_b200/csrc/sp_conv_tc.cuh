@@ -359,12 +359,14 @@ static inline int& sp_tc_terms_ref() {
     if (v < 0) {
         v = 4;
         const char* e = getenv("SP_TC_TERMS");
-        if (e && (e[0] == '0' || e[0] == '2' || e[0] == '3' || e[0] == '4')) v = e[0] - '0';
+        if (e && e[0] >= '0' && e[0] <= '5') v = e[0] - '0';
     }
     return v;
 }
 static inline int sp_tc_terms() { return sp_tc_terms_ref(); }
-static inline int sp_tc_image_terms() { return sp_tc_terms() == 4 ? 3 : sp_tc_terms(); }   // bf16 terms of the weight image
+static inline int sp_tc_image_terms() { return (sp_tc_terms() == 4 || sp_tc_terms() == 5) ? 3 : sp_tc_terms(); }   // bf16 terms of the weight image
+// generation-3 kernel (sp_conv_tc3.cuh): mode 5 = three-term fp32-grade arithmetic, mode 1 = bf16 mode (one term, RN)
+static inline bool sp_tc_gen3() { return sp_tc_terms() == 5 || sp_tc_terms() == 1; }
 
 struct SpTcCfg { int cip, cop, td, passes, nslices; };   // pipelined kernel: input-channel passes of 16, output slices of 16 (Co > 24)
 
@@ -374,7 +376,8 @@ static inline bool sp_tc_corr_supported(const SpConvDesc* d, SpTcCfg* cfg) {
     // the pipelined kernel also serves wider layers: 17..24 output channels as one 24-wide pass, more as slices of 16 (each its
     // own launch into a channel slice of dst), and up to six input-channel passes of 16 whose raw sums accumulate in dst
     // (the 24-channel level of the CAE, every Block3x3x3 of the U-Net: Unet3D.py:19,22)
-    const int comax = (sp_tc_terms() == 4) ? 96 : 16, cimax = (sp_tc_terms() == 4) ? 96 : 16;
+    const bool wide = sp_tc_terms() == 4 || sp_tc_gen3();
+    const int comax = wide ? 96 : 16, cimax = wide ? 96 : 16;
     if (d->Ci > cimax || d->Co > comax || d->Ci < 8 || d->Co < 8) return false;   // narrower layers: FFMA tier (2- / 8-wide passes)
     const int64_t ov = (int64_t)d->Do * d->Ho * d->Wo;
     if (ov < 4096 || d->Wo < 8 || d->Ho < 16) return false;      // (the CAE's 32-channel level: 7x27x27 per sample)

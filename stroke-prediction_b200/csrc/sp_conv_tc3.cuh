@@ -1,0 +1,468 @@
+// sp_conv_tc3.cuh — third-generation tcgen05 / TMEM correlation for the 3x3x3 stride-1 layers (Cae3D.py:44,52,55,186-211;
+// Unet3D.py:19,22) and, through flipped taps, their dgrads.  Same split-bf16 arithmetic as sp_conv_tc2.cuh (three bf16 terms
+// per fp32 operand, products of order <= 2, leading products and corrections in separate accumulators), restructured around the
+// two things ncu showed binding generation 2 (tensor pipe 12-23 % active: staging and MMA issue, not the pipe):
+//
+//  * kw-stacked N.  The three taps along w share ONE A tile: D[voxel, (kw, co)] = sum_ci X[voxel][ci] * W[kd,kh,kw][co][ci], so a
+//    (kd, kh) pair is ONE MMA per activation term with N = 3 x Co x terms (144 / 96 / 48 columns for 16 channels) instead of
+//    three with N = 48 / 32 / 16: 27 MMAs per 128-row tile instead of 81, each long enough (72 / 48 / 24 pipe cycles) to keep the
+//    tensor pipe fed.  The epilogue adds the three kw partial sums from NEIGHBOURING rows (out[w] = D0[w] + D1[w+1] + D2[w+2]):
+//    rows are (h, w'') with w'' fastest, so that is two warp shuffles per column; a 16-wide row yields 14 outputs.
+//    Accuracy is unchanged: every leading accumulator still takes 9 accumulations (kd, kh), the epilogue adds 3 of them in RN.
+//  * rolling depth window.  A CTA owns a (8 rows x 14 columns) output patch and walks along depth: every input plane (10 x 16
+//    halo voxels) is staged ONCE into a ring of 6 shared-memory planes and used by the three output planes around it (generation 2
+//    staged 4 halo planes per 2 output planes: 2.0x the loads, splits and stores per output).  The pipeline never drains: ring,
+//    accumulator and barrier phases run on global counters across the CTA's work items.
+//
+// Roles (one persistent CTA per SM, 21 warps): warps 0-7 epilogue (two groups of four alternate output planes; TMEM lane
+// quarter = warp % 4), warps 8-17 staging (one (voxel, 8-channel chunk) item per thread and plane, the next plane's global loads
+// in flight while the current one is split and stored), warps 18-20 one MMA-issuing thread each (output plane q -> issuer
+// q % NACC, accumulator q % NACC: MMAs of one thread retire one after the other, different issuers overlap).
+// NS = 1 is the bf16 mode: operands rounded to ONE bf16 term (RN), one MMA per (kd, kh), fp32 accumulation.
+#pragma once
+#include "sp_conv_tc2.cuh"
+
+namespace sp_tc3 {
+
+using namespace sp_tc;
+using sp_tc2::mbar_arrive;
+using sp_tc2::split8_trunc3;
+using sp_tc2::tmem_ld_n;
+
+constexpr int TW = 16, TWV = 14, TH = 8, IH = TH + 2;   // MMA rows = 16 w'' x 8 h; 14 x 8 outputs per plane
+constexpr int PSLOTS = IH * TW;                          // 160 sixteen-byte slots per (term, chunk) plane
+constexpr int CHS = PSLOTS + 4;                          // chunk-plane stride: odd multiple of 64 B (bank spread of the 2 K chunks)
+constexpr int RING = 6;                                  // staged input planes in flight
+constexpr int NEPI_G = 2, NEPI_W = 4 * NEPI_G;           // epilogue groups / warps
+constexpr int NSTG_W = 10, NSTG = NSTG_W * 32;           // staging warps / threads: 320 = one item per thread and plane
+constexpr int NISS_W = 3;                                // MMA issuer warps (NACC of them active)
+constexpr int NWARPS3 = NEPI_W + NSTG_W + NISS_W;        // 21
+constexpr int NTHREADS3 = NWARPS3 * 32;                  // 672
+static_assert(PSLOTS * 2 == NSTG, "one (slot, chunk) item per staging thread");
+
+template <int COP, int NS>
+struct Tc3 {
+    static constexpr int TS = (3 * COP + 15) / 16 * 16;          // N rows / TMEM columns per weight term: 3 kw x COP, padded to 16
+    static constexpr int NTOT = NS * TS;                         // rows of the weight image per ((kd, kh), chunk) = N of the a1 MMA
+    static constexpr int BROWS = NTOT + 4;                       // padded chunk stride of the image in shared memory
+    static constexpr int ACOLS = NTOT;                           // TMEM columns per output plane: [main | cA | cB]
+    static constexpr int NACC = (512 / ACOLS) < 3 ? (512 / ACOLS) : 3;
+    static constexpr int SLOT_U4 = NS * 2 * CHS;                 // uint4 per ring slot: [term][chunk][CHS]
+    static constexpr int WIMG = 9 * 2 * NTOT;                    // global image (uint4)
+    static constexpr int WIMGS = 9 * 2 * BROWS;                  // shared-memory image (uint4)
+    static constexpr size_t SMEM = ((size_t)RING * SLOT_U4 + WIMGS) * 16 + 256;
+    static_assert(NTOT % 16 == 0 && NTOT <= 256, "UMMA M = 128 needs N % 16 == 0, N <= 256");
+    static_assert(NACC >= 2, "two accumulators in flight at least");
+};
+static_assert(Tc3<24, 3>::SMEM <= 227 * 1024, "tc3: shared memory");
+
+// ---- weight image -----------------------------------------------------------------------------------------------------
+// img[((kd*3+kh) * 2 + chunk) * NTOT + term * TS + kw * COP + n] = 8 bf16 {term of Wsrc(n0 + n, k0 + chunk*8 + j, tap)}, zero rows
+// between 3*COP and TS.  transposed: GEMM N = conv-ci, K = conv-co, taps flipped (sp_corrT as a correlation).
+template <int NS>
+__global__ void pack_wimg3_kernel(const float* __restrict__ w, int Co, int Ci, int transposed, int COP, int TS, int k0, int n0,
+                                  uint4* __restrict__ img) {
+    const int NTOT = NS * TS;
+    const int total = 9 * 2 * TS;
+    const int Nn = transposed ? Ci : Co, Kk = transposed ? Co : Ci;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int row = i % TS;                       // kw * COP + n, or padding
+        const int chunk = (i / TS) % 2;
+        const int t9 = i / (2 * TS);
+        const int kw = row / COP, nl = row % COP;
+        const int n = n0 + nl;
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int k = k0 + chunk * 8 + j;
+            float x = 0.f;
+            if (kw < 3 && n < Nn && k < Kk) {
+                const int tap = t9 * 3 + kw;
+                x = transposed ? w[((int64_t)k * Ci + n) * 27 + (26 - tap)] : w[((int64_t)n * Ci + k) * 27 + tap];
+            }
+            v[j] = x;
+        }
+        uint4 o[3];
+        if (NS == 3) {
+            split8<3>(v, o);
+        } else {
+            o[0] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+        }
+#pragma unroll
+        for (int s = 0; s < NS; ++s) img[(t9 * 2 + chunk) * NTOT + s * TS + row] = o[s];
+    }
+}
+
+template <int N>
+__device__ __forceinline__ void tmem_ld_issue(uint32_t taddr, uint32_t* r) {
+#pragma unroll
+    for (int c = 0; c < N; c += 8)
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=r"(r[c]), "=r"(r[c + 1]), "=r"(r[c + 2]), "=r"(r[c + 3]), "=r"(r[c + 4]), "=r"(r[c + 5]), "=r"(r[c + 6]), "=r"(r[c + 7])
+                     : "r"(taddr + c) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+struct Item3 { int n, oh0, ow0, od_lo, L; };
+
+// accum != 0: add the raw sums already in dst (later input-channel passes); fin == 0: store raw sums (no bias, no activation).
+// sstride: floats between the scale / shift rows of two statistics groups (the layer's full channel count when src is a slice).
+template <int COP, int NS>
+__global__ void __launch_bounds__(NTHREADS3, 1)
+corr3_tc3_kernel(SpConvDesc d, int nPerG, int tiles_w, int tiles_h, int nseg, int seg_len, int total_items,
+                 const float* __restrict__ src, const uint4* __restrict__ wimg, const float* __restrict__ bias,
+                 const float* __restrict__ scale, const float* __restrict__ shift, int sstride, int accum, int fin,
+                 float* __restrict__ dst, long long* __restrict__ prof) {
+    using T = Tc3<COP, NS>;
+    constexpr int TS = T::TS, NTOT = T::NTOT, BROWS = T::BROWS, ACOLS = T::ACOLS, NACC = T::NACC, SLOT_U4 = T::SLOT_U4;
+    constexpr int WIMG = T::WIMG, WIMGS = T::WIMGS;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint4* As = reinterpret_cast<uint4*>(smem_raw);                          // [RING][NS][2][CHS]
+    uint4* Bs = As + (size_t)RING * SLOT_U4;                                 // weight image [9][2][BROWS]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(Bs + WIMGS);                 // a_full[RING] a_empty[RING] t_full[3] t_empty[3]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * RING + 6);
+    const bool pr = (prof != nullptr) && (blockIdx.x == 0);
+    long long pw0 = 0, pw1 = 0, pwk = 0;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    for (int i = tid; i < WIMG; i += NTHREADS3) Bs[(i / NTOT) * BROWS + (i % NTOT)] = wimg[i];
+    if (tid == 0) {
+        for (int s = 0; s < RING; ++s) {
+            mbar_init(smem_u32(&bars[s]), NSTG);                 // a_full: every staging thread
+            mbar_init(smem_u32(&bars[RING + s]), 3);             // a_empty: one tcgen05.commit per output plane that read the slot
+        }
+        for (int a = 0; a < 3; ++a) {
+            mbar_init(smem_u32(&bars[2 * RING + a]), 1);         // t_full: the issuer of the plane
+            mbar_init(smem_u32(&bars[2 * RING + 3 + a]), 128);   // t_empty: the 128 threads of the draining epilogue group
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) tmem_alloc<512>(tmem_slot);
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t a_full = smem_u32(&bars[0]), a_empty = smem_u32(&bars[RING]);
+    const uint32_t t_full = smem_u32(&bars[2 * RING]), t_empty = smem_u32(&bars[2 * RING + 3]);
+
+    auto item_of = [&](int item) {
+        Item3 it;
+        int t = item;
+        const int sg = t % nseg; t /= nseg;
+        const int tw = t % tiles_w; t /= tiles_w;
+        const int th_ = t % tiles_h;
+        it.n = t / tiles_h;
+        it.ow0 = tw * TWV; it.oh0 = th_ * TH;
+        it.od_lo = sg * seg_len;
+        it.L = (d.Do - it.od_lo < seg_len) ? d.Do - it.od_lo : seg_len;
+        return it;
+    };
+
+    if (warp >= NEPI_W && warp < NEPI_W + NSTG_W) {
+        // =================================================================== staging warps
+        const int st = tid - NEPI_W * 32;                        // 0..319
+        const int chunk = st & 1, slot = st >> 1;                // this thread's item of every plane
+        const int hy = slot / TW, wx = slot % TW;
+        const int c = chunk * 8;
+        const bool vec = (d.ldi % 4 == 0);
+        uint32_t gin = 0;                                        // global input-plane counter of this CTA
+        for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+            const Item3 it = item_of(item);
+            const int g = it.n / nPerG;
+            float bsc[8], bsh[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const bool okc = scale && (c + j < d.Ci);
+                bsc[j] = okc ? scale[(int64_t)g * sstride + c + j] : 1.f;
+                bsh[j] = okc ? shift[(int64_t)g * sstride + c + j] : 0.f;
+            }
+            const int gh = it.oh0 - d.ph + hy, gw = it.ow0 - d.pw + wx;
+            const bool in_hw = gh >= 0 && gh < d.Hi && gw >= 0 && gw < d.Wi && c < d.Ci;
+            const float* colp = src + (((int64_t)it.n * d.Di * d.Hi + gh) * d.Wi + gw) * d.ldi + c;   // + gd * Hi*Wi*ldi
+            const int64_t dstride = (int64_t)d.Hi * d.Wi * d.ldi;
+            const int id0 = it.od_lo - d.pd;
+            const int nplanes = it.L + 2;
+            auto load_plane = [&](int ip, float4& a, float4& b) -> bool {
+                const int gd = id0 + ip;
+                a = make_float4(0.f, 0.f, 0.f, 0.f);
+                b = a;
+                if (!(in_hw && gd >= 0 && gd < d.Di)) return false;
+                const float* p = colp + (int64_t)gd * dstride;
+                if (vec && c + 8 <= d.Ci) {
+                    a = *reinterpret_cast<const float4*>(p);
+                    b = *reinterpret_cast<const float4*>(p + 4);
+                } else {
+                    float e[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) e[j] = (c + j < d.Ci) ? p[j] : 0.f;
+                    a = make_float4(e[0], e[1], e[2], e[3]);
+                    b = make_float4(e[4], e[5], e[6], e[7]);
+                }
+                return true;
+            };
+            float4 ca, cb, na, nb;
+            bool cin = load_plane(0, ca, cb), nin = false;
+#pragma unroll 1
+            for (int ip = 0; ip < nplanes; ++ip, ++gin) {
+                if (ip + 1 < nplanes) nin = load_plane(ip + 1, na, nb);      // in flight while this plane is split and stored
+                const uint32_t s = gin % RING, use = gin / RING;
+                long long c0 = pr ? clock64() : 0;
+                mbar_wait(a_empty + 8 * s, (use & 1) ^ 1);       // the output planes that read this slot RING planes ago are done
+                long long c1 = pr ? clock64() : 0;
+                pw0 += c1 - c0;
+                float v[8] = {ca.x, ca.y, ca.z, ca.w, cb.x, cb.y, cb.z, cb.w};
+                if (cin && scale) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) v[j] = fmaf(v[j], bsc[j], bsh[j]);      // channels >= Ci: 0 * 1 + 0
+                }
+                uint4* Ab = As + (size_t)s * SLOT_U4 + (size_t)chunk * CHS + slot;
+                if (NS == 3) {
+                    uint4 o[3];
+                    split8_trunc3(v, o);
+#pragma unroll
+                    for (int s2 = 0; s2 < 3; ++s2) Ab[(size_t)s2 * 2 * CHS] = o[s2];
+                } else {
+                    Ab[0] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+                }
+                fence_async_smem();                              // generic-proxy writes -> visible to the tensor core
+                mbar_arrive(a_full + 8 * s);
+                ca = na; cb = nb; cin = nin;
+                if (pr) pwk += clock64() - c1;
+            }
+        }
+        if (pr && st == 0) { prof[4] = pw0; prof[5] = pwk; }
+    } else if (warp >= NEPI_W + NSTG_W) {
+        // =================================================================== MMA issue: one thread per issuer warp
+        const int iss = warp - (NEPI_W + NSTG_W);
+        if (lane == 0 && iss < NACC) {
+            const uint32_t a_base = smem_u32(As), b_base = smem_u32(Bs);
+            const uint64_t db0 = umma_desc(b_base, BROWS * 16, 128);
+            uint32_t q = 0, gbase = 0;                           // global output-plane / input-plane counters
+            int nq = 0;
+            for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+                const Item3 it = item_of(item);
+                for (int od = 0; od < it.L; ++od, ++q) {
+                    if ((int)(q % NACC) != iss) continue;
+                    const uint32_t g2 = gbase + od + 2;          // the last of the three input planes this output plane reads
+                    long long c0 = pr ? clock64() : 0;
+                    mbar_wait(a_full + 8 * (g2 % RING), (g2 / RING) & 1);
+                    long long c1 = pr ? clock64() : 0;
+                    const uint32_t acc = q % NACC;
+                    mbar_wait(t_empty + 8 * acc, ((q / NACC) & 1) ^ 1);      // the epilogue drained this accumulator
+                    long long c2 = pr ? clock64() : 0;
+                    pw0 += c1 - c0; pw1 += c2 - c1;
+                    tc_fence_after();
+                    const uint32_t dk = tmem_base + acc * ACOLS;
+#pragma unroll 1
+                    for (int kd = 0; kd < 3; ++kd) {
+                        const uint32_t s = (gbase + od + kd) % RING;
+                        const uint32_t a_slot = a_base + s * (SLOT_U4 * 16);
+#pragma unroll
+                        for (int kh = 0; kh < 3; ++kh) {
+                            const uint64_t db = db0 + (uint64_t)((kd * 3 + kh) * 2 * BROWS);
+                            const uint64_t da = umma_desc(a_slot + (uint32_t)(kh * TW * 16), CHS * 16, 128);
+                            const uint32_t nfirst = (kd | kh) != 0;
+                            //   a1 x [w1|w2|w3] -> [main | cA | cB];  a2 x [w1|w2] -> [cA | cB];  a3 x [w1] -> cA
+                            umma_bf16(dk, da, db, umma_idesc_bf16(NTOT), nfirst);
+                            if (NS == 3) {
+                                umma_bf16(dk + (uint32_t)TS, da + (uint64_t)(1 * 2 * CHS), db, umma_idesc_bf16(2 * TS), 1u);
+                                umma_bf16(dk + (uint32_t)TS, da + (uint64_t)(2 * 2 * CHS), db, umma_idesc_bf16(TS), 1u);
+                            }
+                        }
+                    }
+                    umma_commit(t_full + 8 * acc);               // accumulator complete -> epilogue
+                    // release the input planes: slot of plane ip is free once its (up to) three reading output planes are done;
+                    // planes at the ends of a segment have fewer readers, their last reader arrives for the missing ones
+                    for (int kd = 0; kd < 3; ++kd) {
+                        const int ip = od + kd;
+                        const int last = ip < it.L - 1 ? ip : it.L - 1, first = ip - 2 > 0 ? ip - 2 : 0;
+                        const int narr = 1 + (od == last ? 3 - (last - first + 1) : 0);
+                        const uint32_t s = (gbase + ip) % RING;
+                        for (int a = 0; a < narr; ++a) umma_commit(a_empty + 8 * s);
+                    }
+                    if (pr) pwk += clock64() - c2;
+                    ++nq;
+                }
+                gbase += it.L + 2;
+            }
+            if (pr && iss == 0) { prof[0] = pw0; prof[1] = pw1; prof[2] = pwk; prof[3] = nq; }
+        }
+    } else {
+        // =================================================================== epilogue warps (TMEM lane quarter = warp % 4)
+        const int grp = warp >> 2, q4 = warp & 3;
+        const int r = q4 * 32 + lane;                            // GEMM row = (h, w'') of the tile
+        const int hy = r / TW, wx = r % TW;
+        float bch[COP];
+#pragma unroll
+        for (int j = 0; j < COP; ++j) bch[j] = (bias && fin && j < d.Co) ? bias[j] : 0.f;
+        uint32_t q = 0;
+        for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+            const Item3 it = item_of(item);
+            const int oh = it.oh0 + hy, ow = it.ow0 + wx;
+            const bool valid_hw = wx < TWV && oh < d.Ho && ow < d.Wo;
+            for (int od = 0; od < it.L; ++od, ++q) {
+                if ((int)(q % NEPI_G) != grp) continue;
+                const uint32_t acc = q % NACC;
+                long long c0 = pr ? clock64() : 0;
+                mbar_wait(t_full + 8 * acc, (q / NACC) & 1);
+                long long c1 = pr ? clock64() : 0;
+                pw0 += c1 - c0;
+                tc_fence_after();
+                const uint32_t ta = tmem_base + ((uint32_t)(q4 * 32) << 16) + acc * ACOLS;
+                float out[COP];
+#pragma unroll
+                for (int kw = 0; kw < 3; ++kw) {
+                    float s[COP];
+                    if (NS == 3) {
+                        uint32_t m[COP], a[COP], b[COP];
+                        tmem_ld_issue<COP>(ta + kw * COP, m);                  // main
+                        tmem_ld_issue<COP>(ta + TS + kw * COP, a);             // cA
+                        tmem_ld_issue<COP>(ta + 2 * TS + kw * COP, b);         // cB
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < COP; ++j)
+                            s[j] = (__uint_as_float(b[j]) + __uint_as_float(a[j])) + __uint_as_float(m[j]);   // corrections first
+                    } else {
+                        uint32_t m[COP];
+                        tmem_ld_issue<COP>(ta + kw * COP, m);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < COP; ++j) s[j] = __uint_as_float(m[j]);
+                    }
+                    if (kw == 2) {
+                        tc_fence_before();
+                        mbar_arrive(t_empty + 8 * acc);          // this accumulator may be overwritten
+                    }
+                    // out[w] = D0[w] + D1[w + 1] + D2[w + 2]: rows w'' + kw of the same h are lanes + kw of this warp
+#pragma unroll
+                    for (int j = 0; j < COP; ++j) {
+                        const float t = (kw == 0) ? s[j] : __shfl_down_sync(0xffffffffu, s[j], kw);
+                        out[j] = (kw == 0) ? t : out[j] + t;
+                    }
+                }
+                if (valid_hw) {
+                    const int odg = it.od_lo + od;
+                    float* yp = dst + ((((int64_t)it.n * d.Do + odg) * d.Ho + oh) * d.Wo + ow) * d.ldo;
+                    const bool vecy = (d.ldo % 4 == 0) && d.Co == COP;
+                    if (accum) {                                  // raw sums of the earlier input-channel passes
+                        if (vecy) {
+#pragma unroll
+                            for (int j4 = 0; j4 < COP / 4; ++j4) {
+                                const float4 o = reinterpret_cast<const float4*>(yp)[j4];
+                                out[4 * j4] += o.x; out[4 * j4 + 1] += o.y; out[4 * j4 + 2] += o.z; out[4 * j4 + 3] += o.w;
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < COP; ++j)
+                                if (j < d.Co) out[j] += yp[j];
+                        }
+                    }
+                    if (fin) {
+#pragma unroll
+                        for (int j = 0; j < COP; ++j) out[j] = sp_act_fwd(out[j] + bch[j], d.act, d.alpha);
+                    }
+                    if (vecy) {
+#pragma unroll
+                        for (int j4 = 0; j4 < COP / 4; ++j4)
+                            reinterpret_cast<float4*>(yp)[j4] = make_float4(out[4 * j4], out[4 * j4 + 1], out[4 * j4 + 2], out[4 * j4 + 3]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < COP; ++j)
+                            if (j < d.Co) yp[j] = out[j];
+                    }
+                }
+                if (pr) pwk += clock64() - c1;
+            }
+        }
+        if (pr && tid == 0) { prof[6] = pw0; prof[7] = pwk; }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (warp == 0) tmem_dealloc<512>(tmem_base);
+}
+
+}  // namespace sp_tc3
+
+static inline size_t sp_tc3_wimg_u4(int cop, int ns) { return (size_t)9 * 2 * ns * ((3 * cop + 15) / 16 * 16); }
+
+// one image per (output slice, input-channel pass), image (s, p) at index s * passes + p
+static inline int sp_tc3_pack_launch(const SpConvDesc* d, int transposed, int ns, int cop, const float* w, void* img, cudaStream_t st,
+                                     int passes = 1, int nslices = 1) {
+    const int ts = (3 * cop + 15) / 16 * 16;
+    const int total = 9 * 2 * ts;
+    const int blocks = (total + 255) / 256;
+    const size_t img_u4 = sp_tc3_wimg_u4(cop, ns);
+    for (int sl = 0; sl < nslices; ++sl)
+        for (int p = 0; p < passes; ++p) {
+            uint4* ip = (uint4*)img + (size_t)(sl * passes + p) * img_u4;
+            if (ns == 3) sp_tc3::pack_wimg3_kernel<3><<<blocks, 256, 0, st>>>(w, d->Co, d->Ci, transposed, cop, ts, 16 * p, 16 * sl, ip);
+            else sp_tc3::pack_wimg3_kernel<1><<<blocks, 256, 0, st>>>(w, d->Co, d->Ci, transposed, cop, ts, 16 * p, 16 * sl, ip);
+            SP_LAUNCH_OK("pack_wimg3_kernel");
+        }
+    return 0;
+}
+
+template <int COP, int NS>
+static inline int sp_tc3_corr_launch_t(const SpConvDesc* d, int nPerG, const float* src, const uint4* wimg, const float* bias,
+                                       const float* scale, const float* shift, int sstride, int accum, int fin, float* dst,
+                                       cudaStream_t st, long long* prof) {
+    using namespace sp_tc3;
+    const int tiles_w = (d->Wo + TWV - 1) / TWV, tiles_h = (d->Ho + TH - 1) / TH;
+    const int64_t columns = (int64_t)tiles_w * tiles_h * d->N;
+    // depth segments: whole columns when there are enough of them to balance the SMs, else split (2 extra halo planes per segment)
+    const int sms = sp_num_sms();
+    int nseg = 1;
+    if (columns < 8LL * sms) {
+        nseg = (int)((8LL * sms + columns - 1) / columns);
+        const int max_seg = d->Do / 6 > 1 ? d->Do / 6 : 1;
+        if (nseg > max_seg) nseg = max_seg;
+    }
+    const int seg_len = (d->Do + nseg - 1) / nseg;
+    nseg = (d->Do + seg_len - 1) / seg_len;
+    const int64_t total = columns * nseg;
+    SP_REQUIRE(total < (1LL << 31), "tc3 corr: too many work items");
+    static bool attr = false;
+    if (!attr) {
+        SP_CUDA(cudaFuncSetAttribute(corr3_tc3_kernel<COP, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Tc3<COP, NS>::SMEM));
+        attr = true;
+    }
+    int grid = sms;
+    if (grid > total) grid = (int)total;
+    corr3_tc3_kernel<COP, NS><<<grid, NTHREADS3, Tc3<COP, NS>::SMEM, st>>>(*d, nPerG, tiles_w, tiles_h, nseg, seg_len, (int)total, src, wimg,
+                                                                           bias, scale, shift, sstride, accum, fin, dst, prof);
+    SP_LAUNCH_OK("corr3_tc3_kernel");
+    return 0;
+}
+
+// d->Ci <= 16, d->Co <= 24: one launch.  Wider layers: slices of 16 output channels (each its own launch into a channel slice of
+// dst), input channels in passes of 16 whose raw sums accumulate in dst.  ns = 3: fp32-grade split arithmetic, 1: bf16 mode.
+static inline int sp_tc3_corr_launch(const SpConvDesc* d, int nPerG, int ns, const float* src, const uint4* wimg, const float* bias,
+                                     const float* scale, const float* shift, float* dst, cudaStream_t st, long long* prof = nullptr) {
+    const int cop = (d->Co > 16 && d->Co <= 24) ? 24 : 16;
+    const int nsl = (d->Co <= 24) ? 1 : (d->Co + 15) / 16;
+    const int npass = (d->Ci + 15) / 16;
+    const size_t img_u4 = sp_tc3_wimg_u4(cop, ns);
+    for (int sl = 0; sl < nsl; ++sl)
+        for (int p = 0; p < npass; ++p) {
+            SpConvDesc s = *d;
+            s.Ci = (d->Ci - 16 * p < 16) ? d->Ci - 16 * p : 16;
+            if (nsl > 1) s.Co = (d->Co - 16 * sl < 16) ? d->Co - 16 * sl : 16;
+            const float* sp = src + 16 * p;
+            const float* scp = scale ? scale + 16 * p : nullptr;
+            const float* shp = shift ? shift + 16 * p : nullptr;
+            const float* bp = bias ? bias + 16 * sl : nullptr;
+            float* dp = dst + 16 * sl;
+            const uint4* ip = wimg + (size_t)(sl * npass + p) * img_u4;
+            const int accum = p > 0, fin = p == npass - 1;
+            int e;
+            if (cop == 24) e = ns == 3 ? sp_tc3_corr_launch_t<24, 3>(&s, nPerG, sp, ip, bp, scp, shp, d->Ci, accum, fin, dp, st, prof)
+                                       : sp_tc3_corr_launch_t<24, 1>(&s, nPerG, sp, ip, bp, scp, shp, d->Ci, accum, fin, dp, st, prof);
+            else e = ns == 3 ? sp_tc3_corr_launch_t<16, 3>(&s, nPerG, sp, ip, bp, scp, shp, d->Ci, accum, fin, dp, st, prof)
+                             : sp_tc3_corr_launch_t<16, 1>(&s, nPerG, sp, ip, bp, scp, shp, d->Ci, accum, fin, dp, st, prof);
+            if (e) return e;
+        }
+    return 0;
+}

@@ -440,7 +440,8 @@ def group_volumes(ts):
     if all(t.is_cuda for t in ts) and _adjacent_views(ts):
         B, C, D, H, W = ts[0].shape
         return ts[0].as_strided((len(ts) * B, C, D, H, W), ts[0].stride())
-    return torch.cat([ops.as_vol(t) if t.is_cuda else t for t in ts], dim=0)
+    # (a tensor that requires grad must reach the autograd node untouched: the layout kernel is not differentiable)
+    return torch.cat([ops.as_vol(t) if (t.is_cuda and not t.requires_grad) else t for t in ts], dim=0)
 
 
 class _SplitGroups(torch.autograd.Function):

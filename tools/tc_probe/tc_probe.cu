@@ -7,7 +7,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <vector>
-#include "../../stroke-prediction_b200/csrc/sp_conv_tc2.cuh"
+#include "../../stroke-prediction_b200/csrc/sp_conv_tc3.cuh"
 
 void sp_set_error(const char* fmt, ...) {
     va_list ap;
@@ -69,6 +69,11 @@ static int run_gpu(const SpConvDesc& d, const float* dx, const float* dw, const 
 }
 
 static int launch(int ns, const SpConvDesc& d, const float* dx, const float* dw, const float* dsc, const float* dsh, float* dy, void* dimg) {
+    if (ns == 33 || ns == 31) {   // generation 3 (kw-stacked N, rolling depth window): three terms / bf16 mode
+        const int t = ns == 33 ? 3 : 1;
+        if (sp_tc3_pack_launch(&d, 0, t, 16, dw, dimg, 0)) return 1;
+        return sp_tc3_corr_launch(&d, d.N, t, dx, (const uint4*)dimg, nullptr, dsc, dsh, dy, 0, g_prof);
+    }
     if (ns == 32) {   // pipelined kernel (three terms, split accumulators)
         if (sp_tc_pack_launch(&d, 0, 3, 16, 16, dw, dimg, 0)) return 1;
         return sp_tc2_corr_launch(&d, d.N, dx, (const uint4*)dimg, nullptr, dsc, dsh, dy, 0, g_prof, g_terms);
@@ -86,7 +91,7 @@ int main(int argc, char** argv) {
         float *dx, *dy, *dw;
         void* dimg;
         CK(cudaMalloc(&dx, nx * 4)); CK(cudaMalloc(&dy, ny * 4)); CK(cudaMalloc(&dw, 16 * 16 * 27 * 4));
-        CK(cudaMalloc(&dimg, sp_tc_wimg_bytes(16, 16, 3)));
+        CK(cudaMalloc(&dimg, sp_tc_wimg_bytes(16, 16, 3) + sp_tc3_wimg_u4(16, 3) * 16));
         CK(cudaMemset(dx, 0, nx * 4)); CK(cudaMemset(dw, 0, 16 * 16 * 27 * 4));
         cudaEvent_t e0, e1;
         CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
@@ -103,6 +108,17 @@ int main(int argc, char** argv) {
         const double flop = 2.0 * ny * 27 * 16, bytes = 4.0 * (nx + ny);
         printf("time ns=%d: %.3f ms  %.1f TFLOP/s (fp32-equivalent)  %.0f GB/s algorithmic\n", ns, ms, flop / ms * 1e-9, bytes / ms * 1e-6);
         CK(cudaMalloc(&g_prof, 64)); CK(cudaMemset(g_prof, 0, 64));
+        if (ns == 33 || ns == 31) {
+            launch(ns, d, dx, dw, nullptr, nullptr, dy, dimg);
+            CK(cudaDeviceSynchronize());
+            long long hp[8];
+            CK(cudaMemcpy(hp, g_prof, 64, cudaMemcpyDeviceToHost));
+            const long long t = hp[3] ? hp[3] : 1;
+            printf("  CTA0 cycles per output plane of issuer 0 (%lld planes = 1/3 of the CTA's): issuer: wait a_full %lld, wait t_empty %lld, issue+commit %lld | "
+                   "stager (per input plane, ~3x as many): wait a_empty %lld, work %lld | epilogue group 0 (per plane, 1.5x as many): wait t_full %lld, work %lld\n",
+                   t, hp[0] / t, hp[1] / t, hp[2] / t, hp[4] / (3 * t), hp[5] / (3 * t), hp[6] * 2 / (3 * t), hp[7] * 2 / (3 * t));
+            return 0;
+        }
         if (ns == 32) {
             launch(ns, d, dx, dw, nullptr, nullptr, dy, dimg);
             CK(cudaDeviceSynchronize());
@@ -137,7 +153,7 @@ int main(int argc, char** argv) {
     float *dx, *dy, *dw, *dsc = nullptr, *dsh = nullptr;
     void* dimg;
     CK(cudaMalloc(&dx, nx * 4)); CK(cudaMalloc(&dy, ny * 4)); CK(cudaMalloc(&dw, w.size() * 4));
-    CK(cudaMalloc(&dimg, sp_tc_wimg_bytes(16, 16, 3)));
+    CK(cudaMalloc(&dimg, sp_tc_wimg_bytes(16, 16, 3) + sp_tc3_wimg_u4(16, 3) * 16));
     CK(cudaMemcpy(dx, x.data(), nx * 4, cudaMemcpyHostToDevice));
     if (!sc.empty()) {
         CK(cudaMalloc(&dsc, 64)); CK(cudaMalloc(&dsh, 64));
