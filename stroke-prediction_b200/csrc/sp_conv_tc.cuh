@@ -347,9 +347,11 @@ corr3_tc_kernel(SpConvDesc d, int nPerG, int tiles_w, int tiles_h, int tiles_d, 
 }  // namespace sp_tc
 
 // ---- host side --------------------------------------------------------------------------------------------------------
-// Mode of the tensor-core tier for the 8..16-channel 3x3x3 stride-1 correlations:
-//   4 (default)  pipelined three-term kernel with split accumulators (sp_conv_tc2.cuh): per-layer forward rel-L2 1.3e-7 against
-//                2.6e-7 for an IEEE fp32 FFMA chain on the same data — fp32-grade, 2.6x the FFMA tier's speed
+// Mode of the tensor-core tier for the 8..96-channel 3x3x3 stride-1 correlations:
+//   5 (default)  generation 3 (sp_conv_tc3.cuh): three-term split arithmetic, kw-stacked N, rolling depth window: per-layer forward
+//                rel-L2 1.3e-7 against 2.6e-7 for an IEEE fp32 FFMA chain on the same data — fp32-grade, 4.5x the FFMA tier's speed
+//   1            bf16 mode: generation-3 kernel with ONE bf16 term per operand (RN) and fp32 accumulation (per-layer rel-L2 ~2.5e-3)
+//   4            generation 2: pipelined three-term kernel with split accumulators (sp_conv_tc2.cuh), same accuracy as 5
 //   0            tier off: the exact-fp32 FFMA tier serves every layer
 //   2 / 3        first-generation kernels (one accumulator per output, 2 / 3 bf16 terms: rel-L2 4.8e-6 / 1.4e-6 because the tensor
 //                core's fp32 accumulator truncates); kept for A/B measurements
@@ -357,7 +359,7 @@ corr3_tc_kernel(SpConvDesc d, int nPerG, int tiles_w, int tiles_h, int tiles_d, 
 static inline int& sp_tc_terms_ref() {
     static int v = -1;
     if (v < 0) {
-        v = 4;
+        v = 5;
         const char* e = getenv("SP_TC_TERMS");
         if (e && e[0] >= '0' && e[0] <= '5') v = e[0] - '0';
     }

@@ -10,7 +10,7 @@
 //    rows are (h, w'') with w'' fastest, so that is two warp shuffles per column; a 16-wide row yields 14 outputs.
 //    Accuracy is unchanged: every leading accumulator still takes 9 accumulations (kd, kh), the epilogue adds 3 of them in RN.
 //  * rolling depth window.  A CTA owns a (8 rows x 14 columns) output patch and walks along depth: every input plane (10 x 16
-//    halo voxels) is staged ONCE into a ring of 6 shared-memory planes and used by the three output planes around it (generation 2
+//    halo voxels) is staged ONCE into a ring of 9 (bf16 mode: 16) shared-memory planes and used by the three output planes around it (generation 2
 //    staged 4 halo planes per 2 output planes: 2.0x the loads, splits and stores per output).  The pipeline never drains: ring,
 //    accumulator and barrier phases run on global counters across the CTA's work items.
 //
@@ -32,7 +32,6 @@ using sp_tc2::tmem_ld_n;
 constexpr int TW = 16, TWV = 14, TH = 8, IH = TH + 2;   // MMA rows = 16 w'' x 8 h; 14 x 8 outputs per plane
 constexpr int PSLOTS = IH * TW;                          // 160 sixteen-byte slots per (term, chunk) plane
 constexpr int CHS = PSLOTS + 4;                          // chunk-plane stride: odd multiple of 64 B (bank spread of the 2 K chunks)
-constexpr int RING = 6;                                  // staged input planes in flight
 constexpr int NEPI_G = 2, NEPI_W = 4 * NEPI_G;           // epilogue groups / warps
 constexpr int NSTG_W = 10, NSTG = NSTG_W * 32;           // staging warps / threads: 320 = one item per thread and plane
 constexpr int NISS_W = 3;                                // MMA issuer warps (NACC of them active)
@@ -48,13 +47,19 @@ struct Tc3 {
     static constexpr int ACOLS = NTOT;                           // TMEM columns per output plane: [main | cA | cB]
     static constexpr int NACC = (512 / ACOLS) < 3 ? (512 / ACOLS) : 3;
     static constexpr int SLOT_U4 = NS * 2 * CHS;                 // uint4 per ring slot: [term][chunk][CHS]
+    // staged input planes in flight: NACC issuers hold NACC + 2 planes; the rest is the stager's lead over them (measured with
+    // 6: issuers waited for planes 25 % of the time while the stager waited for slots)
+    static constexpr int RING = NS == 3 ? 9 : 16;
+    // planes of global loads a staging thread keeps in flight (registers): bf16 mode is HBM-bound at ~740 cycles per plane,
+    // below the ~1.5 k cycle load latency under load
+    static constexpr int PF = NS == 3 ? 2 : 4;
     static constexpr int WIMG = 9 * 2 * NTOT;                    // global image (uint4)
     static constexpr int WIMGS = 9 * 2 * BROWS;                  // shared-memory image (uint4)
     static constexpr size_t SMEM = ((size_t)RING * SLOT_U4 + WIMGS) * 16 + 256;
     static_assert(NTOT % 16 == 0 && NTOT <= 256, "UMMA M = 128 needs N % 16 == 0, N <= 256");
     static_assert(NACC >= 2, "two accumulators in flight at least");
 };
-static_assert(Tc3<24, 3>::SMEM <= 227 * 1024, "tc3: shared memory");
+static_assert(Tc3<24, 3>::SMEM <= 227 * 1024 && Tc3<24, 1>::SMEM <= 227 * 1024, "tc3: shared memory");
 
 // ---- weight image -----------------------------------------------------------------------------------------------------
 // img[((kd*3+kh) * 2 + chunk) * NTOT + term * TS + kw * COP + n] = 8 bf16 {term of Wsrc(n0 + n, k0 + chunk*8 + j, tap)}, zero rows
@@ -115,7 +120,7 @@ corr3_tc3_kernel(SpConvDesc d, int nPerG, int tiles_w, int tiles_h, int nseg, in
                  float* __restrict__ dst, long long* __restrict__ prof) {
     using T = Tc3<COP, NS>;
     constexpr int TS = T::TS, NTOT = T::NTOT, BROWS = T::BROWS, ACOLS = T::ACOLS, NACC = T::NACC, SLOT_U4 = T::SLOT_U4;
-    constexpr int WIMG = T::WIMG, WIMGS = T::WIMGS;
+    constexpr int WIMG = T::WIMG, WIMGS = T::WIMGS, RING = T::RING, PF = T::PF;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint4* As = reinterpret_cast<uint4*>(smem_raw);                          // [RING][NS][2][CHS]
     uint4* Bs = As + (size_t)RING * SLOT_U4;                                 // weight image [9][2][BROWS]
@@ -201,34 +206,47 @@ corr3_tc3_kernel(SpConvDesc d, int nPerG, int tiles_w, int tiles_h, int nseg, in
                 }
                 return true;
             };
-            float4 ca, cb, na, nb;
-            bool cin = load_plane(0, ca, cb), nin = false;
+            // register ring of PF planes: plane ip lives in entry ip % PF; after it is consumed its entry is reloaded with
+            // plane ip + PF, so PF - 1 .. PF planes of loads are in flight while one is split and stored
+            float4 pa[PF], pb[PF];
+            bool pin[PF];
+#pragma unroll
+            for (int u = 0; u < PF; ++u) {
+                pin[u] = false;
+                if (u < nplanes) pin[u] = load_plane(u, pa[u], pb[u]);
+            }
 #pragma unroll 1
-            for (int ip = 0; ip < nplanes; ++ip, ++gin) {
-                if (ip + 1 < nplanes) nin = load_plane(ip + 1, na, nb);      // in flight while this plane is split and stored
-                const uint32_t s = gin % RING, use = gin / RING;
-                long long c0 = pr ? clock64() : 0;
-                mbar_wait(a_empty + 8 * s, (use & 1) ^ 1);       // the output planes that read this slot RING planes ago are done
-                long long c1 = pr ? clock64() : 0;
-                pw0 += c1 - c0;
-                float v[8] = {ca.x, ca.y, ca.z, ca.w, cb.x, cb.y, cb.z, cb.w};
-                if (cin && scale) {
+            for (int ip0 = 0; ip0 < nplanes; ip0 += PF) {
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) v[j] = fmaf(v[j], bsc[j], bsh[j]);      // channels >= Ci: 0 * 1 + 0
-                }
-                uint4* Ab = As + (size_t)s * SLOT_U4 + (size_t)chunk * CHS + slot;
-                if (NS == 3) {
-                    uint4 o[3];
-                    split8_trunc3(v, o);
+                for (int u = 0; u < PF; ++u) {
+                    const int ip = ip0 + u;
+                    if (ip < nplanes) {
+                        const uint32_t s = gin % RING, use = gin / RING;
+                        long long c0 = pr ? clock64() : 0;
+                        mbar_wait(a_empty + 8 * s, (use & 1) ^ 1);   // the output planes that read this slot RING planes ago are done
+                        long long c1 = pr ? clock64() : 0;
+                        pw0 += c1 - c0;
+                        float v[8] = {pa[u].x, pa[u].y, pa[u].z, pa[u].w, pb[u].x, pb[u].y, pb[u].z, pb[u].w};
+                        if (pin[u] && scale) {
 #pragma unroll
-                    for (int s2 = 0; s2 < 3; ++s2) Ab[(size_t)s2 * 2 * CHS] = o[s2];
-                } else {
-                    Ab[0] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+                            for (int j = 0; j < 8; ++j) v[j] = fmaf(v[j], bsc[j], bsh[j]);      // channels >= Ci: 0 * 1 + 0
+                        }
+                        if (ip + PF < nplanes) pin[u] = load_plane(ip + PF, pa[u], pb[u]);
+                        uint4* Ab = As + (size_t)s * SLOT_U4 + (size_t)chunk * CHS + slot;
+                        if (NS == 3) {
+                            uint4 o[3];
+                            split8_trunc3(v, o);
+#pragma unroll
+                            for (int s2 = 0; s2 < 3; ++s2) Ab[(size_t)s2 * 2 * CHS] = o[s2];
+                        } else {
+                            Ab[0] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+                        }
+                        fence_async_smem();                          // generic-proxy writes -> visible to the tensor core
+                        mbar_arrive(a_full + 8 * s);
+                        ++gin;
+                        if (pr) pwk += clock64() - c1;
+                    }
                 }
-                fence_async_smem();                              // generic-proxy writes -> visible to the tensor core
-                mbar_arrive(a_full + 8 * s);
-                ca = na; cb = nb; cin = nin;
-                if (pr) pwk += clock64() - c1;
             }
         }
         if (pr && st == 0) { prof[4] = pw0; prof[5] = pwk; }

@@ -22,6 +22,10 @@ from . import ops
 from .ops import ACT_ELU, ACT_LEAKY, ACT_NONE, ACT_SIGMOID
 
 _weights_epoch = 0
+# Called as hook(plan) when ALL backward passes of a SeqPlan belonging to the current step are done, i.e. its parameters'
+# gradients are final (as many seq_backward calls as gradient-tracked seq_forward calls).  parallel.GradientAllReduce uses
+# it to start the all-reduce of that plan's slice of the flat gradient buffer while the rest of the backward still runs.
+plan_backward_hooks = []
 DEBUG_GZ = None     # diagnostics only (tools/diag_chain.py): a list receiving (plan, unit index, dL/d(conv output))
 DEBUG_ACTS = None   # diagnostics only: a list receiving (plan, [input, unit outputs...]) per forward pass
 
@@ -269,8 +273,11 @@ class SeqSaved:
         self.G = 1
 
 
-def seq_forward(plan, x, G=1):
-    """x: NDHWC volume with N = G * B.  Returns (y, SeqSaved)."""
+def seq_forward(plan, x, G=1, track=False):
+    """x: NDHWC volume with N = G * B.  Returns (y, SeqSaved).  track: a backward pass will follow (counted for the
+    plan_backward_hooks)."""
+    if track:
+        plan.pending_backward = getattr(plan, 'pending_backward', 0) + 1
     saved = SeqSaved()
     saved.G = G
     saved.acts.append(x)
@@ -305,6 +312,17 @@ def seq_forward(plan, x, G=1):
 
 
 def seq_backward(plan, saved, gy, need_input_grad, want):
+    out = _seq_backward_impl(plan, saved, gy, need_input_grad, want)
+    pending = getattr(plan, 'pending_backward', 0)
+    if pending > 0:
+        plan.pending_backward = pending - 1
+        if pending == 1:
+            for hook in plan_backward_hooks:
+                hook(plan)
+    return out
+
+
+def _seq_backward_impl(plan, saved, gy, need_input_grad, want):
     """gy: gradient w.r.t. the chain output (post-activation).  `want(param)` tells whether a parameter gradient is
     needed.  Returns (gx or None, {param: grad})."""
     G = saved.G
@@ -399,7 +417,7 @@ class SeqFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, plan, G, *params):
         xv = ops.as_vol(x)
-        y, saved = seq_forward(plan, xv, G)
+        y, saved = seq_forward(plan, xv, G, track=any(ctx.needs_input_grad))
         ctx.plan, ctx.saved, ctx.params = plan, saved, params
         return y
 
@@ -525,29 +543,29 @@ def _crop_offsets(big, small):
     return tuple((b - s) // 2 for b, s in zip(big.shape[2:], small.shape[2:]))
 
 
-def unet_forward(plan, x):
+def unet_forward(plan, x, track=False):
     b = plan.blocks
     S = {}
-    y1, S["b1"] = seq_forward(b[0], x)
+    y1, S["b1"] = seq_forward(b[0], x, track=track)
     p1 = ops.maxpool2_fwd(y1)
-    y2, S["b2"] = seq_forward(b[1], p1)
+    y2, S["b2"] = seq_forward(b[1], p1, track=track)
     p2 = ops.maxpool2_fwd(y2)
-    y3, S["b3"] = seq_forward(b[2], p2)
+    y3, S["b3"] = seq_forward(b[2], p2, track=track)
     N, C3, D3, H3, W3 = y3.shape
     C2 = y2.shape[1]
     cat4 = ops.new_vol(N, C3 + C2, 2 * D3, 2 * H3, 2 * W3, x.device)
     ops.upsample2_fwd(y3, cat4, 0, _align(plan.unet, "upsa34"))
     off4 = _crop_offsets(y2, cat4)
     ops.crop_into(y2, cat4, C3, off4)
-    y4, S["b4"] = seq_forward(b[3], cat4)
+    y4, S["b4"] = seq_forward(b[3], cat4, track=track)
     N, C4, D4, H4, W4 = y4.shape
     C1 = y1.shape[1]
     cat5 = ops.new_vol(N, C4 + C1, 2 * D4, 2 * H4, 2 * W4, x.device)
     ops.upsample2_fwd(y4, cat5, 0, _align(plan.unet, "upsa45"))
     off5 = _crop_offsets(y1, cat5)
     ops.crop_into(y1, cat5, C4, off5)
-    y5, S["b5"] = seq_forward(b[4], cat5)
-    seg, S["cls"] = seq_forward(plan.classify, y5)
+    y5, S["b5"] = seq_forward(b[4], cat5, track=track)
+    seg, S["cls"] = seq_forward(plan.classify, y5, track=track)
     S.update(p1=p1, p2=p2, off4=off4, off5=off5, C1=C1, C2=C2, C3=C3, C4=C4)
     return seg, S
 
@@ -584,7 +602,7 @@ class UnetFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, plan, *params):
         xv = ops.as_vol(x)
-        seg, S = unet_forward(plan, xv)
+        seg, S = unet_forward(plan, xv, track=any(ctx.needs_input_grad))
         ctx.plan, ctx.S, ctx.params = plan, S, params
         ctx.seg_shape = seg.shape
         outs = tuple(ops.extract_channel(seg, c) for c in range(seg.shape[1]))

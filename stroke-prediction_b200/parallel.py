@@ -41,22 +41,101 @@ def broadcast_parameters(module, src=0, group=None):
 
 
 class GradientAllReduce:
-    """Callable placed between backward and the optimizer step."""
+    """Callable placed between backward and the optimizer step (Learner.py:121-122).
 
-    def __init__(self, optimizer, group=None):
+    The gradient exchange is OVERLAPPED with the backward pass: the engine reports every layer plan whose parameter
+    gradients are final (``engine.plan_backward_hooks``: the decoder's plan fires before the encoder's backward has started,
+    every U-Net block fires as the backward walks up the network), and the slice of the flat gradient buffer that holds
+    that plan's parameters is all-reduced asynchronously right away (NCCL orders it after the kernels already queued on the
+    compute stream and runs it next to the remaining backward kernels).  ``__call__`` reduces whatever was not covered,
+    then makes the compute stream wait for all pieces.  Reducing a buffer in slices is the same elementwise sum as reducing
+    it at once, so results do not depend on the overlap.  ``overlap=False`` restores the single blocking all-reduce."""
+
+    def __init__(self, optimizer, group=None, overlap=True):
         self.optimizer = optimizer
         self.group = group
         self.world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
         sink = optimizer.attach_grad_sink() if hasattr(optimizer, "attach_grad_sink") else None
+        self.sink = sink
         self.flat = sink.flat if sink is not None else None
         optimizer.grad_scale = 1.0 / self.world
         self.calls = 0
+        self.overlap = bool(overlap) and self.flat is not None
+        self._done = []          # [lo, hi) element ranges of the flat buffer already handed to the collective this step
+        self._work = []
+        self.early_elements = 0  # elements reduced before __call__ in the last step (diagnostics / tests)
+        self._hook = None
+        if self.overlap:
+            from . import engine
+            self._hook = self.plan_ready
+            engine.plan_backward_hooks.append(self._hook)
+
+    def close(self):
+        if self._hook is not None:
+            from . import engine
+            if self._hook in engine.plan_backward_hooks:
+                engine.plan_backward_hooks.remove(self._hook)
+            self._hook = None
+
+    # ------------------------------------------------------------------------------------------ buckets
+    def plan_range(self, plan):
+        """[lo, hi) of the flat buffer covered by `plan`'s parameters, or None if they are not ours / not one contiguous run."""
+        offs = self.sink._offsets
+        spans = []
+        for p in plan.params():
+            o = offs.get(id(p))
+            if o is None:
+                if p.requires_grad:
+                    return None
+                continue
+            spans.append((o, o + (p.numel() + 3) // 4 * 4))
+        if not spans:
+            return None
+        spans.sort()
+        for (a0, a1), (b0, b1) in zip(spans, spans[1:]):
+            if b0 != a1:
+                return None
+        return spans[0][0], min(spans[-1][1], self.flat.numel())
+
+    def plan_ready(self, plan):
+        if self.world == 1 or not self.overlap or not self.sink.params:
+            return
+        r = self.plan_range(plan)
+        if r is not None:
+            self.bucket_ready(r[0], r[1])
+
+    def bucket_ready(self, lo, hi):
+        """Start the all-reduce of flat[lo:hi) (skipping parts already started this step)."""
+        for a, b in self._uncovered(lo, hi):
+            self._work.append(dist.all_reduce(self.flat[a:b], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+            self._done.append((a, b))
+            self.early_elements += b - a
+
+    def _uncovered(self, lo, hi):
+        gaps, cur = [], lo
+        for a, b in sorted(self._done):
+            if b <= cur or a >= hi:
+                continue
+            if a > cur:
+                gaps.append((cur, min(a, hi)))
+            cur = max(cur, b)
+            if cur >= hi:
+                break
+        if cur < hi:
+            gaps.append((cur, hi))
+        return gaps
 
     def __call__(self):
         if self.world == 1:
             return
         if self.flat is not None:
-            allreduce_flat_(self.flat, self.group)
+            early = self.early_elements
+            for a, b in self._uncovered(0, self.flat.numel()):
+                self._work.append(dist.all_reduce(self.flat[a:b], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+            for w in self._work:
+                w.wait()                 # stream-ordered for NCCL (the compute stream waits), blocking for gloo
+            self._work, self._done = [], []
+            self.last_early_elements, self.early_elements = early, 0
         else:
             for g in self.optimizer.param_groups:
                 for p in g["params"]:

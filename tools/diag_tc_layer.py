@@ -12,7 +12,7 @@ import torch.nn as nn
 from stroke_prediction_b200 import engine, ops
 from util import rel_l2
 
-modes = [int(m) for m in (sys.argv[1].split(",") if len(sys.argv) > 1 else "4,0".split(","))]
+modes = [int(m) for m in (sys.argv[1].split(",") if len(sys.argv) > 1 else "5,4,0".split(","))]
 cases = [("unet block5 conv b", 2, 16, 16, (30, 130, 130), 0), ("unet block5 conv b (patch)", 2, 16, 16, (30, 66, 66), 0),
          ("cae dec.28", 4, 16, 16, (28, 126, 126), (1, 2, 2)), ("cae enc.10", 4, 24, 24, (14, 62, 62), (1, 0, 0)),
          ("unet block5 conv a", 2, 48, 16, (32, 132, 132), 0)]
@@ -30,7 +30,7 @@ for name, N, ci, co, size, pad in cases:
         for label, dtype in (("cpu64", torch.float64), ("cpu32", torch.float32)):
             c = conv.to(dtype)
             c.zero_grad()
-            xi = x.to(dtype).requires_grad_(True)
+            xi = x.detach().clone().to(dtype).requires_grad_(True)
             y = c(xi)
             y.backward(g.to(dtype))
             res[label] = (y.detach(), xi.grad, c.weight.grad.clone())
@@ -40,7 +40,7 @@ for name, N, ci, co, size, pad in cases:
             seq = nn.Sequential(nn.Conv3d(ci, co, 3, padding=pad)).cuda()
             seq[0].load_state_dict(conv.state_dict())
             plan = engine.SeqPlan(seq)
-            xi = x.cuda().requires_grad_(True)
+            xi = x.detach().clone().cuda().requires_grad_(True)
             y = engine.run_sequential(plan, xi)
             y.backward(g.cuda())
             res["gpu tc=%d" % mode] = (y.detach(), xi.grad, seq[0].weight.grad.clone())
@@ -48,4 +48,4 @@ for name, N, ci, co, size, pad in cases:
         print("%-28s grad=%-6s" % (name, gkind), " | ".join(
             "%s: y %.1e dx %.1e dw %.1e" % (k, rel_l2(v[0], ref[0]), rel_l2(v[1], ref[1]), rel_l2(v[2], ref[2]))
             for k, v in res.items() if k != "cpu64"))
-ops.set_tc_terms(4)
+ops.set_tc_terms(5)

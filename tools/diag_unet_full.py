@@ -44,7 +44,7 @@ for _ in range(draws - 1):
     floors.append({n: rel_l2(a[n], b[n]) for n in names})
 
 res = {}
-for mode in (4, 0):
+for mode in (5, 4, 0):
     ops.set_tc_terms(mode)
     torch.manual_seed(35)
     m = Unet3D([2, 16, 32, 64, 32, 16, 32, 2])
@@ -58,9 +58,9 @@ for mode in (4, 0):
     loss.backward()
     res[mode] = {n: rel_l2(p.grad, g64[n]) for n, p in m.named_parameters()}
     opt.detach_grad_sink()
-ops.set_tc_terms(4)
-print("%-34s %9s %9s | floor draws" % ("tensor", "tc", "ffma"))
+ops.set_tc_terms(5)
+print("%-34s %9s %9s %9s | floor draws" % ("tensor", "tc3", "tc2", "ffma"))
 for n in names:
     fl = [f[n] for f in floors]
-    flag = "  <-- tc > 2 x max floor" if res[4][n] > max(1e-4, 2 * max(fl)) else ""
-    print("%-34s %.2e %.2e | %s%s" % (n, res[4][n], res[0][n], " ".join("%.1e" % v for v in fl), flag))
+    flag = "  <-- tc3 > 2 x max floor" if res[5][n] > max(1e-4, 2 * max(fl)) else ""
+    print("%-34s %.2e %.2e %.2e | %s%s" % (n, res[5][n], res[4][n], res[0][n], " ".join("%.1e" % v for v in fl), flag))
