@@ -407,6 +407,8 @@ class Workload:
         return self.learner.train_batch(self.host, EPOCH).loss
 
     def close(self):
+        if self.learner._grad_sync is not None:
+            self.learner._grad_sync.close()
         self.opt.detach_grad_sink()
 
 

@@ -55,7 +55,12 @@ struct Tc3 {
     static constexpr int PF = NS == 3 ? 2 : 4;
     static constexpr int WIMG = 9 * 2 * NTOT;                    // global image (uint4)
     static constexpr int WIMGS = 9 * 2 * BROWS;                  // shared-memory image (uint4)
-    static constexpr size_t SMEM = ((size_t)RING * SLOT_U4 + WIMGS) * 16 + 256;
+    // t_full barriers: plane q is drained by epilogue group q % NEPI_G from accumulator q % NACC.  A group must see EVERY phase
+    // of a barrier it waits on (a parity wait cannot tell phase p from p + 2), so there is one barrier per (accumulator, group)
+    // combination = q % lcm(NACC, NEPI_G), each completing once per NTF planes, always awaited by the same group.
+    static constexpr int NTF = (NACC % NEPI_G == 0) ? NACC : NACC * NEPI_G;
+    static constexpr int NBARS = 2 * RING + NTF + 3;
+    static constexpr size_t SMEM = ((size_t)RING * SLOT_U4 + WIMGS) * 16 + NBARS * 8 + 64;   // + barriers + TMEM slot
     static_assert(NTOT % 16 == 0 && NTOT <= 256, "UMMA M = 128 needs N % 16 == 0, N <= 256");
     static_assert(NACC >= 2, "two accumulators in flight at least");
 };
@@ -110,6 +115,27 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 
 struct Item3 { int n, oh0, ow0, od_lo, L; };
 
+// Diagnostics (tools/tc_probe): with SP_TC3_DEBUG a wait that times out records who waited for what and lets the kernel run to
+// its end with garbage instead of trapping, so the host can read the record.  [0] = code of the first timeout, [1] = its counter.
+__device__ unsigned long long sp_tc3_dbg[4];
+
+__device__ __forceinline__ void mbar_wait3(uint32_t bar, uint32_t parity, int dbg, unsigned code, unsigned counter) {
+    if (!dbg) {
+        mbar_wait(bar, parity);
+        return;
+    }
+    if (sp_tc3_dbg[0] != 0ull) return;                    // somebody timed out already: drain
+    uint32_t ok = 0;
+    for (uint32_t it = 0; it < (1u << 20); ++it) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        if (ok) return;
+        if ((it & 1023) == 1023 && sp_tc3_dbg[0] != 0ull) return;
+    }
+    if (atomicCAS(&sp_tc3_dbg[0], 0ull, (unsigned long long)code | ((unsigned long long)blockIdx.x << 32)) == 0ull)
+        sp_tc3_dbg[1] = counter | ((unsigned long long)parity << 32);
+}
+
 // accum != 0: add the raw sums already in dst (later input-channel passes); fin == 0: store raw sums (no bias, no activation).
 // sstride: floats between the scale / shift rows of two statistics groups (the layer's full channel count when src is a slice).
 template <int COP, int NS>
@@ -117,15 +143,15 @@ __global__ void __launch_bounds__(NTHREADS3, 1)
 corr3_tc3_kernel(SpConvDesc d, int nPerG, int tiles_w, int tiles_h, int nseg, int seg_len, int total_items,
                  const float* __restrict__ src, const uint4* __restrict__ wimg, const float* __restrict__ bias,
                  const float* __restrict__ scale, const float* __restrict__ shift, int sstride, int accum, int fin,
-                 float* __restrict__ dst, long long* __restrict__ prof) {
+                 float* __restrict__ dst, long long* __restrict__ prof, int dbg) {
     using T = Tc3<COP, NS>;
     constexpr int TS = T::TS, NTOT = T::NTOT, BROWS = T::BROWS, ACOLS = T::ACOLS, NACC = T::NACC, SLOT_U4 = T::SLOT_U4;
-    constexpr int WIMG = T::WIMG, WIMGS = T::WIMGS, RING = T::RING, PF = T::PF;
+    constexpr int WIMG = T::WIMG, WIMGS = T::WIMGS, RING = T::RING, PF = T::PF, NTF = T::NTF;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint4* As = reinterpret_cast<uint4*>(smem_raw);                          // [RING][NS][2][CHS]
     uint4* Bs = As + (size_t)RING * SLOT_U4;                                 // weight image [9][2][BROWS]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(Bs + WIMGS);                 // a_full[RING] a_empty[RING] t_full[3] t_empty[3]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * RING + 6);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(Bs + WIMGS);                 // a_full[RING] a_empty[RING] t_full[NTF] t_empty[3]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + T::NBARS);
     const bool pr = (prof != nullptr) && (blockIdx.x == 0);
     long long pw0 = 0, pw1 = 0, pwk = 0;
 
@@ -136,10 +162,8 @@ corr3_tc3_kernel(SpConvDesc d, int nPerG, int tiles_w, int tiles_h, int nseg, in
             mbar_init(smem_u32(&bars[s]), NSTG);                 // a_full: every staging thread
             mbar_init(smem_u32(&bars[RING + s]), 3);             // a_empty: one tcgen05.commit per output plane that read the slot
         }
-        for (int a = 0; a < 3; ++a) {
-            mbar_init(smem_u32(&bars[2 * RING + a]), 1);         // t_full: the issuer of the plane
-            mbar_init(smem_u32(&bars[2 * RING + 3 + a]), 128);   // t_empty: the 128 threads of the draining epilogue group
-        }
+        for (int a = 0; a < NTF; ++a) mbar_init(smem_u32(&bars[2 * RING + a]), 1);         // t_full: the issuer of the plane
+        for (int a = 0; a < 3; ++a) mbar_init(smem_u32(&bars[2 * RING + NTF + a]), 128);   // t_empty: the draining epilogue group
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) tmem_alloc<512>(tmem_slot);
@@ -149,7 +173,7 @@ corr3_tc3_kernel(SpConvDesc d, int nPerG, int tiles_w, int tiles_h, int nseg, in
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t a_full = smem_u32(&bars[0]), a_empty = smem_u32(&bars[RING]);
-    const uint32_t t_full = smem_u32(&bars[2 * RING]), t_empty = smem_u32(&bars[2 * RING + 3]);
+    const uint32_t t_full = smem_u32(&bars[2 * RING]), t_empty = smem_u32(&bars[2 * RING + NTF]);
 
     auto item_of = [&](int item) {
         Item3 it;
@@ -223,7 +247,7 @@ corr3_tc3_kernel(SpConvDesc d, int nPerG, int tiles_w, int tiles_h, int nseg, in
                     if (ip < nplanes) {
                         const uint32_t s = gin % RING, use = gin / RING;
                         long long c0 = pr ? clock64() : 0;
-                        mbar_wait(a_empty + 8 * s, (use & 1) ^ 1);   // the output planes that read this slot RING planes ago are done
+                        mbar_wait3(a_empty + 8 * s, (use & 1) ^ 1, dbg, 0x100u + s, gin);   // the output planes that read this slot RING planes ago are done
                         long long c1 = pr ? clock64() : 0;
                         pw0 += c1 - c0;
                         float v[8] = {pa[u].x, pa[u].y, pa[u].z, pa[u].w, pb[u].x, pb[u].y, pb[u].z, pb[u].w};
@@ -264,10 +288,10 @@ corr3_tc3_kernel(SpConvDesc d, int nPerG, int tiles_w, int tiles_h, int nseg, in
                     if ((int)(q % NACC) != iss) continue;
                     const uint32_t g2 = gbase + od + 2;          // the last of the three input planes this output plane reads
                     long long c0 = pr ? clock64() : 0;
-                    mbar_wait(a_full + 8 * (g2 % RING), (g2 / RING) & 1);
+                    mbar_wait3(a_full + 8 * (g2 % RING), (g2 / RING) & 1, dbg, 0x200u + (g2 % RING) + 16u * iss, g2);
                     long long c1 = pr ? clock64() : 0;
                     const uint32_t acc = q % NACC;
-                    mbar_wait(t_empty + 8 * acc, ((q / NACC) & 1) ^ 1);      // the epilogue drained this accumulator
+                    mbar_wait3(t_empty + 8 * acc, ((q / NACC) & 1) ^ 1, dbg, 0x300u + acc, q);      // the epilogue drained this accumulator
                     long long c2 = pr ? clock64() : 0;
                     pw0 += c1 - c0; pw1 += c2 - c1;
                     tc_fence_after();
@@ -289,7 +313,7 @@ corr3_tc3_kernel(SpConvDesc d, int nPerG, int tiles_w, int tiles_h, int nseg, in
                             }
                         }
                     }
-                    umma_commit(t_full + 8 * acc);               // accumulator complete -> epilogue
+                    umma_commit(t_full + 8 * (q % NTF));         // accumulator complete -> the epilogue group of this plane
                     // release the input planes: slot of plane ip is free once its (up to) three reading output planes are done;
                     // planes at the ends of a segment have fewer readers, their last reader arrives for the missing ones
                     for (int kd = 0; kd < 3; ++kd) {
@@ -323,7 +347,7 @@ corr3_tc3_kernel(SpConvDesc d, int nPerG, int tiles_w, int tiles_h, int nseg, in
                 if ((int)(q % NEPI_G) != grp) continue;
                 const uint32_t acc = q % NACC;
                 long long c0 = pr ? clock64() : 0;
-                mbar_wait(t_full + 8 * acc, (q / NACC) & 1);
+                mbar_wait3(t_full + 8 * (q % NTF), (q / NTF) & 1, dbg, 0x400u + acc + 16u * grp, q);
                 long long c1 = pr ? clock64() : 0;
                 pw0 += c1 - c0;
                 tc_fence_after();
@@ -448,9 +472,17 @@ static inline int sp_tc3_corr_launch_t(const SpConvDesc* d, int nPerG, const flo
         attr = true;
     }
     int grid = sms;
+    static int dbg = -1, dbg_grid = 0;                   // diagnostics: SP_TC3_DEBUG=1 (timeout records), SP_TC3_GRID=n (CTAs)
+    if (dbg < 0) {
+        const char* e = getenv("SP_TC3_DEBUG");
+        dbg = (e && e[0] == '1') ? 1 : 0;
+        const char* g = getenv("SP_TC3_GRID");
+        dbg_grid = g ? atoi(g) : 0;
+    }
+    if (dbg_grid > 0 && dbg_grid < grid) grid = dbg_grid;
     if (grid > total) grid = (int)total;
     corr3_tc3_kernel<COP, NS><<<grid, NTHREADS3, Tc3<COP, NS>::SMEM, st>>>(*d, nPerG, tiles_w, tiles_h, nseg, seg_len, (int)total, src, wimg,
-                                                                           bias, scale, shift, sstride, accum, fin, dst, prof);
+                                                                           bias, scale, shift, sstride, accum, fin, dst, prof, dbg);
     SP_LAUNCH_OK("corr3_tc3_kernel");
     return 0;
 }

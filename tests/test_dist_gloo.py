@@ -40,19 +40,32 @@ class _FakeOpt:
     def __init__(self, params):
         self.param_groups = [{"params": params}]
         self.grad_scale = 1.0
-        n = sum(p.numel() for p in params)
-        self.flat = torch.zeros(n)
+        pad = lambda n: (n + 3) // 4 * 4                 # engine.GradSink keeps every view 16-byte aligned
+        self.flat = torch.zeros(sum(pad(p.numel()) for p in params))
+        self.offsets = {}
         off = 0
         for p in params:
             p.grad = self.flat[off:off + p.numel()].view(p.shape)
-            off += p.numel()
+            self.offsets[id(p)] = off
+            off += pad(p.numel())
+        self.params = params
 
     def attach_grad_sink(self):
         class S:
             pass
         s = S()
-        s.flat = self.flat
+        s.flat, s._offsets, s.params = self.flat, self.offsets, self.params
         return s
+
+
+class _FakePlan:
+    """What engine.plan_backward_hooks hands over: something with .params() (engine.SeqPlan)."""
+
+    def __init__(self, module):
+        self._params = list(module.parameters())
+
+    def params(self):
+        return self._params
 
 
 def _worker(rank, world, port, out):
@@ -72,11 +85,37 @@ def _worker(rank, world, port, out):
     sd = O.clone_state(cae.state_dict(), requires_grad=True)
     g = _local_grads(sd, shard)
     names = [n for n, _ in cae.named_parameters()]
+    # backward order of the CAE: the decoder's gradients are final first -> its slice is reduced while the "encoder backward"
+    # (here: the copy of the encoder gradients) still runs; the call between backward and step covers the rest
+    dec_plan, enc_plan = _FakePlan(cae.dec.decoder), _FakePlan(cae.enc.encoder)
+    dec_ids = {id(p) for p in dec_plan.params()}
+    with torch.no_grad():
+        for n, p in zip(names, params):
+            if id(p) in dec_ids:
+                p.grad.copy_(g[n])
+    lo, hi = sync.plan_range(dec_plan)
+    assert hi - lo >= sum(p.numel() for p in dec_plan.params()) and sync.plan_range(enc_plan)[1] == lo
+    sync.plan_ready(dec_plan)
+    sync.plan_ready(dec_plan)                # a second notification must not reduce the slice twice
+    assert sync.early_elements == hi - lo
+    with torch.no_grad():
+        for n, p in zip(names, params):
+            if id(p) not in dec_ids:
+                p.grad.copy_(g[n])
+    sync()
+    assert sync.last_early_elements == hi - lo and sync.early_elements == 0 and not sync._done and not sync._work
+    averaged = {n: (p.grad * opt.grad_scale).clone() for n, p in zip(names, params)}
+    # a second step without any early notification: one collective over the whole buffer, same arithmetic
     with torch.no_grad():
         for n, p in zip(names, params):
             p.grad.copy_(g[n])
     sync()
-    averaged = {n: (p.grad * opt.grad_scale).clone() for n, p in zip(names, params)}
+    for n, p in zip(names, params):
+        assert torch.equal(p.grad * opt.grad_scale, averaged[n]), n
+    assert sync._uncovered(0, 10) == [(0, 10)]
+    sync._done = [(2, 4), (6, 8)]
+    assert sync._uncovered(0, 10) == [(0, 2), (4, 6), (8, 10)] and sync._uncovered(3, 7) == [(4, 6)]
+    sync._done = []
     if rank == 0:
         torch.save({"avg": averaged, "sd": {k: v.detach() for k, v in cae.state_dict().items()}}, out)
     dist.barrier()

@@ -16,16 +16,24 @@ modes = [int(m) for m in (sys.argv[1].split(",") if len(sys.argv) > 1 else "5,4,
 cases = [("unet block5 conv b", 2, 16, 16, (30, 130, 130), 0), ("unet block5 conv b (patch)", 2, 16, 16, (30, 66, 66), 0),
          ("cae dec.28", 4, 16, 16, (28, 126, 126), (1, 2, 2)), ("cae enc.10", 4, 24, 24, (14, 62, 62), (1, 0, 0)),
          ("unet block5 conv a", 2, 48, 16, (32, 132, 132), 0)]
+if os.environ.get("DIAG_CENTER"):    # zero-mean input (what BatchNorm hands the convolution in the real networks)
+    cases = [c[:1] + c[1:] for c in cases[:3]]
 for name, N, ci, co, size, pad in cases:
     torch.manual_seed(1)
     conv = nn.Conv3d(ci, co, 3, padding=pad)
     x = torch.randn(N, ci, *size)
     x = torch.where(x > 0, x, 0.01 * x) * 1.3 + 0.2          # post-LeakyReLU-like input with a mean
+    if os.environ.get("DIAG_CENTER"):
+        x = x - x.mean(dim=(0, 2, 3, 4), keepdim=True)
     y64 = conv.double()(x.double())
-    for gkind in ("randn", "sparse"):
+    for gkind in ("randn", "sparse", "sparse0", "tail"):
         g = torch.randn(y64.shape)
-        if gkind == "sparse":
+        if gkind == "sparse":        # a few huge values + small ones with a common offset
             g = g * (torch.rand(y64.shape) < 0.02).float() * 50 + 1e-3 * torch.randn(y64.shape) + 3e-3
+        elif gkind == "sparse0":     # the same without the offset
+            g = g * (torch.rand(y64.shape) < 0.02).float() * 50 + 1e-3 * torch.randn(y64.shape)
+        elif gkind == "tail":        # log-normal magnitudes (4 decades), random signs
+            g = g.sign() * torch.exp(2.3 * torch.randn(y64.shape))
         res = {}
         for label, dtype in (("cpu64", torch.float64), ("cpu32", torch.float32)):
             c = conv.to(dtype)

@@ -97,6 +97,15 @@ int main(int argc, char** argv) {
         CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
         for (int it = 0; it < 3; ++it) if (launch(ns, d, dx, dw, nullptr, nullptr, dy, dimg)) return 3;
         CK(cudaDeviceSynchronize());
+        if (ns == 33 || ns == 31) {
+            unsigned long long info[4] = {0, 0, 0, 0};
+            CK(cudaMemcpyFromSymbol(info, sp_tc3::sp_tc3_dbg, sizeof(info)));
+            if (info[0]) {
+                printf("TIMEOUT: code 0x%llx cta %llu counter %llu parity %llu\n", info[0] & 0xffffffffull, info[0] >> 32,
+                       info[1] & 0xffffffffull, info[1] >> 32);
+                return 5;
+            }
+        }
         CK(cudaEventRecord(e0));
         const int reps = 10;
         for (int it = 0; it < reps; ++it) launch(ns, d, dx, dw, nullptr, nullptr, dy, dimg);
@@ -138,7 +147,8 @@ int main(int argc, char** argv) {
         return 0;
     }
     const bool onehot = !strcmp(mode, "onehot");
-    SpConvDesc d = make_desc(2, 9, 37, 21, 16, 16, 1, 0, 2);     // partial tiles in every direction, padding in d and w
+    SpConvDesc d = getenv("SP_PROBE_BIG") ? make_desc(3, 14, 45, 61, 16, 16, 1, 2, 2)
+                                          : make_desc(2, 9, 37, 21, 16, 16, 1, 0, 2);     // partial tiles in every direction, padding in d and w
     const size_t nx = (size_t)d.N * d.Di * d.Hi * d.Wi * d.Ci, ny = (size_t)d.N * d.Do * d.Ho * d.Wo * d.Co;
     std::vector<float> x(nx), w((size_t)16 * 16 * 27, 0.f), sc, sh;
     srand(1234);
@@ -174,6 +184,13 @@ int main(int argc, char** argv) {
         if (launch(ns, d, dx, dw, dsc, dsh, dy, dimg)) return 3;
         cudaError_t e = cudaDeviceSynchronize();
         if (e != cudaSuccess) { printf("kernel failed: %s\n", cudaGetErrorString(e)); return 4; }
+        if (ns == 33 || ns == 31) {
+            unsigned long long info[4] = {0, 0, 0, 0};
+            CK(cudaMemcpyFromSymbol(info, sp_tc3::sp_tc3_dbg, sizeof(info)));
+            if (info[0]) printf("TIMEOUT: code 0x%llx (0x1xx stager a_empty[slot], 0x2xx issuer a_full[slot + 16 iss], 0x3xx issuer t_empty[acc], "
+                                "0x4xx epilogue t_full[acc + 16 grp]) cta %llu counter %llu parity %llu\n", info[0] & 0xffffffffull, info[0] >> 32,
+                                info[1] & 0xffffffffull, info[1] >> 32);
+        }
         CK(cudaMemcpy(y.data(), dy, ny * 4, cudaMemcpyDeviceToHost));
         cpu_corr(d, x, w, sc, sh, ref);
         double num = 0, den = 0, maxabs = 0;
