@@ -15,7 +15,7 @@ from util import rel_l2
 modes = [int(m) for m in (sys.argv[1].split(",") if len(sys.argv) > 1 else "5,4,0".split(","))]
 cases = [("unet block5 conv b", 2, 16, 16, (30, 130, 130), 0), ("unet block5 conv b (patch)", 2, 16, 16, (30, 66, 66), 0),
          ("cae dec.28", 4, 16, 16, (28, 126, 126), (1, 2, 2)), ("cae enc.10", 4, 24, 24, (14, 62, 62), (1, 0, 0)),
-         ("unet block5 conv a", 2, 48, 16, (32, 132, 132), 0)]
+         ("unet block5 conv a", 2, 48, 16, (32, 132, 132), 0), ("unet block2 conv b", 2, 32, 32, (30, 80, 80), 0)]
 if os.environ.get("DIAG_CENTER"):    # zero-mean input (what BatchNorm hands the convolution in the real networks)
     cases = [c[:1] + c[1:] for c in cases[:3]]
 for name, N, ci, co, size, pad in cases:
@@ -26,7 +26,7 @@ for name, N, ci, co, size, pad in cases:
     if os.environ.get("DIAG_CENTER"):
         x = x - x.mean(dim=(0, 2, 3, 4), keepdim=True)
     y64 = conv.double()(x.double())
-    for gkind in ("randn", "sparse", "sparse0", "tail"):
+    for gkind in os.environ.get("DIAG_GRADS", "randn,sparse,sparse0,tail").split(","):
         g = torch.randn(y64.shape)
         if gkind == "sparse":        # a few huge values + small ones with a common offset
             g = g * (torch.rand(y64.shape) < 0.02).float() * 50 + 1e-3 * torch.randn(y64.shape) + 3e-3

@@ -193,16 +193,18 @@ int main(int argc, char** argv) {
         }
         CK(cudaMemcpy(y.data(), dy, ny * 4, cudaMemcpyDeviceToHost));
         cpu_corr(d, x, w, sc, sh, ref);
-        double num = 0, den = 0, maxabs = 0;
+        double num = 0, den = 0, maxabs = 0, esum = 0, esgn = 0, esum_par[2] = {0, 0};
         size_t nbad = 0, first_bad = (size_t)-1;
         for (size_t i = 0; i < ny; ++i) {
             const double e2 = (double)y[i] - ref[i];
+            esum += e2; esgn += e2 * (ref[i] > 0 ? 1.0 : -1.0);
+            esum_par[(i / ((size_t)d.Co * d.Wo * d.Ho)) % d.Do & 1] += e2;
             num += e2 * e2; den += ref[i] * ref[i];
             if (fabs(e2) > maxabs) maxabs = fabs(e2);
             if (!(fabs(e2) <= 1e-3 * (1.0 + fabs(ref[i])))) { if (nbad == 0) first_bad = i; ++nbad; }
         }
         if (!onehot) {   // what an IEEE fp32 FFMA chain (the exact tier) gives on the same data
-            double n32 = 0;
+            double n32 = 0, s32 = 0, g32 = 0;
             for (int nn = 0; nn < d.N; ++nn)
                 for (int od = 0; od < d.Do; ++od)
                     for (int oh = 0; oh < d.Ho; ++oh)
@@ -220,9 +222,16 @@ int main(int argc, char** argv) {
                                                 acc = fmaf(xv, w[((size_t)co * d.Ci + ci) * 27 + (kd * 3 + kh) * 3 + kw], acc);
                                             }
                                 const double e3 = (double)acc - ref[((((size_t)nn * d.Do + od) * d.Ho + oh) * d.Wo + ow) * d.Co + co];
-                                n32 += e3 * e3;
+                                n32 += e3 * e3; s32 += e3;
+                                g32 += e3 * (ref[((((size_t)nn * d.Do + od) * d.Ho + oh) * d.Wo + ow) * d.Co + co] > 0 ? 1.0 : -1.0);
                             }
-            printf("fp32 FFMA chain (CPU) rel-L2 %.3e\n", sqrt(n32 / (den > 0 ? den : 1)));
+            printf("fp32 FFMA chain (CPU) rel-L2 %.3e   signed error / rms: mean %.3e, mean(e * sign) %.3e\n", sqrt(n32 / (den > 0 ? den : 1)),
+                   s32 / ny / sqrt(den / ny), g32 / ny / sqrt(den / ny));
+        }
+        if (!onehot) {
+            const double rms = sqrt(den / ny);
+            printf("signed error / rms(ref): mean %.3e (even planes %.3e, odd planes %.3e), mean(e * sign(ref)) %.3e   [rms error %.3e]\n",
+                   esum / ny / rms, esum_par[0] / (ny / 2) / rms, esum_par[1] / (ny / 2) / rms, esgn / ny / rms, sqrt(num / ny) / rms);
         }
         if (onehot) printf("onehot tap %2d ci %2d co %2d: ", cases[cs][0], cases[cs][1], cases[cs][2]);
         printf("ns=%d rel-L2 %.3e max-abs %.3e mismatches %zu / %zu\n", ns, sqrt(num / (den > 0 ? den : 1)), maxabs, nbad, ny);
