@@ -54,9 +54,73 @@ static inline int sp_num_sms() {
 static inline int64_t sp_cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 // ---- activations ----------------------------------------------------------------------------
+// expm1 on v <= 0 for the ELU epilogues (16 .. 24 evaluations per output voxel in the tensor-core tiers' epilogue warps), branch
+// free.  |v| < 1/4: degree-8 Taylor polynomial in Horner form (truncation v^9 / 9! < 1e-9 relative).  Otherwise exp(v) - 1 with
+// exp by Cody-Waite range reduction (n = rint(v log2 e), r = v - n ln 2 in two steps, |r| <= 0.347), a degree-7 polynomial
+// (r^8 / 8! < 5e-9) and the scaling 2^n applied to the exponent field; |result| >= 0.22, so the subtraction costs < 3e-7 relative.
+// Measured against fp64 on 2.2 M points: max relative error 1.3e-7 (libm's expm1f in fp32: 1.9e-7).
+__device__ __forceinline__ float sp_exp_nonpos(float v) {
+    v = fmaxf(v, -87.f);
+    const float t = fmaf(v, 1.442695041f, 12582912.f);           // 1.5 * 2^23: n = rint(v * log2 e) lands in the low mantissa bits
+    const float n = t - 12582912.f;
+    float r = fmaf(n, -0.693145752f, v);
+    r = fmaf(n, -1.428606765e-6f, r);
+    float p = fmaf(r, 1.f / 5040.f, 1.f / 720.f);
+    p = fmaf(r, p, 1.f / 120.f);
+    p = fmaf(r, p, 1.f / 24.f);
+    p = fmaf(r, p, 1.f / 6.f);
+    p = fmaf(r, p, 0.5f);
+    p = fmaf(r, p, 1.f);
+    p = fmaf(r, p, 1.f);
+    return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
+__device__ __forceinline__ float sp_expm1_neg(float v) {
+    const float p = fmaf(v, fmaf(v, fmaf(v, fmaf(v, fmaf(v, fmaf(v, fmaf(v, 1.f / 40320.f, 1.f / 5040.f), 1.f / 720.f), 1.f / 120.f),
+                                                  1.f / 24.f), 1.f / 6.f), 0.5f), 1.f);
+    return v > -0.25f ? v * p : sp_exp_nonpos(v) - 1.f;
+}
+// ELU of N values at once, written level by level so that the N independent dependency chains (~26 dependent FMAs each) are
+// interleaved in the instruction stream.  Evaluated one value after the other (what the compiler emits for a loop over
+// sp_act_fwd) the epilogue warps of the tensor-core tiers issued one instruction every ~4 cycles: ncu stall_wait 3 : 1 selected.
+template <int N>
+__device__ __forceinline__ void sp_elu_n(float* v, float alpha) {
+    float x[N], t[N], r[N], p[N], q[N];
+#pragma unroll
+    for (int j = 0; j < N; ++j) x[j] = fminf(v[j], 0.f);
+#pragma unroll
+    for (int j = 0; j < N; ++j) t[j] = fmaf(fmaxf(x[j], -87.f), 1.442695041f, 12582912.f);
+#pragma unroll
+    for (int j = 0; j < N; ++j) r[j] = fmaf(t[j] - 12582912.f, -0.693145752f, fmaxf(x[j], -87.f));
+#pragma unroll
+    for (int j = 0; j < N; ++j) r[j] = fmaf(t[j] - 12582912.f, -1.428606765e-6f, r[j]);
+#pragma unroll
+    for (int j = 0; j < N; ++j) { p[j] = fmaf(r[j], 1.f / 5040.f, 1.f / 720.f); q[j] = fmaf(x[j], 1.f / 40320.f, 1.f / 5040.f); }
+#pragma unroll
+    for (int j = 0; j < N; ++j) { p[j] = fmaf(r[j], p[j], 1.f / 120.f); q[j] = fmaf(x[j], q[j], 1.f / 720.f); }
+#pragma unroll
+    for (int j = 0; j < N; ++j) { p[j] = fmaf(r[j], p[j], 1.f / 24.f); q[j] = fmaf(x[j], q[j], 1.f / 120.f); }
+#pragma unroll
+    for (int j = 0; j < N; ++j) { p[j] = fmaf(r[j], p[j], 1.f / 6.f); q[j] = fmaf(x[j], q[j], 1.f / 24.f); }
+#pragma unroll
+    for (int j = 0; j < N; ++j) { p[j] = fmaf(r[j], p[j], 0.5f); q[j] = fmaf(x[j], q[j], 1.f / 6.f); }
+#pragma unroll
+    for (int j = 0; j < N; ++j) { p[j] = fmaf(r[j], p[j], 1.f); q[j] = fmaf(x[j], q[j], 0.5f); }
+#pragma unroll
+    for (int j = 0; j < N; ++j) { p[j] = fmaf(r[j], p[j], 1.f); q[j] = fmaf(x[j], q[j], 1.f); }
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+        const float e = __int_as_float(__float_as_int(p[j]) + (__float_as_int(t[j]) << 23)) - 1.f;      // exp(x) - 1
+        const float m = x[j] > -0.25f ? x[j] * q[j] : e;                                                  // expm1(x), x <= 0
+        v[j] = fmaf(alpha, m, fmaxf(v[j], 0.f));
+    }
+}
+
 __device__ __forceinline__ float sp_act_fwd(float v, int act, float alpha) {
     switch (act) {
-        case SP_ACT_ELU:     return v > 0.f ? v : alpha * expm1f(v);
+        // max(v, 0) + alpha * expm1(min(v, 0)): the same value as the two-sided definition (expm1(0) = 0) but straight-line code.
+        // Written as `v > 0 ? v : ...` the compiler branches around the exponential PER ELEMENT, which serialises the 8 .. 16
+        // independent evaluations of an epilogue thread (measured: 285 cycles per evaluation, +0.86 ms on the 16 -> 16 layer).
+        case SP_ACT_ELU:     return fmaf(alpha, sp_expm1_neg(fminf(v, 0.f)), fmaxf(v, 0.f));
         case SP_ACT_LEAKY:   return v > 0.f ? v : alpha * v;
         case SP_ACT_SIGMOID: return 1.f / (1.f + expf(-v));
         default:             return v;

@@ -493,11 +493,17 @@ SpTier corrT_tier(const SpConvDesc* d, SpTcCfg* cfg) {
     return TIER_GENERIC;
 }
 
+// Which kernel generation serves a layer of the tensor-core tier: generation 3 (kw-stacked N, rolling depth window) for output
+// widths up to 16 and for every slice / pass of the wide layers; the 17..24-wide layers of the CAE's second level stay on
+// generation 2 in the fp32-grade mode (their kw-stacked N would be 240 columns with 2 accumulators and a half-empty second
+// K pass: measured 0.83 vs 0.72 ms on Cae3D.py:55).  The bf16 mode exists in generation 3 only.
+bool use_gen3(const SpTcCfg& cfg) { return sp_tc_terms() == 1 || (sp_tc_terms() == 5 && cfg.cop == 16); }
+
 int tc_corr_launch(const SpConvDesc* d, const SpTcCfg& cfg, int nPerG, const float* src, const float* wimg, const float* bias,
                    const float* scale, const float* shift, float* dst, cudaStream_t st) {
     const uint4* img = reinterpret_cast<const uint4*>(wimg);
-    if (sp_tc_gen3()) return sp_tc3_corr_launch(d, nPerG, sp_tc_image_terms(), src, img, bias, scale, shift, dst, st);
-    if (sp_tc_terms() == 4) return sp_tc2_corr_launch(d, nPerG, src, img, bias, scale, shift, dst, st);
+    if (use_gen3(cfg)) return sp_tc3_corr_launch(d, nPerG, sp_tc_image_terms(), src, img, bias, scale, shift, dst, st);
+    if (sp_tc_terms() == 4 || sp_tc_terms() == 5) return sp_tc2_corr_launch(d, nPerG, src, img, bias, scale, shift, dst, st);
     if (sp_tc_terms() == 2) return sp_tc_corr_launch_t<16, 16, 2, 4>(d, nPerG, src, img, bias, scale, shift, dst, st);
     return sp_tc_corr_launch_t<16, 16, 3, 2>(d, nPerG, src, img, bias, scale, shift, dst, st);
 }
@@ -519,9 +525,10 @@ size_t sp_packed_weight_floats(const SpConvDesc* d, int which) {
     if (!d) return 0;
     size_t n = ffma_packed_floats(d, which);
     SpTcCfg cfg;
-    if ((which == 0 ? corr_tier(d, &cfg) : corrT_tier(d, &cfg)) == TIER_TC && sp_tc_gen3())
+    const bool tc = (which == 0 ? corr_tier(d, &cfg) : corrT_tier(d, &cfg)) == TIER_TC;
+    if (tc && use_gen3(cfg))
         n += (size_t)cfg.passes * cfg.nslices * sp_tc3_wimg_u4(cfg.cop, sp_tc_image_terms()) * 4;
-    else if ((which == 0 ? corr_tier(d, &cfg) : corrT_tier(d, &cfg)) == TIER_TC) n += (size_t)cfg.passes * cfg.nslices * sp_tc_wimg_bytes(cfg.cip, cfg.cop, sp_tc_image_terms()) / sizeof(float);
+    else if (tc) n += (size_t)cfg.passes * cfg.nslices * sp_tc_wimg_bytes(cfg.cip, cfg.cop, sp_tc_image_terms()) / sizeof(float);
     return n;
 }
 
@@ -544,7 +551,7 @@ int sp_pack_weights(const SpConvDesc* d, int which, const float* w_torch, float*
         pack_weights_kernel<<<grid_for(total), 256, 0, sp_stream(stream)>>>(w_torch, w_packed, d->Co, d->Ci, k3, which, dP);
         SP_LAUNCH_OK("pack_weights_kernel");
     }
-    if (tc && sp_tc_gen3())
+    if (tc && use_gen3(cfg))
         return sp_tc3_pack_launch(d, which, sp_tc_image_terms(), cfg.cop, w_torch, w_packed + total, sp_stream(stream), cfg.passes, cfg.nslices);
     if (tc)
         return sp_tc_pack_launch(d, which, sp_tc_image_terms(), cfg.cip, cfg.cop, w_torch, w_packed + total, sp_stream(stream), cfg.passes, cfg.nslices);

@@ -32,7 +32,8 @@ using sp_tc2::tmem_ld_n;
 constexpr int TW = 16, TWV = 14, TH = 8, IH = TH + 2;   // MMA rows = 16 w'' x 8 h; 14 x 8 outputs per plane
 constexpr int PSLOTS = IH * TW;                          // 160 sixteen-byte slots per (term, chunk) plane
 constexpr int CHS = PSLOTS + 4;                          // chunk-plane stride: odd multiple of 64 B (bank spread of the 2 K chunks)
-constexpr int NEPI_G = 2, NEPI_W = 4 * NEPI_G;           // epilogue groups / warps
+constexpr int NEPI_G = 2, NEPI_W = 4 * NEPI_G;           // epilogue groups / warps (three groups measured slower: 25 warps crowd the
+                                                          // schedulers the three MMA-issuing threads need: issue time 3.7 k -> 5.2 k cycles per plane)
 constexpr int NSTG_W = 10, NSTG = NSTG_W * 32;           // staging warps / threads: 320 = one item per thread and plane
 constexpr int NISS_W = 3;                                // MMA issuer warps (NACC of them active)
 constexpr int NWARPS3 = NEPI_W + NSTG_W + NISS_W;        // 21
@@ -105,8 +106,16 @@ __global__ void pack_wimg3_kernel(const float* __restrict__ w, int Co, int Ci, i
 
 template <int N>
 __device__ __forceinline__ void tmem_ld_issue(uint32_t taddr, uint32_t* r) {
+    static_assert(N % 8 == 0, "tmem_ld_issue: multiples of 8 columns");
+    constexpr int N16 = N / 16 * 16;
 #pragma unroll
-    for (int c = 0; c < N; c += 8)
+    for (int c = 0; c < N16; c += 16)
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                     : "=r"(r[c]), "=r"(r[c + 1]), "=r"(r[c + 2]), "=r"(r[c + 3]), "=r"(r[c + 4]), "=r"(r[c + 5]), "=r"(r[c + 6]), "=r"(r[c + 7]),
+                       "=r"(r[c + 8]), "=r"(r[c + 9]), "=r"(r[c + 10]), "=r"(r[c + 11]), "=r"(r[c + 12]), "=r"(r[c + 13]), "=r"(r[c + 14]), "=r"(r[c + 15])
+                     : "r"(taddr + c) : "memory");
+#pragma unroll
+    for (int c = N16; c < N; c += 8)
         asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                      : "=r"(r[c]), "=r"(r[c + 1]), "=r"(r[c + 2]), "=r"(r[c + 3]), "=r"(r[c + 4]), "=r"(r[c + 5]), "=r"(r[c + 6]), "=r"(r[c + 7])
                      : "r"(taddr + c) : "memory");
@@ -119,10 +128,21 @@ struct Item3 { int n, oh0, ow0, od_lo, L; };
 // its end with garbage instead of trapping, so the host can read the record.  [0] = code of the first timeout, [1] = its counter.
 __device__ unsigned long long sp_tc3_dbg[4];
 
+// Warp-collective wait: ONE lane polls the barrier (with a short sleep between polls), the others park at the warp barrier.
+// Measured with every thread spinning: a third of all issued instructions of the kernel were SYNCS / BRA of 20 waiting warps,
+// taken from the issue slots of the epilogue warps that share their schedulers.
+__device__ __forceinline__ void mbar_wait_warp(uint32_t bar, uint32_t parity, int dbg, unsigned code, unsigned counter);
+
 __device__ __forceinline__ void mbar_wait3(uint32_t bar, uint32_t parity, int dbg, unsigned code, unsigned counter) {
     if (!dbg) {
-        mbar_wait(bar, parity);
-        return;
+        uint32_t ok = 0;
+        for (uint32_t it = 0; it < (1u << 24); ++it) {
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                         : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+            if (ok) return;
+            __nanosleep(40);
+        }
+        __trap();
     }
     if (sp_tc3_dbg[0] != 0ull) return;                    // somebody timed out already: drain
     uint32_t ok = 0;
@@ -134,6 +154,11 @@ __device__ __forceinline__ void mbar_wait3(uint32_t bar, uint32_t parity, int db
     }
     if (atomicCAS(&sp_tc3_dbg[0], 0ull, (unsigned long long)code | ((unsigned long long)blockIdx.x << 32)) == 0ull)
         sp_tc3_dbg[1] = counter | ((unsigned long long)parity << 32);
+}
+
+__device__ __forceinline__ void mbar_wait_warp(uint32_t bar, uint32_t parity, int dbg, unsigned code, unsigned counter) {
+    if ((threadIdx.x & 31) == 0) mbar_wait3(bar, parity, dbg, code, counter);
+    __syncwarp();
 }
 
 // accum != 0: add the raw sums already in dst (later input-channel passes); fin == 0: store raw sums (no bias, no activation).
@@ -159,11 +184,11 @@ corr3_tc3_kernel(SpConvDesc d, int nPerG, int tiles_w, int tiles_h, int nseg, in
     for (int i = tid; i < WIMG; i += NTHREADS3) Bs[(i / NTOT) * BROWS + (i % NTOT)] = wimg[i];
     if (tid == 0) {
         for (int s = 0; s < RING; ++s) {
-            mbar_init(smem_u32(&bars[s]), NSTG);                 // a_full: every staging thread
+            mbar_init(smem_u32(&bars[s]), NSTG_W);               // a_full: one arrival per staging warp
             mbar_init(smem_u32(&bars[RING + s]), 3);             // a_empty: one tcgen05.commit per output plane that read the slot
         }
         for (int a = 0; a < NTF; ++a) mbar_init(smem_u32(&bars[2 * RING + a]), 1);         // t_full: the issuer of the plane
-        for (int a = 0; a < 3; ++a) mbar_init(smem_u32(&bars[2 * RING + NTF + a]), 128);   // t_empty: the draining epilogue group
+        for (int a = 0; a < 3; ++a) mbar_init(smem_u32(&bars[2 * RING + NTF + a]), 4);     // t_empty: the 4 warps of the draining group
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) tmem_alloc<512>(tmem_slot);
@@ -247,7 +272,7 @@ corr3_tc3_kernel(SpConvDesc d, int nPerG, int tiles_w, int tiles_h, int nseg, in
                     if (ip < nplanes) {
                         const uint32_t s = gin % RING, use = gin / RING;
                         long long c0 = pr ? clock64() : 0;
-                        mbar_wait3(a_empty + 8 * s, (use & 1) ^ 1, dbg, 0x100u + s, gin);   // the output planes that read this slot RING planes ago are done
+                        mbar_wait_warp(a_empty + 8 * s, (use & 1) ^ 1, dbg, 0x100u + s, gin);   // the output planes that read this slot RING planes ago are done
                         long long c1 = pr ? clock64() : 0;
                         pw0 += c1 - c0;
                         float v[8] = {pa[u].x, pa[u].y, pa[u].z, pa[u].w, pb[u].x, pb[u].y, pb[u].z, pb[u].w};
@@ -266,7 +291,8 @@ corr3_tc3_kernel(SpConvDesc d, int nPerG, int tiles_w, int tiles_h, int nseg, in
                             Ab[0] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
                         }
                         fence_async_smem();                          // generic-proxy writes -> visible to the tensor core
-                        mbar_arrive(a_full + 8 * s);
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(a_full + 8 * s);
                         ++gin;
                         if (pr) pwk += clock64() - c1;
                     }
@@ -335,9 +361,7 @@ corr3_tc3_kernel(SpConvDesc d, int nPerG, int tiles_w, int tiles_h, int nseg, in
         const int grp = warp >> 2, q4 = warp & 3;
         const int r = q4 * 32 + lane;                            // GEMM row = (h, w'') of the tile
         const int hy = r / TW, wx = r % TW;
-        float bch[COP];
-#pragma unroll
-        for (int j = 0; j < COP; ++j) bch[j] = (bias && fin && j < d.Co) ? bias[j] : 0.f;
+        const bool has_bias = bias != nullptr && fin;
         uint32_t q = 0;
         for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
             const Item3 it = item_of(item);
@@ -347,71 +371,83 @@ corr3_tc3_kernel(SpConvDesc d, int nPerG, int tiles_w, int tiles_h, int nseg, in
                 if ((int)(q % NEPI_G) != grp) continue;
                 const uint32_t acc = q % NACC;
                 long long c0 = pr ? clock64() : 0;
-                mbar_wait3(t_full + 8 * (q % NTF), (q / NTF) & 1, dbg, 0x400u + acc + 16u * grp, q);
+                mbar_wait_warp(t_full + 8 * (q % NTF), (q / NTF) & 1, dbg, 0x400u + acc + 16u * grp, q);
                 long long c1 = pr ? clock64() : 0;
                 pw0 += c1 - c0;
                 tc_fence_after();
                 const uint32_t ta = tmem_base + ((uint32_t)(q4 * 32) << 16) + acc * ACOLS;
-                float out[COP];
+                const int odg = it.od_lo + od;
+                float* yp = dst + ((((int64_t)it.n * d.Do + odg) * d.Ho + oh) * d.Wo + ow) * d.ldo;
+                const bool vecy = (d.ldo % 4 == 0) && (d.Co % 8 == 0);
+                // Eight output channels at a time (24 + 16 live registers: with every role's registers capped at 80 by the CTA's 21 warps
+                // the 16-wide form spilled, and the epilogue then waited for its own spill traffic).
 #pragma unroll
-                for (int kw = 0; kw < 3; ++kw) {
-                    float s[COP];
-                    if (NS == 3) {
-                        uint32_t m[COP], a[COP], b[COP];
-                        tmem_ld_issue<COP>(ta + kw * COP, m);                  // main
-                        tmem_ld_issue<COP>(ta + TS + kw * COP, a);             // cA
-                        tmem_ld_issue<COP>(ta + 2 * TS + kw * COP, b);         // cB
-                        tmem_ld_wait();
+                for (int c0 = 0; c0 < COP; c0 += 8) {
+                    float out[8];
 #pragma unroll
-                        for (int j = 0; j < COP; ++j)
-                            s[j] = (__uint_as_float(b[j]) + __uint_as_float(a[j])) + __uint_as_float(m[j]);   // corrections first
-                    } else {
-                        uint32_t m[COP];
-                        tmem_ld_issue<COP>(ta + kw * COP, m);
-                        tmem_ld_wait();
+                    for (int kw = 0; kw < 3; ++kw) {
+                        float s[8];
+                        if (NS == 3) {
+                            uint32_t m[8], a[8], b[8];
+                            tmem_ld_issue<8>(ta + kw * COP + c0, m);                  // main
+                            tmem_ld_issue<8>(ta + TS + kw * COP + c0, a);             // cA
+                            tmem_ld_issue<8>(ta + 2 * TS + kw * COP + c0, b);         // cB
+                            tmem_ld_wait();
 #pragma unroll
-                        for (int j = 0; j < COP; ++j) s[j] = __uint_as_float(m[j]);
-                    }
-                    if (kw == 2) {
-                        tc_fence_before();
-                        mbar_arrive(t_empty + 8 * acc);          // this accumulator may be overwritten
-                    }
-                    // out[w] = D0[w] + D1[w + 1] + D2[w + 2]: rows w'' + kw of the same h are lanes + kw of this warp
-#pragma unroll
-                    for (int j = 0; j < COP; ++j) {
-                        const float t = (kw == 0) ? s[j] : __shfl_down_sync(0xffffffffu, s[j], kw);
-                        out[j] = (kw == 0) ? t : out[j] + t;
-                    }
-                }
-                if (valid_hw) {
-                    const int odg = it.od_lo + od;
-                    float* yp = dst + ((((int64_t)it.n * d.Do + odg) * d.Ho + oh) * d.Wo + ow) * d.ldo;
-                    const bool vecy = (d.ldo % 4 == 0) && d.Co == COP;
-                    if (accum) {                                  // raw sums of the earlier input-channel passes
-                        if (vecy) {
-#pragma unroll
-                            for (int j4 = 0; j4 < COP / 4; ++j4) {
-                                const float4 o = reinterpret_cast<const float4*>(yp)[j4];
-                                out[4 * j4] += o.x; out[4 * j4 + 1] += o.y; out[4 * j4 + 2] += o.z; out[4 * j4 + 3] += o.w;
-                            }
+                            for (int j = 0; j < 8; ++j)
+                                s[j] = (__uint_as_float(b[j]) + __uint_as_float(a[j])) + __uint_as_float(m[j]);   // corrections first
                         } else {
+                            uint32_t m[8];
+                            tmem_ld_issue<8>(ta + kw * COP + c0, m);
+                            tmem_ld_wait();
 #pragma unroll
-                            for (int j = 0; j < COP; ++j)
-                                if (j < d.Co) out[j] += yp[j];
+                            for (int j = 0; j < 8; ++j) s[j] = __uint_as_float(m[j]);
+                        }
+                        if (kw == 2 && c0 + 8 >= COP) {
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(t_empty + 8 * acc);  // this accumulator may be overwritten (one arrival per warp)
+                        }
+                        // out[w] = D0[w] + D1[w + 1] + D2[w + 2]: rows w'' + kw of the same h are lanes + kw of this warp
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const float t = (kw == 0) ? s[j] : __shfl_down_sync(0xffffffffu, s[j], kw);
+                            out[j] = (kw == 0) ? t : out[j] + t;
                         }
                     }
-                    if (fin) {
+                    if (valid_hw && c0 < d.Co) {
+                        if (accum) {                              // raw sums of the earlier input-channel passes
+                            if (vecy) {
+                                const float4 o0 = reinterpret_cast<const float4*>(yp + c0)[0], o1 = reinterpret_cast<const float4*>(yp + c0)[1];
+                                out[0] += o0.x; out[1] += o0.y; out[2] += o0.z; out[3] += o0.w;
+                                out[4] += o1.x; out[5] += o1.y; out[6] += o1.z; out[7] += o1.w;
+                            } else {
 #pragma unroll
-                        for (int j = 0; j < COP; ++j) out[j] = sp_act_fwd(out[j] + bch[j], d.act, d.alpha);
-                    }
-                    if (vecy) {
+                                for (int j = 0; j < 8; ++j)
+                                    if (c0 + j < d.Co) out[j] += yp[c0 + j];
+                            }
+                        }
+                        if (fin) {
+                            float bch[8];                         // (read per use: L1-resident, and no registers held across the plane loop)
 #pragma unroll
-                        for (int j4 = 0; j4 < COP / 4; ++j4)
-                            reinterpret_cast<float4*>(yp)[j4] = make_float4(out[4 * j4], out[4 * j4 + 1], out[4 * j4 + 2], out[4 * j4 + 3]);
-                    } else {
+                            for (int j = 0; j < 8; ++j) bch[j] = (has_bias && c0 + j < d.Co) ? __ldg(bias + c0 + j) : 0.f;
+                            if (d.act == SP_ACT_ELU) {
 #pragma unroll
-                        for (int j = 0; j < COP; ++j)
-                            if (j < d.Co) yp[j] = out[j];
+                                for (int j = 0; j < 8; ++j) out[j] += bch[j];
+                                sp_elu_n<8>(out, d.alpha);
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) out[j] = sp_act_fwd(out[j] + bch[j], d.act, d.alpha);
+                            }
+                        }
+                        if (vecy) {
+                            reinterpret_cast<float4*>(yp + c0)[0] = make_float4(out[0], out[1], out[2], out[3]);
+                            reinterpret_cast<float4*>(yp + c0)[1] = make_float4(out[4], out[5], out[6], out[7]);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j)
+                                if (c0 + j < d.Co) yp[c0 + j] = out[j];
+                        }
                     }
                 }
                 if (pr) pwk += clock64() - c1;

@@ -7,6 +7,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <vector>
+#include <algorithm>
 #include "../../stroke-prediction_b200/csrc/sp_conv_tc3.cuh"
 
 void sp_set_error(const char* fmt, ...) {
@@ -87,15 +88,28 @@ int main(int argc, char** argv) {
     if (argc > 3) g_terms = atoi(argv[3]);
     if (!strcmp(mode, "time")) {
         SpConvDesc d = make_desc(32, 28, 124, 124, 16, 16, 1, 2, 2);
+        const bool full = getenv("SP_PROBE_ELU") != nullptr;        // BatchNorm prologue + ELU epilogue like the forward pass in the network
+        if (full && getenv("SP_PROBE_ELU")[0] == '1') { d.act = SP_ACT_ELU; d.alpha = 1.f; }
+        if (full && getenv("SP_PROBE_ELU")[0] == '3') { d.act = SP_ACT_LEAKY; d.alpha = 0.01f; }
         const size_t nx = (size_t)d.N * d.Di * d.Hi * d.Wi * d.Ci, ny = (size_t)d.N * d.Do * d.Ho * d.Wo * d.Co;
         float *dx, *dy, *dw;
         void* dimg;
         CK(cudaMalloc(&dx, nx * 4)); CK(cudaMalloc(&dy, ny * 4)); CK(cudaMalloc(&dw, 16 * 16 * 27 * 4));
         CK(cudaMalloc(&dimg, sp_tc_wimg_bytes(16, 16, 3) + sp_tc3_wimg_u4(16, 3) * 16));
         CK(cudaMemset(dx, 0, nx * 4)); CK(cudaMemset(dw, 0, 16 * 16 * 27 * 4));
+        float *tsc = nullptr, *tsh = nullptr;
+        if (full) {
+            std::vector<float> hx(1 << 20), hw(16 * 16 * 27), one(16, 1.1f), sh(16, -0.1f);
+            for (auto& v : hx) v = (float)rand() / RAND_MAX * 2.f - 1.f;
+            for (auto& v : hw) v = ((float)rand() / RAND_MAX - 0.5f) * 0.3f;
+            for (size_t o = 0; o < nx; o += hx.size()) CK(cudaMemcpy(dx + o, hx.data(), std::min(hx.size(), nx - o) * 4, cudaMemcpyHostToDevice));
+            CK(cudaMemcpy(dw, hw.data(), hw.size() * 4, cudaMemcpyHostToDevice));
+            CK(cudaMalloc(&tsc, 64)); CK(cudaMalloc(&tsh, 64));
+            CK(cudaMemcpy(tsc, one.data(), 64, cudaMemcpyHostToDevice)); CK(cudaMemcpy(tsh, sh.data(), 64, cudaMemcpyHostToDevice));
+        }
         cudaEvent_t e0, e1;
         CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
-        for (int it = 0; it < 3; ++it) if (launch(ns, d, dx, dw, nullptr, nullptr, dy, dimg)) return 3;
+        for (int it = 0; it < 3; ++it) if (launch(ns, d, dx, dw, tsc, tsh, dy, dimg)) return 3;
         CK(cudaDeviceSynchronize());
         if (ns == 33 || ns == 31) {
             unsigned long long info[4] = {0, 0, 0, 0};
@@ -108,7 +122,7 @@ int main(int argc, char** argv) {
         }
         CK(cudaEventRecord(e0));
         const int reps = 10;
-        for (int it = 0; it < reps; ++it) launch(ns, d, dx, dw, nullptr, nullptr, dy, dimg);
+        for (int it = 0; it < reps; ++it) launch(ns, d, dx, dw, tsc, tsh, dy, dimg);
         CK(cudaEventRecord(e1));
         CK(cudaDeviceSynchronize());
         float ms;
@@ -118,7 +132,7 @@ int main(int argc, char** argv) {
         printf("time ns=%d: %.3f ms  %.1f TFLOP/s (fp32-equivalent)  %.0f GB/s algorithmic\n", ns, ms, flop / ms * 1e-9, bytes / ms * 1e-6);
         CK(cudaMalloc(&g_prof, 64)); CK(cudaMemset(g_prof, 0, 64));
         if (ns == 33 || ns == 31) {
-            launch(ns, d, dx, dw, nullptr, nullptr, dy, dimg);
+            launch(ns, d, dx, dw, tsc, tsh, dy, dimg);
             CK(cudaDeviceSynchronize());
             long long hp[8];
             CK(cudaMemcpy(hp, g_prof, 64, cudaMemcpyDeviceToHost));
