@@ -117,10 +117,10 @@ __device__ __forceinline__ void sp_elu_n(float* v, float alpha) {
 
 __device__ __forceinline__ float sp_act_fwd(float v, int act, float alpha) {
     switch (act) {
-        // max(v, 0) + alpha * expm1(min(v, 0)): the same value as the two-sided definition (expm1(0) = 0) but straight-line code.
-        // Written as `v > 0 ? v : ...` the compiler branches around the exponential PER ELEMENT, which serialises the 8 .. 16
-        // independent evaluations of an epilogue thread (measured: 285 cycles per evaluation, +0.86 ms on the 16 -> 16 layer).
-        case SP_ACT_ELU:     return fmaf(alpha, sp_expm1_neg(fminf(v, 0.f)), fmaxf(v, 0.f));
+        // (two-sided form on purpose: it keeps this switch a real branch on the uniform `act`.  Written as straight-line code the
+        // whole switch is if-converted and every LeakyReLU / linear layer pays for the exponential: U-Net step +4 %.  Epilogues that
+        // evaluate many ELUs per thread dispatch on `act` once and call sp_elu_n.)
+        case SP_ACT_ELU:     return v > 0.f ? v : alpha * sp_expm1_neg(v);
         case SP_ACT_LEAKY:   return v > 0.f ? v : alpha * v;
         case SP_ACT_SIGMOID: return 1.f / (1.f + expf(-v));
         default:             return v;

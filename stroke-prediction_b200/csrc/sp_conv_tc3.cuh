@@ -431,13 +431,17 @@ corr3_tc3_kernel(SpConvDesc d, int nPerG, int tiles_w, int tiles_h, int nseg, in
                             float bch[8];                         // (read per use: L1-resident, and no registers held across the plane loop)
 #pragma unroll
                             for (int j = 0; j < 8; ++j) bch[j] = (has_bias && c0 + j < d.Co) ? __ldg(bias + c0 + j) : 0.f;
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) out[j] += bch[j];
+                            // one branch on the (uniform) activation per octet, never per element
                             if (d.act == SP_ACT_ELU) {
-#pragma unroll
-                                for (int j = 0; j < 8; ++j) out[j] += bch[j];
                                 sp_elu_n<8>(out, d.alpha);
-                            } else {
+                            } else if (d.act == SP_ACT_LEAKY) {
 #pragma unroll
-                                for (int j = 0; j < 8; ++j) out[j] = sp_act_fwd(out[j] + bch[j], d.act, d.alpha);
+                                for (int j = 0; j < 8; ++j) out[j] = fmaxf(out[j], 0.f) + d.alpha * fminf(out[j], 0.f);
+                            } else if (d.act == SP_ACT_SIGMOID) {
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) out[j] = 1.f / (1.f + expf(-out[j]));
                             }
                         }
                         if (vecy) {
