@@ -78,7 +78,7 @@ __global__ void __launch_bounds__(NTHREADS_W, 1)
 wgrad3_tc24_kernel(SpConvDesc d, int nPerG, int tiles_w, int tiles_h, int total_cols, int drain_every, int b0, int nblk,
                    const float* __restrict__ X, const float* __restrict__ i_scale, const float* __restrict__ i_shift,
                    const float* __restrict__ dZ, const float* __restrict__ o_scale, const float* __restrict__ o_shift,
-                   float* __restrict__ ws, long long* __restrict__ prof) {
+                   float* __restrict__ ws, long long* __restrict__ prof, int nt) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     unsigned char* a_reg = smem_raw;                                          // [buf][term][4][voxel] x 16 B
     unsigned char* x_reg = smem_raw + A_REGION_B;                             // [term][slot][row][group][w] x 16 B
@@ -230,7 +230,12 @@ wgrad3_tc24_kernel(SpConvDesc d, int nPerG, int tiles_w, int tiles_h, int total_
                             }
                         }
                         uint4 o[3];
-                        split8_trunc3(v, o);
+                        if (nt == 1) {      // bf16 mode: ONE bf16 term (round to nearest); the other two term planes are zero
+                            o[0] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+                            o[1] = o[2] = make_uint4(0u, 0u, 0u, 0u);
+                        } else {
+                            split8_trunc3(v, o);
+                        }
                         unsigned char* dstp = (isz ? a_reg : x_reg) + dsto[u];
                         const int tstride = isz ? (MROWS == 128 ? 4 : 2) * PS : X_TERM_B;
 #pragma unroll
@@ -274,8 +279,7 @@ wgrad3_tc24_kernel(SpConvDesc d, int nPerG, int tiles_w, int tiles_h, int total_
                     for (int ks = 0; ks < TWW / 16; ++ks) {
                         const uint64_t da = da0 + (uint64_t)(r * TWW + ks * 16);
                         const uint64_t db = db0 + (uint64_t)((r * X_ROW_B + ks * 256) >> 4);
-#pragma unroll
-                        for (int tx = 2; tx >= 0; --tx) {
+                        for (int tx = nt - 1; tx >= 0; --tx) {
                             umma_bf16(dcol, da, db + (uint64_t)((tx * X_TERM_B) >> 4), IDESC, fresh ? 0u : 1u);
                             fresh = false;
                         }
@@ -388,11 +392,11 @@ static inline int sp_tc24_wgrad_launch(const SpConvDesc* d, int nPerG, const flo
         if (d->Co <= 16)
             wgrad3_tc24_kernel<64><<<p.grid, NTHREADS_W, SMEM_W, st>>>(*d, nPerG, p.tiles_w, p.tiles_h, (int)p.total, drain_every, b0, nblk,
                                                                        iside, i_scale, i_shift, oside, o_scale, o_shift, ws,
-                                                                       pass == 0 ? prof : nullptr);
+                                                                       pass == 0 ? prof : nullptr, sp_tc_terms() == 1 ? 1 : 3);
         else
             wgrad3_tc24_kernel<128><<<p.grid, NTHREADS_W, SMEM_W, st>>>(*d, nPerG, p.tiles_w, p.tiles_h, (int)p.total, drain_every, b0, nblk,
                                                                         iside, i_scale, i_shift, oside, o_scale, o_shift, ws,
-                                                                        pass == 0 ? prof : nullptr);
+                                                                        pass == 0 ? prof : nullptr, sp_tc_terms() == 1 ? 1 : 3);
         SP_LAUNCH_OK("wgrad3_tc24_kernel");
     }
     const int64_t wn = (int64_t)d->Co * d->Ci * 27;

@@ -973,3 +973,50 @@ def test_sdm_baseline_matches_scipy_restatement():
     # degenerate case: empty core -> artificial core at the penumbra's centre of mass (reference :24-29)
     rc2, _, _ = sdm.sdm_interpolate(torch.zeros_like(core).cuda(), penu.cuda(), tt)
     assert float(rc2.min()) == 0.0 and int((rc2 == 0).sum()) == 63      # 3 dilations of one voxel by the 3-D cross: |x|+|y|+|z| <= 3 -> 63 voxels
+
+
+def test_cae_bf16_mode_against_oracle():
+    """bf16 mode (BASELINE north_star "bf16 mode within a stated looser tolerance", configs[2]): tensor-core operands are one bf16
+    term, accumulation / storage / BatchNorm statistics / loss sums / master weights stay fp32.  Stated tolerance, against the fp32
+    oracle at the named shape: latents and reconstructions 2e-2 relative, loss 1e-2 relative, thresholded Dice within 1e-2; three
+    training steps follow the oracle's loss trajectory within 2e-2."""
+    from stroke_prediction_b200 import ops
+    A = _api()
+    ch = [1, 16, 24, 32, 100, 800, 1]
+    torch.manual_seed(63)
+    cae = A.Cae3D(A.Enc3D(128, 28, ch, 5, 1.0), A.Dec3D(128, 28, ch, 5, 1.0))
+    sd = O.clone_state(cae.state_dict(), requires_grad=True)
+    cae = cae.cuda().train()
+    ops.set_tc_terms(1)
+    try:
+        opt = torch.optim.Adam(cae.parameters(), lr=1e-3, weight_decay=1e-5)
+        learner = A.CaeReconstructionLearner(None, None, cae, opt, None, 10, None, "/tmp/x", A.BatchDiceLoss([1.0]))
+        names = [k for k, v in sd.items() if v.requires_grad]
+        m = {k: torch.zeros_like(sd[k]) for k in names}
+        v = {k: torch.zeros_like(sd[k]) for k in names}
+        for it in range(3):
+            batch = A.data.synthetic_cae_batch(2, seed=70 + it)
+            labels = batch[A.data.KEY_LABELS]
+            step = O.time_to_treatment(batch[A.data.KEY_GLOBAL])
+            if it == 0:
+                with torch.no_grad():
+                    dto = learner.inference_step(batch)
+                    lat, rec = O.cae_forward(O.clone_state({k: t.detach() for k, t in sd.items()}), ch, 1.0, True, labels[:, 0:1], labels[:, 1:2],
+                                             labels[:, 2:3], step)
+                for k in ("core", "penu", "lesion", "interpolation"):
+                    assert rel_l2(getattr(dto.latents.gtruth, k), lat[k]) < 2e-2, k
+                    r = getattr(dto.reconstructions.gtruth, k)
+                    assert rel_l2(r, rec[k]) < 2e-2, k
+                    assert abs(_dice_binary(r.cpu(), rec[k]) - 1.0) < 1e-2 or float((rec[k] > 0.5).sum()) == 0
+                cae.load_state_dict({k: t.detach() for k, t in sd.items()})      # undo the running-statistics update of the probe pass
+            got = learner.train_batch(batch, 60).loss
+            lat, rec = O.cae_forward(sd, ch, 1.0, True, labels[:, 0:1], labels[:, 1:2], labels[:, 2:3], step)
+            loss = O.cae_reconstruction_loss(lat, rec, labels[:, 0:1], labels[:, 1:2], labels[:, 2:3], 60)
+            grads = O.grads_of(loss, sd)
+            with torch.no_grad():
+                for k in names:
+                    newp, m[k], v[k] = O.adam_step(sd[k], grads[k], m[k], v[k], it + 1)
+                    sd[k].copy_(newp)
+            assert abs(got - loss.item()) < (1e-2 if it == 0 else 2e-2) * max(1.0, abs(loss.item())), (it, got, loss.item())
+    finally:
+        ops.set_tc_terms(5)
