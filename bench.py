@@ -418,23 +418,37 @@ def CaeReconstructionLearner_(*a, **k):
 
 
 def dp_check(w, world, dev):
-    """N > 1 correctness evidence on the CUDA path (one extra step, not timed): (1) the all-reduced flat gradient equals the
-    sum of the per-rank local gradients gathered separately; (2) after the optimizer step every rank holds bit-identical
-    parameters (64-bit checksum + max |difference| against rank 0)."""
+    """N > 1 correctness evidence on the CUDA path (two extra steps, not timed): (1) with the overlap switched off, the all-reduced
+    flat gradient equals the sum of the per-rank local gradients gathered separately; (2) the same step with the all-reduce
+    overlapped with the backward pass (slices reduced as soon as their plans are done) gives the same gradient; (3) after the
+    optimizer step every rank holds bit-identical parameters (64-bit checksum + max |difference| against rank 0)."""
     import torch.distributed as dist
     sink = w.opt._sink
-    dto = w.forward(w.make_dto() if w.make_dto is not None else None)
-    loss = w.learner.loss_step(dto, EPOCH)
-    w.opt.zero_grad()
-    loss.backward()
+    sync = w.learner._grad_sync
+
+    def backward_only():
+        dto = w.forward(w.make_dto() if w.make_dto is not None else None)
+        loss = w.learner.loss_step(dto, EPOCH)
+        w.opt.zero_grad()
+        loss.backward()
+
+    was = sync.overlap
+    sync.overlap = False
+    backward_only()
     local = sink.flat.clone()
     gathered = [torch.empty_like(local) for _ in range(world)]
     dist.all_gather(gathered, local)
     want = torch.stack(gathered).double().sum(0)
-    w.learner._grad_sync()
-    got = sink.flat.double()
+    sync()
+    got = sink.flat.double().clone()
     err = float((got - want).abs().max())
     ref = float(want.abs().max())
+    sync.overlap = was
+    # the BatchNorm running statistics moved during the first pass; gradients do not depend on them (training mode)
+    backward_only()
+    sync()
+    early = getattr(sync, "last_early_elements", 0)
+    err_overlap = float((sink.flat.double() - got).abs().max())
     views_ok = all(p.grad is not None and p.grad.data_ptr() >= sink.flat.data_ptr() and
                    p.grad.data_ptr() < sink.flat.data_ptr() + 4 * sink.flat.numel() for p in sink.params)
     w.opt.step()
@@ -447,6 +461,8 @@ def dp_check(w, world, dev):
     chks = [torch.empty_like(chk) for _ in range(world)]
     dist.all_gather(chks, chk)
     return {"ranks": world, "allreduce_max_abs_err": err, "grad_max_abs": ref, "allreduce_rel_err": err / ref if ref else None,
+            "overlapped_vs_blocking_max_abs_diff": err_overlap, "elements_reduced_during_backward": int(early),
+            "flat_gradient_elements": int(sink.flat.numel()),
             "grad_views_alias_flat_buffer": bool(views_ok), "param_max_abs_diff_vs_rank0": float(pdiff.item()),
             "param_checksums_equal": len({int(c.item()) for c in chks}) == 1, "grad_scale": w.opt.grad_scale}
 

@@ -14,12 +14,17 @@
 //    staged 4 halo planes per 2 output planes: 2.0x the loads, splits and stores per output).  The pipeline never drains: ring,
 //    accumulator and barrier phases run on global counters across the CTA's work items.
 //
-// Roles (one persistent CTA per SM, 21 warps): warps 0-7 epilogue (two groups of four alternate output planes; TMEM lane
+//  * TMA staging.  One thread streams the raw fp32 halo planes with cp.async.bulk.tensor (5-D tensor map of the NDHWC source,
+//    box [16 c][16 w][10 h]): zero padding, ragged edge tiles and channels >= Ci arrive as zeros, the staging warps only convert
+//    (BatchNorm, split) from shared memory to the UMMA layout — no address arithmetic, bounds checks or global-load latency.
+//
+// Roles (one persistent CTA per SM, 22 warps; the last one is the TMA producer): warps 0-7 epilogue (two groups of four alternate output planes; TMEM lane
 // quarter = warp % 4), warps 8-17 staging (one (voxel, 8-channel chunk) item per thread and plane, the next plane's global loads
 // in flight while the current one is split and stored), warps 18-20 one MMA-issuing thread each (output plane q -> issuer
 // q % NACC, accumulator q % NACC: MMAs of one thread retire one after the other, different issuers overlap).
 // NS = 1 is the bf16 mode: operands rounded to ONE bf16 term (RN), one MMA per (kd, kh), fp32 accumulation.
 #pragma once
+#include <cuda.h>
 #include "sp_conv_tc2.cuh"
 
 namespace sp_tc3 {
@@ -36,8 +41,9 @@ constexpr int NEPI_G = 2, NEPI_W = 4 * NEPI_G;           // epilogue groups / wa
                                                           // schedulers the three MMA-issuing threads need: issue time 3.7 k -> 5.2 k cycles per plane)
 constexpr int NSTG_W = 10, NSTG = NSTG_W * 32;           // staging warps / threads: 320 = one item per thread and plane
 constexpr int NISS_W = 3;                                // MMA issuer warps (NACC of them active)
-constexpr int NWARPS3 = NEPI_W + NSTG_W + NISS_W;        // 21
-constexpr int NTHREADS3 = NWARPS3 * 32;                  // 672
+constexpr int NWARPS3 = NEPI_W + NSTG_W + NISS_W + 1;    // 22: + the TMA producer warp
+constexpr int NTHREADS3 = NWARPS3 * 32;                  // 704
+constexpr int RAW_B = PSLOTS * 16 * 4;                   // one raw fp32 halo plane as TMA lands it: [10 h][16 w][16 c] = 10240 B
 static_assert(PSLOTS * 2 == NSTG, "one (slot, chunk) item per staging thread");
 
 template <int COP, int NS>
@@ -50,7 +56,7 @@ struct Tc3 {
     static constexpr int SLOT_U4 = NS * 2 * CHS;                 // uint4 per ring slot: [term][chunk][CHS]
     // staged input planes in flight: NACC issuers hold NACC + 2 planes; the rest is the stager's lead over them (measured with
     // 6: issuers waited for planes 25 % of the time while the stager waited for slots)
-    static constexpr int RING = NS == 3 ? 9 : 16;
+    static constexpr int RING = NS == 3 ? (COP <= 16 ? 9 : 7) : 16;
     // planes of global loads a staging thread keeps in flight (registers): bf16 mode is HBM-bound at ~740 cycles per plane,
     // below the ~1.5 k cycle load latency under load
     static constexpr int PF = NS == 3 ? 2 : 4;
@@ -60,12 +66,14 @@ struct Tc3 {
     // of a barrier it waits on (a parity wait cannot tell phase p from p + 2), so there is one barrier per (accumulator, group)
     // combination = q % lcm(NACC, NEPI_G), each completing once per NTF planes, always awaited by the same group.
     static constexpr int NTF = (NACC % NEPI_G == 0) ? NACC : NACC * NEPI_G;
-    static constexpr int NBARS = 2 * RING + NTF + 3;
-    static constexpr size_t SMEM = ((size_t)RING * SLOT_U4 + WIMGS) * 16 + NBARS * 8 + 64;   // + barriers + TMEM slot
+    // raw fp32 planes in flight between the TMA producer and the staging warps (bf16 mode is HBM-bound: deeper)
+    static constexpr int KR = NS == 3 ? 4 : 8;
+    static constexpr int NBARS = 2 * RING + NTF + 3 + 2 * KR;
+    static constexpr size_t SMEM = (size_t)KR * RAW_B + ((size_t)RING * SLOT_U4 + WIMGS) * 16 + NBARS * 8 + 64;   // + barriers + TMEM slot
     static_assert(NTOT % 16 == 0 && NTOT <= 256, "UMMA M = 128 needs N % 16 == 0, N <= 256");
     static_assert(NACC >= 2, "two accumulators in flight at least");
 };
-static_assert(Tc3<24, 3>::SMEM <= 227 * 1024 && Tc3<24, 1>::SMEM <= 227 * 1024, "tc3: shared memory");
+static_assert(Tc3<16, 3>::SMEM <= 227 * 1024 && Tc3<24, 3>::SMEM <= 227 * 1024 && Tc3<24, 1>::SMEM <= 227 * 1024, "tc3: shared memory");
 
 // ---- weight image -----------------------------------------------------------------------------------------------------
 // img[((kd*3+kh) * 2 + chunk) * NTOT + term * TS + kw * COP + n] = 8 bf16 {term of Wsrc(n0 + n, k0 + chunk*8 + j, tap)}, zero rows
@@ -168,12 +176,13 @@ __global__ void __launch_bounds__(NTHREADS3, 1)
 corr3_tc3_kernel(SpConvDesc d, int nPerG, int tiles_w, int tiles_h, int nseg, int seg_len, int total_items,
                  const float* __restrict__ src, const uint4* __restrict__ wimg, const float* __restrict__ bias,
                  const float* __restrict__ scale, const float* __restrict__ shift, int sstride, int accum, int fin,
-                 float* __restrict__ dst, long long* __restrict__ prof, int dbg) {
+                 float* __restrict__ dst, long long* __restrict__ prof, int dbg, const __grid_constant__ CUtensorMap tmap, int use_tma) {
     using T = Tc3<COP, NS>;
     constexpr int TS = T::TS, NTOT = T::NTOT, BROWS = T::BROWS, ACOLS = T::ACOLS, NACC = T::NACC, SLOT_U4 = T::SLOT_U4;
-    constexpr int WIMG = T::WIMG, WIMGS = T::WIMGS, RING = T::RING, PF = T::PF, NTF = T::NTF;
+    constexpr int WIMG = T::WIMG, WIMGS = T::WIMGS, RING = T::RING, PF = T::PF, NTF = T::NTF, KR = T::KR;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    uint4* As = reinterpret_cast<uint4*>(smem_raw);                          // [RING][NS][2][CHS]
+    unsigned char* raw = smem_raw;                                          // [KR][10 h][16 w][16 c] fp32, written by TMA
+    uint4* As = reinterpret_cast<uint4*>(smem_raw + (size_t)KR * RAW_B);     // [RING][NS][2][CHS]
     uint4* Bs = As + (size_t)RING * SLOT_U4;                                 // weight image [9][2][BROWS]
     uint64_t* bars = reinterpret_cast<uint64_t*>(Bs + WIMGS);                 // a_full[RING] a_empty[RING] t_full[NTF] t_empty[3]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + T::NBARS);
@@ -189,6 +198,10 @@ corr3_tc3_kernel(SpConvDesc d, int nPerG, int tiles_w, int tiles_h, int nseg, in
         }
         for (int a = 0; a < NTF; ++a) mbar_init(smem_u32(&bars[2 * RING + a]), 1);         // t_full: the issuer of the plane
         for (int a = 0; a < 3; ++a) mbar_init(smem_u32(&bars[2 * RING + NTF + a]), 4);     // t_empty: the 4 warps of the draining group
+        for (int k = 0; k < KR; ++k) {
+            mbar_init(smem_u32(&bars[2 * RING + NTF + 3 + k]), 1);                          // raw_full: the producer's expect_tx arrival
+            mbar_init(smem_u32(&bars[2 * RING + NTF + 3 + KR + k]), NSTG_W);                // raw_empty: one arrival per staging warp
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) tmem_alloc<512>(tmem_slot);
@@ -199,6 +212,7 @@ corr3_tc3_kernel(SpConvDesc d, int nPerG, int tiles_w, int tiles_h, int nseg, in
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t a_full = smem_u32(&bars[0]), a_empty = smem_u32(&bars[RING]);
     const uint32_t t_full = smem_u32(&bars[2 * RING]), t_empty = smem_u32(&bars[2 * RING + NTF]);
+    const uint32_t raw_full = smem_u32(&bars[2 * RING + NTF + 3]), raw_empty = smem_u32(&bars[2 * RING + NTF + 3 + KR]);
 
     auto item_of = [&](int item) {
         Item3 it;
@@ -213,7 +227,30 @@ corr3_tc3_kernel(SpConvDesc d, int nPerG, int tiles_w, int tiles_h, int nseg, in
         return it;
     };
 
-    if (warp >= NEPI_W && warp < NEPI_W + NSTG_W) {
+    if (warp == NWARPS3 - 1) {
+        // =================================================================== TMA producer: one thread streams the raw halo planes
+        // One cp.async.bulk.tensor per input plane: box [16 c][16 w][10 h] of the fp32 NDHWC source at (signed) coordinates
+        // (0, ow0 - pw, oh0 - ph, id, n); everything outside the tensor — the zero padding of the convolution, ragged edge tiles,
+        // channels >= Ci — arrives as zeros.  No address arithmetic, bounds checks or load latency in the staging warps.
+        if (lane == 0 && use_tma) {
+            asm volatile("prefetch.tensormap [%0];" :: "l"(reinterpret_cast<uint64_t>(&tmap)) : "memory");
+            uint32_t gp = 0;
+            for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+                const Item3 it = item_of(item);
+                const int c_w = it.ow0 - d.pw, c_h = it.oh0 - d.ph, c_d0 = it.od_lo - d.pd;
+                for (int ip = 0; ip < it.L + 2; ++ip, ++gp) {
+                    const uint32_t k = gp % KR, use = gp / KR;
+                    mbar_wait3(raw_empty + 8 * k, (use & 1) ^ 1, dbg, 0x500u + k, gp);      // the staging warps have read this slot
+                    const uint32_t bar = raw_full + 8 * k, dsts = smem_u32(raw + (size_t)k * RAW_B);
+                    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"((uint32_t)RAW_B) : "memory");
+                    asm volatile(
+                        "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
+                        :: "r"(dsts), "l"(reinterpret_cast<uint64_t>(&tmap)), "r"(0), "r"(c_w), "r"(c_h), "r"(c_d0 + ip), "r"(it.n), "r"(bar)
+                        : "memory");
+                }
+            }
+        }
+    } else if (warp >= NEPI_W && warp < NEPI_W + NSTG_W) {
         // =================================================================== staging warps
         const int st = tid - NEPI_W * 32;                        // 0..319
         const int chunk = st & 1, slot = st >> 1;                // this thread's item of every plane
@@ -255,6 +292,48 @@ corr3_tc3_kernel(SpConvDesc d, int nPerG, int tiles_w, int tiles_h, int nseg, in
                 }
                 return true;
             };
+            if (use_tma) {
+                // raw plane from the TMA ring -> (BN) -> split -> UMMA layout.  Whether a voxel is real (BatchNorm applies) or padding
+                // (stays exactly zero after BatchNorm, Cae3D.py:40-41) is pure coordinate arithmetic.
+#pragma unroll 1
+                for (int ip = 0; ip < nplanes; ++ip, ++gin) {
+                    const uint32_t k = gin % KR, ruse = gin / KR;
+                    mbar_wait_warp(raw_full + 8 * k, ruse & 1, dbg, 0x600u + k, gin);
+                    const float4* rp = reinterpret_cast<const float4*>(raw + (size_t)k * RAW_B + (size_t)(slot * 16 + c) * 4);
+                    const float4 ra = rp[0], rb = rp[1];
+                    // generic-proxy reads before the async-proxy (TMA) write that refills this slot: a cross-proxy WAR needs the proxy
+                    // fence as well as the barrier (without it ~4 % of the launches had a few stale voxels)
+                    fence_async_smem();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(raw_empty + 8 * k);           // the raw slot may be refilled
+                    const int gd = id0 + ip;
+                    float v[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
+                    if (scale && in_hw && gd >= 0 && gd < d.Di) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) v[j] = fmaf(v[j], bsc[j], bsh[j]);          // channels >= Ci: 0 * 1 + 0
+                    }
+                    const uint32_t s = gin % RING, use = gin / RING;
+                    long long c0 = pr ? clock64() : 0;
+                    mbar_wait_warp(a_empty + 8 * s, (use & 1) ^ 1, dbg, 0x100u + s, gin);
+                    long long c1 = pr ? clock64() : 0;
+                    pw0 += c1 - c0;
+                    uint4* Ab = As + (size_t)s * SLOT_U4 + (size_t)chunk * CHS + slot;
+                    if (NS == 3) {
+                        uint4 o[3];
+                        split8_trunc3(v, o);
+#pragma unroll
+                        for (int s2 = 0; s2 < 3; ++s2) Ab[(size_t)s2 * 2 * CHS] = o[s2];
+                    } else {
+                        Ab[0] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+                    }
+                    fence_async_smem();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(a_full + 8 * s);
+                    if (pr) pwk += clock64() - c1;
+                }
+                continue;
+            }
+            // (fallback when the source cannot be described by a tensor map: channel stride not a multiple of 16 bytes)
             // register ring of PF planes: plane ip lives in entry ip % PF; after it is consumed its entry is reloaded with
             // plane ip + PF, so PF - 1 .. PF planes of loads are in flight while one is split and stored
             float4 pa[PF], pb[PF];
@@ -468,6 +547,37 @@ corr3_tc3_kernel(SpConvDesc d, int nPerG, int tiles_w, int tiles_h, int nseg, in
 
 }  // namespace sp_tc3
 
+// ---- TMA: tensor map of the fp32 NDHWC source --------------------------------------------------------------------------
+typedef CUresult (*SpEncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                    const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static inline SpEncodeTiledFn sp_tma_encoder() {
+    static SpEncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {       // the driver entry point through the runtime: no link-time dependency on libcuda
+        tried = true;
+        const char* off = getenv("SP_TC3_NO_TMA");
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (!(off && off[0] == '1') && cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<SpEncodeTiledFn>(p);
+    }
+    return fn;
+}
+// 5-D map (c, w, h, d, n) of `src` (ci channels used of ldi per voxel) with the box [16 c][16 w][10 h][1][1]; false when the
+// source cannot be described (voxel stride not a multiple of 16 bytes, misaligned base): the kernel then stages with plain loads
+static inline bool sp_tc3_make_tmap(const SpConvDesc* d, const float* src, CUtensorMap* tm) {
+    SpEncodeTiledFn enc = sp_tma_encoder();
+    if (!enc || d->ldi % 4 != 0 || (reinterpret_cast<uintptr_t>(src) & 15) != 0) return false;
+    const cuuint64_t dims[5] = {(cuuint64_t)d->Ci, (cuuint64_t)d->Wi, (cuuint64_t)d->Hi, (cuuint64_t)d->Di, (cuuint64_t)d->N};
+    const cuuint64_t vs = (cuuint64_t)d->ldi * 4;
+    const cuuint64_t strides[4] = {vs, vs * d->Wi, vs * d->Wi * d->Hi, vs * d->Wi * d->Hi * d->Di};
+    const cuuint32_t box[5] = {16, (cuuint32_t)sp_tc3::TW, (cuuint32_t)sp_tc3::IH, 1, 1};
+    const cuuint32_t es[5] = {1, 1, 1, 1, 1};
+    return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<float*>(src), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 static inline size_t sp_tc3_wimg_u4(int cop, int ns) { return (size_t)9 * 2 * ns * ((3 * cop + 15) / 16 * 16); }
 
 // one image per (output slice, input-channel pass), image (s, p) at index s * passes + p
@@ -521,8 +631,11 @@ static inline int sp_tc3_corr_launch_t(const SpConvDesc* d, int nPerG, const flo
     }
     if (dbg_grid > 0 && dbg_grid < grid) grid = dbg_grid;
     if (grid > total) grid = (int)total;
+    alignas(64) CUtensorMap tm;
+    memset(&tm, 0, sizeof(tm));
+    const int use_tma = sp_tc3_make_tmap(d, src, &tm) ? 1 : 0;
     corr3_tc3_kernel<COP, NS><<<grid, NTHREADS3, Tc3<COP, NS>::SMEM, st>>>(*d, nPerG, tiles_w, tiles_h, nseg, seg_len, (int)total, src, wimg,
-                                                                           bias, scale, shift, sstride, accum, fin, dst, prof, dbg);
+                                                                           bias, scale, shift, sstride, accum, fin, dst, prof, dbg, tm, use_tma);
     SP_LAUNCH_OK("corr3_tc3_kernel");
     return 0;
 }

@@ -188,6 +188,29 @@ int main(int argc, char** argv) {
     int bad_cases = 0;
     const int ncases = onehot ? 6 : 1;
     const int cases[6][3] = {{13, 5, 3}, {0, 0, 0}, {26, 15, 15}, {1, 8, 7}, {9, 7, 8}, {3, 12, 1}};   // tap, ci, co
+    const int repeat = getenv("SP_PROBE_REPEAT") ? atoi(getenv("SP_PROBE_REPEAT")) : 1;
+    if (repeat > 1) {   // stress: the same launch many times, every result compared with the first one bit for bit
+        CK(cudaMemcpy(dw, w.data(), w.size() * 4, cudaMemcpyHostToDevice));
+        std::vector<float> y0(ny);
+        int nfail = 0;
+        for (int r = 0; r < repeat; ++r) {
+            CK(cudaMemset(dy, 0xff, ny * 4));
+            if (launch(ns, d, dx, dw, dsc, dsh, dy, dimg)) return 3;
+            CK(cudaDeviceSynchronize());
+            CK(cudaMemcpy(y.data(), dy, ny * 4, cudaMemcpyDeviceToHost));
+            if (r == 0) { y0 = y; continue; }
+            size_t nd = 0, first = 0;
+            for (size_t i = 0; i < ny; ++i) if (memcmp(&y[i], &y0[i], 4) != 0) { if (!nd) first = i; ++nd; }
+            if (nd) {
+                ++nfail;
+                size_t u = first / d.Co; const int w2 = u % d.Wo; u /= d.Wo; const int h2 = u % d.Ho; u /= d.Ho;
+                printf("  run %d differs from run 0 in %zu values, first at n %d od %d oh %d ow %d co %d (%g vs %g)\n", r, nd, (int)(u / d.Do),
+                       (int)(u % d.Do), h2, w2, (int)(first % d.Co), y[first], y0[first]);
+            }
+        }
+        printf("stress: %d of %d runs differ from the first\n", nfail, repeat - 1);
+        return nfail ? 1 : 0;
+    }
     for (int cs = 0; cs < ncases; ++cs) {
         if (onehot) {
             std::fill(w.begin(), w.end(), 0.f);
@@ -249,6 +272,18 @@ int main(int argc, char** argv) {
         }
         if (onehot) printf("onehot tap %2d ci %2d co %2d: ", cases[cs][0], cases[cs][1], cases[cs][2]);
         printf("ns=%d rel-L2 %.3e max-abs %.3e mismatches %zu / %zu\n", ns, sqrt(num / (den > 0 ? den : 1)), maxabs, nbad, ny);
+        if (nbad && !onehot) {       // where are they?  (n, od) histogram and the tiles (oh / 8, ow / 14) touched
+            std::vector<int> hist((size_t)d.N * d.Do, 0);
+            int shown = 0;
+            for (size_t k = 0; k < ny; ++k)
+                if (!(fabs((double)y[k] - ref[k]) <= 1e-3 * (1.0 + fabs(ref[k])))) {
+                    size_t u = k / d.Co;
+                    const int w2 = u % d.Wo; u /= d.Wo; const int h2 = u % d.Ho; u /= d.Ho;
+                    ++hist[u];
+                    if (shown < 12 && (k % d.Co) == 0) { printf("   bad n %d od %d oh %d ow %d (tile %d,%d; row-in-tile %d col %d) got %g exp %g\n", (int)(u / d.Do), (int)(u % d.Do), h2, w2, h2 / 8, w2 / 14, h2 % 8, w2 % 14, y[k], ref[k]); ++shown; }
+                }
+            for (size_t u = 0; u < hist.size(); ++u) if (hist[u]) printf("   n %d od %d: %d bad values\n", (int)(u / d.Do), (int)(u % d.Do), hist[u]);
+        }
         if (nbad) {
             ++bad_cases;
             size_t i = first_bad;
