@@ -18,18 +18,25 @@ constexpr int EDT_INF = 1 << 29;     // "no feature on this line yet"; INF + 2 *
 // border_value = 0).  all_border != 0: some axis of the caller's array has extent 1, so every set voxel has an outside
 // neighbour along it and the erosion is empty (that is what MedPy computes on the reference's B x 1 x D x H x W arrays).
 __global__ void border_kernel(const float* __restrict__ v, int n0, int n1, int n2, int n3, float thr, int all_border,
-                              uint8_t* __restrict__ border, unsigned long long* __restrict__ count) {
+                              uint8_t* __restrict__ border, unsigned long long* __restrict__ count, int* __restrict__ bb) {
     const int64_t total = (int64_t)n0 * n1 * n2 * n3;
     unsigned int local = 0;
+    int lo[4] = {1 << 30, 1 << 30, 1 << 30, 1 << 30}, hi[4] = {-1, -1, -1, -1};
     for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
         const bool obj = v[e] > thr;
         bool b = obj;
-        if (obj && !all_border) {
+        if (obj) {
             int64_t t = e;
             const int i3 = (int)(t % n3); t /= n3;
             const int i2 = (int)(t % n2); t /= n2;
             const int i1 = (int)(t % n1);
             const int i0 = (int)(t / n1);
+            // bounding box of the union of both masks (this kernel runs once per mask on the same box)
+            lo[0] = i0 < lo[0] ? i0 : lo[0]; hi[0] = i0 > hi[0] ? i0 : hi[0];
+            lo[1] = i1 < lo[1] ? i1 : lo[1]; hi[1] = i1 > hi[1] ? i1 : hi[1];
+            lo[2] = i2 < lo[2] ? i2 : lo[2]; hi[2] = i2 > hi[2] ? i2 : hi[2];
+            lo[3] = i3 < lo[3] ? i3 : lo[3]; hi[3] = i3 > hi[3] ? i3 : hi[3];
+          if (!all_border) {
             const int64_t s2 = n3, s1 = (int64_t)n2 * n3, s0 = (int64_t)n1 * n2 * n3;
             bool inner = true;      // every neighbour inside the array and set
             inner = inner && i3 > 0 && i3 < n3 - 1 && v[e - 1] > thr && v[e + 1] > thr;
@@ -37,9 +44,19 @@ __global__ void border_kernel(const float* __restrict__ v, int n0, int n1, int n
             inner = inner && (n1 == 1 || (i1 > 0 && i1 < n1 - 1 && v[e - s1] > thr && v[e + s1] > thr));
             inner = inner && (n0 == 1 || (i0 > 0 && i0 < n0 - 1 && v[e - s0] > thr && v[e + s0] > thr));
             b = !inner;
+          }
         }
         border[e] = b ? 1 : 0;
         local += b ? 1u : 0u;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        for (int o = 16; o > 0; o >>= 1) {
+            const int l = __shfl_xor_sync(0xffffffffu, lo[k], o), h = __shfl_xor_sync(0xffffffffu, hi[k], o);
+            lo[k] = l < lo[k] ? l : lo[k];
+            hi[k] = h > hi[k] ? h : hi[k];
+        }
+        if ((threadIdx.x & 31) == 0 && hi[k] >= 0) { atomicMin(&bb[2 * k], lo[k]); atomicMax(&bb[2 * k + 1], hi[k]); }
     }
     // block count -> one atomic (integer: order-independent, deterministic)
     for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
@@ -62,28 +79,165 @@ __global__ void feature_kernel(const float* __restrict__ v, int64_t total, float
     }
 }
 
+// Bounding box (per lattice axis) of the union of both thresholded masks, gathered by border_kernel: bb[2a] = lowest,
+// bb[2a+1] = highest index on axis a (initialised to extent / -1).  Every distance the surface metrics read is taken AT a voxel of one mask TO a voxel of the
+// other, so the transform only has to be exact inside this box: the passes skip lattice points outside it and scan their lines
+// only across it.  The box lives in device memory — no host synchronisation — and typically holds 20 - 30 % of the lattice.
+__global__ void bbox_init_kernel(int* bb, int n0, int n1, int n2, int n3) {
+    if (threadIdx.x < 4) {
+        const int n[4] = {n0, n1, n2, n3};
+        bb[2 * threadIdx.x] = n[threadIdx.x];
+        bb[2 * threadIdx.x + 1] = -1;
+    }
+}
+
 // One separable pass of the exact squared Euclidean distance transform along the axis of extent n and element stride s:
 //   out[i] = min_j ( in[j] + (i - j)^2 )          (FIRST: in[j] = feat[j] ? 0 : INF)
 // One thread per lattice point; for s > 1 the threads of a warp walk 32 neighbouring lines in lock step (coalesced), for
 // s == 1 they share one line (broadcast).
+// First pass (contiguous axis): squared distance to the nearest feature of the same line.  One warp per line: the line's feature
+// bits are gathered with ballots (32 positions each), every lane then finds the nearest set bit to the left and to the right of
+// its positions with clz / ffs on the chunk masks — O(1) work per lattice point instead of a scan over the line.
+__global__ void edt_first_kernel(const uint8_t* __restrict__ feat, int n0, int n1, int n2, int n3, const int* __restrict__ bb,
+                                 int* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t lines = (int64_t)n0 * n1 * n2;
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    const int lo3 = bb ? bb[6] : 0, hi3 = bb ? bb[7] : n3 - 1;
+    if (hi3 < lo3) return;
+    const int c_lo = lo3 >> 5, c_hi = hi3 >> 5;                       // 32-wide chunks that intersect the box
+    for (int64_t line = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; line < lines; line += warps) {
+        if (bb) {
+            int64_t t = line;
+            const int c2 = (int)(t % n2); t /= n2;
+            const int c1 = (int)(t % n1);
+            const int c0 = (int)(t / n1);
+            if (c0 < bb[0] || c0 > bb[1] || c1 < bb[2] || c1 > bb[3] || c2 < bb[4] || c2 > bb[5]) continue;
+        }
+        const uint8_t* f = feat + line * n3;
+        int* o = out + line * n3;
+        uint32_t mask[8];                                             // extents are capped at 256 for this kernel
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const int i = c * 32 + lane;
+            mask[c] = (c >= c_lo && c <= c_hi) ? __ballot_sync(0xffffffffu, i >= lo3 && i <= hi3 && f[i] != 0) : 0u;
+        }
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const int i = c * 32 + lane;
+            if (c < c_lo || c > c_hi || i < lo3 || i > hi3) continue;
+            int best = EDT_INF;
+            // nearest feature at or left of i
+            uint32_t m = mask[c] & (0xffffffffu >> (31 - lane));
+            int pos = m ? c * 32 + 31 - __clz(m) : -1;
+#pragma unroll
+            for (int cc = 7; cc >= 0; --cc)
+                if (cc < c && pos < 0 && mask[cc]) pos = cc * 32 + 31 - __clz(mask[cc]);
+            if (pos >= 0) best = (i - pos) * (i - pos);
+            // nearest feature right of i
+            m = lane < 31 ? mask[c] & (0xffffffffu << (lane + 1)) : 0u;
+            pos = m ? c * 32 + __ffs(m) - 1 : -1;
+#pragma unroll
+            for (int cc = 0; cc < 8; ++cc)
+                if (cc > c && pos < 0 && mask[cc]) pos = cc * 32 + __ffs(mask[cc]) - 1;
+            if (pos >= 0) { const int dd = (pos - i) * (pos - i); best = dd < best ? dd : best; }
+            o[i] = best;
+        }
+    }
+}
+
+// Later passes (axis stride >= n3), shared-memory form for extents <= 256: a CTA takes a tile of 32 neighbouring lines (32
+// consecutive positions of the contiguous axis), loads the tile once (coalesced rows of 128 bytes) and evaluates the lower envelope
+// from shared memory (column = lane: conflict free).  The global-memory form below re-reads its line from L2 for every candidate.
+__global__ void edt_tile_kernel(const int* __restrict__ in, int n0, int n1, int n2, int n3, int axis, const int* __restrict__ bb,
+                                int* __restrict__ out) {
+    extern __shared__ int tile[];                        // [ext][32]
+    const int ext[4] = {n0, n1, n2, n3};
+    const int64_t str[4] = {(int64_t)n1 * n2 * n3, (int64_t)n2 * n3, (int64_t)n3, 1};
+    int lo[4], hi[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { lo[k] = bb ? bb[2 * k] : 0; hi[k] = bb ? bb[2 * k + 1] : ext[k] - 1; }
+    if (hi[0] < lo[0]) return;
+    // tiles: the two lattice axes other than `axis` and 3 (call them p, q) x chunks of 32 along axis 3, all restricted to the box
+    int pa = -1, qa = -1;
+    for (int k = 0; k < 3; ++k)
+        if (k != axis) { if (pa < 0) pa = k; else qa = k; }
+    const int np = hi[pa] - lo[pa] + 1, nq = hi[qa] - lo[qa] + 1;
+    const int w0 = lo[3] & ~31, nwc = (hi[3] - w0) / 32 + 1;
+    const int64_t ntiles = (int64_t)np * nq * nwc;
+    const int na = hi[axis] - lo[axis] + 1;
+    const int64_t sa = str[axis];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5, nty = blockDim.x >> 5;
+    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const int wc = (int)(t % nwc);
+        const int iq = (int)((t / nwc) % nq), ip = (int)(t / ((int64_t)nwc * nq));
+        const int w = w0 + wc * 32 + tx;
+        const bool okw = w >= lo[3] && w <= hi[3];
+        const int64_t base = (int64_t)(lo[pa] + ip) * str[pa] + (int64_t)(lo[qa] + iq) * str[qa] + w;
+        __syncthreads();                                 // the previous tile has been consumed
+        for (int i = ty; i < na; i += nty) tile[i * 32 + tx] = okw ? in[base + (int64_t)(lo[axis] + i) * sa] : EDT_INF;
+        __syncthreads();
+        if (!okw) continue;
+        for (int i = ty; i < na; i += nty) {
+            int best = tile[i * 32 + tx];
+            const int down = i, up = na - 1 - i;
+            const int far = down > up ? down : up;
+            for (int dj = 1; dj <= far && dj * dj < best; ++dj) {
+                const int q = dj * dj;
+                if (dj <= down) { const int v = tile[(i - dj) * 32 + tx] + q; best = v < best ? v : best; }
+                if (dj <= up) { const int v = tile[(i + dj) * 32 + tx] + q; best = v < best ? v : best; }
+            }
+            out[base + (int64_t)(lo[axis] + i) * sa] = best < EDT_INF ? best : EDT_INF;
+        }
+    }
+}
+
 template <bool FIRST>
-__global__ void edt_pass_kernel(const void* __restrict__ in_, int64_t total, int n, int64_t s, int* __restrict__ out) {
+__global__ void edt_pass_kernel(const void* __restrict__ in_, int n0, int n1, int n2, int n3, int axis, const int* __restrict__ bb,
+                                int* __restrict__ out) {
     const uint8_t* feat = reinterpret_cast<const uint8_t*>(in_);
     const int* in = reinterpret_cast<const int*>(in_);
+    const int64_t total = (int64_t)n0 * n1 * n2 * n3;
+    const int ext[4] = {n0, n1, n2, n3};
+    const int64_t str[4] = {(int64_t)n1 * n2 * n3, (int64_t)n2 * n3, (int64_t)n3, 1};
+    int lo[4], hi[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { lo[k] = bb ? bb[2 * k] : 0; hi[k] = bb ? bb[2 * k + 1] : ext[k] - 1; }
+    const int64_t s = str[axis];
     for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
-        const int i = (int)((e / s) % n);
-        const int64_t base = e - (int64_t)i * s;
-        int best = EDT_INF;
+        int64_t t = e;
+        int c[4];
+        c[3] = (int)(t % n3); t /= n3;
+        c[2] = (int)(t % n2); t /= n2;
+        c[1] = (int)(t % n1);
+        c[0] = (int)(t / n1);
+        if (c[0] < lo[0] || c[0] > hi[0] || c[1] < lo[1] || c[1] > hi[1] || c[2] < lo[2] || c[2] > hi[2] || c[3] < lo[3] || c[3] > hi[3])
+            continue;                                   // outside the box: never read by a later pass or by the reduction
+        const int i = c[axis];
+        if (FIRST) {
+            const int64_t base = e - (int64_t)i * s;
+            int best = EDT_INF;
 #pragma unroll 4
-        for (int j = 0; j < n; ++j) {
-            const int dj = i - j;
-            int v;
-            if (FIRST) v = feat[base + (int64_t)j * s] ? 0 : EDT_INF;
-            else v = in[base + (int64_t)j * s];
-            v += dj * dj;
-            best = v < best ? v : best;
+            for (int j = lo[axis]; j <= hi[axis]; ++j) {
+                const int dj = i - j;
+                const int v = (feat[base + (int64_t)j * s] ? 0 : EDT_INF) + dj * dj;
+                best = v < best ? v : best;
+            }
+            out[e] = best < EDT_INF ? best : EDT_INF;
+        } else {
+            // lower envelope min_j in[j] + (i - j)^2, searched outwards from j = i: a candidate at distance dj can only win
+            // while dj^2 < best, so lattice points near a feature stop after a few steps
+            const int* p = in + e;
+            int best = *p;
+            const int down = i - lo[axis], up = hi[axis] - i;
+            const int far = down > up ? down : up;
+            for (int dj = 1; dj <= far && dj * dj < best; ++dj) {
+                const int q = dj * dj;
+                if (dj <= down) { const int v = p[-(int64_t)dj * s] + q; best = v < best ? v : best; }
+                if (dj <= up) { const int v = p[(int64_t)dj * s] + q; best = v < best ? v : best; }
+            }
+            out[e] = best < EDT_INF ? best : EDT_INF;
         }
-        out[e] = best < EDT_INF ? best : EDT_INF;
     }
 }
 
@@ -124,8 +278,13 @@ __global__ void surf_reduce_kernel(const int* __restrict__ d2, const uint8_t* __
 __global__ void surf_final_kernel(const double* __restrict__ p1, const double* __restrict__ p2, int nblocks,
                                   const int* __restrict__ maxd2, const unsigned long long* __restrict__ counts,
                                   double* __restrict__ out) {
+    // one warp, fixed association: lane l sums partials l, l + 32, ... in order, then a shuffle tree
+    const int lane = threadIdx.x;
     double s1 = 0.0, s2 = 0.0;
-    for (int i = 0; i < nblocks; ++i) { s1 += p1[i]; s2 += p2[i]; }
+    for (int i = lane; i < nblocks; i += 32) { s1 += p1[i]; s2 += p2[i]; }
+    s1 = sp_warp_sum(s1);
+    s2 = sp_warp_sum(s2);
+    if (lane != 0) return;
     const double n1 = (double)counts[0], n2 = (double)counts[1];
     const double inf = __longlong_as_double(0x7ff0000000000000LL);
     out[6] = n1; out[7] = n2;
@@ -161,24 +320,34 @@ int ew_grid(int64_t n, int threads = 256) {
 
 constexpr int RED_BLOCKS = 592;     // 4 x 148
 
-// exact squared EDT of `feat` (1 = feature) over the lattice (n0..n3): result in `a` (scratch `b`); both int32 [total]
-int edt_run(const uint8_t* feat, int n0, int n1, int n2, int n3, int* a, int* b, cudaStream_t st) {
+// exact squared EDT of `feat` (1 = feature) over the lattice (n0..n3), restricted to the box `bb` (NULL: whole lattice): result
+// in `a` (scratch `b`); both int32 [total]
+int edt_run(const uint8_t* feat, int n0, int n1, int n2, int n3, const int* bb, int* a, int* b, cudaStream_t st) {
     const int64_t total = (int64_t)n0 * n1 * n2 * n3;
     const int g = ew_grid(total);
-    int* cur = a;
-    int* nxt = b;
-    edt_pass_kernel<true><<<g, 256, 0, st>>>(feat, total, n3, 1, cur);
-    SP_LAUNCH_OK("edt_pass_kernel<first>");
+    const int passes = 1 + (n2 > 1) + (n1 > 1) + (n0 > 1);
+    int* cur = (passes & 1) ? a : b;                    // ping-pong so that the last pass lands in `a`
+    int* nxt = (passes & 1) ? b : a;
+    if (n3 <= 256) {
+        edt_first_kernel<<<g, 256, 0, st>>>(feat, n0, n1, n2, n3, bb, cur);
+        SP_LAUNCH_OK("edt_first_kernel");
+    } else {
+        edt_pass_kernel<true><<<g, 256, 0, st>>>(feat, n0, n1, n2, n3, 3, bb, cur);
+        SP_LAUNCH_OK("edt_pass_kernel<first>");
+    }
     const int ext[3] = {n2, n1, n0};
-    const int64_t str[3] = {n3, (int64_t)n2 * n3, (int64_t)n1 * n2 * n3};
     for (int ax = 0; ax < 3; ++ax) {
         if (ext[ax] == 1) continue;
-        edt_pass_kernel<false><<<g, 256, 0, st>>>(cur, total, ext[ax], str[ax], nxt);
-        SP_LAUNCH_OK("edt_pass_kernel");
+        if (ext[ax] <= 256) {
+            edt_tile_kernel<<<sp_num_sms() * 8, 256, (size_t)ext[ax] * 32 * sizeof(int), st>>>(cur, n0, n1, n2, n3, 2 - ax, bb, nxt);
+            SP_LAUNCH_OK("edt_tile_kernel");
+        } else {
+            edt_pass_kernel<false><<<g, 256, 0, st>>>(cur, n0, n1, n2, n3, 2 - ax, bb, nxt);
+            SP_LAUNCH_OK("edt_pass_kernel");
+        }
         int* t = cur; cur = nxt; nxt = t;
     }
-    if (cur != a) SP_CUDA(cudaMemcpyAsync(a, cur, sizeof(int) * total, cudaMemcpyDeviceToDevice, st));
-    return 0;
+    return cur == a ? 0 : (sp_set_error("edt_run: internal ping-pong error"), -1);
 }
 
 size_t align256(size_t v) { return (v + 255) / 256 * 256; }
@@ -210,20 +379,24 @@ int sp_surface_distances(const float* result, const float* target, int n0, int n
     double* part = reinterpret_cast<double*>(p); p += align256(2 * RED_BLOCKS * sizeof(double));
     unsigned long long* counts = reinterpret_cast<unsigned long long*>(p);      // [2]
     int* maxd2 = reinterpret_cast<int*>(counts + 2);                            // [2]
+    int* bb = maxd2 + 2;                                                        // [8]
     SP_CUDA(cudaMemsetAsync(counts, 0, 256, st));
     const int g = ew_grid(total);
-    border_kernel<<<g, 256, 0, st>>>(result, n0, n1, n2, n3, threshold, all_border, br, counts);
+    bbox_init_kernel<<<1, 32, 0, st>>>(bb, n0, n1, n2, n3);
+    SP_LAUNCH_OK("bbox_init_kernel");
+
+    border_kernel<<<g, 256, 0, st>>>(result, n0, n1, n2, n3, threshold, all_border, br, counts, bb);
     SP_LAUNCH_OK("border_kernel");
-    border_kernel<<<g, 256, 0, st>>>(target, n0, n1, n2, n3, threshold, all_border, bt, counts + 1);
+    border_kernel<<<g, 256, 0, st>>>(target, n0, n1, n2, n3, threshold, all_border, bt, counts + 1, bb);
     SP_LAUNCH_OK("border_kernel");
     // distances to the target's border, read at the result's border — and the other way round
-    if (int e = edt_run(bt, n0, n1, n2, n3, da, db, st)) return e;
+    if (int e = edt_run(bt, n0, n1, n2, n3, bb, da, db, st)) return e;
     surf_reduce_kernel<<<RED_BLOCKS, 256, 0, st>>>(da, br, total, part, maxd2);
     SP_LAUNCH_OK("surf_reduce_kernel");
-    if (int e = edt_run(br, n0, n1, n2, n3, da, db, st)) return e;
+    if (int e = edt_run(br, n0, n1, n2, n3, bb, da, db, st)) return e;
     surf_reduce_kernel<<<RED_BLOCKS, 256, 0, st>>>(da, bt, total, part + RED_BLOCKS, maxd2 + 1);
     SP_LAUNCH_OK("surf_reduce_kernel");
-    surf_final_kernel<<<1, 1, 0, st>>>(part, part + RED_BLOCKS, RED_BLOCKS, maxd2, counts, out8);
+    surf_final_kernel<<<1, 32, 0, st>>>(part, part + RED_BLOCKS, RED_BLOCKS, maxd2, counts, out8);
     SP_LAUNCH_OK("surf_final_kernel");
     return 0;
 }
@@ -250,11 +423,11 @@ int sp_signed_distance(const float* mask, int n0, int n1, int n2, int n3, float 
     // distance of object voxels to the nearest background voxel: features = background
     feature_kernel<<<g, 256, 0, st>>>(mask, total, threshold, 0, feat);
     SP_LAUNCH_OK("feature_kernel");
-    if (int e = edt_run(feat, n0, n1, n2, n3, din, tmp, st)) return e;
+    if (int e = edt_run(feat, n0, n1, n2, n3, nullptr, din, tmp, st)) return e;
     // distance of background voxels to the nearest object voxel: features = object
     feature_kernel<<<g, 256, 0, st>>>(mask, total, threshold, outside_is_lt ? 2 : 1, feat);
     SP_LAUNCH_OK("feature_kernel");
-    if (int e = edt_run(feat, n0, n1, n2, n3, dout, tmp, st)) return e;
+    if (int e = edt_run(feat, n0, n1, n2, n3, nullptr, dout, tmp, st)) return e;
     sdm_combine_kernel<<<g, 256, 0, st>>>(din, dout, total, sign, out);
     SP_LAUNCH_OK("sdm_combine_kernel");
     return 0;
