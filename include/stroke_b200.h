@@ -78,6 +78,11 @@ const char* sp_last_error(void);
  */
 int         sp_get_tc_terms(void);
 int         sp_set_tc_terms(int terms);
+/* Weight gradient of the 9..16-channel 3x3x3 stride-1 layers (Cae3D.py:44,208,211; Unet3D.py:22; wider layers as 16-channel
+ * slice pairs): generation 2 (default, sp_wgrad_tc4.cuh) = one M 128 x N 96 tcgen05.mma per (16 voxels, kd) on two
+ * round-to-nearest bf16 terms per operand, generation 1 (sp_wgrad_tc.cuh) = 27 M 64 x N 48 MMAs on three exact terms.
+ * max_ctas > 0 caps the persistent grid (tests: several tile columns per CTA on small volumes), 0 = one CTA per SM. */
+int         sp_set_wgrad_tc_options(int generation, int max_ctas);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Convolution family.  Replaces nn.Conv3d (Cae3D.py:41,44,48,52,55,59,63,66,70,74,126,128,132,186,189,197,200,

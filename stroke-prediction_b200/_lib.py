@@ -53,6 +53,7 @@ SIGNATURES = {
     "sp_last_error": (ctypes.c_char_p, []),
     "sp_get_tc_terms": (c_int, []),
     "sp_set_tc_terms": (c_int, [c_int]),
+    "sp_set_wgrad_tc_options": (c_int, [c_int, c_int]),
     "sp_packed_weight_floats": (c_size, [_D, c_int]),
     "sp_pack_weights": (c_int, [_D, c_int, c_vp, c_vp, c_vp]),
     "sp_conv_workspace_bytes": (c_size, [_D, c_int]),

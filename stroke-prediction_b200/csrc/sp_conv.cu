@@ -19,6 +19,7 @@
 #include "sp_conv_tc3.cuh"
 #include "sp_wgrad_tc.cuh"
 #include "sp_wgrad_tc24.cuh"
+#include "sp_wgrad_tc4.cuh"
 #include "sp_conv_thin.cuh"
 #include "sp_conv_k2s2.cuh"
 
@@ -521,6 +522,14 @@ int sp_set_tc_terms(int terms) {
     return 0;
 }
 
+int sp_set_wgrad_tc_options(int generation, int max_ctas) {
+    SP_REQUIRE(generation == 1 || generation == 2, "sp_set_wgrad_tc_options: generation must be 1 or 2, got %d", generation);
+    SP_REQUIRE(max_ctas >= 0, "sp_set_wgrad_tc_options: max_ctas must be >= 0, got %d", max_ctas);
+    sp_wtc4_generation_ref() = generation;
+    sp_wtc4_grid_cap_ref() = max_ctas;
+    return 0;
+}
+
 size_t sp_packed_weight_floats(const SpConvDesc* d, int which) {
     if (!d) return 0;
     size_t n = ffma_packed_floats(d, which);
@@ -649,6 +658,10 @@ size_t sp_wgrad_workspace_bytes(const SpConvDesc* d) {
     if (sp_tc_wgrad_workspace_bytes(d) > tiled) tiled = sp_tc_wgrad_workspace_bytes(d);
     if (sp_tc24_wgrad_workspace_bytes(d) > tiled) tiled = sp_tc24_wgrad_workspace_bytes(d);
     if (sp_tc_wgrad_sliced_workspace_bytes(d) > tiled) tiled = sp_tc_wgrad_sliced_workspace_bytes(d);
+    if (d->k == 3 && d->s == 1 && d->Ci > 8 && d->Co > 8) {          // second-generation tcgen05 weight gradient (any G)
+        if (sp_tc4_wgrad_workspace_bytes(d) > tiled && d->Ci <= 16 && d->Co <= 16) tiled = sp_tc4_wgrad_workspace_bytes(d);
+        if (sp_tc4_wgrad_sliced_workspace_bytes(d) > tiled) tiled = sp_tc4_wgrad_sliced_workspace_bytes(d);
+    }
     if (sp_thin_wgrad_workspace_bytes(d) > tiled) tiled = sp_thin_wgrad_workspace_bytes(d);
     if (sp_k2s2_wgrad_workspace_bytes(d) > tiled) tiled = sp_k2s2_wgrad_workspace_bytes(d);
     if (gemm_wgrad(d) && sp_gemm_wgrad_ws_bytes(d) > tiled) tiled = sp_gemm_wgrad_ws_bytes(d);
@@ -672,6 +685,11 @@ int sp_wgrad(const SpConvDesc* d, const float* iside, const float* i_scale, cons
         return sp_k2s2_wgrad_launch(d, nPerG, iside, i_scale, i_shift, oside, o_scale, o_shift, dw, beta, (float*)ws, sp_stream(stream));
     if (sp_thin_wgrad_supported(d))
         return sp_thin_wgrad_launch(d, nPerG, iside, i_scale, i_shift, oside, o_scale, o_shift, dw, beta, (float*)ws, sp_stream(stream));
+    const bool al16 = ((reinterpret_cast<uintptr_t>(iside) | reinterpret_cast<uintptr_t>(oside)) & 15) == 0;
+    if (sp_tc4_wgrad_supported(d, G))
+        return sp_tc4_wgrad_launch(d, nPerG, iside, i_scale, i_shift, oside, o_scale, o_shift, dw, beta, (float*)ws, sp_stream(stream));
+    if (sp_tc4_wgrad_sliced_supported(d, G) && al16)
+        return sp_tc4_wgrad_sliced_launch(d, nPerG, iside, i_scale, i_shift, oside, o_scale, o_shift, dw, beta, (float*)ws, sp_stream(stream));
     if (sp_tc_wgrad_supported(d))
         return sp_tc_wgrad_launch(d, nPerG, iside, i_scale, i_shift, oside, o_scale, o_shift, dw, beta, (float*)ws, sp_stream(stream));
     if (sp_tc_wgrad_sliced_supported(d) && ((reinterpret_cast<uintptr_t>(iside) | reinterpret_cast<uintptr_t>(oside)) & 15) == 0)

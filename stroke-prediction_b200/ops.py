@@ -207,6 +207,12 @@ def get_tc_terms():
     return int(_L().sp_get_tc_terms())
 
 
+def set_wgrad_tc_options(generation=2, max_ctas=0):
+    """Weight-gradient tier of the 16-channel 3x3x3 stride-1 layers (include/stroke_b200.h): generation 2 = M 128 x N 96
+    MMAs on two round-to-nearest bf16 terms (default), 1 = the first-generation kernel; max_ctas caps the persistent grid."""
+    check(_L().sp_set_wgrad_tc_options(int(generation), int(max_ctas)), "sp_set_wgrad_tc_options")
+
+
 def _conv_ws(d, which, device):
     nbytes = _L().sp_conv_workspace_bytes(ctypes.byref(d), which)
     if nbytes == 0:

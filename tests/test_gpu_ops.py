@@ -219,7 +219,8 @@ WGRAD_TC_CASES = [
     ("C", 48, 16, 3, 1, 0, "leaky", (10, 18, 40)),             # Unet3D.py:19 block5: three 16-channel I-side slices, scatter-reduce
     ("C", 40, 12, 3, 1, (1, 1, 1), "elu", (8, 16, 30)),        # ragged last slice (8 channels)
     ("C", 16, 40, 3, 1, (1, 1, 1), "elu", (8, 16, 30)),        # three O-side slices, the last one ragged
-    ("C", 32, 32, 3, 1, 0, "leaky", (10, 18, 40)),             # 2 x 2 slice pairs: more than three -> stays on the FFMA tier
+    ("C", 32, 32, 3, 1, 0, "leaky", (10, 18, 40)),             # 2 x 2 slice pairs (second generation: up to six pairs)
+    ("C", 96, 32, 3, 1, 0, "leaky", (10, 18, 40)),             # Unet3D.py:19 block4: 12 pairs -> stays on the FFMA tier
 ]
 
 
@@ -232,6 +233,40 @@ def test_tensor_core_wgrad_paths(case):
     conv = nn.Conv3d(cin, cout, k, stride=s, padding=p)
     x = torch.randn(4, cin, *size) * 1.5 + 0.3
     _check_sequential(nn.Sequential(nn.BatchNorm3d(cin), conv, _act(act)), x, G=2)
+
+
+@pytest.mark.parametrize("max_ctas", [3, 1])
+@pytest.mark.parametrize("case", WGRAD_TC_CASES[:3] + [WGRAD_TC_CASES[6], WGRAD_TC_CASES[9]],
+                         ids=lambda c: "%s%d-%d_p%s" % (c[0], c[1], c[2], str(c[5]).replace(" ", "")))
+def test_tensor_core_wgrad_several_columns_per_cta(case, max_ctas):
+    """Second-generation kernel with the persistent grid capped at 3 / 1 CTAs: every CTA walks many tile columns, so the
+    first two planes of the next column are staged during the last two steps of the current one (ring of seven planes),
+    statistics groups change between columns of one CTA, and the A buffers / ring slots wrap many times."""
+    _, _, ops = _mods()
+    kind, cin, cout, k, s, p, act, size = case
+    torch.manual_seed(520 + WGRAD_TC_CASES.index(case))
+    conv = nn.Conv3d(cin, cout, k, stride=s, padding=p)
+    x = torch.randn(4, cin, *size) * 1.5 + 0.3
+    ops.set_wgrad_tc_options(2, max_ctas)
+    try:
+        _check_sequential(nn.Sequential(nn.BatchNorm3d(cin), conv, _act(act)), x, G=2)
+    finally:
+        ops.set_wgrad_tc_options(2, 0)
+
+
+@pytest.mark.parametrize("case", WGRAD_TC_CASES[:3], ids=lambda c: "%s%d-%d_p%s" % (c[0], c[1], c[2], str(c[5]).replace(" ", "")))
+def test_tensor_core_wgrad_generation1(case):
+    """First-generation kernel (three exact bf16 terms, M 64 x N 48 MMAs), kept for A/B measurements."""
+    _, _, ops = _mods()
+    kind, cin, cout, k, s, p, act, size = case
+    torch.manual_seed(540 + WGRAD_TC_CASES.index(case))
+    conv = nn.Conv3d(cin, cout, k, stride=s, padding=p)
+    x = torch.randn(4, cin, *size) * 1.5 + 0.3
+    ops.set_wgrad_tc_options(1, 0)
+    try:
+        _check_sequential(nn.Sequential(nn.BatchNorm3d(cin), conv, _act(act)), x, G=2)
+    finally:
+        ops.set_wgrad_tc_options(2, 0)
 
 
 POINTWISE_CASES = [

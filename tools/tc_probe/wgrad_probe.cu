@@ -1,13 +1,14 @@
 // wgrad_probe.cu — standalone mapping / numerics / timing probe of the tcgen05 weight-gradient tier (sp_wgrad_tc.cuh).
 // Diagnostic only: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -o wgrad_probe wgrad_probe.cu
 //   ./wgrad_probe check [drain_every]  : small ragged geometry (padding in d / w, partial tiles) vs a double-precision CPU sum
-//   modes: check | time (16 channels), check24 | time24 (24 channels); suffix 'a' (checka, time24a) = experimental A-in-TMEM kernel
+//   modes: check | time (16 channels; check4 / time4 = second generation, sp_wgrad_tc4.cuh), check24 | time24 (24 channels); suffix 'a' (checka, time24a) = experimental A-in-TMEM kernel
 //   ./wgrad_probe time  [drain_every]  : the 16->16 layer of the CAE decoder at batch 32 (28x126x126 -> 28x128x128, pad 1,2,2)
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
 #include <vector>
 #include "sp_wgrad_tca.cuh"
+#include "../../stroke-prediction_b200/csrc/sp_wgrad_tc4.cuh"
 
 void sp_set_error(const char* fmt, ...) {
     va_list ap;
@@ -43,9 +44,10 @@ static SpConvDesc make_desc(int N, int Di, int Hi, int Wi, int Ci, int Co, int p
     return d;
 }
 
-static bool g_wide = false, g_tca = false;
+static bool g_wide = false, g_tca = false, g_tc4 = false;
 static int launch_wgrad(const SpConvDesc* d, const float* dx, const float* dsc, const float* dsh, const float* dz, float* ddw, float* dws,
                         long long* prof, int drain_every, int mrows) {
+    if (g_tc4) return sp_tc4_wgrad_launch(d, d->N, dx, dsc, dsh, dz, nullptr, nullptr, ddw, 0.f, dws, 0, prof, drain_every);
     if (g_tca) return sp_tca_wgrad_launch(d, d->N, dx, dsc, dsh, dz, nullptr, nullptr, ddw, 0.f, dws, 0, prof, drain_every);
     if (g_wide) return sp_tc24_wgrad_launch(d, d->N, dx, dsc, dsh, dz, nullptr, nullptr, ddw, 0.f, dws, 0, prof, drain_every);
     return sp_tc_wgrad_launch(d, d->N, dx, dsc, dsh, dz, nullptr, nullptr, ddw, 0.f, dws, 0, prof, drain_every, mrows);
@@ -55,6 +57,7 @@ int main(int argc, char** argv) {
     char modebuf[32];
     strncpy(modebuf, argc > 1 ? argv[1] : "check", 31); modebuf[31] = 0;
     if (strlen(modebuf) > 1 && modebuf[strlen(modebuf) - 1] == 'a') { g_tca = true; modebuf[strlen(modebuf) - 1] = 0; }   // checka / time24a: A in TMEM
+    if (strlen(modebuf) > 1 && modebuf[strlen(modebuf) - 1] == '4' && modebuf[strlen(modebuf) - 2] != '2') { g_tc4 = true; modebuf[strlen(modebuf) - 1] = 0; }   // check4 / time4: second generation
     const char* mode = modebuf;
     const int drain_every = argc > 2 ? atoi(argv[2]) : 2;
     const int mrows = argc > 3 ? atoi(argv[3]) : 128;
