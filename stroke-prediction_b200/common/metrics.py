@@ -22,6 +22,32 @@ from .dto.MetricMeasuresDto import BinaryMeasuresDto
 
 SURFACE_DISTANCES = True
 
+# While a `deferred()` context is active, binary_measures_many launches its kernels, returns BinaryMeasuresDto placeholders
+# and leaves the device-to-host read to `finish()`, which fills the placeholders in place.  Learner.train_batch uses it to
+# run the per-batch metrics (they only read the forward outputs) on a side stream while the backward pass and the
+# optimizer step run on the main stream (Learner.py:116-130 computes them after the step; same values).
+_PENDING = None
+
+
+class deferred(object):
+    def __enter__(self):
+        global _PENDING
+        self._prev, self.pending = _PENDING, []
+        _PENDING = self.pending
+        return self
+
+    def __exit__(self, *exc):
+        global _PENDING
+        _PENDING = self._prev
+        return False
+
+    def finish(self):
+        for out, dtos, with_sd in self.pending:
+            for dto, row in zip(dtos, out.cpu().tolist()):
+                new = measures_from_counts(*row[0:4], hd=row[4], assd=row[5]) if with_sd else measures_from_counts(*row[0:4])
+                dto.__dict__.update(new.__dict__)
+        self.pending = []
+
 
 def measures_from_counts(tp, fp, fn, tn, hd=numpy.inf, assd=numpy.inf):
     """medpy.metric.binary dc / precision / sensitivity / specificity from the confusion counts."""
@@ -48,6 +74,10 @@ def binary_measures_many(pairs, binary_threshold=0.5, surface_distances=None):
         ops.binary_counts(r, t, binary_threshold, out=out[i, 0:4])
         if surface_distances:
             ops.surface_distances(r, t, binary_threshold, out=out[i, 4:12])
+    if _PENDING is not None:
+        dtos = [BinaryMeasuresDto(0.0, numpy.inf, numpy.inf, 0.0, 0.0, 0.0) for _ in pairs]
+        _PENDING.append((out, dtos, bool(surface_distances)))
+        return dtos
     host = out.cpu().tolist()
     if surface_distances:
         return [measures_from_counts(*row[0:4], hd=row[4], assd=row[5]) for row in host]

@@ -292,8 +292,10 @@ corr3_tc_pipe_kernel(SpConvDesc d, int nPerG, int tiles_w, int tiles_h, int tile
         // The MMAs of one issuing thread retire strictly one after the other (~80 cycles each whatever N is), MMAs of
         // different issuing WARPS overlap (lanes of one warp do not).  Warp 10 + 3p + kd owns the accumulator block (plane p,
         // kd): 27 MMAs per tile (9 (kh,kw) x 3 terms), all into columns no other issuer touches.
-        if (lane == 0) {
-            const int p = (warp - 10) / 3, kd = (warp - 10) % 3;
+        // (warp-converged issue: the whole warp runs the loop with warp-uniform values, one elected lane issues — umma_bf16_elect)
+        {
+            const int wi = warp_uniform(warp - 10);
+            const int p = wi / 3, kd = wi % 3;
             const uint32_t a_base0 = smem_u32(As), b_base = smem_u32(Bs);
             int it = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
@@ -322,16 +324,16 @@ corr3_tc_pipe_kernel(SpConvDesc d, int nPerG, int tiles_w, int tiles_h, int tile
                         //   a1 x [w1|w2|w3] -> [main | cA | cB];  a2 x [w1|w2] -> [cA | cB];  a3 x [w1] -> cA
                         // (main holds only the nine leading products a1*w1 of this kd; every correction term, 2^-8 .. 2^-16 of
                         // the result, goes to the two correction blocks)
-                        if (dbg_terms & 1) umma_bf16(dk, da, db, umma_idesc_bf16(3 * COP), first);
-                        if (dbg_terms & 2) umma_bf16(dk + (uint32_t)COP, da + (uint64_t)(1 * KCH2 * PSLOTS2), db, umma_idesc_bf16(2 * COP), 1u);
-                        if (dbg_terms & 4) umma_bf16(dk + (uint32_t)COP, da + (uint64_t)(2 * KCH2 * PSLOTS2), db, umma_idesc_bf16(COP), 1u);
+                        if (dbg_terms & 1) umma_bf16_elect(dk, da, db, umma_idesc_bf16(3 * COP), first);
+                        if (dbg_terms & 2) umma_bf16_elect(dk + (uint32_t)COP, da + (uint64_t)(1 * KCH2 * PSLOTS2), db, umma_idesc_bf16(2 * COP), 1u);
+                        if (dbg_terms & 4) umma_bf16_elect(dk + (uint32_t)COP, da + (uint64_t)(2 * KCH2 * PSLOTS2), db, umma_idesc_bf16(COP), 1u);
                     }
                 }
-                umma_commit(t_full + 8 * p);                      // this lane's share of plane p is complete
-                umma_commit(a_empty + 8 * buf);                   // ... and it no longer reads this A buffer
+                umma_commit_elect(t_full + 8 * p);                      // this lane's share of plane p is complete
+                umma_commit_elect(a_empty + 8 * buf);                   // ... and it no longer reads this A buffer
                 if (pr) pwk += clock64() - c3;
             }
-            if (pr && warp == 10) { prof[0] = pw0; prof[1] = pw1; prof[2] = pwk; prof[3] = it; }
+            if (pr && warp == 10 && lane == 0) { prof[0] = pw0; prof[1] = pw1; prof[2] = pwk; prof[3] = it; }
         }
     } else {
         // =================================================================== epilogue warps 0..3 (TMEM lane quarter = warp)

@@ -37,7 +37,10 @@ using sp_tc2::tmem_ld_n;
 constexpr int TW = 16, TWV = 14, TH = 8, IH = TH + 2;   // MMA rows = 16 w'' x 8 h; 14 x 8 outputs per plane
 constexpr int PSLOTS = IH * TW;                          // 160 sixteen-byte slots per (term, chunk) plane
 constexpr int CHS = PSLOTS + 4;                          // chunk-plane stride: odd multiple of 64 B (bank spread of the 2 K chunks)
-constexpr int NEPI_G = 2, NEPI_W = 4 * NEPI_G;           // epilogue groups / warps (three groups measured slower: 25 warps crowd the
+#ifndef SP_TC3_NEPI_G
+#define SP_TC3_NEPI_G 2
+#endif
+constexpr int NEPI_G = SP_TC3_NEPI_G, NEPI_W = 4 * NEPI_G;           // epilogue groups / warps (three groups measured slower: 25 warps crowd the
                                                           // schedulers the three MMA-issuing threads need: issue time 3.7 k -> 5.2 k cycles per plane)
 constexpr int NSTG_W = 10, NSTG = NSTG_W * 32;           // staging warps / threads: 320 = one item per thread and plane
 constexpr int NISS_W = 3;                                // MMA issuer warps (NACC of them active)
@@ -380,9 +383,11 @@ corr3_tc3_kernel(SpConvDesc d, int nPerG, int tiles_w, int tiles_h, int nseg, in
         }
         if (pr && st == 0) { prof[4] = pw0; prof[5] = pwk; }
     } else if (warp >= NEPI_W + NSTG_W) {
-        // =================================================================== MMA issue: one thread per issuer warp
-        const int iss = warp - (NEPI_W + NSTG_W);
-        if (lane == 0 && iss < NACC) {
+        // =================================================================== MMA issue: the whole issuer warp runs the loop with
+        // warp-uniform values, one elected lane issues (umma_bf16_elect: inside an `if (lane == 0)` region every tcgen05.mma is
+        // wrapped in an ELECT / R2UR / BRA.U.ANY loop of ~17 instructions)
+        const int iss = warp_uniform(warp - (NEPI_W + NSTG_W));
+        if (iss < NACC) {
             const uint32_t a_base = smem_u32(As), b_base = smem_u32(Bs);
             const uint64_t db0 = umma_desc(b_base, BROWS * 16, 128);
             uint32_t q = 0, gbase = 0;                           // global output-plane / input-plane counters
@@ -411,14 +416,14 @@ corr3_tc3_kernel(SpConvDesc d, int nPerG, int tiles_w, int tiles_h, int nseg, in
                             const uint64_t da = umma_desc(a_slot + (uint32_t)(kh * TW * 16), CHS * 16, 128);
                             const uint32_t nfirst = (kd | kh) != 0;
                             //   a1 x [w1|w2|w3] -> [main | cA | cB];  a2 x [w1|w2] -> [cA | cB];  a3 x [w1] -> cA
-                            umma_bf16(dk, da, db, umma_idesc_bf16(NTOT), nfirst);
+                            umma_bf16_elect(dk, da, db, umma_idesc_bf16(NTOT), nfirst);
                             if (NS == 3) {
-                                umma_bf16(dk + (uint32_t)TS, da + (uint64_t)(1 * 2 * CHS), db, umma_idesc_bf16(2 * TS), 1u);
-                                umma_bf16(dk + (uint32_t)TS, da + (uint64_t)(2 * 2 * CHS), db, umma_idesc_bf16(TS), 1u);
+                                umma_bf16_elect(dk + (uint32_t)TS, da + (uint64_t)(1 * 2 * CHS), db, umma_idesc_bf16(2 * TS), 1u);
+                                umma_bf16_elect(dk + (uint32_t)TS, da + (uint64_t)(2 * 2 * CHS), db, umma_idesc_bf16(TS), 1u);
                             }
                         }
                     }
-                    umma_commit(t_full + 8 * (q % NTF));         // accumulator complete -> the epilogue group of this plane
+                    umma_commit_elect(t_full + 8 * (q % NTF));         // accumulator complete -> the epilogue group of this plane
                     // release the input planes: slot of plane ip is free once its (up to) three reading output planes are done;
                     // planes at the ends of a segment have fewer readers, their last reader arrives for the missing ones
                     for (int kd = 0; kd < 3; ++kd) {
@@ -426,14 +431,14 @@ corr3_tc3_kernel(SpConvDesc d, int nPerG, int tiles_w, int tiles_h, int nseg, in
                         const int last = ip < it.L - 1 ? ip : it.L - 1, first = ip - 2 > 0 ? ip - 2 : 0;
                         const int narr = 1 + (od == last ? 3 - (last - first + 1) : 0);
                         const uint32_t s = (gbase + ip) % RING;
-                        for (int a = 0; a < narr; ++a) umma_commit(a_empty + 8 * s);
+                        for (int a = 0; a < narr; ++a) umma_commit_elect(a_empty + 8 * s);
                     }
                     if (pr) pwk += clock64() - c2;
                     ++nq;
                 }
                 gbase += it.L + 2;
             }
-            if (pr && iss == 0) { prof[0] = pw0; prof[1] = pw1; prof[2] = pwk; prof[3] = nq; }
+            if (pr && iss == 0 && lane == 0) { prof[0] = pw0; prof[1] = pw1; prof[2] = pwk; prof[3] = nq; }
         }
     } else {
         // =================================================================== epilogue warps (TMEM lane quarter = warp % 4)

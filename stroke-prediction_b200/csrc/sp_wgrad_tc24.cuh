@@ -251,8 +251,9 @@ wgrad3_tc24_kernel(SpConvDesc d, int nPerG, int tiles_w, int tiles_h, int total_
         if (pr && st == 0) { prof[4] = pw0; prof[5] = pwk; }
     } else if (warp >= W_EPI) {
         // =================================================================== MMA issue: warp 4 + i owns block b0 + i
-        const int bi = warp - W_EPI;
-        if (lane == 0 && bi < nblk) {
+        // (warp-converged issue: the whole warp runs the loop with warp-uniform values, one elected lane issues — umma_bf16_elect)
+        const int bi = sp_tc::warp_uniform(warp - W_EPI);
+        if (bi < nblk) {
             const int b = b0 + bi, kd = b / 3, kw = b % 3;
             const uint32_t a_base = smem_u32(a_reg), x_base = smem_u32(x_reg);
             const uint32_t dcol = tmem_base + (uint32_t)(bi * BCOLS);
@@ -280,20 +281,20 @@ wgrad3_tc24_kernel(SpConvDesc d, int nPerG, int tiles_w, int tiles_h, int total_
                         const uint64_t da = da0 + (uint64_t)(r * TWW + ks * 16);
                         const uint64_t db = db0 + (uint64_t)((r * X_ROW_B + ks * 256) >> 4);
                         for (int tx = nt - 1; tx >= 0; --tx) {
-                            umma_bf16(dcol, da, db + (uint64_t)((tx * X_TERM_B) >> 4), IDESC, fresh ? 0u : 1u);
+                            umma_bf16_elect(dcol, da, db + (uint64_t)((tx * X_TERM_B) >> 4), IDESC, fresh ? 0u : 1u);
                             fresh = false;
                         }
                     }
                 }
-                umma_commit(a_empty + 8 * buf);
+                umma_commit_elect(a_empty + 8 * buf);
                 if ((it + 1) % drain_every == 0 || it == nsteps - 1) {
-                    umma_commit(t_full + 8 * bi);
+                    umma_commit_elect(t_full + 8 * bi);
                     fresh = true;
                     ++drains;
                 }
                 if (pr) pwk += clock64() - c2;
             }
-            if (pr && bi == 0) { prof[0] = pw0; prof[1] = pw1; prof[2] = pwk; prof[3] = nsteps; }
+            if (pr && bi == 0 && lane == 0) { prof[0] = pw0; prof[1] = pw1; prof[2] = pwk; prof[3] = nsteps; }
         }
     } else if (warp < 3) {
         // =================================================================== drain: warp t = y term t, lane = co

@@ -549,7 +549,13 @@ static inline int sp_tc4_wgrad_launch(const SpConvDesc* d, int nPerG, const floa
 static inline bool sp_tc4_wgrad_sliced_supported(const SpConvDesc* d, int G) {
     if (sp_tc4_wgrad_disabled() || G < 1 || G > sp_wtc4::MAXG) return false;
     if (d->k != 3 || d->s != 1 || sp_tc_terms() == 0 || sp_tc_wgrad_disabled()) return false;
-    if (d->Ci <= 24 && d->Co <= 24) return false;                    // the single-launch kernels take these
+    static int slice24 = -1;    // SP_WTC4_SLICE24=1: the 17..24-channel layers as (16 + 8)-channel slices instead of sp_wgrad_tc24.cuh
+    if (slice24 < 0) {
+        const char* e = getenv("SP_WTC4_SLICE24");
+        slice24 = (e && e[0] == '1') ? 1 : 0;
+    }
+    const bool is24 = d->Ci <= 24 && d->Co <= 24;
+    if (is24 && (!slice24 || (d->Ci <= 16 && d->Co <= 16))) return false;   // the single-launch kernels take these
     static int maxpairs = -1;   // SP_WTC4_SLICE_PAIRS: most slice pairs taken (every pair re-stages both tiles)
     if (maxpairs < 0) {
         const char* e = getenv("SP_WTC4_SLICE_PAIRS");
@@ -557,7 +563,7 @@ static inline bool sp_tc4_wgrad_sliced_supported(const SpConvDesc* d, int G) {
     }
     if (((d->Ci + 15) / 16) * ((d->Co + 15) / 16) > maxpairs) return false;
     if (d->Ci <= 8 || d->Ci > 96 || d->Co <= 8 || d->Co > 64 || d->ldi % 4 != 0 || d->ldo % 4 != 0) return false;
-    if ((d->Ci % 16 != 0 && d->Ci % 16 <= 8) || (d->Co % 16 != 0 && d->Co % 16 <= 8)) return false;   // a tail slice of <= 8 channels
+    if (!is24 && ((d->Ci % 16 != 0 && d->Ci % 16 <= 8) || (d->Co % 16 != 0 && d->Co % 16 <= 8))) return false;   // a tail slice of <= 8 channels
     if (d->pd > 2 || d->ph > 2 || d->pw > 2) return false;
     const sp_wtc4::Wtc4Plan p = sp_wtc4::plan(d);
     return p.total >= 16 && p.total < (1LL << 31) / (d->Do + 2) && d->Wo >= 24 && d->Do >= 8;

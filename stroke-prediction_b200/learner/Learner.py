@@ -159,9 +159,24 @@ class Learner(Inference):
         torch.save(self.cpu_snapshot(self._model), self.path('save', self.FNB_MODEL, suffix))
 
     # ------------------------------------------------------------------------------------------ hot path
+    OVERLAP_METRICS = True      # per-batch metrics on a side stream, concurrent with backward + optimizer step
+
     def train_batch(self, batch: dict, epoch) -> MetricMeasuresDto:
         dto = self.inference_step(batch)
         loss = self.loss_step(dto, epoch)
+
+        # The per-batch metrics (Learner.py:127) only read the forward outputs: their kernels are launched on a side stream
+        # before the backward pass and their single device-to-host read happens after the optimizer step.
+        pending = side = None
+        if self.OVERLAP_METRICS and loss.is_cuda:
+            from ..common import metrics
+            main = torch.cuda.current_stream()
+            side = self.__dict__.get('_metric_stream')
+            if side is None:
+                side = self._metric_stream = torch.cuda.Stream()
+            side.wait_stream(main)
+            with torch.cuda.stream(side), metrics.deferred() as pending:
+                batch_metrics = self.batch_metrics_step(dto, epoch)
 
         self._optimizer.zero_grad()
         loss.backward()
@@ -169,8 +184,13 @@ class Learner(Inference):
             self._grad_sync()
         self._optimizer.step()
 
-        batch_metrics = self.batch_metrics_step(dto, epoch)
-        batch_metrics.loss = float(loss.detach().reshape(-1)[0].cpu())   # the step's single D2H read
+        if pending is None:
+            batch_metrics = self.batch_metrics_step(dto, epoch)
+        else:
+            with torch.cuda.stream(side):
+                pending.finish()
+            torch.cuda.current_stream().wait_stream(side)       # the forward outputs may be recycled from here on
+        batch_metrics.loss = float(loss.detach().reshape(-1)[0].cpu())   # the step's single D2H read on the main stream
 
         del loss
         del dto

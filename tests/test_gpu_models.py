@@ -338,6 +338,32 @@ def test_three_training_steps_track_the_oracle():
         assert abs(got - loss.item()) < tol * max(1.0, abs(loss.item())), (it, got, loss.item())
 
 
+def test_overlapped_batch_metrics_equal_serial_ones():
+    """train_batch launches the per-batch metrics (counts + exact-EDT surface distances) on a side stream before the backward
+    pass and reads them back after the optimizer step: same metrics, loss and parameters as the serial order of Learner.py:116-130."""
+    A = _api()
+    ch = [1, 4, 6, 8, 10, 12, 1]
+    runs = []
+    for overlap in (True, False):
+        torch.manual_seed(22)
+        cae = A.Cae3D(A.Enc3D(56, 28, ch, 5, 1.0), A.Dec3D(56, 28, ch, 5, 1.0)).cuda().train()
+        opt = torch.optim.Adam(cae.parameters(), lr=1e-3, weight_decay=1e-5, betas=(0.9, 0.999))
+        learner = A.CaeReconstructionLearner(None, None, cae, opt, None, 10, None, "/tmp/x", A.BatchDiceLoss([1.0]))
+        learner.OVERLAP_METRICS = overlap
+        rows = []
+        for it in range(3):
+            batch = A.data.synthetic_cae_batch(2, size=(28, 56, 56), seed=60 + it)
+            m = learner.train_batch(batch, it)
+            rows.append([m.loss] + [getattr(part, f) for part in (m.lesion, m.core, m.penu)
+                                    for f in ("dc", "hd", "assd", "precision", "sensitivity", "specificity")])
+        torch.cuda.synchronize()
+        runs.append((rows, [p.detach().clone() for p in cae.parameters()]))
+    assert runs[0][0] == runs[1][0], (runs[0][0], runs[1][0])
+    assert any(np.isfinite(r[2]) for r in runs[0][0]), "surface distances were expected to be computed"
+    for a, b in zip(runs[0][1], runs[1][1]):
+        assert torch.equal(a, b)
+
+
 def test_tester_eval_batch_one():
     """Tester path: eval mode, batch size 1 (breaks in the reference on current torch)."""
     A = _api()
