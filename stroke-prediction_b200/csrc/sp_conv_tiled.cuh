@@ -286,6 +286,10 @@ template <int CK, int TD, int K, int S>
 static inline int sp_tiled_corr_launch_t(const SpConvDesc* d, int nPerG, const float* src, const float* wp, int flip,
                                          const float* bias, const float* scale, const float* shift, float* dst,
                                          cudaStream_t st) {
+    // stride 2, 24 output channels (Cae3D.py:48): ONE 24-wide pass — the parity-split halo tile (the dominant cost of this
+    // layer: four channel-quad chunks, each staged and synchronised separately) is staged once instead of twice (16 + 8)
+    if (S == 2 && d->Co == 24 && d->ldo % 4 == 0)
+        return sp_tiled_corr_launch_c<CK, TD, K, S, 24>(d, nPerG, 0, 1, src, wp, flip, bias, scale, shift, dst, st);
     const int full = d->Co / 16, rem = d->Co % 16;
     if (full > 0)
         if (int e = sp_tiled_corr_launch_c<CK, TD, K, S, 16>(d, nPerG, 0, full, src, wp, flip, bias, scale, shift, dst, st)) return e;

@@ -549,17 +549,21 @@ static inline int sp_tc4_wgrad_launch(const SpConvDesc* d, int nPerG, const floa
 static inline bool sp_tc4_wgrad_sliced_supported(const SpConvDesc* d, int G) {
     if (sp_tc4_wgrad_disabled() || G < 1 || G > sp_wtc4::MAXG) return false;
     if (d->k != 3 || d->s != 1 || sp_tc_terms() == 0 || sp_tc_wgrad_disabled()) return false;
-    static int slice24 = -1;    // SP_WTC4_SLICE24=1: the 17..24-channel layers as (16 + 8)-channel slices instead of sp_wgrad_tc24.cuh
+    // 17..24-channel layers (Cae3D.py:52,55,186-200) run as (16 + 8)-channel slices as well: measured in the CAE step against
+    // sp_wgrad_tc24.cuh 0.914 -> 0.811 ms (24 -> 24 at batch 32), 0.803 -> 0.407 ms (24 -> 16); SP_WTC4_SLICE24=0 switches back
+    static int slice24 = -1;
     if (slice24 < 0) {
         const char* e = getenv("SP_WTC4_SLICE24");
-        slice24 = (e && e[0] == '1') ? 1 : 0;
+        slice24 = (e && e[0] == '0') ? 0 : 1;
     }
     const bool is24 = d->Ci <= 24 && d->Co <= 24;
     if (is24 && (!slice24 || (d->Ci <= 16 && d->Co <= 16))) return false;   // the single-launch kernels take these
-    static int maxpairs = -1;   // SP_WTC4_SLICE_PAIRS: most slice pairs taken (every pair re-stages both tiles)
+    // most slice pairs taken (every pair re-stages both tiles); measured on the U-Net step (batch 4): 3 / 6 / 12 pairs ->
+    // 21.97 / 21.50 / 21.19 ms (96 -> 32 on 18x68x68 as 12 pairs: 1.86 -> 1.40 ms); SP_WTC4_SLICE_PAIRS overrides
+    static int maxpairs = -1;
     if (maxpairs < 0) {
         const char* e = getenv("SP_WTC4_SLICE_PAIRS");
-        maxpairs = e ? atoi(e) : 6;
+        maxpairs = e ? atoi(e) : 12;
     }
     if (((d->Ci + 15) / 16) * ((d->Co + 15) / 16) > maxpairs) return false;
     if (d->Ci <= 8 || d->Ci > 96 || d->Co <= 8 || d->Co > 64 || d->ldi % 4 != 0 || d->ldo % 4 != 0) return false;

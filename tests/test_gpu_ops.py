@@ -212,15 +212,16 @@ WGRAD_TC_CASES = [
     ("C", 16, 16, 3, 1, (1, 2, 2), "elu", (8, 17, 67)),        # Cae3D.py:208  Wo = 69: three column tiles
     ("C", 16, 16, 3, 1, (1, 0, 0), "elu", (10, 23, 44)),       # Cae3D.py:44   Wo = 42, Ho = 21
     ("C", 10, 14, 3, 1, 1, "leaky", (9, 18, 40)),              # ragged channel halves on both sides
-    # 17..24 channels on either side: three 8-channel groups, two accumulator passes (sp_wgrad_tc24.cuh)
+    # 17..24 channels on either side: (16 + 8)-channel slices of the second-generation kernel (sp_wgrad_tc24.cuh when switched off)
     ("C", 24, 24, 3, 1, (1, 0, 0), "elu", (9, 19, 44)),        # Cae3D.py:52,55
     ("C", 24, 16, 3, 1, (1, 2, 2), "elu", (8, 14, 35)),        # Cae3D.py:200  24 -> 16: the third O-side group is empty
     ("C", 12, 20, 3, 1, 1, "leaky", (10, 17, 33)),             # ragged groups on both sides
     ("C", 48, 16, 3, 1, 0, "leaky", (10, 18, 40)),             # Unet3D.py:19 block5: three 16-channel I-side slices, scatter-reduce
     ("C", 40, 12, 3, 1, (1, 1, 1), "elu", (8, 16, 30)),        # ragged last slice (8 channels)
     ("C", 16, 40, 3, 1, (1, 1, 1), "elu", (8, 16, 30)),        # three O-side slices, the last one ragged
-    ("C", 32, 32, 3, 1, 0, "leaky", (10, 18, 40)),             # 2 x 2 slice pairs (second generation: up to six pairs)
-    ("C", 96, 32, 3, 1, 0, "leaky", (10, 18, 40)),             # Unet3D.py:19 block4: 12 pairs -> stays on the FFMA tier
+    ("C", 32, 32, 3, 1, 0, "leaky", (10, 18, 40)),             # 2 x 2 slice pairs (second generation: up to twelve pairs)
+    ("C", 96, 32, 3, 1, 0, "leaky", (10, 18, 40)),             # Unet3D.py:19 block4: 6 x 2 = 12 slice pairs
+    ("C", 64, 64, 3, 1, 0, "leaky", (10, 18, 40)),             # Unet3D.py:22 block3: 16 pairs -> stays on the FFMA tier
 ]
 
 
@@ -236,7 +237,7 @@ def test_tensor_core_wgrad_paths(case):
 
 
 @pytest.mark.parametrize("max_ctas", [3, 1])
-@pytest.mark.parametrize("case", WGRAD_TC_CASES[:3] + [WGRAD_TC_CASES[6], WGRAD_TC_CASES[9]],
+@pytest.mark.parametrize("case", WGRAD_TC_CASES[:7] + [WGRAD_TC_CASES[9]],
                          ids=lambda c: "%s%d-%d_p%s" % (c[0], c[1], c[2], str(c[5]).replace(" ", "")))
 def test_tensor_core_wgrad_several_columns_per_cta(case, max_ctas):
     """Second-generation kernel with the persistent grid capped at 3 / 1 CTAs: every CTA walks many tile columns, so the
@@ -254,9 +255,10 @@ def test_tensor_core_wgrad_several_columns_per_cta(case, max_ctas):
         ops.set_wgrad_tc_options(2, 0)
 
 
-@pytest.mark.parametrize("case", WGRAD_TC_CASES[:3], ids=lambda c: "%s%d-%d_p%s" % (c[0], c[1], c[2], str(c[5]).replace(" ", "")))
+@pytest.mark.parametrize("case", WGRAD_TC_CASES[:7], ids=lambda c: "%s%d-%d_p%s" % (c[0], c[1], c[2], str(c[5]).replace(" ", "")))
 def test_tensor_core_wgrad_generation1(case):
-    """First-generation kernel (three exact bf16 terms, M 64 x N 48 MMAs), kept for A/B measurements."""
+    """First-generation kernels (three exact bf16 terms: M 64 x N 48 MMAs for 16 channels, sp_wgrad_tc24.cuh for 17..24, the
+    16-channel kernel on slice pairs for 48 -> 16), kept for A/B measurements."""
     _, _, ops = _mods()
     kind, cin, cout, k, s, p, act, size = case
     torch.manual_seed(540 + WGRAD_TC_CASES.index(case))
