@@ -236,6 +236,33 @@ def test_tensor_core_wgrad_paths(case):
     _check_sequential(nn.Sequential(nn.BatchNorm3d(cin), conv, _act(act)), x, G=2)
 
 
+WGRAD_TC_S2_CASES = [
+    # the stride-2 tcgen05 weight gradient (sp_wgrad_tc4s2.cuh): 3x3x3 stride 2 padding 1, 9..16 input channels; one launch per
+    # input-column parity and 16-channel output slice
+    ("C", 16, 24, 3, 2, 1, "elu", (16, 36, 70)),          # Cae3D.py:48   even extents, two column tiles per parity
+    ("C", 16, 24, 3, 2, 1, "elu", (17, 23, 67)),          # odd extents on every axis: ragged last plane / row / column
+    ("C", 12, 16, 3, 2, 1, "leaky", (16, 20, 66)),        # ragged channel half on the I-side, one output slice
+    ("C", 16, 32, 3, 2, 1, "elu", (16, 20, 66)),          # two full output slices
+]
+
+
+@pytest.mark.parametrize("max_ctas", [0, 3])
+@pytest.mark.parametrize("case", WGRAD_TC_S2_CASES, ids=lambda c: "%s%d-%d_%s" % (c[0], c[1], c[2], "x".join(map(str, c[7]))))
+def test_tensor_core_wgrad_stride2(case, max_ctas):
+    """dW of the stride-2 layer from tcgen05 MMAs: input columns split by parity (one launch each), rows / planes read at stride
+    two through the N-group base and a ring that advances two planes per step; also with three CTAs (many columns per CTA)."""
+    _, _, ops = _mods()
+    kind, cin, cout, k, s, p, act, size = case
+    torch.manual_seed(560 + WGRAD_TC_S2_CASES.index(case))
+    conv = nn.Conv3d(cin, cout, k, stride=s, padding=p)
+    x = torch.randn(4, cin, *size) * 1.5 + 0.3
+    ops.set_wgrad_tc_options(2, max_ctas)
+    try:
+        _check_sequential(nn.Sequential(nn.BatchNorm3d(cin), conv, _act(act)), x, G=2)
+    finally:
+        ops.set_wgrad_tc_options(2, 0)
+
+
 @pytest.mark.parametrize("max_ctas", [3, 1])
 @pytest.mark.parametrize("case", WGRAD_TC_CASES[:7] + [WGRAD_TC_CASES[9]],
                          ids=lambda c: "%s%d-%d_p%s" % (c[0], c[1], c[2], str(c[5]).replace(" ", "")))

@@ -9,6 +9,7 @@
 #include <vector>
 #include "sp_wgrad_tca.cuh"
 #include "../../stroke-prediction_b200/csrc/sp_wgrad_tc4.cuh"
+#include "../../stroke-prediction_b200/csrc/sp_wgrad_tc4s2.cuh"
 
 void sp_set_error(const char* fmt, ...) {
     va_list ap;
@@ -44,9 +45,10 @@ static SpConvDesc make_desc(int N, int Di, int Hi, int Wi, int Ci, int Co, int p
     return d;
 }
 
-static bool g_wide = false, g_tca = false, g_tc4 = false;
+static bool g_wide = false, g_tca = false, g_tc4 = false, g_s2 = false;
 static int launch_wgrad(const SpConvDesc* d, const float* dx, const float* dsc, const float* dsh, const float* dz, float* ddw, float* dws,
                         long long* prof, int drain_every, int mrows) {
+    if (g_s2) return sp_tc4s2_wgrad_launch(d, d->N, dx, dsc, dsh, dz, nullptr, nullptr, ddw, 0.f, dws, 0, prof, drain_every);
     if (g_tc4) return sp_tc4_wgrad_launch(d, d->N, dx, dsc, dsh, dz, nullptr, nullptr, ddw, 0.f, dws, 0, prof, drain_every);
     if (g_tca) return sp_tca_wgrad_launch(d, d->N, dx, dsc, dsh, dz, nullptr, nullptr, ddw, 0.f, dws, 0, prof, drain_every);
     if (g_wide) return sp_tc24_wgrad_launch(d, d->N, dx, dsc, dsh, dz, nullptr, nullptr, ddw, 0.f, dws, 0, prof, drain_every);
@@ -57,6 +59,7 @@ int main(int argc, char** argv) {
     char modebuf[32];
     strncpy(modebuf, argc > 1 ? argv[1] : "check", 31); modebuf[31] = 0;
     if (strlen(modebuf) > 1 && modebuf[strlen(modebuf) - 1] == 'a') { g_tca = true; modebuf[strlen(modebuf) - 1] = 0; }   // checka / time24a: A in TMEM
+    if (strlen(modebuf) > 2 && !strcmp(modebuf + strlen(modebuf) - 2, "s2")) { g_s2 = true; modebuf[strlen(modebuf) - 2] = 0; }   // checks2 / times2: stride-2 layer
     if (strlen(modebuf) > 1 && modebuf[strlen(modebuf) - 1] == '4' && modebuf[strlen(modebuf) - 2] != '2') { g_tc4 = true; modebuf[strlen(modebuf) - 1] = 0; }   // check4 / time4: second generation
     const char* mode = modebuf;
     const int drain_every = argc > 2 ? atoi(argv[2]) : 2;
@@ -66,6 +69,11 @@ int main(int argc, char** argv) {
     SpConvDesc d = wide ? (timing ? make_desc(32, 14, 58, 58, 24, 24, 1, 2, 2) : make_desc(2, 9, 21, 45, 24, 20, 1, 0, 2))
                         : (timing ? make_desc(32, 28, 126, 126, 16, 16, 1, 2, 2) : make_desc(2, 9, 21, 45, 16, 16, 1, 0, 2));
     g_wide = wide;
+    if (g_s2) {      // Cae3D.py:48: 16 -> 24, k3 s2 p1 (check: odd depth, ragged tiles)
+        d = timing ? make_desc(24, 28, 124, 124, 16, 24, 1, 1, 1) : make_desc(2, 17, 22, 90, 16, 24, 1, 1, 1);
+        d.s = 2;
+        d.Do = (d.Di + 2 - 3) / 2 + 1; d.Ho = (d.Hi + 2 - 3) / 2 + 1; d.Wo = (d.Wi + 2 - 3) / 2 + 1;
+    }
     const size_t nx = (size_t)d.N * d.Di * d.Hi * d.Wi * d.Ci, nz = (size_t)d.N * d.Do * d.Ho * d.Wo * d.Co;
     const int wn = d.Co * d.Ci * 27;
     const sp_wtc::WtcPlan p = sp_wtc::plan(&d);
@@ -79,7 +87,7 @@ int main(int argc, char** argv) {
     float *dx, *dz, *dsc, *dsh, *dws, *ddw;
     long long* dprof;
     CK(cudaMalloc(&dx, nx * 4)); CK(cudaMalloc(&dz, nz * 4)); CK(cudaMalloc(&dsc, 96)); CK(cudaMalloc(&dsh, 96));
-    CK(cudaMalloc(&dws, (size_t)p.grid * wn * 4)); CK(cudaMalloc(&ddw, wn * 4)); CK(cudaMalloc(&dprof, 128));
+    CK(cudaMalloc(&dws, (size_t)148 * wn * 4 + 1024)); CK(cudaMalloc(&ddw, wn * 4)); CK(cudaMalloc(&dprof, 128));
     CK(cudaMemcpy(dx, x.data(), nx * 4, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(dz, z.data(), nz * 4, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(dsc, sc.data(), 96, cudaMemcpyHostToDevice)); CK(cudaMemcpy(dsh, sh.data(), 96, cudaMemcpyHostToDevice));
@@ -128,7 +136,7 @@ int main(int argc, char** argv) {
                     for (int kd = 0; kd < 3; ++kd)
                         for (int kh = 0; kh < 3; ++kh)
                             for (int kw = 0; kw < 3; ++kw) {
-                                const int id = od - d.pd + kd, ih = oh - d.ph + kh, iw = ow - d.pw + kw;
+                                const int id = od * d.s - d.pd + kd, ih = oh * d.s - d.ph + kh, iw = ow * d.s - d.pw + kw;
                                 if (id < 0 || id >= d.Di || ih < 0 || ih >= d.Hi || iw < 0 || iw >= d.Wi) continue;
                                 const float* xp = &x[((((size_t)n * d.Di + id) * d.Hi + ih) * d.Wi + iw) * d.Ci];
                                 const int tap = (kd * 3 + kh) * 3 + kw;
