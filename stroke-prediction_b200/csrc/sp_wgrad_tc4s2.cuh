@@ -6,16 +6,17 @@
 // Same formulation as sp_wgrad_tc4.cuh (voxels = contraction index, both operands MN-major, ONE M 128 x N 96 MMA per
 // (16 voxels, kd), two round-to-nearest bf16 terms per operand); what the stride changes:
 //   w  The 16 voxels of a K slab must be consecutive in shared memory, but consecutive outputs read every other input
-//      column.  The input columns are therefore split by parity, ONE LAUNCH per parity q: the slab holds the columns
-//      u = 2 j + q, j = j0 .. j0 + 15.  Even columns (q = 0) carry the tap kw = 1 (ow = j); odd columns (q = 1) carry
-//      kw = 2 (ow = j) and kw = 0 (ow = j + 1).  In the row layout of sp_wgrad_tc4.cuh (A_kw'[j] = dZ[j + 1 - kw']) these are
-//      kw' = 1 for q = 0 and kw' = 1 / kw' = 0 for q = 1; the rows of the other kw' are not stored and their results ignored
-//      (wgrad_reduce_s2_kernel picks the taps of the launch's parity).
+//      column.  The input columns are therefore split by parity: a tile column holds the input columns u = 2 j + q of ONE
+//      parity q, j = j0 .. j0 + 31, and the CTAs walk the tile columns of both parities.  Even columns (q = 0) carry the tap
+//      kw = 1 (ow = j); odd columns (q = 1) carry kw = 2 (ow = j) and kw = 0 (ow = j + 1).  The three M row groups of
+//      sp_wgrad_tc4.cuh become tap slots: slot 0 = kw 0 (dZ[j + 1], q = 1), slot 1 = kw 2 (dZ[j], q = 1), slot 2 = kw 1 (dZ[j],
+//      q = 0); the slots of the other parity are stored as zeros, so ONE accumulator set serves both parities.
 //   h  Output row r reads the input rows 2 r - 1 + kh: three CONSECUTIVE rows of the staged tile, starting at row 2 r — the
 //      N groups (kh, term, ci half) keep their uniform stride.  A tile is 2 output rows = 5 input rows.
 //   d  Output plane od reads the input planes 2 od - 1 + kd: the ring advances by TWO planes per step (three at the top of a
 //      column); ring of 8 slots (see the staging schedule for the safety argument).
 // More than 16 output channels (24 here) run as slices of 16 with their own launches, like the wider stride-1 layers.
+// X' staging: thread = (column, channel half, one of the step's two new planes), all five rows of the plane loaded up front.
 // Roles, barriers, drain and accuracy as in sp_wgrad_tc4.cuh.
 #pragma once
 #include "sp_wgrad_tc4.cuh"
@@ -55,10 +56,14 @@ static_assert(A_REGION_B + X_REGION_B >= (NBUF - 1) * A_BUF_B + 16 * PS, "the 16
 static_assert(W_STG_Z * 32 >= 2 * ZW, "staging roles");
 
 struct ColGeo {
-    int n, oh0, j0;
+    int n, oh0, j0, q;
 };
-__device__ __forceinline__ ColGeo col_geo(int col, int tiles_w, int tiles_h) {
+// tile columns of parity 0 come first (total0 of them, tiles_w0 per row block), then those of parity 1
+__device__ __forceinline__ ColGeo col_geo(int col, int total0, int tiles_w0, int tiles_w1, int tiles_h) {
     ColGeo c;
+    c.q = col >= total0 ? 1 : 0;
+    if (c.q) col -= total0;
+    const int tiles_w = c.q ? tiles_w1 : tiles_w0;
     const int tw = col % tiles_w;
     col /= tiles_w;
     c.oh0 = (col % tiles_h) * THW;
@@ -67,9 +72,8 @@ __device__ __forceinline__ ColGeo col_geo(int col, int tiles_w, int tiles_h) {
     return c;
 }
 
-// q = parity of the input columns of this launch (0: even, tap kw = 1; 1: odd, taps kw = 0 and 2)
 __global__ void __launch_bounds__(NTHREADS_S2, 1)
-wgrad3_tc4s2_kernel(SpConvDesc d, int nPerG, int G, int q, int tiles_w, int tiles_h, int total_cols, int drain_every, int isstride,
+wgrad3_tc4s2_kernel(SpConvDesc d, int nPerG, int G, int total0, int tiles_w0, int tiles_w1, int tiles_h, int total_cols, int drain_every, int isstride,
                     int osstride, const float* __restrict__ X, const float* __restrict__ i_scale, const float* __restrict__ i_shift,
                     const float* __restrict__ dZ, const float* __restrict__ o_scale, const float* __restrict__ o_shift,
                     float* __restrict__ ws, long long* __restrict__ prof, int nt) {
@@ -86,9 +90,6 @@ wgrad3_tc4s2_kernel(SpConvDesc d, int nPerG, int G, int q, int tiles_w, int tile
     long long pw0 = 0, pw1 = 0, pwk = 0;
 
     for (int i = tid; i < ACC_ROWS * ACC_LD; i += NTHREADS_S2) acc[i] = 0.f;
-    // rows of the kw' that this parity does not store must not hold NaN / Inf patterns: 0 * NaN would poison nothing (every
-    // accumulator row only sees its own A row), but keep the operand buffers defined anyway
-    for (int i = tid; i < A_REGION_B / 16; i += NTHREADS_S2) reinterpret_cast<uint4*>(a_reg)[i] = make_uint4(0u, 0u, 0u, 0u);
     for (int i = tid; i < G * 32; i += NTHREADS_S2) {
         const int g = i >> 5, j = i & 31, c = j & 15;
         float v = (j < 16) ? 1.f : 0.f;
@@ -131,13 +132,14 @@ wgrad3_tc4s2_kernel(SpConvDesc d, int nPerG, int G, int q, int tiles_w, int tile
         const bool vec_i = (d.ldi % 4 == 0) && ((reinterpret_cast<uintptr_t>(X) & 15) == 0);
         const bool vec_o = (d.ldo % 4 == 0) && ((reinterpret_cast<uintptr_t>(dZ) & 15) == 0);
         const int64_t xs_n = (int64_t)d.Di * d.Hi * d.Wi * d.ldi, zs_n = (int64_t)Do * d.Ho * d.Wo * d.ldo;
-        const int wx = st & 31, xhalf = (st >> 5) & 1, hy0 = st >> 6;      // X' role: rows hy0, hy0 + 2, hy0 + 4 (< 5)
+        const int wx = st & 31, xhalf = (st >> 5) & 1, xp = st >> 6;       // X' role: plane xp of the step's pair, all five rows
         const bool zact = !isx && st < 2 * ZW;                             // dZ role: (channel half, dZ column), two rows
         const int zhalf = st >= ZW ? 1 : 0, zj = st - zhalf * ZW;
         for (int it = grp; it < nsteps; it += NGRP) {
             const int buf = it % NBUF, use = it / NBUF;
             const int cl = it / Do, od = it - cl * Do;
-            const ColGeo cg = col_geo((int)blockIdx.x + cl * (int)gridDim.x, tiles_w, tiles_h);
+            const ColGeo cg = col_geo((int)blockIdx.x + cl * (int)gridDim.x, total0, tiles_w0, tiles_w1, tiles_h);
+            const int q = cg.q;
             bool waited = false;
             long long c1 = pr ? clock64() : 0;
             if (isx) {
@@ -149,20 +151,22 @@ wgrad3_tc4s2_kernel(SpConvDesc d, int nPerG, int G, int q, int tiles_w, int tile
                 // base jumps by three — by the step three before as well): that step's MMAs have been waited for (a_empty).
                 const int np = (od == 0) ? 3 : 2;
 #pragma unroll 1
-                for (int p = 0; p < np; ++p) {
-                    const int pj = 2 * od + 2 - p;                      // newest first; p == 2 only at od == 0 (plane 0)
+                for (int round = 0; round * 2 < np; ++round) {
+                    const int pidx = round * 2 + xp;                    // newest plane first; index 2 only at od == 0 (plane 0)
+                    const bool have = pidx < np;
+                    const int pj = 2 * od + 2 - pidx;
                     const int seq = cl * PPC + pj;
-                    const int gd = pj - 1, gw = 2 * (cg.j0 + wx) + q, gh0 = 2 * cg.oh0 - 1 + hy0;
+                    const int gd = pj - 1, gw = 2 * (cg.j0 + wx) + q, gh0 = 2 * cg.oh0 - 1;
                     const int ch = xhalf * 8;
-                    const bool okp = gd >= 0 && gd < d.Di && gw < d.Wi;
+                    const bool okp = have && gd >= 0 && gd < d.Di && gw < d.Wi;
                     const float* pp = X + (int64_t)cg.n * xs_n + (((int64_t)gd * d.Hi + gh0) * d.Wi + gw) * d.ldi + ch;
-                    const int64_t rstep = (int64_t)2 * d.Wi * d.ldi;
-                    float4 ra[3], rb[3];
-                    bool ok[3];
+                    const int64_t rstep = (int64_t)d.Wi * d.ldi;
+                    float4 ra[XH], rb[XH];
+                    bool ok[XH];
 #pragma unroll
-                    for (int i = 0; i < 3; ++i) {
-                        const int gh = gh0 + 2 * i;
-                        ok[i] = okp && hy0 + 2 * i < XH && gh >= 0 && gh < d.Hi;
+                    for (int i = 0; i < XH; ++i) {
+                        const int gh = gh0 + i;
+                        ok[i] = okp && gh >= 0 && gh < d.Hi;
                         ra[i] = make_float4(0.f, 0.f, 0.f, 0.f);
                         rb[i] = ra[i];
                         if (ok[i]) {
@@ -182,9 +186,9 @@ wgrad3_tc4s2_kernel(SpConvDesc d, int nPerG, int G, int q, int tiles_w, int tile
                     const float* cf = coef + (cg.n / nPerG) * 32 + ch;
                     const float4 s0 = *reinterpret_cast<const float4*>(cf), s1 = *reinterpret_cast<const float4*>(cf + 4);
                     const float4 h0 = *reinterpret_cast<const float4*>(cf + 16), h1 = *reinterpret_cast<const float4*>(cf + 20);
-                    uint4 o1[3], o2[3];
+                    uint4 o1[XH], o2[XH];
 #pragma unroll
-                    for (int i = 0; i < 3; ++i) {
+                    for (int i = 0; i < XH; ++i) {
                         float v[8] = {ra[i].x, ra[i].y, ra[i].z, ra[i].w, rb[i].x, rb[i].y, rb[i].z, rb[i].w};
                         if (ok[i]) {
                             v[0] = fmaf(v[0], s0.x, h0.x); v[1] = fmaf(v[1], s0.y, h0.y); v[2] = fmaf(v[2], s0.z, h0.z); v[3] = fmaf(v[3], s0.w, h0.w);
@@ -198,12 +202,12 @@ wgrad3_tc4s2_kernel(SpConvDesc d, int nPerG, int G, int q, int tiles_w, int tile
                         waited = true;
                         if (pr) { const long long c2 = clock64(); pw0 += c2 - c1; c1 = c2; }
                     }
-                    unsigned char* dp = x_reg + (seq % NSLOT) * X_PLANE_B + (hy0 * 4 + xhalf) * RS + wx * 16;
+                    if (have) {
+                        unsigned char* dp = x_reg + (seq % NSLOT) * X_PLANE_B + xhalf * RS + wx * 16;
 #pragma unroll
-                    for (int i = 0; i < 3; ++i) {
-                        if (hy0 + 2 * i < XH) {
-                            *reinterpret_cast<uint4*>(dp + i * 8 * RS) = o1[i];
-                            *reinterpret_cast<uint4*>(dp + i * 8 * RS + 2 * RS) = o2[i];
+                        for (int i = 0; i < XH; ++i) {
+                            *reinterpret_cast<uint4*>(dp + i * 4 * RS) = o1[i];
+                            *reinterpret_cast<uint4*>(dp + i * 4 * RS + 2 * RS) = o2[i];
                         }
                     }
                 }
@@ -250,16 +254,20 @@ wgrad3_tc4s2_kernel(SpConvDesc d, int nPerG, int G, int q, int tiles_w, int tile
                 mbar_wait_warp(a_empty + 8 * buf, (use & 1) ^ 1);
                 if (pr) { const long long c2 = clock64(); pw0 += c2 - c1; c1 = c2; }
                 if (zact) {
-                    unsigned char* dp = a_reg + buf * A_BUF_B + zhalf * PS + (zj - 2) * 16;      // + kw' * (2 PS + 16) + row * TU * 16
+                    // slot 0 = kw 0 <- dZ[j + 1] (k = zj - 2), slot 1 = kw 2 <- dZ[j] (k = zj - 1): odd columns; slot 2 = kw 1 <- dZ[j]
+                    // (k = zj - 1): even columns; the other parity's slots get zeros (every (slot, k) is written every step)
+                    unsigned char* dp = a_reg + buf * A_BUF_B + zhalf * PS;
+                    const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
-                    for (int kw = 0; kw < 2; ++kw) {                     // kw' = 2 belongs to neither parity
-                        const int k = zj - 2 + kw;
-                        if (k >= 0 && k < TU && (kw == 1 || q == 1)) {
+                    for (int slot = 0; slot < 3; ++slot) {
+                        const int k = zj - (slot == 0 ? 2 : 1);
+                        const bool data = (slot == 2) ? (q == 0) : (q == 1);
+                        if (k >= 0 && k < TU) {
 #pragma unroll
                             for (int i = 0; i < THW; ++i) {
-                                unsigned char* p8 = dp + kw * (2 * PS + 16) + i * (TU * 16);
-                                *reinterpret_cast<uint4*>(p8) = o1[i];
-                                *reinterpret_cast<uint4*>(p8 + 6 * PS) = o2[i];
+                                unsigned char* p8 = dp + slot * 2 * PS + k * 16 + i * (TU * 16);
+                                *reinterpret_cast<uint4*>(p8) = data ? o1[i] : z4;
+                                *reinterpret_cast<uint4*>(p8 + 6 * PS) = data ? o2[i] : z4;
                             }
                         }
                     }
@@ -356,8 +364,7 @@ wgrad3_tc4s2_kernel(SpConvDesc d, int nPerG, int G, int q, int tiles_w, int tile
     __syncthreads();
     tc_fence_after();
     if (warp == 0) tmem_dealloc<512>(tmem_base);
-    // fold the two y terms (small first); this CTA's partial as [co][ci][kd][kh][kw'] (the reduce kernel maps kw' to the taps
-    // of the launch's parity)
+    // fold the two y terms (small first); this CTA's partial as [co][ci][kd][kh][slot] (slot -> kw in wgrad_reduce_s2_kernel)
     const int wn = d.Co * d.Ci * 27;
     float* wsp = ws + (int64_t)blockIdx.x * wn;
     for (int i = tid; i < wn; i += NTHREADS_S2) {
@@ -369,42 +376,34 @@ wgrad3_tc4s2_kernel(SpConvDesc d, int nPerG, int G, int q, int tiles_w, int tile
     }
 }
 
-// dw[co0 + co][ci0 + ci][kd][kh][kw] = beta * dw + sum_chunks ws[chunk][co][ci][kd][kh][kw'] for the taps of parity q:
-// q = 0: kw = 1 <- kw' = 1;   q = 1: kw = 0 <- kw' = 0, kw = 2 <- kw' = 1
-__global__ void wgrad_reduce_s2_kernel(const float* __restrict__ ws, int chunks, int cos, int cs, int Ci, int co0, int ci0, int q,
+// dw[co0 + co][ci0 + ci][kd][kh][kw] = beta * dw + sum_chunks ws[chunk][co][ci][kd][kh][slot], slot 0 / 1 / 2 = kw 0 / 2 / 1
+__global__ void wgrad_reduce_s2_kernel(const float* __restrict__ ws, int chunks, int cos, int cs, int Ci, int co0, int ci0,
                                        float* __restrict__ dw, float beta) {
-    const int ntap = q ? 18 : 9;
-    const int total = cos * cs * ntap;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= total) return;
-    const int t = i % ntap, ci = (i / ntap) % cs, co = i / (ntap * cs);
-    const int kdh = q ? t / 2 : t;                      // kd * 3 + kh
-    const int kwp = q ? 1 - (t & 1) : 1;                // kw' (q = 1: t even -> kw' 1 -> kw 2; t odd -> kw' 0 -> kw 0)
-    const int kw = q ? (kwp == 1 ? 2 : 0) : 1;
     const int wn = cos * cs * 27;
-    const int src = (co * cs + ci) * 27 + kdh * 3 + kwp;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= wn) return;
+    const int tap = i % 27, ci = (i / 27) % cs, co = i / (27 * cs);
+    const int slot = tap % 3, kw = slot == 0 ? 0 : (slot == 1 ? 2 : 1);
     float s = 0.f;
-    for (int c = 0; c < chunks; ++c) s += ws[(int64_t)c * wn + src];
-    float* o = dw + ((int64_t)(co0 + co) * Ci + ci0 + ci) * 27 + kdh * 3 + kw;
+    for (int c = 0; c < chunks; ++c) s += ws[(int64_t)c * wn + i];
+    float* o = dw + ((int64_t)(co0 + co) * Ci + ci0 + ci) * 27 + (tap - slot) + kw;
     *o = (beta != 0.f ? beta * *o : 0.f) + s;
 }
 
 struct Plan {
-    int tiles_w[2], tiles_h, grid[2];
-    int64_t total[2];
+    int tiles_w[2], tiles_h, grid;
+    int64_t total0, total;      // tile columns of parity 0 / of both parities
 };
 static inline Plan plan(const SpConvDesc* d) {
     Plan p;
     p.tiles_h = (d->Ho + THW - 1) / THW;
+    for (int q = 0; q < 2; ++q) p.tiles_w[q] = ((d->Wi + 1 - q) / 2 + TU - 1) / TU;      // input columns of parity q, 32 per tile
+    p.total0 = (int64_t)p.tiles_w[0] * p.tiles_h * d->N;
+    p.total = p.total0 + (int64_t)p.tiles_w[1] * p.tiles_h * d->N;
+    p.grid = sp_num_sms();
     const int cap = sp_wtc4_grid_cap_ref();
-    for (int q = 0; q < 2; ++q) {
-        const int nj = (d->Wi + 1 - q) / 2;                             // input columns of parity q
-        p.tiles_w[q] = (nj + TU - 1) / TU;
-        p.total[q] = (int64_t)p.tiles_w[q] * p.tiles_h * d->N;
-        p.grid[q] = sp_num_sms();
-        if (cap > 0 && p.grid[q] > cap) p.grid[q] = cap;
-        if (p.grid[q] > p.total[q]) p.grid[q] = (int)p.total[q];
-    }
+    if (cap > 0 && p.grid > cap) p.grid = cap;
+    if (p.grid > p.total) p.grid = (int)p.total;
     return p;
 }
 
@@ -418,18 +417,16 @@ static inline bool sp_tc4s2_wgrad_supported(const SpConvDesc* d, int G) {
     if (d->Ci <= 8 || d->Ci > 16 || d->Co <= 8 || d->Co > 32 || d->ldi % 4 != 0 || d->ldo % 4 != 0) return false;
     if (d->Wi < 2 || d->Do < 4 || d->Wo < 16) return false;
     const sp_wtc4s2::Plan p = sp_wtc4s2::plan(d);
-    return p.total[1] >= 16 && p.total[0] < (1LL << 31) / (2 * d->Do + 1);
+    return p.total >= 32 && p.total < (1LL << 31) / (2 * d->Do + 1);
 }
 
 static inline size_t sp_tc4s2_wgrad_workspace_bytes(const SpConvDesc* d) {
-    const sp_wtc4s2::Plan p = sp_wtc4s2::plan(d);
-    const int g = p.grid[0] > p.grid[1] ? p.grid[0] : p.grid[1];
-    return (size_t)g * 16 * 16 * 27 * sizeof(float);                    // one (slice, parity) launch at a time (stream-ordered reuse)
+    return (size_t)sp_wtc4s2::plan(d).grid * 16 * 16 * 27 * sizeof(float);       // one output slice at a time (stream-ordered reuse)
 }
 
 static inline int sp_tc4s2_wgrad_launch(const SpConvDesc* d, int nPerG, const float* iside, const float* i_scale, const float* i_shift,
                                         const float* oside, const float* o_scale, const float* o_shift, float* dw, float beta, float* ws,
-                                        cudaStream_t st, long long* prof = nullptr, int drain_every = 6) {
+                                        cudaStream_t st, long long* prof = nullptr, int drain_every = 12) {   // 12 steps x 4 MMAs = the 48 accumulations per drain of sp_wgrad_tc4.cuh
     using namespace sp_wtc4s2;
     const Plan p = plan(d);
     static bool attr = false;
@@ -439,18 +436,17 @@ static inline int sp_tc4s2_wgrad_launch(const SpConvDesc* d, int nPerG, const fl
     }
     const int G = d->N / nPerG;
     const int nso = (d->Co + 15) / 16;
-    for (int co = 0; co < nso; ++co)
-        for (int q = 0; q < 2; ++q) {
-            SpConvDesc s = *d;
-            s.Co = (d->Co - 16 * co < 16) ? d->Co - 16 * co : 16;
-            wgrad3_tc4s2_kernel<<<p.grid[q], NTHREADS_S2, SMEM, st>>>(s, nPerG, G, q, p.tiles_w[q], p.tiles_h, (int)p.total[q], drain_every, d->Ci,
-                                                                   d->Co, iside, i_scale, i_shift, oside + 16 * co,
-                                                                   o_scale ? o_scale + 16 * co : nullptr, o_shift ? o_shift + 16 * co : nullptr,
-                                                                   ws, (co == 0 && q == 1) ? prof : nullptr, sp_tc_terms() == 1 ? 1 : 2);
-            SP_LAUNCH_OK("wgrad3_tc4s2_kernel");
-            const int total = s.Co * s.Ci * (q ? 18 : 9);
-            wgrad_reduce_s2_kernel<<<(total + 255) / 256, 256, 0, st>>>(ws, p.grid[q], s.Co, s.Ci, d->Ci, 16 * co, 0, q, dw, beta);
-            SP_LAUNCH_OK("wgrad_reduce_s2_kernel");
-        }
+    for (int co = 0; co < nso; ++co) {
+        SpConvDesc s = *d;
+        s.Co = (d->Co - 16 * co < 16) ? d->Co - 16 * co : 16;
+        wgrad3_tc4s2_kernel<<<p.grid, NTHREADS_S2, SMEM, st>>>(s, nPerG, G, (int)p.total0, p.tiles_w[0], p.tiles_w[1], p.tiles_h, (int)p.total,
+                                                               drain_every, d->Ci, d->Co, iside, i_scale, i_shift, oside + 16 * co,
+                                                               o_scale ? o_scale + 16 * co : nullptr, o_shift ? o_shift + 16 * co : nullptr, ws,
+                                                               co == 0 ? prof : nullptr, sp_tc_terms() == 1 ? 1 : 2);
+        SP_LAUNCH_OK("wgrad3_tc4s2_kernel");
+        const int wn = s.Co * s.Ci * 27;
+        wgrad_reduce_s2_kernel<<<(wn + 255) / 256, 256, 0, st>>>(ws, p.grid, s.Co, s.Ci, d->Ci, 16 * co, 0, dw, beta);
+        SP_LAUNCH_OK("wgrad_reduce_s2_kernel");
+    }
     return 0;
 }

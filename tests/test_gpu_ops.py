@@ -237,8 +237,8 @@ def test_tensor_core_wgrad_paths(case):
 
 
 WGRAD_TC_S2_CASES = [
-    # the stride-2 tcgen05 weight gradient (sp_wgrad_tc4s2.cuh): 3x3x3 stride 2 padding 1, 9..16 input channels; one launch per
-    # input-column parity and 16-channel output slice
+    # the stride-2 tcgen05 weight gradient (sp_wgrad_tc4s2.cuh): 3x3x3 stride 2 padding 1, 9..16 input channels; tile columns of
+    # both input-column parities in one launch per 16-channel output slice
     ("C", 16, 24, 3, 2, 1, "elu", (16, 36, 70)),          # Cae3D.py:48   even extents, two column tiles per parity
     ("C", 16, 24, 3, 2, 1, "elu", (17, 23, 67)),          # odd extents on every axis: ragged last plane / row / column
     ("C", 12, 16, 3, 2, 1, "leaky", (16, 20, 66)),        # ragged channel half on the I-side, one output slice
@@ -249,7 +249,7 @@ WGRAD_TC_S2_CASES = [
 @pytest.mark.parametrize("max_ctas", [0, 3])
 @pytest.mark.parametrize("case", WGRAD_TC_S2_CASES, ids=lambda c: "%s%d-%d_%s" % (c[0], c[1], c[2], "x".join(map(str, c[7]))))
 def test_tensor_core_wgrad_stride2(case, max_ctas):
-    """dW of the stride-2 layer from tcgen05 MMAs: input columns split by parity (one launch each), rows / planes read at stride
+    """dW of the stride-2 layer from tcgen05 MMAs: input columns split by parity (tap slots along M), rows / planes read at stride
     two through the N-group base and a ring that advances two planes per step; also with three CTAs (many columns per CTA)."""
     _, _, ops = _mods()
     kind, cin, cout, k, s, p, act, size = case
