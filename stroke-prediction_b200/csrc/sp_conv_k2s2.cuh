@@ -11,6 +11,13 @@
 #pragma once
 #include "sp_common.cuh"
 
+#ifndef SP_K2S2_UP_MINB
+// resident CTAs per SM asked of ptxas (ncu r02: latency-bound at 24 % occupancy with 91 registers; three CTAs: 0.697 -> 0.674 ms;
+// the down kernel got slower with four: 0.588 -> 0.607 ms)
+#define SP_K2S2_UP_MINB 3
+#define SP_K2S2_DOWN_MINB 1
+#define SP_K2S2_WGRAD_MINB 2
+#endif
 namespace sp_k2s2 {
 
 constexpr int NT = 256;
@@ -18,7 +25,7 @@ constexpr int NT = 256;
 // src = O-side [N][Do][Ho][Wo][ldo] (Co channels, optional affine), dst = I-side [N][2Do][2Ho][2Wo][ldi] (Ci channels).
 // wt: Wt[tap][co][ciP].  Shared memory: 8 * Co * ciP floats.
 template <int SQ>      // source channel quads (Co / 4): all loads of a voxel are issued before the first FMA
-__global__ void __launch_bounds__(NT)
+__global__ void __launch_bounds__(NT, SP_K2S2_UP_MINB)
 k2s2_up_kernel(SpConvDesc d, int nPerG, int ciP, const float* __restrict__ src, const float* __restrict__ wt,
                const float* __restrict__ bias, const float* __restrict__ scale, const float* __restrict__ shift, float* __restrict__ dst) {
     extern __shared__ __align__(16) float wsm[];
@@ -81,7 +88,7 @@ k2s2_up_kernel(SpConvDesc d, int nPerG, int ciP, const float* __restrict__ src, 
 
 // src = I-side (Ci channels, optional affine), dst = O-side (Co channels).  wc: Wc[tap][ci][coP].  Shared memory: 8 * Ci * coP floats.
 template <int SQ>      // source channel quads (Ci / 4)
-__global__ void __launch_bounds__(NT)
+__global__ void __launch_bounds__(NT, SP_K2S2_DOWN_MINB)
 k2s2_down_kernel(SpConvDesc d, int nPerG, int coP, const float* __restrict__ src, const float* __restrict__ wc,
                  const float* __restrict__ bias, const float* __restrict__ scale, const float* __restrict__ shift, float* __restrict__ dst) {
     extern __shared__ __align__(16) float wsm[];
@@ -138,7 +145,7 @@ k2s2_down_kernel(SpConvDesc d, int nPerG, int coP, const float* __restrict__ src
 }
 
 // ws[cta][co][ci][8].  blockIdx.y = pass over 16 output channels.  LPV = 8 * Ci/4 threads per voxel.
-__global__ void __launch_bounds__(NT, 2)
+__global__ void __launch_bounds__(NT, SP_K2S2_WGRAD_MINB)
 k2s2_wgrad_kernel(SpConvDesc d, int nPerG, const float* __restrict__ iside, const float* __restrict__ i_scale,
                   const float* __restrict__ i_shift, const float* __restrict__ oside, const float* __restrict__ o_scale,
                   const float* __restrict__ o_shift, float* __restrict__ ws) {

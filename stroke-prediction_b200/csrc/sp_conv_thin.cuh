@@ -11,6 +11,11 @@
 #pragma once
 #include "sp_common.cuh"
 
+#ifndef SP_THIN_FWD_MINB
+#define SP_THIN_FWD_MINB 2
+#define SP_THIN_BWD_MINB 2
+#define SP_THIN_WGRAD_MINB 1
+#endif
 namespace sp_thin {
 
 constexpr int TW = 32, TH = 8, TD = 4;           // forward output tile
@@ -21,7 +26,7 @@ constexpr int NT = 256;
 // ---------------------------------------------------------------------------------------------------------------- forward
 // wp: packed [tap][ci][coP]; flip != 0 reads tap 26 - t.  blockIdx.y = pass over 16 output channels.
 template <int CI>
-__global__ void __launch_bounds__(NT, 2)
+__global__ void __launch_bounds__(NT, SP_THIN_FWD_MINB)
 thin_fwd_kernel(SpConvDesc d, int nPerG, int coP, int tiles_w, int tiles_h, int tiles_d, const float* __restrict__ src,
                 const float* __restrict__ wp, int flip, const float* __restrict__ bias, const float* __restrict__ scale,
                 const float* __restrict__ shift, float* __restrict__ dst) {
@@ -127,7 +132,7 @@ constexpr int BRW = BXW | 1;                     // odd row stride (float4 units
 constexpr int BPLANE = BXD * BXH * BRW + 1;      // quad plane stride, 16 bytes off a multiple of 128
 constexpr size_t BWD_SMEM = (size_t)4 * BPLANE * 16;
 
-__global__ void __launch_bounds__(BNT, 2)
+__global__ void __launch_bounds__(BNT, SP_THIN_BWD_MINB)
 thin_bwd_kernel(SpConvDesc f, int nPerG, int ciP, int tiles_w, int tiles_h, int tiles_d, const float* __restrict__ src,
                 const float* __restrict__ wt, const float* __restrict__ bias, const float* __restrict__ scale,
                 const float* __restrict__ shift, float* __restrict__ dst) {
@@ -266,7 +271,7 @@ thin_bwd_kernel(SpConvDesc f, int nPerG, int ciP, int tiles_w, int tiles_h, int 
 // rounded up to a power of two), 32 / LPV rows per warp (consecutive oh: their input rows overlap in L1).
 // ws[cta][co][ci][27].
 template <int CIP>
-__global__ void __launch_bounds__(NT, 1)
+__global__ void __launch_bounds__(NT, SP_THIN_WGRAD_MINB)
 thin_wgrad_kernel(SpConvDesc d, int nPerG, int64_t total_rows, const float* __restrict__ X, const float* __restrict__ i_scale,
                   const float* __restrict__ i_shift, const float* __restrict__ dZ, const float* __restrict__ o_scale,
                   const float* __restrict__ o_shift, float* __restrict__ ws) {

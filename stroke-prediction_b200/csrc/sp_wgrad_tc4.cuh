@@ -515,7 +515,7 @@ static inline bool sp_tc4_wgrad_supported(const SpConvDesc* d, int G) {
     if (d->Ci <= 8 || d->Ci > 16 || d->Co <= 8 || d->Co > 16) return false;
     if (d->pd > 2 || d->ph > 2 || d->pw > 2) return false;
     const sp_wtc4::Wtc4Plan p = sp_wtc4::plan(d);
-    return p.total >= 16 && p.total < (1LL << 31) / (d->Do + 2) && d->Wo >= 24 && d->Do >= 8;
+    return p.total >= 16 && p.total < (1LL << 31) / (d->Do + 2) && d->Wo >= 24 && d->Do >= 4;
 }
 
 static inline size_t sp_tc4_wgrad_workspace_bytes(const SpConvDesc* d) {
@@ -567,10 +567,9 @@ static inline bool sp_tc4_wgrad_sliced_supported(const SpConvDesc* d, int G) {
     }
     if (((d->Ci + 15) / 16) * ((d->Co + 15) / 16) > maxpairs) return false;
     if (d->Ci <= 8 || d->Ci > 96 || d->Co <= 8 || d->Co > 64 || d->ldi % 4 != 0 || d->ldo % 4 != 0) return false;
-    if (!is24 && ((d->Ci % 16 != 0 && d->Ci % 16 <= 8) || (d->Co % 16 != 0 && d->Co % 16 <= 8))) return false;   // a tail slice of <= 8 channels
     if (d->pd > 2 || d->ph > 2 || d->pw > 2) return false;
     const sp_wtc4::Wtc4Plan p = sp_wtc4::plan(d);
-    return p.total >= 16 && p.total < (1LL << 31) / (d->Do + 2) && d->Wo >= 24 && d->Do >= 8;
+    return p.total >= 16 && p.total < (1LL << 31) / (d->Do + 2) && d->Wo >= 24 && d->Do >= 4;
 }
 
 static inline size_t sp_tc4_wgrad_sliced_workspace_bytes(const SpConvDesc* d) {

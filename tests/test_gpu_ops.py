@@ -222,6 +222,7 @@ WGRAD_TC_CASES = [
     ("C", 32, 32, 3, 1, 0, "leaky", (10, 18, 40)),             # 2 x 2 slice pairs (second generation: up to twelve pairs)
     ("C", 96, 32, 3, 1, 0, "leaky", (10, 18, 40)),             # Unet3D.py:19 block4: 6 x 2 = 12 slice pairs
     ("C", 64, 64, 3, 1, 0, "leaky", (10, 18, 40)),             # Unet3D.py:22 block3: 16 pairs -> stays on the FFMA tier
+    ("C", 32, 32, 3, 1, (1, 2, 2), "elu", (5, 25, 25)),        # Cae3D.py:186: shallow volume (Do = 5), one column tile, 4 pairs
 ]
 
 
