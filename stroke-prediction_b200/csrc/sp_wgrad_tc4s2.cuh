@@ -73,7 +73,7 @@ __device__ __forceinline__ ColGeo col_geo(int col, int total0, int tiles_w0, int
 }
 
 __global__ void __launch_bounds__(NTHREADS_S2, 1)
-wgrad3_tc4s2_kernel(SpConvDesc d, int nPerG, int G, int total0, int tiles_w0, int tiles_w1, int tiles_h, int total_cols, int drain_every, int isstride,
+wgrad3_tc4s2_kernel(SpConvDesc d, int kk, int nPerG, int G, int total0, int tiles_w0, int tiles_w1, int tiles_h, int total_cols, int drain_every, int isstride,
                     int osstride, const float* __restrict__ X, const float* __restrict__ i_scale, const float* __restrict__ i_shift,
                     const float* __restrict__ dZ, const float* __restrict__ o_scale, const float* __restrict__ o_shift,
                     float* __restrict__ ws, long long* __restrict__ prof, int nt) {
@@ -99,7 +99,7 @@ wgrad3_tc4s2_kernel(SpConvDesc d, int nPerG, int G, int total0, int tiles_w0, in
     if (tid == 0) {
         for (int b = 0; b < NBUF; ++b) {
             mbar_init(smem_u32(&bars[b]), W_STG_G);
-            mbar_init(smem_u32(&bars[NBUF + b]), NBLK);
+            mbar_init(smem_u32(&bars[NBUF + b]), kk);                  // a_empty[b]: one commit per active issuer (kd < kk)
         }
         for (int b = 0; b < NBLK; ++b) {
             mbar_init(smem_u32(&bars[2 * NBUF + b]), 1);
@@ -120,7 +120,9 @@ wgrad3_tc4s2_kernel(SpConvDesc d, int nPerG, int G, int total0, int tiles_w0, in
     const int Do = d.Do;
     const int nsteps = ncols * Do;
     const int ndrains = (nsteps + drain_every - 1) / drain_every;
-    const int PPC = 2 * Do + 1;                                         // planes per column in the ring's sequence numbering
+    const int pad = kk - 2;                                             // k3: padding 1, k2: padding 0 (both: input index 2 o - pad + tap)
+    const int PPC = 2 * Do + pad;                                       // planes per column in the ring's sequence numbering
+    const int xh = 2 * THW + pad;                                       // input rows of a tile that are read
 
     if (warp >= W_EPI + W_MMA) {
         // =================================================================== staging: group grp takes the steps it = grp (mod NGRP)
@@ -149,14 +151,14 @@ wgrad3_tc4s2_kernel(SpConvDesc d, int nPerG, int G, int total0, int tiles_w0, in
                 // highest of these (window base + 2 - 8 = base - 6) was last read by the step three before (whose window reaches
                 // its base + 2 = this base - 4 >= base - 6 ... base - 5 within a column, and across a column change — where the
                 // base jumps by three — by the step three before as well): that step's MMAs have been waited for (a_empty).
-                const int np = (od == 0) ? 3 : 2;
+                const int np = (od == 0 && kk == 3) ? 3 : 2;          // k2: windows do not overlap, planes 2 od and 2 od + 1
 #pragma unroll 1
                 for (int round = 0; round * 2 < np; ++round) {
                     const int pidx = round * 2 + xp;                    // newest plane first; index 2 only at od == 0 (plane 0)
                     const bool have = pidx < np;
-                    const int pj = 2 * od + 2 - pidx;
+                    const int pj = 2 * od + kk - 1 - pidx;
                     const int seq = cl * PPC + pj;
-                    const int gd = pj - 1, gw = 2 * (cg.j0 + wx) + q, gh0 = 2 * cg.oh0 - 1;
+                    const int gd = pj - pad, gw = 2 * (cg.j0 + wx) + q, gh0 = 2 * cg.oh0 - pad;
                     const int ch = xhalf * 8;
                     const bool okp = have && gd >= 0 && gd < d.Di && gw < d.Wi;
                     const float* pp = X + (int64_t)cg.n * xs_n + (((int64_t)gd * d.Hi + gh0) * d.Wi + gw) * d.ldi + ch;
@@ -166,7 +168,7 @@ wgrad3_tc4s2_kernel(SpConvDesc d, int nPerG, int G, int total0, int tiles_w0, in
 #pragma unroll
                     for (int i = 0; i < XH; ++i) {
                         const int gh = gh0 + i;
-                        ok[i] = okp && gh >= 0 && gh < d.Hi;
+                        ok[i] = okp && i < xh && gh >= 0 && gh < d.Hi;
                         ra[i] = make_float4(0.f, 0.f, 0.f, 0.f);
                         rb[i] = ra[i];
                         if (ok[i]) {
@@ -261,7 +263,8 @@ wgrad3_tc4s2_kernel(SpConvDesc d, int nPerG, int G, int total0, int tiles_w0, in
 #pragma unroll
                     for (int slot = 0; slot < 3; ++slot) {
                         const int k = zj - (slot == 0 ? 2 : 1);
-                        const bool data = (slot == 2) ? (q == 0) : (q == 1);
+                        // k2: slot 2 = kw 0 <- dZ[j] (even columns), slot 1 = kw 1 <- dZ[j] (odd columns), slot 0 unused
+                        const bool data = (slot == 2) ? (q == 0) : (q == 1 && (kk == 3 || slot == 1));
                         if (k >= 0 && k < TU) {
 #pragma unroll
                             for (int i = 0; i < THW; ++i) {
@@ -286,10 +289,10 @@ wgrad3_tc4s2_kernel(SpConvDesc d, int nPerG, int G, int total0, int tiles_w0, in
             const int kd = warp_uniform(warp - W_EPI);
             const uint32_t a_base = smem_u32(a_reg), x_base = smem_u32(x_reg);
             const uint32_t dcol = tmem_base + (uint32_t)(kd * BCOLS);
-            constexpr uint32_t IDESC = idesc_mn(128, BCOLS);
+            const uint32_t IDESC = idesc_mn(128, kk * 32);                  // N = (kh < kk, term, ci)
             bool fresh = true;
             int drains = 0;
-            for (int it = 0; it < nsteps; ++it) {
+            for (int it = 0; it < (kd < kk ? nsteps : 0); ++it) {
                 const int buf = it % NBUF, use = it / NBUF;
                 const int cl = it / Do, od = it - cl * Do;
                 long long c0 = pr ? clock64() : 0;
@@ -300,7 +303,7 @@ wgrad3_tc4s2_kernel(SpConvDesc d, int nPerG, int G, int total0, int tiles_w0, in
                 long long c2 = pr ? clock64() : 0;
                 pw1 += c2 - c1;
                 tc_fence_after();
-                const int slot = (cl * PPC + 2 * od + kd) % NSLOT;     // input plane 2 od - 1 + kd of this column
+                const int slot = (cl * PPC + 2 * od + kd) % NSLOT;     // input plane 2 od - pad + kd of this column
                 const uint64_t da0 = umma_desc(a_base + (uint32_t)(buf * A_BUF_B), 128, PS);
                 const uint64_t db0 = umma_desc(x_base + (uint32_t)(slot * X_PLANE_B), 128, RS);
 #pragma unroll
@@ -328,17 +331,17 @@ wgrad3_tc4s2_kernel(SpConvDesc d, int nPerG, int G, int total0, int tiles_w0, in
         float* arow = acc + (size_t)(warp * 32 + lane) * ACC_LD;
         for (int dr = 0; dr < ndrains; ++dr) {
 #pragma unroll 1
-            for (int kd = 0; kd < NBLK; ++kd) {
+            for (int kd = 0; kd < kk; ++kd) {
                 long long c0 = pr ? clock64() : 0;
                 mbar_wait_warp(t_full + 8 * kd, dr & 1);
                 long long c1 = pr ? clock64() : 0;
                 pw0 += c1 - c0;
                 tc_fence_after();
 #pragma unroll 1
-                for (int kh = 0; kh < 3; ++kh) {
+                for (int kh = 0; kh < kk; ++kh) {
                     float v[32];
                     tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(kd * BCOLS + kh * 32), v);
-                    if (kh == 2) {
+                    if (kh == kk - 1) {
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) mbar_arrive(t_empty + 8 * kd);
@@ -376,17 +379,22 @@ wgrad3_tc4s2_kernel(SpConvDesc d, int nPerG, int G, int total0, int tiles_w0, in
     }
 }
 
-// dw[co0 + co][ci0 + ci][kd][kh][kw] = beta * dw + sum_chunks ws[chunk][co][ci][kd][kh][slot], slot 0 / 1 / 2 = kw 0 / 2 / 1
-__global__ void wgrad_reduce_s2_kernel(const float* __restrict__ ws, int chunks, int cos, int cs, int Ci, int co0, int ci0,
+// dw[co0 + co][ci0 + ci][kd][kh][kw] (kk^3 taps) = beta * dw + sum_chunks ws[chunk][co][ci][(kd * 3 + kh) * 3 + slot];
+// k3: slot 0 / 1 / 2 = kw 0 / 2 / 1;  k2: slot 2 / 1 = kw 0 / 1
+__global__ void wgrad_reduce_s2_kernel(const float* __restrict__ ws, int chunks, int cos, int cs, int Ci, int co0, int ci0, int kk,
                                        float* __restrict__ dw, float beta) {
-    const int wn = cos * cs * 27;
+    const int k3 = kk * kk * kk;
+    const int total = cos * cs * k3;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= wn) return;
-    const int tap = i % 27, ci = (i / 27) % cs, co = i / (27 * cs);
-    const int slot = tap % 3, kw = slot == 0 ? 0 : (slot == 1 ? 2 : 1);
+    if (i >= total) return;
+    const int tap = i % k3, ci = (i / k3) % cs, co = i / (k3 * cs);
+    const int kw = tap % kk, kh = (tap / kk) % kk, kd = tap / (kk * kk);
+    const int slot = (kk == 3) ? (kw == 0 ? 0 : (kw == 2 ? 1 : 2)) : (kw == 0 ? 2 : 1);
+    const int wn = cos * cs * 27;
+    const int src = (co * cs + ci) * 27 + (kd * 3 + kh) * 3 + slot;
     float s = 0.f;
-    for (int c = 0; c < chunks; ++c) s += ws[(int64_t)c * wn + i];
-    float* o = dw + ((int64_t)(co0 + co) * Ci + ci0 + ci) * 27 + (tap - slot) + kw;
+    for (int c = 0; c < chunks; ++c) s += ws[(int64_t)c * wn + src];
+    float* o = dw + ((int64_t)(co0 + co) * Ci + ci0 + ci) * k3 + tap;
     *o = (beta != 0.f ? beta * *o : 0.f) + s;
 }
 
@@ -409,12 +417,16 @@ static inline Plan plan(const SpConvDesc* d) {
 
 }  // namespace sp_wtc4s2
 
-// Cae3D.py:48 (16 -> 24) and every other 3x3x3 stride-2 padding-1 layer with 9..16 input channels
+// Cae3D.py:48 (16 -> 24), Cae3D.py:59 (24 -> 32): 3x3x3 stride-2 padding-1 layers, and the decoder's ConvTranspose3d k2 s2 steps
+// (Cae3D.py:193,204: 24 -> 24, 16 -> 16; kk = 2: two taps per axis, no overlap between windows), 9..32 channels, as slices of 16
 static inline bool sp_tc4s2_wgrad_supported(const SpConvDesc* d, int G) {
     if (sp_tc4_wgrad_disabled() || G < 1 || G > sp_wtc4s2::MAXG) return false;
-    if (d->k != 3 || d->s != 2 || sp_tc_terms() == 0 || sp_tc_wgrad_disabled()) return false;
-    if (d->pd != 1 || d->ph != 1 || d->pw != 1) return false;
-    if (d->Ci <= 8 || d->Ci > 16 || d->Co <= 8 || d->Co > 32 || d->ldi % 4 != 0 || d->ldo % 4 != 0) return false;
+    if ((d->k != 3 && d->k != 2) || d->s != 2 || sp_tc_terms() == 0 || sp_tc_wgrad_disabled()) return false;
+    const int pad = d->k - 2;                                            // Conv3d(k3, s2, p1) / ConvTranspose3d(k2, s2, p0)
+    if (d->pd != pad || d->ph != pad || d->pw != pad) return false;
+    // k2 layers with more than 16 channels stay on sp_conv_k2s2.cuh: measured 0.29 (k2s2 kernel) vs 0.37 ms (2 x 2 slices) on Cae3D.py:193
+    if (d->k == 2 && (d->Ci > 16 || d->Co > 16)) return false;
+    if (d->Ci <= 8 || d->Ci > 32 || d->Co <= 8 || d->Co > 32 || d->ldi % 4 != 0 || d->ldo % 4 != 0) return false;   // up to 2 x 2 slices
     if (d->Wi < 2 || d->Do < 4 || d->Wo < 16) return false;
     const sp_wtc4s2::Plan p = sp_wtc4s2::plan(d);
     return p.total >= 32 && p.total < (1LL << 31) / (2 * d->Do + 1);
@@ -435,18 +447,21 @@ static inline int sp_tc4s2_wgrad_launch(const SpConvDesc* d, int nPerG, const fl
         attr = true;
     }
     const int G = d->N / nPerG;
-    const int nso = (d->Co + 15) / 16;
-    for (int co = 0; co < nso; ++co) {
-        SpConvDesc s = *d;
-        s.Co = (d->Co - 16 * co < 16) ? d->Co - 16 * co : 16;
-        wgrad3_tc4s2_kernel<<<p.grid, NTHREADS_S2, SMEM, st>>>(s, nPerG, G, (int)p.total0, p.tiles_w[0], p.tiles_w[1], p.tiles_h, (int)p.total,
-                                                               drain_every, d->Ci, d->Co, iside, i_scale, i_shift, oside + 16 * co,
-                                                               o_scale ? o_scale + 16 * co : nullptr, o_shift ? o_shift + 16 * co : nullptr, ws,
-                                                               co == 0 ? prof : nullptr, sp_tc_terms() == 1 ? 1 : 2);
-        SP_LAUNCH_OK("wgrad3_tc4s2_kernel");
-        const int wn = s.Co * s.Ci * 27;
-        wgrad_reduce_s2_kernel<<<(wn + 255) / 256, 256, 0, st>>>(ws, p.grid, s.Co, s.Ci, d->Ci, 16 * co, 0, dw, beta);
-        SP_LAUNCH_OK("wgrad_reduce_s2_kernel");
-    }
+    const int nsi = (d->Ci + 15) / 16, nso = (d->Co + 15) / 16;
+    for (int co = 0; co < nso; ++co)
+        for (int c = 0; c < nsi; ++c) {
+            SpConvDesc s = *d;
+            s.Ci = (d->Ci - 16 * c < 16) ? d->Ci - 16 * c : 16;
+            s.Co = (d->Co - 16 * co < 16) ? d->Co - 16 * co : 16;
+            wgrad3_tc4s2_kernel<<<p.grid, NTHREADS_S2, SMEM, st>>>(s, d->k, nPerG, G, (int)p.total0, p.tiles_w[0], p.tiles_w[1], p.tiles_h, (int)p.total,
+                                                                   drain_every, d->Ci, d->Co, iside + 16 * c, i_scale ? i_scale + 16 * c : nullptr,
+                                                                   i_shift ? i_shift + 16 * c : nullptr, oside + 16 * co,
+                                                                   o_scale ? o_scale + 16 * co : nullptr, o_shift ? o_shift + 16 * co : nullptr, ws,
+                                                                   (co == 0 && c == 0) ? prof : nullptr, sp_tc_terms() == 1 ? 1 : 2);
+            SP_LAUNCH_OK("wgrad3_tc4s2_kernel");
+            const int wn = s.Co * s.Ci * d->k * d->k * d->k;
+            wgrad_reduce_s2_kernel<<<(wn + 255) / 256, 256, 0, st>>>(ws, p.grid, s.Co, s.Ci, d->Ci, 16 * co, 16 * c, d->k, dw, beta);
+            SP_LAUNCH_OK("wgrad_reduce_s2_kernel");
+        }
     return 0;
 }

@@ -164,13 +164,21 @@ STRIDED_TILED_CASES = [
 ]
 
 
+@pytest.mark.parametrize("wgrad_generation", [2, 1])
 @pytest.mark.parametrize("case", STRIDED_TILED_CASES, ids=lambda c: "%s%d-%d_k%dp%s" % (c[0], c[1], c[2], c[3], str(c[5]).replace(" ", "")))
-def test_strided_tiled_paths(case):
+def test_strided_tiled_paths(case, wgrad_generation):
+    """wgrad_generation 2: the weight gradients of the 9..32-channel k3 s2 p1 / k2 s2 layers come from the stride-2 tcgen05 kernel
+    (sp_wgrad_tc4s2.cuh); 1: from the FFMA tiers (tiled / k2s2 kernels), which stay the fallback for every other geometry."""
+    _, _, ops = _mods()
     kind, cin, cout, k, s, p, act, size = case
     torch.manual_seed(400 + STRIDED_TILED_CASES.index(case))
     conv = nn.ConvTranspose3d(cin, cout, k, stride=s, padding=p) if kind == "T" else nn.Conv3d(cin, cout, k, stride=s, padding=p)
     x = torch.randn(2, cin, *size) * 1.5 + 0.3
-    _check_sequential(nn.Sequential(nn.BatchNorm3d(cin), conv, _act(act)), x, G=2)
+    ops.set_wgrad_tc_options(wgrad_generation, 0)
+    try:
+        _check_sequential(nn.Sequential(nn.BatchNorm3d(cin), conv, _act(act)), x, G=2)
+    finally:
+        ops.set_wgrad_tc_options(2, 0)
 
 
 TC_CASES = [
@@ -244,6 +252,7 @@ WGRAD_TC_S2_CASES = [
     ("C", 16, 24, 3, 2, 1, "elu", (17, 23, 67)),          # odd extents on every axis: ragged last plane / row / column
     ("C", 12, 16, 3, 2, 1, "leaky", (16, 20, 66)),        # ragged channel half on the I-side, one output slice
     ("C", 16, 32, 3, 2, 1, "elu", (16, 20, 66)),          # two full output slices
+    ("C", 24, 32, 3, 2, 1, "elu", (14, 30, 58)),          # Cae3D.py:59   two input slices (16 + 8) x two output slices
 ]
 
 
