@@ -512,7 +512,10 @@ static inline bool sp_tc4_wgrad_disabled() { return sp_wtc4_generation_ref() != 
 static inline bool sp_tc4_wgrad_supported(const SpConvDesc* d, int G) {
     if (sp_tc4_wgrad_disabled() || G < 1 || G > sp_wtc4::MAXG) return false;
     if (d->k != 3 || d->s != 1 || sp_tc_terms() == 0 || sp_tc_wgrad_disabled()) return false;
-    if (d->Ci <= 8 || d->Ci > 16 || d->Co <= 8 || d->Co > 16) return false;
+    // 2..8 input channels (Unet3D.py:19 block1: 2 -> 16; Enc3DCtp: 3 channels): the upper channel half of X' is staged as zeros —
+    // the MMA work is wasted but the kernel is bound by staging, not by the tensor pipe: 1.22 -> 0.6 ms against the thin-input
+    // kernel on the U-Net's first layer; a single input channel (Cae3D.py:41) stays on sp_conv_thin.cuh (0.83 vs 0.9 ms)
+    if (d->Ci < 2 || d->Ci > 16 || d->Co <= 8 || d->Co > 16) return false;
     if (d->pd > 2 || d->ph > 2 || d->pw > 2) return false;
     const sp_wtc4::Wtc4Plan p = sp_wtc4::plan(d);
     return p.total >= 16 && p.total < (1LL << 31) / (d->Do + 2) && d->Wo >= 24 && d->Do >= 4;

@@ -231,6 +231,8 @@ WGRAD_TC_CASES = [
     ("C", 96, 32, 3, 1, 0, "leaky", (10, 18, 40)),             # Unet3D.py:19 block4: 6 x 2 = 12 slice pairs
     ("C", 64, 64, 3, 1, 0, "leaky", (10, 18, 40)),             # Unet3D.py:22 block3: 16 pairs -> stays on the FFMA tier
     ("C", 32, 32, 3, 1, (1, 2, 2), "elu", (5, 25, 25)),        # Cae3D.py:186: shallow volume (Do = 5), one column tile, 4 pairs
+    ("C", 2, 16, 3, 1, 0, "leaky", (10, 24, 44)),              # Unet3D.py:19 block1: two input channels (upper channel half = zeros)
+    ("C", 3, 16, 3, 1, (1, 0, 0), "elu", (10, 24, 44)),        # Enc3DCtp: three input channels, floats per voxel not a multiple of 4
 ]
 
 
@@ -847,3 +849,33 @@ def test_tensor_core_tier_is_deterministic(mode):
             assert torch.equal(xg.grad, g0)
     finally:
         ops.set_tc_terms(5)
+
+
+@pytest.mark.parametrize("layer", ["s1", "s2", "k2s2"])
+@pytest.mark.parametrize("max_ctas", [0, 5])
+def test_tensor_core_weight_gradient_is_deterministic(layer, max_ctas):
+    """The weight-gradient kernels (three staging groups running ahead through a ring of planes, elected MMA issue, periodic TMEM
+    drains, fixed-order reduction of the per-CTA partials) must give bit-identical dW launch after launch, also when every CTA
+    walks many tile columns."""
+    engine, _, ops = _mods()
+    torch.manual_seed(78)
+    conv = {"s1": nn.Conv3d(16, 16, 3, padding=(1, 2, 2)), "s2": nn.Conv3d(16, 24, 3, stride=2, padding=1),
+            "k2s2": nn.ConvTranspose3d(16, 16, 2, stride=2)}[layer]
+    seq = nn.Sequential(nn.BatchNorm3d(16), conv, nn.ELU(1.0)).cuda().train()
+    size = (7, 20, 23) if layer == "k2s2" else (14, 45, 61)
+    x = (torch.randn(4, 16, *size) * 1.5 + 0.3).cuda()
+    ops.set_wgrad_tc_options(2, max_ctas)
+    try:
+        plan = engine.SeqPlan(seq)
+        first = None
+        for _ in range(40):
+            for p in seq.parameters():
+                p.grad = None
+            engine.run_sequential(plan, x).square().sum().backward()
+            g = conv.weight.grad.clone()
+            if first is None:
+                first = g
+                assert torch.isfinite(first).all() and float(first.abs().max()) > 0
+            assert torch.equal(g, first)
+    finally:
+        ops.set_wgrad_tc_options(2, 0)
