@@ -660,10 +660,8 @@ size_t sp_wgrad_workspace_bytes(const SpConvDesc* d) {
     if (sp_tc24_wgrad_workspace_bytes(d) > tiled) tiled = sp_tc24_wgrad_workspace_bytes(d);
     if (sp_tc_wgrad_sliced_workspace_bytes(d) > tiled) tiled = sp_tc_wgrad_sliced_workspace_bytes(d);
     if ((d->k == 3 || d->k == 2) && d->s == 2 && d->Ci > 8 && d->Ci <= 32 && sp_tc4s2_wgrad_workspace_bytes(d) > tiled) tiled = sp_tc4s2_wgrad_workspace_bytes(d);
-    if (d->k == 3 && d->s == 1 && d->Ci >= 2 && d->Co > 8) {         // second-generation tcgen05 weight gradient (any G)
-        if (sp_tc4_wgrad_workspace_bytes(d) > tiled && d->Ci <= 16 && d->Co <= 16) tiled = sp_tc4_wgrad_workspace_bytes(d);
-        if (sp_tc4_wgrad_sliced_workspace_bytes(d) > tiled) tiled = sp_tc4_wgrad_sliced_workspace_bytes(d);
-    }
+    if (d->k == 3 && d->s == 1 && d->Ci >= 2 && d->Co > 8 && d->Ci <= 96 && d->Co <= 64 && sp_tc4_wgrad_workspace_bytes(d) > tiled)
+        tiled = sp_tc4_wgrad_workspace_bytes(d);      // second-generation tcgen05 weight gradient (any G)
     if (sp_thin_wgrad_workspace_bytes(d) > tiled) tiled = sp_thin_wgrad_workspace_bytes(d);
     if (sp_k2s2_wgrad_workspace_bytes(d) > tiled) tiled = sp_k2s2_wgrad_workspace_bytes(d);
     if (gemm_wgrad(d) && sp_gemm_wgrad_ws_bytes(d) > tiled) tiled = sp_gemm_wgrad_ws_bytes(d);
@@ -687,15 +685,11 @@ int sp_wgrad(const SpConvDesc* d, const float* iside, const float* i_scale, cons
         return sp_tc4s2_wgrad_launch(d, nPerG, iside, i_scale, i_shift, oside, o_scale, o_shift, dw, beta, (float*)ws, sp_stream(stream));
     if (sp_k2s2_supported(d) && sp_k2s2_aligned(iside, oside))
         return sp_k2s2_wgrad_launch(d, nPerG, iside, i_scale, i_shift, oside, o_scale, o_shift, dw, beta, (float*)ws, sp_stream(stream));
-    if (d->Ci >= 2 && sp_tc4_wgrad_supported(d, G))
+    if (d->Ci >= 2 && sp_tc4_wgrad_supported(d, G) && sp_tc4_wgrad_aligned(d, iside, oside))
         return sp_tc4_wgrad_launch(d, nPerG, iside, i_scale, i_shift, oside, o_scale, o_shift, dw, beta, (float*)ws, sp_stream(stream));
     if (sp_thin_wgrad_supported(d))
         return sp_thin_wgrad_launch(d, nPerG, iside, i_scale, i_shift, oside, o_scale, o_shift, dw, beta, (float*)ws, sp_stream(stream));
     const bool al16 = ((reinterpret_cast<uintptr_t>(iside) | reinterpret_cast<uintptr_t>(oside)) & 15) == 0;
-    if (sp_tc4_wgrad_supported(d, G))
-        return sp_tc4_wgrad_launch(d, nPerG, iside, i_scale, i_shift, oside, o_scale, o_shift, dw, beta, (float*)ws, sp_stream(stream));
-    if (sp_tc4_wgrad_sliced_supported(d, G) && al16)
-        return sp_tc4_wgrad_sliced_launch(d, nPerG, iside, i_scale, i_shift, oside, o_scale, o_shift, dw, beta, (float*)ws, sp_stream(stream));
     if (sp_tc_wgrad_supported(d))
         return sp_tc_wgrad_launch(d, nPerG, iside, i_scale, i_shift, oside, o_scale, o_shift, dw, beta, (float*)ws, sp_stream(stream));
     if (sp_tc_wgrad_sliced_supported(d) && ((reinterpret_cast<uintptr_t>(iside) | reinterpret_cast<uintptr_t>(oside)) & 15) == 0)

@@ -81,7 +81,9 @@ constexpr int ACC_ROWS = 96;                       // (term_y, kw, co)
 constexpr int ACC_LD = 148;                        // floats per row: 144 columns (kd, kh, ci) + pad (4 x odd: conflict-free rows)
 constexpr int ACC_B = ACC_ROWS * ACC_LD * 4;       // 56832
 constexpr int MAXG = 16;                           // BatchNorm statistics groups whose coefficients fit the shared table
-constexpr int COEF_B = MAXG * 32 * 4;
+constexpr int MAXSI = 6;                            // 16-channel input slices of one launch (96 channels)
+constexpr int COEF_B = MAXG * MAXSI * 32 * 4;
+constexpr int WS_SLOT = 16 * 16 * 27;               // floats of one (CTA, slice pair) partial: [co 16][ci 16][27]
 constexpr int W_EPI = 4, W_MMA = 3, W_STG_X = 4, W_STG_Z = 3, W_STG_G = W_STG_X + W_STG_Z, NGRP = NBUF;
 static_assert(W_STG_X * 32 == 2 * 2 * TU && W_STG_Z * 32 >= 2 * ZW && XH == 6, "staging roles");
 constexpr int NTHREADS4 = (W_EPI + W_MMA + NGRP * W_STG_G) * 32;   // 736
@@ -165,21 +167,63 @@ __device__ __forceinline__ void split8_rn2(const float* v, uint4& o1, uint4& o2,
     o2 = (nt == 1) ? make_uint4(0u, 0u, 0u, 0u) : make_uint4(p2[0], p2[1], p2[2], p2[3]);
 }
 
-struct ColGeo {
-    int n, oh0, u0;
+// One work item = one tile column (n, 4 output rows, 32 input columns) of one slice pair (16 input x 16 output channels of the
+// layer).  Items are numbered pair-major and dealt out round-robin (CTA b takes b, b + grid, ...: CTAs running side by side
+// work on neighbouring tile columns, whose halo rows and dZ columns they share through L2 — contiguous ranges per CTA measured
+// 1.15 -> 1.40 ms on the 16 -> 16 layer).  The accumulators are flushed to ws[pair][cta] at every pair change,
+// wgrad_reduce_pairs_kernel folds the partials of a pair in CTA order.
+struct ItemGeo {
+    int n, oh0, u0;             // tile column
+    int pair, cs, ci0, co0;     // slice pair, input slice index, first input / output channel
+    int cie, coe;               // channels of the slices (<= 16)
 };
-__device__ __forceinline__ ColGeo col_geo(int col, int tiles_w, int tiles_h) {
-    ColGeo c;
+// `pair` = a lower bound of the item's pair (the pair of an earlier item of the same CTA): the staging loops walk their items in
+// increasing order, so the pair arithmetic costs a compare per item and a few divisions per pair change — with a division by
+// total_cols per item the 16 -> 16 layer measured 1.36 instead of 1.16 ms (the staging warps' address arithmetic is on the critical
+// path of the pipeline although they wait for buffers most of the time).
+// MULTI == false: the layer is ONE pair (Ci, Co <= 16) — no pair arithmetic at all, the slice bounds are the kernel parameters
+// (measured on the 16 -> 16 layer: 1.16 ms against 1.36 ms through the general form).
+template <bool MULTI>
+__device__ __forceinline__ ItemGeo item_geo(int item, int pair, int total_cols, int tiles_w, int tiles_h, int nsi, int Ci, int Co) {
+    ItemGeo c;
+    if (!MULTI) {
+        c.pair = 0;
+        int col0 = item;
+        const int tw0 = col0 % tiles_w;
+        col0 /= tiles_w;
+        c.oh0 = (col0 % tiles_h) * THW;
+        c.n = col0 / tiles_h;
+        c.u0 = tw0 * TU;
+        c.cs = 0; c.ci0 = 0; c.co0 = 0; c.cie = Ci; c.coe = Co;
+        return c;
+    }
+    int lo = pair * total_cols;
+    while (item >= lo + total_cols) { lo += total_cols; ++pair; }
+    c.pair = pair;
+    int col = item - lo;
     const int tw = col % tiles_w;
     col /= tiles_w;
     c.oh0 = (col % tiles_h) * THW;
     c.n = col / tiles_h;
     c.u0 = tw * TU;
+    if (nsi == 1) {                      // output slices only (or a single pair)
+        c.cs = 0;
+        c.ci0 = 0;
+        c.co0 = pair * 16;
+    } else {
+        c.cs = pair % nsi;
+        c.ci0 = c.cs * 16;
+        c.co0 = (pair / nsi) * 16;
+    }
+    c.cie = Ci - c.ci0 < 16 ? Ci - c.ci0 : 16;
+    c.coe = Co - c.co0 < 16 ? Co - c.co0 : 16;
     return c;
 }
+__device__ __forceinline__ void drain_bar_sync() { asm volatile("bar.sync 1, 96;" ::: "memory"); }   // the three drain warps
 
+template <bool MULTI>
 __global__ void __launch_bounds__(NTHREADS4, 1)
-wgrad3_tc4_kernel(SpConvDesc d, int nPerG, int G, int tiles_w, int tiles_h, int total_cols, int drain_every, int isstride, int osstride,
+wgrad3_tc4_kernel(SpConvDesc d, int nPerG, int G, int tiles_w, int tiles_h, int total_cols, int nsi, int items_total, int drain_every,
                   const float* __restrict__ X, const float* __restrict__ i_scale, const float* __restrict__ i_shift,
                   const float* __restrict__ dZ, const float* __restrict__ o_scale, const float* __restrict__ o_shift,
                   float* __restrict__ ws, long long* __restrict__ prof, int nt) {
@@ -196,10 +240,10 @@ wgrad3_tc4_kernel(SpConvDesc d, int nPerG, int G, int tiles_w, int tiles_h, int 
     long long pw0 = 0, pw1 = 0, pwk = 0;
 
     for (int i = tid; i < ACC_ROWS * ACC_LD; i += NTHREADS4) acc[i] = 0.f;
-    for (int i = tid; i < G * 32; i += NTHREADS4) {
-        const int g = i >> 5, j = i & 31, c = j & 15;
+    for (int i = tid; i < G * nsi * 32; i += NTHREADS4) {           // [g][input slice][scale 16 | shift 16]
+        const int g = i / (nsi * 32), j = i & 31, c = ((i >> 5) % nsi) * 16 + (j & 15);
         float v = (j < 16) ? 1.f : 0.f;
-        if (i_scale && c < d.Ci) v = (j < 16) ? i_scale[(int64_t)g * isstride + c] : i_shift[(int64_t)g * isstride + c];
+        if (i_scale && c < d.Ci) v = (j < 16) ? i_scale[(int64_t)g * d.Ci + c] : i_shift[(int64_t)g * d.Ci + c];
         coef[i] = v;
     }
     if (tid == 0) {
@@ -221,11 +265,17 @@ wgrad3_tc4_kernel(SpConvDesc d, int nPerG, int G, int tiles_w, int tiles_h, int 
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t a_full = smem_u32(&bars[0]), a_empty = smem_u32(&bars[NBUF]);
     const uint32_t t_full = smem_u32(&bars[2 * NBUF]), t_empty = smem_u32(&bars[2 * NBUF + NBLK]);
+    const long long t_start = pr ? clock64() : 0;                      // prof[10..13]: CTA 0 time line (issuer done, drain done, exit)
 
-    const int ncols = (total_cols - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // columns of this CTA
+    const int first = (int)blockIdx.x, istep = (int)gridDim.x;         // this CTA's items: first + cl * istep
+    const int ncols = (items_total - first + istep - 1) / istep;
     const int Do = d.Do;
     const int nsteps = ncols * Do;
-    const int ndrains = (nsteps + drain_every - 1) / drain_every;
+    // last step of a slice pair inside this CTA: accumulators are drained and the partial is flushed
+    // (no division per step in the issuing / draining loops: they walk (cl, od) incrementally, the pair test runs once per column)
+    auto pair_end = [&](int cl, int od) {
+        return od == Do - 1 && (cl == ncols - 1 || (first + (cl + 1) * istep) / total_cols != (first + cl * istep) / total_cols);
+    };
     const int PPC = Do + 2;                                             // planes per column in the ring's sequence numbering
 
     if (warp >= W_EPI + W_MMA) {
@@ -247,10 +297,12 @@ wgrad3_tc4_kernel(SpConvDesc d, int nPerG, int G, int tiles_w, int tiles_h, int 
         // dZ role
         const bool zact = !isx && st < 2 * ZW;
         const int zhalf = st >= ZW ? 1 : 0, zj = st - zhalf * ZW;
-        for (int it = grp; it < nsteps; it += NGRP) {
-            const int buf = it % NBUF, use = it / NBUF;
-            const int cl = it / Do, od = it - cl * Do;
-            const ColGeo cg = col_geo((int)blockIdx.x + cl * (int)gridDim.x, tiles_w, tiles_h);
+        int cl = grp / Do, od = grp - cl * Do, use = 0, pair_lb = 0;
+        for (int it = grp; it < nsteps; it += NGRP, ++use) {
+            const int buf = grp;                                         // NGRP == NBUF: group = buffer, use = it / NBUF
+            while (od >= Do) { od -= Do; ++cl; }
+            const ItemGeo cg = item_geo<MULTI>(first + cl * istep, pair_lb, total_cols, tiles_w, tiles_h, nsi, d.Ci, d.Co);
+            pair_lb = cg.pair;
             bool waited = false;
             long long c1 = pr ? clock64() : 0;
             if (isx) {
@@ -268,13 +320,13 @@ wgrad3_tc4_kernel(SpConvDesc d, int nPerG, int G, int tiles_w, int tiles_h, int 
 #pragma unroll 1
                 for (int p = 0; p < np; ++p) {
                     const bool nx = (p == 1) && next1;
-                    const ColGeo c = nx ? col_geo((int)blockIdx.x + (cl + 1) * (int)gridDim.x, tiles_w, tiles_h) : cg;
+                    const ItemGeo c = nx ? item_geo<MULTI>(first + (cl + 1) * istep, cg.pair, total_cols, tiles_w, tiles_h, nsi, d.Ci, d.Co) : cg;
                     const int pj = (p == 0) ? od + 2 : nx ? od - (Do - 2) : p - 1;          // plane of its column
                     const int seq = (nx ? cl + 1 : cl) * PPC + pj;
                     const int gd = pj - d.pd, gw = c.u0 + wx, gh0 = c.oh0 - d.ph + hy0;
                     const int ch = xhalf * 8;
-                    const bool okp = gd >= 0 && gd < d.Di && gw < d.Wi;
-                    const float* pp = X + (int64_t)c.n * xs_n + (((int64_t)gd * d.Hi + gh0) * d.Wi + gw) * d.ldi + ch;
+                    const bool okp = gd >= 0 && gd < d.Di && gw < d.Wi && ch < c.cie;
+                    const float* pp = X + (int64_t)c.n * xs_n + (((int64_t)gd * d.Hi + gh0) * d.Wi + gw) * d.ldi + c.ci0 + ch;
                     const int64_t rstep = (int64_t)2 * d.Wi * d.ldi;
                     float4 ra[3], rb[3];
                     bool ok[3];
@@ -286,13 +338,13 @@ wgrad3_tc4_kernel(SpConvDesc d, int nPerG, int G, int tiles_w, int tiles_h, int 
                         rb[i] = ra[i];
                         if (ok[i]) {
                             const float* q = pp + i * rstep;
-                            if (vec_i && ch + 8 <= d.Ci) {
+                            if (vec_i && ch + 8 <= c.cie) {
                                 ra[i] = *reinterpret_cast<const float4*>(q);
                                 rb[i] = *reinterpret_cast<const float4*>(q + 4);
                             } else {
                                 float e[8];
 #pragma unroll
-                                for (int j = 0; j < 8; ++j) e[j] = (ch + j < d.Ci) ? q[j] : 0.f;
+                                for (int j = 0; j < 8; ++j) e[j] = (ch + j < c.cie) ? q[j] : 0.f;
                                 ra[i] = make_float4(e[0], e[1], e[2], e[3]);
                                 rb[i] = make_float4(e[4], e[5], e[6], e[7]);
                             }
@@ -300,7 +352,7 @@ wgrad3_tc4_kernel(SpConvDesc d, int nPerG, int G, int tiles_w, int tiles_h, int 
                     }
                     // convert BEFORE the buffer is waited for: after the wait only the stores remain (the time from "MMAs of step
                     // it - NBUF done" to "step it staged" is what the issuers see as staging latency)
-                    const float* cf = coef + (c.n / nPerG) * 32 + ch;
+                    const float* cf = coef + ((c.n / nPerG) * nsi + c.cs) * 32 + ch;
                     const float4 s0 = *reinterpret_cast<const float4*>(cf), s1 = *reinterpret_cast<const float4*>(cf + 4);
                     const float4 h0 = *reinterpret_cast<const float4*>(cf + 16), h1 = *reinterpret_cast<const float4*>(cf + 20);
                     uint4 o1[3], o2[3];
@@ -327,10 +379,10 @@ wgrad3_tc4_kernel(SpConvDesc d, int nPerG, int G, int tiles_w, int tiles_h, int 
                     }
                 }
             } else {
-                const float* zn = dZ + (int64_t)cg.n * zs_n;
+                const float* zn = dZ + (int64_t)cg.n * zs_n + cg.co0;
                 const int gz = cg.n / nPerG;
                 const int gw = cg.u0 + d.pw - 2 + zj, ch = zhalf * 8;
-                const bool okc = zact && gw >= 0 && gw < d.Wo && ch < d.Co;
+                const bool okc = zact && gw >= 0 && gw < d.Wo && ch < cg.coe;
                 const float* pp = zn + (((int64_t)od * d.Ho + cg.oh0) * d.Wo + gw) * d.ldo + ch;
                 const int64_t rstep = (int64_t)d.Wo * d.ldo;
                 float4 ra[THW], rb[THW];
@@ -342,13 +394,13 @@ wgrad3_tc4_kernel(SpConvDesc d, int nPerG, int G, int tiles_w, int tiles_h, int 
                     rb[i] = ra[i];
                     if (ok[i]) {
                         const float* q = pp + i * rstep;
-                        if (vec_o && ch + 8 <= d.Co) {
+                        if (vec_o && ch + 8 <= cg.coe) {
                             ra[i] = *reinterpret_cast<const float4*>(q);
                             rb[i] = *reinterpret_cast<const float4*>(q + 4);
                         } else {
                             float e[8];
 #pragma unroll
-                            for (int j = 0; j < 8; ++j) e[j] = (ch + j < d.Co) ? q[j] : 0.f;
+                            for (int j = 0; j < 8; ++j) e[j] = (ch + j < cg.coe) ? q[j] : 0.f;
                             ra[i] = make_float4(e[0], e[1], e[2], e[3]);
                             rb[i] = make_float4(e[4], e[5], e[6], e[7]);
                         }
@@ -361,7 +413,7 @@ wgrad3_tc4_kernel(SpConvDesc d, int nPerG, int G, int tiles_w, int tiles_h, int 
                     if (ok[i] && o_scale) {
 #pragma unroll
                         for (int j = 0; j < 8; ++j)
-                            if (ch + j < d.Co) v[j] = fmaf(v[j], o_scale[(int64_t)gz * osstride + ch + j], o_shift[(int64_t)gz * osstride + ch + j]);
+                            if (ch + j < cg.coe) v[j] = fmaf(v[j], o_scale[(int64_t)gz * d.Co + cg.co0 + ch + j], o_shift[(int64_t)gz * d.Co + cg.co0 + ch + j]);
                     }
                     split8_rn2(v, o1[i], o2[i], nt);
                 }
@@ -388,6 +440,7 @@ wgrad3_tc4_kernel(SpConvDesc d, int nPerG, int G, int tiles_w, int tiles_h, int 
             __syncwarp();
             if (lane == 0) mbar_arrive(a_full + 8 * buf);
             if (pr) pwk += clock64() - c1;
+            od += NGRP;
         }
         if (pr && grp == 0 && wig == 0 && lane == 0) { prof[4] = pw0; prof[5] = pwk; }
         if (pr && grp == 0 && wig == W_STG_X && lane == 0) { prof[8] = pw0; prof[9] = pwk; }
@@ -400,10 +453,9 @@ wgrad3_tc4_kernel(SpConvDesc d, int nPerG, int G, int tiles_w, int tiles_h, int 
             const uint32_t dcol = tmem_base + (uint32_t)(kd * BCOLS);
             constexpr uint32_t IDESC = idesc_mn(128, BCOLS);
             bool fresh = true;
-            int drains = 0;
+            int drains = 0, sp = 0;                                          // sp: steps since the last pair change
+            int cl = 0, od = 0, buf = 0, use = 0, ring = kd;                // ring = (cl * PPC + od + kd) % NSLOT
             for (int it = 0; it < nsteps; ++it) {
-                const int buf = it % NBUF, use = it / NBUF;
-                const int cl = it / Do, od = it - cl * Do;
                 long long c0 = pr ? clock64() : 0;
                 mbar_wait_issuer(a_full + 8 * buf, use & 1);
                 long long c1 = pr ? clock64() : 0;
@@ -412,7 +464,7 @@ wgrad3_tc4_kernel(SpConvDesc d, int nPerG, int G, int tiles_w, int tiles_h, int 
                 long long c2 = pr ? clock64() : 0;
                 pw1 += c2 - c1;
                 tc_fence_after();
-                const int slot = (cl * PPC + od + kd) % NSLOT;        // plane od - pd + kd of this column
+                const int slot = ring;                                // plane od - pd + kd of this column
                 const uint64_t da0 = umma_desc(a_base + (uint32_t)(buf * A_BUF_B), 128, PS);
                 const uint64_t db0 = umma_desc(x_base + (uint32_t)(slot * X_PLANE_B), 128, RS);
 #pragma unroll
@@ -426,81 +478,132 @@ wgrad3_tc4_kernel(SpConvDesc d, int nPerG, int G, int tiles_w, int tiles_h, int 
                     }
                 }
                 umma_commit_elect(a_empty + 8 * buf);
-                if ((it + 1) % drain_every == 0 || it == nsteps - 1) {
+                const bool pend = pair_end(cl, od);
+                if (sp + 1 == drain_every || pend) {
                     umma_commit_elect(t_full + 8 * kd);
                     fresh = true;
                     ++drains;
+                    sp = 0;
+                } else {
+                    ++sp;
                 }
                 if (pr) pwk += clock64() - c2;
+                if (++buf == NBUF) { buf = 0; ++use; }
+                int adv = 1;                                           // ring numbers to the next step's window: 3 across a column change
+                if (++od == Do) { od = 0; ++cl; adv = 3; }
+                ring += adv;
+                if (ring >= NSLOT) ring -= NSLOT;
             }
-            if (pr && kd == 0 && lane == 0) { prof[0] = pw0; prof[1] = pw1; prof[2] = pwk; prof[3] = nsteps; }
+            if (pr && kd == 0 && lane == 0) { prof[0] = pw0; prof[1] = pw1; prof[2] = pwk; prof[3] = nsteps; prof[10] = clock64() - t_start; }
         }
     } else if (warp < 3) {
         // =================================================================== drain: warp q holds accumulator rows 32q .. 32q+31
         float* arow = acc + (size_t)(warp * 32 + lane) * ACC_LD;
-        for (int dr = 0; dr < ndrains; ++dr) {
+        int dr = 0;
+        for (int cl = 0; cl < ncols;) {
+            // run of this CTA's columns that belong to one slice pair: (run * Do) steps, a drain every drain_every steps and at its end
+            const int item0 = first + cl * istep;
+            const int pair = item0 / total_cols;
+            int run = ((pair + 1) * total_cols - item0 + istep - 1) / istep;
+            if (run > ncols - cl) run = ncols - cl;
+            const int ndr = (run * Do + drain_every - 1) / drain_every;
+            for (int k = 0; k < ndr; ++k, ++dr) {
 #pragma unroll 1
-            for (int kd = 0; kd < NBLK; ++kd) {
-                long long c0 = pr ? clock64() : 0;
-                mbar_wait_warp(t_full + 8 * kd, dr & 1);
-                long long c1 = pr ? clock64() : 0;
-                pw0 += c1 - c0;
-                tc_fence_after();
+                for (int kd = 0; kd < NBLK; ++kd) {
+                    long long c0 = pr ? clock64() : 0;
+                    mbar_wait_warp(t_full + 8 * kd, dr & 1);
+                    long long c1 = pr ? clock64() : 0;
+                    pw0 += c1 - c0;
+                    tc_fence_after();
 #pragma unroll 1
-                for (int kh = 0; kh < 3; ++kh) {
-                    float v[32];                               // [x term 1: ci 0..15 | x term 2: ci 0..15]
-                    tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(kd * BCOLS + kh * 32), v);
-                    if (kh == 2) {                             // the block is in registers / shared memory: it may be overwritten
-                        tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(t_empty + 8 * kd);
-                    }
-                    float4* ap = reinterpret_cast<float4*>(arow + kd * 48 + kh * 16);
+                    for (int kh = 0; kh < 3; ++kh) {
+                        float v[32];                               // [x term 1: ci 0..15 | x term 2: ci 0..15]
+                        tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(kd * BCOLS + kh * 32), v);
+                        if (kh == 2) {                             // the block is in registers / shared memory: it may be overwritten
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(t_empty + 8 * kd);
+                        }
+                        float4* ap = reinterpret_cast<float4*>(arow + kd * 48 + kh * 16);
 #pragma unroll
-                    for (int j4 = 0; j4 < 4; ++j4) {
-                        float4 a = ap[j4];
-                        a.x += v[4 * j4] + v[16 + 4 * j4];
-                        a.y += v[4 * j4 + 1] + v[17 + 4 * j4];
-                        a.z += v[4 * j4 + 2] + v[18 + 4 * j4];
-                        a.w += v[4 * j4 + 3] + v[19 + 4 * j4];
-                        ap[j4] = a;
+                        for (int j4 = 0; j4 < 4; ++j4) {
+                            float4 a = ap[j4];
+                            a.x += v[4 * j4] + v[16 + 4 * j4];
+                            a.y += v[4 * j4 + 1] + v[17 + 4 * j4];
+                            a.z += v[4 * j4 + 2] + v[18 + 4 * j4];
+                            a.w += v[4 * j4 + 3] + v[19 + 4 * j4];
+                            ap[j4] = a;
+                        }
                     }
+                    if (pr) pwk += clock64() - c1;
                 }
-                if (pr) pwk += clock64() - c1;
             }
+            // flush: fold the two y terms (small first) and write this CTA's partial of the pair as [co 16][ci 16][27]
+            float* wsp = ws + ((int64_t)pair * istep + first) * WS_SLOT;
+            drain_bar_sync();                                      // every drain warp has added its rows
+            for (int i = warp * 32 + lane; i < WS_SLOT; i += 96) {
+                const int tap = i % 27, ci = (i / 27) & 15, co = i / (27 * 16);
+                const int kd = tap / 9, kh = (tap / 3) % 3, kw = tap % 3;
+                const int col = kd * 48 + kh * 16 + ci;
+                const int r0 = (kw * 2 + (co >> 3)) * 8 + (co & 7);          // term 0; term 1 lies 48 rows below
+                wsp[i] = acc[(r0 + 48) * ACC_LD + col] + acc[r0 * ACC_LD + col];
+            }
+            drain_bar_sync();                                      // rows are read across warps above
+            for (int j = 0; j < ACC_LD; ++j) arow[j] = 0.f;        // own row only: the next drain of this thread follows in order
+            cl += run;
         }
-        if (pr && tid == 0) { prof[6] = pw0; prof[7] = pwk; }
+        if (pr && tid == 0) { prof[6] = pw0; prof[7] = pwk; prof[11] = clock64() - t_start; }
     }
 
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     if (warp == 0) tmem_dealloc<512>(tmem_base);
-    // fold the two y terms (small first) and write this CTA's partial in torch layout dW[co][ci][tap]
-    const int wn = d.Co * d.Ci * 27;
-    float* wsp = ws + (int64_t)blockIdx.x * wn;
-    for (int i = tid; i < wn; i += NTHREADS4) {
-        const int tap = i % 27, ci = (i / 27) % d.Ci, co = i / (27 * d.Ci);
-        const int kd = tap / 9, kh = (tap / 3) % 3, kw = tap % 3;
-        const int col = kd * 48 + kh * 16 + ci;
-        const int r0 = (kw * 2 + (co >> 3)) * 8 + (co & 7);      // term 0; term 1 lies 48 rows below
-        wsp[i] = acc[(r0 + 48) * ACC_LD + col] + acc[r0 * ACC_LD + col];
+    if (pr && tid == 0) prof[12] = clock64() - t_start;
+}
+
+// dw[co][ci][tap] (torch layout, the whole layer) = beta * dw + the per-CTA partials of every slice pair, folded in CTA order
+__global__ void wgrad_reduce_pairs_kernel(const float* __restrict__ ws, int T, int grid, int nsi, int npairs, int Ci, int Co,
+                                          float* __restrict__ dw, float beta) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= npairs * WS_SLOT) return;
+    const int pair = i / WS_SLOT, e = i - pair * WS_SLOT;
+    const int tap = e % 27, ci = (e / 27) & 15, co = e / (27 * 16);
+    const int gci = (pair % nsi) * 16 + ci, gco = (pair / nsi) * 16 + co;
+    if (gci >= Ci || gco >= Co) return;
+    // the CTAs that hold items of the pair form a cyclic range: all of them when T >= grid, else T CTAs from (pair * T) % grid
+    const int cnt = T >= grid ? grid : T;
+    int b = T >= grid ? 0 : (int)(((int64_t)pair * T) % grid);
+    const float* base = ws + (int64_t)pair * grid * WS_SLOT + e;
+    float s = 0.f;
+#pragma unroll 8
+    for (int k = 0; k < cnt; ++k) {                    // fixed order; the loads of a batch of iterations are independent
+        s += base[(int64_t)b * WS_SLOT];
+        if (++b == grid) b = 0;
     }
+    float* o = dw + ((int64_t)gco * Ci + gci) * 27 + tap;
+    *o = (beta != 0.f ? beta * *o : 0.f) + s;
 }
 
 struct Wtc4Plan {
-    int tiles_w, tiles_h, grid;
-    int64_t total;      // columns (n, 4 output rows, 32 input columns); each is walked along the depth axis
+    int tiles_w, tiles_h, grid, nsi, nso, npairs;
+    int64_t total;      // tile columns (n, 4 output rows, 32 input columns) of ONE slice pair; each is walked along the depth axis
+    int64_t items;      // npairs * total
 };
 static inline Wtc4Plan plan(const SpConvDesc* d) {
     Wtc4Plan p;
     p.tiles_w = (d->Wi + TU - 1) / TU;
     p.tiles_h = (d->Ho + THW - 1) / THW;
     p.total = (int64_t)p.tiles_w * p.tiles_h * d->N;
+    p.nsi = (d->Ci + 15) / 16;
+    p.nso = (d->Co + 15) / 16;
+    p.npairs = p.nsi * p.nso;
+    p.items = p.total * p.npairs;
     p.grid = sp_num_sms();
     const int cap = sp_wtc4_grid_cap_ref();   // tests: several columns per CTA on a small geometry
     if (cap > 0 && p.grid > cap) p.grid = cap;
-    if (p.grid > p.total) p.grid = (int)p.total;
+    if (p.grid > p.items) p.grid = (int)p.items;
+    if (p.grid < 1) p.grid = 1;
     return p;
 }
 
@@ -508,21 +611,39 @@ static inline Wtc4Plan plan(const SpConvDesc* d) {
 
 static inline bool sp_tc4_wgrad_disabled() { return sp_wtc4_generation_ref() != 2; }
 
-// same layers as sp_tc_wgrad_supported; G = statistics groups of the launch
+// 3x3x3 stride-1 layers with 2..96 input and 9..64 output channels: ONE launch walks the tile columns of every 16 x 16 channel
+// slice pair (Cae3D.py:44,208,211 and Unet3D.py:22: one pair; Cae3D.py:52,55,186-200: 2..4 pairs; Unet3D.py:19,22: up to 16).
+// G = statistics groups of the launch.
 static inline bool sp_tc4_wgrad_supported(const SpConvDesc* d, int G) {
     if (sp_tc4_wgrad_disabled() || G < 1 || G > sp_wtc4::MAXG) return false;
     if (d->k != 3 || d->s != 1 || sp_tc_terms() == 0 || sp_tc_wgrad_disabled()) return false;
     // 2..8 input channels (Unet3D.py:19 block1: 2 -> 16; Enc3DCtp: 3 channels): the upper channel half of X' is staged as zeros —
-    // the MMA work is wasted but the kernel is bound by staging, not by the tensor pipe: 1.22 -> 0.6 ms against the thin-input
+    // the MMA work is wasted but the kernel is bound by staging, not by the tensor pipe: 1.22 -> 0.70 ms against the thin-input
     // kernel on the U-Net's first layer; a single input channel (Cae3D.py:41) stays on sp_conv_thin.cuh (0.83 vs 0.9 ms)
-    if (d->Ci < 2 || d->Ci > 16 || d->Co <= 8 || d->Co > 16) return false;
+    if (d->Ci < 2 || d->Ci > 16 * sp_wtc4::MAXSI || d->Co <= 8 || d->Co > 64) return false;
+    if (d->Ci > 16 || d->Co > 16) {          // slices: 16-byte aligned channel slices; no slice of fewer than ... channels is excluded
+        if (d->ldi % 4 != 0 || d->ldo % 4 != 0) return false;
+        static int maxpairs = -1;            // SP_WTC4_SLICE_PAIRS: most slice pairs taken (every pair re-stages both tiles)
+        if (maxpairs < 0) {
+            const char* e = getenv("SP_WTC4_SLICE_PAIRS");
+            maxpairs = e ? atoi(e) : 16;
+        }
+        if (((d->Ci + 15) / 16) * ((d->Co + 15) / 16) > maxpairs) return false;
+    }
     if (d->pd > 2 || d->ph > 2 || d->pw > 2) return false;
     const sp_wtc4::Wtc4Plan p = sp_wtc4::plan(d);
-    return p.total >= 16 && p.total < (1LL << 31) / (d->Do + 2) && d->Wo >= 24 && d->Do >= 4;
+    return p.total >= 16 && p.items < (1LL << 31) / (d->Do + 2) && d->Wo >= 24 && d->Do >= 4;
 }
 
 static inline size_t sp_tc4_wgrad_workspace_bytes(const SpConvDesc* d) {
-    return (size_t)sp_wtc4::plan(d).grid * d->Co * d->Ci * 27 * sizeof(float);
+    const sp_wtc4::Wtc4Plan p = sp_wtc4::plan(d);
+    return (size_t)p.grid * p.npairs * sp_wtc4::WS_SLOT * sizeof(float);
+}
+
+// pointers of sliced layers must be 16-byte aligned (float4 loads of a channel slice)
+static inline bool sp_tc4_wgrad_aligned(const SpConvDesc* d, const void* iside, const void* oside) {
+    if (d->Ci <= 16 && d->Co <= 16) return true;
+    return ((reinterpret_cast<uintptr_t>(iside) | reinterpret_cast<uintptr_t>(oside)) & 15) == 0;
 }
 
 static inline int sp_tc4_wgrad_launch(const SpConvDesc* d, int nPerG, const float* iside, const float* i_scale, const float* i_shift,
@@ -532,79 +653,20 @@ static inline int sp_tc4_wgrad_launch(const SpConvDesc* d, int nPerG, const floa
     const Wtc4Plan p = plan(d);
     static bool attr = false;
     if (!attr) {
-        SP_CUDA(cudaFuncSetAttribute(wgrad3_tc4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM4));
+        SP_CUDA(cudaFuncSetAttribute(wgrad3_tc4_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM4));
+        SP_CUDA(cudaFuncSetAttribute(wgrad3_tc4_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM4));
         attr = true;
     }
     const int G = d->N / nPerG;
-    wgrad3_tc4_kernel<<<p.grid, NTHREADS4, SMEM4, st>>>(*d, nPerG, G, p.tiles_w, p.tiles_h, (int)p.total, drain_every, d->Ci, d->Co, iside,
-                                                        i_scale, i_shift, oside, o_scale, o_shift, ws, prof, sp_tc_terms() == 1 ? 1 : 2);
+    if (p.npairs == 1)
+        wgrad3_tc4_kernel<false><<<p.grid, NTHREADS4, SMEM4, st>>>(*d, nPerG, G, p.tiles_w, p.tiles_h, (int)p.total, p.nsi, (int)p.items, drain_every,
+                                                                   iside, i_scale, i_shift, oside, o_scale, o_shift, ws, prof, sp_tc_terms() == 1 ? 1 : 2);
+    else
+        wgrad3_tc4_kernel<true><<<p.grid, NTHREADS4, SMEM4, st>>>(*d, nPerG, G, p.tiles_w, p.tiles_h, (int)p.total, p.nsi, (int)p.items, drain_every,
+                                                                  iside, i_scale, i_shift, oside, o_scale, o_shift, ws, prof, sp_tc_terms() == 1 ? 1 : 2);
     SP_LAUNCH_OK("wgrad3_tc4_kernel");
-    const int64_t wn = (int64_t)d->Co * d->Ci * 27;
-    int64_t rb = (wn + 255) / 256;
-    wgrad_reduce_kernel<<<(int)rb, 256, 0, st>>>(ws, p.grid, wn, dw, beta);
-    SP_LAUNCH_OK("wgrad_reduce_kernel");
-    return 0;
-}
-
-// ---- wider layers (Unet3D.py:19,22: 48 -> 16, 32 -> 32, 96 -> 32, ...): both sides run as slices of 16 channels through the
-// kernel above (X + 16 c / dZ + 16 c' with the layer's row strides and its slices of the affine coefficients); every slice
-// pair has its own per-CTA partials, which wgrad_reduce_slice_kernel folds into dW[16 c' + co][16 c + ci][tap].
-static inline bool sp_tc4_wgrad_sliced_supported(const SpConvDesc* d, int G) {
-    if (sp_tc4_wgrad_disabled() || G < 1 || G > sp_wtc4::MAXG) return false;
-    if (d->k != 3 || d->s != 1 || sp_tc_terms() == 0 || sp_tc_wgrad_disabled()) return false;
-    // 17..24-channel layers (Cae3D.py:52,55,186-200) run as (16 + 8)-channel slices as well: measured in the CAE step against
-    // sp_wgrad_tc24.cuh 0.914 -> 0.811 ms (24 -> 24 at batch 32), 0.803 -> 0.407 ms (24 -> 16); SP_WTC4_SLICE24=0 switches back
-    static int slice24 = -1;
-    if (slice24 < 0) {
-        const char* e = getenv("SP_WTC4_SLICE24");
-        slice24 = (e && e[0] == '0') ? 0 : 1;
-    }
-    const bool is24 = d->Ci <= 24 && d->Co <= 24;
-    if (is24 && (!slice24 || (d->Ci <= 16 && d->Co <= 16))) return false;   // the single-launch kernels take these
-    // most slice pairs taken (every pair re-stages both tiles); measured on the U-Net step (batch 4): 3 / 6 / 12 pairs ->
-    // 21.97 / 21.50 / 21.19 ms (96 -> 32 on 18x68x68 as 12 pairs: 1.86 -> 1.40 ms); SP_WTC4_SLICE_PAIRS overrides
-    static int maxpairs = -1;
-    if (maxpairs < 0) {
-        const char* e = getenv("SP_WTC4_SLICE_PAIRS");
-        maxpairs = e ? atoi(e) : 12;
-    }
-    if (((d->Ci + 15) / 16) * ((d->Co + 15) / 16) > maxpairs) return false;
-    if (d->Ci <= 8 || d->Ci > 96 || d->Co <= 8 || d->Co > 64 || d->ldi % 4 != 0 || d->ldo % 4 != 0) return false;
-    if (d->pd > 2 || d->ph > 2 || d->pw > 2) return false;
-    const sp_wtc4::Wtc4Plan p = sp_wtc4::plan(d);
-    return p.total >= 16 && p.total < (1LL << 31) / (d->Do + 2) && d->Wo >= 24 && d->Do >= 4;
-}
-
-static inline size_t sp_tc4_wgrad_sliced_workspace_bytes(const SpConvDesc* d) {
-    return (size_t)sp_wtc4::plan(d).grid * 16 * 16 * 27 * sizeof(float);       // one slice pair at a time (stream-ordered reuse)
-}
-
-static inline int sp_tc4_wgrad_sliced_launch(const SpConvDesc* d, int nPerG, const float* iside, const float* i_scale,
-                                             const float* i_shift, const float* oside, const float* o_scale, const float* o_shift,
-                                             float* dw, float beta, float* ws, cudaStream_t st, int drain_every = 6) {
-    using namespace sp_wtc4;
-    const Wtc4Plan p = plan(d);
-    static bool attr = false;
-    if (!attr) {
-        SP_CUDA(cudaFuncSetAttribute(wgrad3_tc4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM4));
-        attr = true;
-    }
-    const int G = d->N / nPerG;
-    const int nsi = (d->Ci + 15) / 16, nso = (d->Co + 15) / 16;
-    for (int co = 0; co < nso; ++co)
-        for (int c = 0; c < nsi; ++c) {
-            SpConvDesc s = *d;
-            s.Ci = (d->Ci - 16 * c < 16) ? d->Ci - 16 * c : 16;
-            s.Co = (d->Co - 16 * co < 16) ? d->Co - 16 * co : 16;
-            wgrad3_tc4_kernel<<<p.grid, NTHREADS4, SMEM4, st>>>(s, nPerG, G, p.tiles_w, p.tiles_h, (int)p.total, drain_every, d->Ci, d->Co,
-                                                                iside + 16 * c, i_scale ? i_scale + 16 * c : nullptr,
-                                                                i_shift ? i_shift + 16 * c : nullptr, oside + 16 * co,
-                                                                o_scale ? o_scale + 16 * co : nullptr,
-                                                                o_shift ? o_shift + 16 * co : nullptr, ws, nullptr, sp_tc_terms() == 1 ? 1 : 2);
-            SP_LAUNCH_OK("wgrad3_tc4_kernel");
-            const int wn = s.Co * s.Ci * 27;
-            wgrad_reduce_slice_kernel<<<(wn + 255) / 256, 256, 0, st>>>(ws, p.grid, s.Co, s.Ci, d->Ci, 16 * co, 16 * c, dw, beta);
-            SP_LAUNCH_OK("wgrad_reduce_slice_kernel");
-        }
+    const int n = p.npairs * WS_SLOT;
+    wgrad_reduce_pairs_kernel<<<(n + 255) / 256, 256, 0, st>>>(ws, (int)p.total, p.grid, p.nsi, p.npairs, d->Ci, d->Co, dw, beta);
+    SP_LAUNCH_OK("wgrad_reduce_pairs_kernel");
     return 0;
 }

@@ -87,7 +87,7 @@ int main(int argc, char** argv) {
     float *dx, *dz, *dsc, *dsh, *dws, *ddw;
     long long* dprof;
     CK(cudaMalloc(&dx, nx * 4)); CK(cudaMalloc(&dz, nz * 4)); CK(cudaMalloc(&dsc, 96)); CK(cudaMalloc(&dsh, 96));
-    CK(cudaMalloc(&dws, (size_t)148 * wn * 4 + 1024)); CK(cudaMalloc(&ddw, wn * 4)); CK(cudaMalloc(&dprof, 128));
+    CK(cudaMalloc(&dws, (size_t)148 * wn * 4 + (size_t)148 * 16 * 6912 * 4)); CK(cudaMalloc(&ddw, wn * 4)); CK(cudaMalloc(&dprof, 128));
     CK(cudaMemcpy(dx, x.data(), nx * 4, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(dz, z.data(), nz * 4, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(dsc, sc.data(), 96, cudaMemcpyHostToDevice)); CK(cudaMemcpy(dsh, sh.data(), 96, cudaMemcpyHostToDevice));
@@ -117,6 +117,7 @@ int main(int argc, char** argv) {
         const long long t = hp[3] ? hp[3] : 1;
         printf("  CTA0 cycles per step (%lld steps): issuer 0: wait a_full %lld, wait t_empty %lld, issue %lld | stager: wait a_empty %lld, work %lld | "
                "drain warp 0: wait t_full %lld, work %lld | issuer s_full wait %lld | producer: wait s_free %lld, work %lld\n", t, hp[0] / t, hp[1] / t, hp[2] / t, hp[4] / t, hp[5] / t, hp[6] / t, hp[7] / t, hp[8] / t, hp[9] / t, hp[10] / t);
+        printf("  CTA0 time line (cycles after the prologue): issuer loop done %lld, drain + flush done %lld, exit %lld\n", hp[10], hp[11], hp[12]);
         return 0;
     }
 
