@@ -67,8 +67,8 @@ const char* sp_last_error(void);
 /*
  * Tensor-core tiers of the 3x3x3 stride-1 layers (Cae3D.py:44,52,55,63,66,186-211; Unet3D.py:19,22): forward and dgrad with
  * 8..96 channels on either side (mode 4), weight gradients with 9..24 channels (wider I-sides as 16-channel slices).  Every
- * fp32 operand is staged as three bf16 terms (exact split), the products of order <= 2 (forward / dgrad) or all nine
- * products (weight gradient) are accumulated by tcgen05.mma in TMEM:
+ * fp32 operand of the forward / dgrad kernels is staged as three bf16 terms (exact split), the products of order <= 2 are
+ * accumulated by tcgen05.mma in TMEM (weight gradients: see sp_set_wgrad_tc_options):
  *   4 (default)  pipelined kernels, leading products in one accumulator per kd and corrections in separate columns: per-layer
  *                forward rel-L2 1.3e-7, weight gradient 5.7e-7 (an IEEE fp32 FFMA chain: 2.6e-7 / 1.7e-6 on the same data)
  *   0            tiers off (exact-fp32 FFMA tiers everywhere, weight gradients included)
@@ -78,9 +78,11 @@ const char* sp_last_error(void);
  */
 int         sp_get_tc_terms(void);
 int         sp_set_tc_terms(int terms);
-/* Weight gradient of the 9..16-channel 3x3x3 stride-1 layers (Cae3D.py:44,208,211; Unet3D.py:22; wider layers as 16-channel
- * slice pairs): generation 2 (default, sp_wgrad_tc4.cuh) = one M 128 x N 96 tcgen05.mma per (16 voxels, kd) on two
- * round-to-nearest bf16 terms per operand, generation 1 (sp_wgrad_tc.cuh) = 27 M 64 x N 48 MMAs on three exact terms.
+/* Weight gradients on tcgen05 (Cae3D.py:44-66,186-211, 48, 59, 204; Unet3D.py:19,22).  Generation 2 (default): 3x3x3 stride-1
+ * layers with 2..96 input and 9..64 output channels in ONE launch over all 16 x 16 channel slice pairs (sp_wgrad_tc4.cuh: one
+ * M 128 x N 96 tcgen05.mma per (16 voxels, kd), two round-to-nearest bf16 terms per operand) and the stride-2 layers Conv3d k3 s2 p1 /
+ * ConvTranspose3d k2 s2 with 9..32 channels (sp_wgrad_tc4s2.cuh).  Generation 1: the first-generation kernels (sp_wgrad_tc.cuh,
+ * sp_wgrad_tc24.cuh: 27 M 64 x N 48 MMAs on three exact terms) for 9..24-channel stride-1 layers, FFMA tiers for everything else.
  * max_ctas > 0 caps the persistent grid (tests: several tile columns per CTA on small volumes), 0 = one CTA per SM. */
 int         sp_set_wgrad_tc_options(int generation, int max_ctas);
 
