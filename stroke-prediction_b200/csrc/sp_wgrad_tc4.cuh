@@ -177,46 +177,46 @@ struct ItemGeo {
     int pair, cs, ci0, co0;     // slice pair, input slice index, first input / output channel
     int cie, coe;               // channels of the slices (<= 16)
 };
-// `pair` = a lower bound of the item's pair (the pair of an earlier item of the same CTA): the staging loops walk their items in
-// increasing order, so the pair arithmetic costs a compare per item and a few divisions per pair change — with a division by
-// total_cols per item the 16 -> 16 layer measured 1.36 instead of 1.16 ms (the staging warps' address arithmetic is on the critical
-// path of the pipeline although they wait for buffers most of the time).
+// The staging loops walk their items in increasing order and keep the pair-derived fields in a PairWalk: a compare per item, the
+// divisions only at a pair change (with a division by total_cols per item the 16 -> 16 layer measured 1.36 instead of 1.16 ms:
+// the staging warps' address arithmetic is on the critical path of the pipeline although they wait for buffers most of the time).
+struct PairWalk {
+    int pair, lo, cs, ci0, co0, cie, coe;
+};
+__device__ __forceinline__ PairWalk pair_walk_init(int nsi, int Ci, int Co) {
+    PairWalk w;
+    w.pair = 0; w.lo = 0; w.cs = 0; w.ci0 = 0; w.co0 = 0;
+    w.cie = Ci < 16 ? Ci : 16;
+    w.coe = Co < 16 ? Co : 16;
+    return w;
+}
+__device__ __forceinline__ void pair_walk_to(PairWalk& w, int item, int total_cols, int nsi, int Ci, int Co) {
+    if (item < w.lo + total_cols) return;
+    while (item >= w.lo + total_cols) { w.lo += total_cols; ++w.pair; }
+    w.cs = w.pair % nsi;
+    w.ci0 = w.cs * 16;
+    w.co0 = (w.pair / nsi) * 16;
+    w.cie = Ci - w.ci0 < 16 ? Ci - w.ci0 : 16;
+    w.coe = Co - w.co0 < 16 ? Co - w.co0 : 16;
+}
 // MULTI == false: the layer is ONE pair (Ci, Co <= 16) — no pair arithmetic at all, the slice bounds are the kernel parameters
 // (measured on the 16 -> 16 layer: 1.16 ms against 1.36 ms through the general form).
 template <bool MULTI>
-__device__ __forceinline__ ItemGeo item_geo(int item, int pair, int total_cols, int tiles_w, int tiles_h, int nsi, int Ci, int Co) {
+__device__ __forceinline__ ItemGeo item_geo(int item, PairWalk w, int total_cols, int tiles_w, int tiles_h, int nsi, int Ci, int Co) {
     ItemGeo c;
-    if (!MULTI) {
-        c.pair = 0;
-        int col0 = item;
-        const int tw0 = col0 % tiles_w;
-        col0 /= tiles_w;
-        c.oh0 = (col0 % tiles_h) * THW;
-        c.n = col0 / tiles_h;
-        c.u0 = tw0 * TU;
-        c.cs = 0; c.ci0 = 0; c.co0 = 0; c.cie = Ci; c.coe = Co;
-        return c;
+    int col = item;
+    if (MULTI) {
+        pair_walk_to(w, item, total_cols, nsi, Ci, Co);
+        col = item - w.lo;
+        c.pair = w.pair; c.cs = w.cs; c.ci0 = w.ci0; c.co0 = w.co0; c.cie = w.cie; c.coe = w.coe;
+    } else {
+        c.pair = 0; c.cs = 0; c.ci0 = 0; c.co0 = 0; c.cie = Ci; c.coe = Co;
     }
-    int lo = pair * total_cols;
-    while (item >= lo + total_cols) { lo += total_cols; ++pair; }
-    c.pair = pair;
-    int col = item - lo;
     const int tw = col % tiles_w;
     col /= tiles_w;
     c.oh0 = (col % tiles_h) * THW;
     c.n = col / tiles_h;
     c.u0 = tw * TU;
-    if (nsi == 1) {                      // output slices only (or a single pair)
-        c.cs = 0;
-        c.ci0 = 0;
-        c.co0 = pair * 16;
-    } else {
-        c.cs = pair % nsi;
-        c.ci0 = c.cs * 16;
-        c.co0 = (pair / nsi) * 16;
-    }
-    c.cie = Ci - c.ci0 < 16 ? Ci - c.ci0 : 16;
-    c.coe = Co - c.co0 < 16 ? Co - c.co0 : 16;
     return c;
 }
 __device__ __forceinline__ void drain_bar_sync() { asm volatile("bar.sync 1, 96;" ::: "memory"); }   // the three drain warps
@@ -297,12 +297,13 @@ wgrad3_tc4_kernel(SpConvDesc d, int nPerG, int G, int tiles_w, int tiles_h, int 
         // dZ role
         const bool zact = !isx && st < 2 * ZW;
         const int zhalf = st >= ZW ? 1 : 0, zj = st - zhalf * ZW;
-        int cl = grp / Do, od = grp - cl * Do, use = 0, pair_lb = 0;
+        int cl = grp / Do, od = grp - cl * Do, use = 0;
+        PairWalk pw = pair_walk_init(nsi, d.Ci, d.Co);
         for (int it = grp; it < nsteps; it += NGRP, ++use) {
             const int buf = grp;                                         // NGRP == NBUF: group = buffer, use = it / NBUF
             while (od >= Do) { od -= Do; ++cl; }
-            const ItemGeo cg = item_geo<MULTI>(first + cl * istep, pair_lb, total_cols, tiles_w, tiles_h, nsi, d.Ci, d.Co);
-            pair_lb = cg.pair;
+            if (MULTI) pair_walk_to(pw, first + cl * istep, total_cols, nsi, d.Ci, d.Co);
+            const ItemGeo cg = item_geo<MULTI>(first + cl * istep, pw, total_cols, tiles_w, tiles_h, nsi, d.Ci, d.Co);
             bool waited = false;
             long long c1 = pr ? clock64() : 0;
             if (isx) {
@@ -320,7 +321,7 @@ wgrad3_tc4_kernel(SpConvDesc d, int nPerG, int G, int tiles_w, int tiles_h, int 
 #pragma unroll 1
                 for (int p = 0; p < np; ++p) {
                     const bool nx = (p == 1) && next1;
-                    const ItemGeo c = nx ? item_geo<MULTI>(first + (cl + 1) * istep, cg.pair, total_cols, tiles_w, tiles_h, nsi, d.Ci, d.Co) : cg;
+                    const ItemGeo c = nx ? item_geo<MULTI>(first + (cl + 1) * istep, pw, total_cols, tiles_w, tiles_h, nsi, d.Ci, d.Co) : cg;
                     const int pj = (p == 0) ? od + 2 : nx ? od - (Do - 2) : p - 1;          // plane of its column
                     const int seq = (nx ? cl + 1 : cl) * PPC + pj;
                     const int gd = pj - d.pd, gw = c.u0 + wx, gh0 = c.oh0 - d.ph + hy0;
