@@ -33,63 +33,78 @@ sgemm_kernel(int M, int N, int K, int k_per_slice, const float* __restrict__ A, 
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
     const bool va = (lda % 4 == 0), vb = (ldb % 4 == 0);
 
-    for (int k0 = kbeg; k0 < kend; k0 += BK) {
-        // ---- A tile
+    // Register double buffering: the global loads of k-tile i + 1 are issued before the FFMAs of k-tile i (the kernel runs with
+    // a handful of warps per SM on the bottleneck layers: without the prefetch every k-tile paid a full load latency).
+    float ra[4];
+    float4 rb;
+    auto load_tiles = [&](int k0) {
         if (TA == 0) {
             const int row = t >> 2, kq = (t & 3) * 4;
             const int m = m0 + row, k = k0 + kq;
-            float v[4] = {0.f, 0.f, 0.f, 0.f};
+            ra[0] = ra[1] = ra[2] = ra[3] = 0.f;
             if (m < M) {
                 const float* p = A + (int64_t)m * lda + k;
                 if (va && k + 3 < kend) {
                     const float4 q = *reinterpret_cast<const float4*>(p);
-                    v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+                    ra[0] = q.x; ra[1] = q.y; ra[2] = q.z; ra[3] = q.w;
                 } else {
 #pragma unroll
                     for (int u = 0; u < 4; ++u)
-                        if (k + u < kend) v[u] = p[u];
+                        if (k + u < kend) ra[u] = p[u];
                 }
             }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) As[kq + u][row] = v[u];
         } else {
             const int krow = t >> 4, mq = (t & 15) * 4;
             const int k = k0 + krow, m = m0 + mq;
-            float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+            ra[0] = ra[1] = ra[2] = ra[3] = 0.f;
             if (k < kend) {
                 const float* p = A + (int64_t)k * lda + m;
                 if (va && m + 3 < M) {
-                    q = *reinterpret_cast<const float4*>(p);
+                    const float4 q = *reinterpret_cast<const float4*>(p);
+                    ra[0] = q.x; ra[1] = q.y; ra[2] = q.z; ra[3] = q.w;
                 } else {
-                    float v[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
                     for (int u = 0; u < 4; ++u)
-                        if (m + u < M) v[u] = p[u];
-                    q = make_float4(v[0], v[1], v[2], v[3]);
+                        if (m + u < M) ra[u] = p[u];
                 }
             }
-            *reinterpret_cast<float4*>(&As[krow][mq]) = q;
         }
-        // ---- B tile
         {
             const int krow = t >> 4, nq = (t & 15) * 4;
             const int k = k0 + krow, n = n0 + nq;
-            float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+            rb = make_float4(0.f, 0.f, 0.f, 0.f);
             if (k < kend) {
                 const float* p = B + (int64_t)k * ldb + n;
                 if (vb && n + 3 < N) {
-                    q = *reinterpret_cast<const float4*>(p);
+                    rb = *reinterpret_cast<const float4*>(p);
                 } else {
                     float v[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
                     for (int u = 0; u < 4; ++u)
                         if (n + u < N) v[u] = p[u];
-                    q = make_float4(v[0], v[1], v[2], v[3]);
+                    rb = make_float4(v[0], v[1], v[2], v[3]);
                 }
             }
-            *reinterpret_cast<float4*>(&Bs[krow][nq]) = q;
         }
+    };
+    auto store_tiles = [&]() {
+        if (TA == 0) {
+            const int row = t >> 2, kq = (t & 3) * 4;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) As[kq + u][row] = ra[u];
+        } else {
+            const int krow = t >> 4, mq = (t & 15) * 4;
+            *reinterpret_cast<float4*>(&As[krow][mq]) = make_float4(ra[0], ra[1], ra[2], ra[3]);
+        }
+        const int krow = t >> 4, nq = (t & 15) * 4;
+        *reinterpret_cast<float4*>(&Bs[krow][nq]) = rb;
+    };
+
+    if (kbeg < kend) load_tiles(kbeg);
+    for (int k0 = kbeg; k0 < kend; k0 += BK) {
+        store_tiles();
         __syncthreads();
+        if (k0 + BK < kend) load_tiles(k0 + BK);
 #pragma unroll
         for (int kk = 0; kk < BK; ++kk) {
             const float4 a = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
@@ -209,6 +224,19 @@ wgrad_fold_kernel(const float* __restrict__ part, int slices, int k3, int Ci, in
     }
 }
 
+// dst[m][n] = act(bias[n] + sum_z part[z][m][n]): epilogue of the split-K forward (fixed order over the slices)
+__global__ void __launch_bounds__(256)
+corr_fold_kernel(const float* __restrict__ part, int slices, int64_t M, int N, const float* __restrict__ bias, int act, float alpha,
+                 float* __restrict__ dst, int ldc) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= M * N) return;
+    const int64_t m = i / N;
+    const int n = (int)(i - m * N);
+    float v = 0.f;
+    for (int z = 0; z < slices; ++z) v += part[(int64_t)z * M * N + i];
+    dst[m * ldc + n] = sp_act_fwd(v + (bias ? bias[n] : 0.f), act, alpha);
+}
+
 // which = 1 pack of the GEMM tier: Wt[co][tap][ciP]
 __global__ void pack_wt_gemm_kernel(const float* __restrict__ w, float* __restrict__ wp, int Co, int Ci, int k3, int ciP) {
     const int64_t total = (int64_t)Co * k3 * ciP;
@@ -233,6 +261,7 @@ struct Plan {
     int kdim, k3, ciP;  // tap*Ci + ci columns; taps; padded I-side channels of the corrT pack
     int slices;         // split of the rows for wgrad
     int64_t rows_per_slice;
+    int fslices, fk_per_slice;   // split of K = kdim for the forward (the tiles alone are 1..2 CTAs per SM: latency-bound)
 };
 
 static inline Plan plan(const SpConvDesc* d) {
@@ -249,6 +278,15 @@ static inline Plan plan(const SpConvDesc* d) {
     if (s < 1) s = 1;
     p.rows_per_slice = sp_cdiv(sp_cdiv(p.M, s), BK) * BK;
     p.slices = (int)sp_cdiv(p.M, p.rows_per_slice);
+    {
+        const int64_t ftiles = sp_cdiv(p.M, BM) * sp_cdiv(d->Co, BN);
+        int64_t fs = sp_cdiv(4 * (int64_t)sp_num_sms(), ftiles);
+        if (fs > p.kdim / 128) fs = p.kdim / 128;
+        if (fs > 16) fs = 16;
+        if (fs < 1) fs = 1;
+        p.fk_per_slice = (int)(sp_cdiv(sp_cdiv(p.kdim, fs), BK) * BK);
+        p.fslices = (int)sp_cdiv(p.kdim, p.fk_per_slice);
+    }
     return p;
 }
 
@@ -272,7 +310,7 @@ static inline bool sp_gemm_serves(const SpConvDesc* d) {
 
 static inline size_t sp_gemm_corr_ws_bytes(const SpConvDesc* d) {
     const sp_gemm::Plan p = sp_gemm::plan(d);
-    return (size_t)p.M * p.kdim * sizeof(float);
+    return ((size_t)p.M * p.kdim + (p.fslices > 1 ? (size_t)p.fslices * p.M * d->Co : 0)) * sizeof(float);
 }
 static inline size_t sp_gemm_corrT_ws_bytes(const SpConvDesc* d) {
     const sp_gemm::Plan p = sp_gemm::plan(d);
@@ -290,9 +328,19 @@ static inline int sp_gemm_corr_launch(const SpConvDesc* d, int nPerG, const floa
     const int coP = (d->Co + 15) / 16 * 16;
     im2col_kernel<<<ew_blocks(p.M * p.kdim), 256, 0, st>>>(*d, nPerG, src, scale, shift, ws);
     SP_LAUNCH_OK("im2col_kernel");
-    dim3 grid((unsigned)sp_cdiv(d->Co, BN), (unsigned)sp_cdiv(p.M, BM), 1);
-    sgemm_kernel<0, 1><<<grid, 256, 0, st>>>((int)p.M, d->Co, p.kdim, p.kdim, ws, p.kdim, wp, coP, dst, d->ldo, 0, bias, d->act, d->alpha);
+    if (p.fslices <= 1) {
+        dim3 grid((unsigned)sp_cdiv(d->Co, BN), (unsigned)sp_cdiv(p.M, BM), 1);
+        sgemm_kernel<0, 1><<<grid, 256, 0, st>>>((int)p.M, d->Co, p.kdim, p.kdim, ws, p.kdim, wp, coP, dst, d->ldo, 0, bias, d->act, d->alpha);
+        SP_LAUNCH_OK("sgemm_kernel");
+        return 0;
+    }
+    // split K: partial products of every K slice, then bias + activation in the fold (fixed order)
+    float* part = ws + (size_t)p.M * p.kdim;
+    dim3 grid((unsigned)sp_cdiv(d->Co, BN), (unsigned)sp_cdiv(p.M, BM), (unsigned)p.fslices);
+    sgemm_kernel<0, 0><<<grid, 256, 0, st>>>((int)p.M, d->Co, p.kdim, p.fk_per_slice, ws, p.kdim, wp, coP, part, d->Co, (int64_t)p.M * d->Co, nullptr, 0, 0.f);
     SP_LAUNCH_OK("sgemm_kernel");
+    corr_fold_kernel<<<ew_blocks(p.M * d->Co), 256, 0, st>>>(part, p.fslices, p.M, d->Co, bias, d->act, d->alpha, dst, d->ldo);
+    SP_LAUNCH_OK("corr_fold_kernel");
     return 0;
 }
 
