@@ -495,16 +495,25 @@ SpTier corrT_tier(const SpConvDesc* d, SpTcCfg* cfg) {
     return TIER_GENERIC;
 }
 
-// Which kernel generation serves a layer of the tensor-core tier: generation 3 (kw-stacked N, rolling depth window) for output
-// widths up to 16 and for every slice / pass of the wide layers; the 17..24-wide layers of the CAE's second level stay on
-// generation 2 in the fp32-grade mode (their kw-stacked N would be 240 columns with 2 accumulators and a half-empty second
-// K pass: measured 0.83 vs 0.72 ms on Cae3D.py:55).  The bf16 mode exists in generation 3 only.
-bool use_gen3(const SpTcCfg& cfg) { return sp_tc_terms() == 1 || (sp_tc_terms() == 5 && cfg.cop == 16); }
+// Which kernel generation serves a layer of the tensor-core tier: generation 3 (kw-stacked N, rolling depth window, TMA) for output
+// widths up to 16 and for every slice / pass of the wide layers; for the 17..24-wide layers of the CAE's second level (kw-stacked N =
+// 240 columns, 2 accumulators, a half-empty second K pass) it depends on the direction.  The bf16 mode exists in generation 3 only.
+// which = 0: sp_corr (forward of a Conv3d), 1: sp_corrT (its dgrad).  Measured in the CAE step after the elected-issue / TMA work:
+// the 24-wide FORWARDS are faster on generation 3 (0.795 -> 0.654, 0.527 -> 0.488, 0.518 -> 0.482 ms), their dgrads on generation 2
+// (0.488 vs 0.588, 0.381 vs 0.445 ms).
+bool use_gen3(const SpTcCfg& cfg, int which) {
+    static int g2 = -1;   // SP_TC3_COP24=0: generation 2 for every 17..24-wide layer (A/B checks)
+    if (g2 < 0) {
+        const char* e = getenv("SP_TC3_COP24");
+        g2 = (e && e[0] == '0') ? 1 : 0;
+    }
+    return sp_tc_terms() == 1 || (sp_tc_terms() == 5 && (cfg.cop == 16 || (which == 0 && !g2)));
+}
 
-int tc_corr_launch(const SpConvDesc* d, const SpTcCfg& cfg, int nPerG, const float* src, const float* wimg, const float* bias,
+int tc_corr_launch(const SpConvDesc* d, const SpTcCfg& cfg, int which, int nPerG, const float* src, const float* wimg, const float* bias,
                    const float* scale, const float* shift, float* dst, cudaStream_t st) {
     const uint4* img = reinterpret_cast<const uint4*>(wimg);
-    if (use_gen3(cfg)) return sp_tc3_corr_launch(d, nPerG, sp_tc_image_terms(), src, img, bias, scale, shift, dst, st);
+    if (use_gen3(cfg, which)) return sp_tc3_corr_launch(d, nPerG, sp_tc_image_terms(), src, img, bias, scale, shift, dst, st);
     if (sp_tc_terms() == 4 || sp_tc_terms() == 5) return sp_tc2_corr_launch(d, nPerG, src, img, bias, scale, shift, dst, st);
     if (sp_tc_terms() == 2) return sp_tc_corr_launch_t<16, 16, 2, 4>(d, nPerG, src, img, bias, scale, shift, dst, st);
     return sp_tc_corr_launch_t<16, 16, 3, 2>(d, nPerG, src, img, bias, scale, shift, dst, st);
@@ -536,7 +545,7 @@ size_t sp_packed_weight_floats(const SpConvDesc* d, int which) {
     size_t n = ffma_packed_floats(d, which);
     SpTcCfg cfg;
     const bool tc = (which == 0 ? corr_tier(d, &cfg) : corrT_tier(d, &cfg)) == TIER_TC;
-    if (tc && use_gen3(cfg))
+    if (tc && use_gen3(cfg, which))
         n += (size_t)cfg.passes * cfg.nslices * sp_tc3_wimg_u4(cfg.cop, sp_tc_image_terms()) * 4;
     else if (tc) n += (size_t)cfg.passes * cfg.nslices * sp_tc_wimg_bytes(cfg.cip, cfg.cop, sp_tc_image_terms()) / sizeof(float);
     return n;
@@ -561,7 +570,7 @@ int sp_pack_weights(const SpConvDesc* d, int which, const float* w_torch, float*
         pack_weights_kernel<<<grid_for(total), 256, 0, sp_stream(stream)>>>(w_torch, w_packed, d->Co, d->Ci, k3, which, dP);
         SP_LAUNCH_OK("pack_weights_kernel");
     }
-    if (tc && use_gen3(cfg))
+    if (tc && use_gen3(cfg, which))
         return sp_tc3_pack_launch(d, which, sp_tc_image_terms(), cfg.cop, w_torch, w_packed + total, sp_stream(stream), cfg.passes, cfg.nslices);
     if (tc)
         return sp_tc_pack_launch(d, which, sp_tc_image_terms(), cfg.cip, cfg.cop, w_torch, w_packed + total, sp_stream(stream), cfg.passes, cfg.nslices);
@@ -591,7 +600,7 @@ int sp_corr(const SpConvDesc* d, const float* src, const float* wp, const float*
     SpTcCfg cfg;
     const SpTier tier = corr_tier(d, &cfg);
     if (tier == TIER_TC)
-        return tc_corr_launch(d, cfg, nPerG, src, wp + ffma_packed_floats(d, 0), bias, scale, shift, dst, sp_stream(stream));
+        return tc_corr_launch(d, cfg, 0, nPerG, src, wp + ffma_packed_floats(d, 0), bias, scale, shift, dst, sp_stream(stream));
     if (sp_k2s2_supported(d) && sp_k2s2_aligned(src, dst) && (!bias || sp_k2s2_aligned(bias, wp)))
         return sp_k2s2_down_launch(d, nPerG, src, wp, bias, scale, shift, dst, sp_stream(stream));
     if (sp_thin_fwd_supported(d)) return sp_thin_fwd_launch(d, nPerG, src, wp, /*flip=*/0, bias, scale, shift, dst, sp_stream(stream));
@@ -627,7 +636,7 @@ int sp_corrT(const SpConvDesc* d, const float* src, const float* wp, const float
         // padding k-1-p; Wt[tap][co][ciP] read with flipped tap index is exactly that correlation's Wc.
         const SpConvDesc f = flipped_desc(d);
         if (tier == TIER_TC)
-            return tc_corr_launch(&f, cfg, nPerG, src, wp + ffma_packed_floats(d, 1), bias, scale, shift, dst, sp_stream(stream));
+            return tc_corr_launch(&f, cfg, 1, nPerG, src, wp + ffma_packed_floats(d, 1), bias, scale, shift, dst, sp_stream(stream));
         if (sp_thin_bwd_supported(&f)) return sp_thin_bwd_launch(&f, nPerG, src, wp, bias, scale, shift, dst, sp_stream(stream));
         if (f.pd >= 0 && f.ph >= 0 && f.pw >= 0 && sp_tiled_corr_supported(&f))
             return sp_tiled_corr_launch(&f, nPerG, src, wp, /*flip=*/1, bias, scale, shift, dst, sp_stream(stream));

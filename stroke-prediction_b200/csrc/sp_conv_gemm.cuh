@@ -314,13 +314,13 @@ wgrad_fold_kernel(const float* __restrict__ part, int slices, int k3, int Ci, in
 __global__ void __launch_bounds__(256)
 corr_fold_kernel(const float* __restrict__ part, int slices, int64_t M, int N, const float* __restrict__ bias, int act, float alpha,
                  float* __restrict__ dst, int ldc) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= M * N) return;
-    const int64_t m = i / N;
-    const int n = (int)(i - m * N);
-    float v = 0.f;
-    for (int z = 0; z < slices; ++z) v += part[(int64_t)z * M * N + i];
-    dst[m * ldc + n] = sp_act_fwd(v + (bias ? bias[n] : 0.f), act, alpha);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < M * N; i += (int64_t)gridDim.x * blockDim.x) {   // ew_blocks caps the grid
+        const int64_t m = i / N;
+        const int n = (int)(i - m * N);
+        float v = 0.f;
+        for (int z = 0; z < slices; ++z) v += part[(int64_t)z * M * N + i];
+        dst[m * ldc + n] = sp_act_fwd(v + (bias ? bias[n] : 0.f), act, alpha);
+    }
 }
 
 // which = 1 pack of the GEMM tier: Wt[co][tap][ciP]
@@ -367,6 +367,12 @@ static inline Plan plan(const SpConvDesc* d) {
     {
         const int64_t ftiles = sp_cdiv(p.M, BM) * sp_cdiv(d->Co, BN);
         int64_t fs = sp_cdiv(4 * (int64_t)sp_num_sms(), ftiles);
+        static int nosplit = -1;   // SP_GEMM_NOSPLITK=1: single-slice forward (A/B checks)
+        if (nosplit < 0) {
+            const char* e = getenv("SP_GEMM_NOSPLITK");
+            nosplit = (e && e[0] == '1') ? 1 : 0;
+        }
+        if (nosplit) fs = 1;
         if (fs > p.kdim / 128) fs = p.kdim / 128;
         if (fs > 16) fs = 16;
         if (fs < 1) fs = 1;

@@ -127,6 +127,21 @@ def test_fused_unit_forward_backward(case, with_bn):
     _check_sequential(nn.Sequential(*mods), x)
 
 
+@pytest.mark.parametrize("kind", ["C", "T"])
+def test_paper_width_bottleneck_at_batch_8(kind):
+    """Cae3D.py:74 / :178 at fc = 800 and the stacked batch of a training step (8 samples): 800 rows x 800 columns of GEMM output —
+    more elements than the capped element-wise grids of the GEMM tier hold threads (their kernels must grid-stride), split-K forward
+    with several slices, 128-bit im2col / col2im."""
+    torch.manual_seed(150)
+    if kind == "C":
+        conv, x = nn.Conv3d(100, 800, 3), torch.randn(8, 100, 3, 12, 12) * 1.5 + 0.3
+        mods = [nn.BatchNorm3d(100), conv, nn.ELU(1.0, True)]
+    else:
+        conv, x = nn.ConvTranspose3d(800, 100, 3), torch.randn(8, 800, 1, 10, 10) * 1.5 + 0.3
+        mods = [nn.BatchNorm3d(800), conv, nn.ELU(1.0, True)]
+    _check_sequential(nn.Sequential(*mods), x, G=2)
+
+
 TILED_CASES = [
     # big enough (>= 2048 output voxels, Wo >= 8) to take the shared-memory tiled 3x3x3 path, with ragged tile edges
     ("C", 16, 16, 3, 1, (1, 0, 0), "elu", (9, 20, 37)),        # Cae3D.py:44
