@@ -1,5 +1,6 @@
-// sp_wgrad_tc4.cuh — second-generation tcgen05 / TMEM weight gradient of the 16-channel 3x3x3 stride-1 layers
-// (Cae3D.py:44,208,211; Unet3D.py:22), the three largest kernels of the CAE training step.
+// sp_wgrad_tc4.cuh — second-generation tcgen05 / TMEM weight gradient of the 3x3x3 stride-1 layers: 16 x 16 channels per slice
+// pair (Cae3D.py:44,208,211; Unet3D.py:22 — the three largest kernels of the round-1 CAE training step), wider layers (up to
+// 96 -> 64: Cae3D.py:52,55,186-200; Unet3D.py:19,22) as several slice pairs walked by ONE launch, thin inputs (2..8 channels).
 //
 //   dW[co][ci][kd][kh][kw] = sum_{n,od,oh,ow} dZ[n,od,oh,ow,co] * X'[n, od-pd+kd, oh-ph+kh, ow-pw+kw, ci]
 //
@@ -32,7 +33,8 @@
 // a fixed (row set, channel half, column), so a step costs a few pointer increments.  A CTA walks a column (n, 4 output
 // rows, 32 input columns) along the depth axis through a ring of seven X' planes; the first two planes of the NEXT column
 // are staged during the last two steps of the current one, so every step but the CTA's first stages one or two planes.
-// Partials of every CTA go to ws[cta][co][ci][27] (torch layout) and are folded in fixed order by wgrad_reduce_kernel.
+// Work items = (slice pair, tile column), dealt out round-robin over the CTAs; the drain warps flush the accumulators to
+// ws[pair][cta] as [co 16][ci 16][27] at every pair change, wgrad_reduce_pairs_kernel folds them in CTA order (deterministic).
 #pragma once
 #include "sp_wgrad_tc.cuh"
 
