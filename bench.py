@@ -37,7 +37,7 @@ SCALED_CAE = (60, 256, 256)       # BASELINE configs[4]; D = 64 does not round-t
 SCALED_UNET_OUT = (64, 256, 256)  # input 2 x 104 x 296 x 296
 EPOCH = 60            # ramp factor f = 1 (CaeReconstructionLearner.py:53)
 UNIT = "volumes/s"
-FFMA_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12     # 148 SMs x 128 FP32 lanes x 2 flop x max SM clock (no measured figure)
+FFMA_PEAK_TFLOPS = 63.8      # MEASURED on the pool's B200 (tools/microbench/ffma_rate, profiles/r02_ffma_rate.log); nominal 148 x 128 x 2 x 1.965 GHz = 74.4
 
 
 def metric_name(workload):
