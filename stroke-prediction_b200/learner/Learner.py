@@ -196,6 +196,63 @@ class Learner(Inference):
         del dto
         return batch_metrics
 
+    # keys of a batch dict whose tensors are only consumed on the device (the clinical scalars are read on the host)
+    PREFETCH_KEYS = ('images', 'labels')
+
+    def prefetched(self, loader):
+        """Iterate `loader` one batch ahead: the host-to-device copy of batch i + 1 (its `images` / `labels` tensors; pinned host
+        memory makes the copy asynchronous) is issued on a copy stream while batch i trains, so the epoch loop of `run_training`
+        (Learner.py:161-163) never waits for PCIe.  `inference_step` takes tensors that are already on the device as they are."""
+        dev = self.device if self.is_cuda else None
+        if dev is None:
+            for batch in loader:
+                yield batch
+            return
+        copy = self.__dict__.get('_copy_stream')
+        if copy is None:
+            copy = self._copy_stream = torch.cuda.Stream(dev)
+            self._copy_bufs = {}                    # (key, slot) -> persistent device staging tensor (no allocator traffic per step)
+        bufs = self._copy_bufs
+        free = [None, None]                         # main-stream event: the step that consumed this slot has been queued
+
+        def stage(batch, slot):
+            out = dict(batch)
+            if free[slot] is not None:
+                copy.wait_event(free[slot])         # do not overwrite a buffer the main stream still reads
+            with torch.cuda.stream(copy):
+                for k in self.PREFETCH_KEYS:
+                    v = out.get(k)
+                    if torch.is_tensor(v) and not v.is_cuda and v.numel() >= 1 << 16:
+                        b = bufs.get((k, slot))
+                        if b is None or b.shape != v.shape or b.dtype != v.dtype:
+                            b = bufs[(k, slot)] = torch.empty(v.shape, dtype=v.dtype, device=dev)
+                        b.copy_(v, non_blocking=v.is_pinned())
+                        out[k] = b
+            return out, copy.record_event()
+
+        it = iter(loader)
+        try:
+            nxt = stage(next(it), 0)
+        except StopIteration:
+            return
+        slot = 0
+        while nxt is not None:
+            cur, ev = nxt
+            try:
+                nxt = stage(next(it), slot ^ 1)
+            except StopIteration:
+                nxt = None
+            main = torch.cuda.current_stream(dev)
+            main.wait_event(ev)
+            yield cur                               # the caller trains on `cur` (main stream) before asking for the next batch
+            free[slot] = torch.cuda.current_stream(dev).record_event()
+            slot ^= 1
+
+    def train_batches(self, loader, epoch):
+        """`train_batch` over `loader` with the next batch's H2D copy overlapped (what `run_training` runs per epoch)."""
+        for batch in self.prefetched(loader):
+            yield self.train_batch(batch, epoch)
+
     def enable_data_parallel(self, process_group=None):
         """Batch-sharded training over torch.distributed (one process per GPU): gradients are summed with one
         all-reduce of the flat gradient buffer and averaged inside the Adam kernel (DDP semantics)."""
@@ -242,8 +299,8 @@ class Learner(Inference):
             # (1) training
             self._model.train()
             epoch_metrics = MetricMeasuresDtoInit.init_dto()
-            for batch in self._dataloader_training:
-                epoch_metrics.add(self.train_batch(batch, epoch))
+            for batch_metrics in self.train_batches(self._dataloader_training, epoch):
+                epoch_metrics.add(batch_metrics)
             epoch_metrics.div(len(self._dataloader_training))
             self.print_epoch(epoch, 'training', epoch_metrics)
             self._metric_dtos['training'].append(epoch_metrics)

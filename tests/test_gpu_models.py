@@ -364,6 +364,27 @@ def test_overlapped_batch_metrics_equal_serial_ones():
         assert torch.equal(a, b)
 
 
+def test_prefetched_epoch_loop_equals_plain_train_batch():
+    """Learner.train_batches (the epoch loop of run_training: host-to-device copy of batch i + 1 on a copy stream while batch i
+    trains) gives the same metrics and parameters as calling train_batch on the host batches one after the other."""
+    A = _api()
+    ch = [1, 4, 6, 8, 10, 12, 1]
+    batches = [{k: (v.pin_memory() if torch.is_tensor(v) else v) for k, v in A.data.synthetic_cae_batch(2, size=(28, 56, 56), seed=80 + i).items()}
+               for i in range(4)]
+    runs = []
+    for prefetch in (True, False):
+        torch.manual_seed(24)
+        cae = A.Cae3D(A.Enc3D(56, 28, ch, 5, 1.0), A.Dec3D(56, 28, ch, 5, 1.0)).cuda().train()
+        opt = torch.optim.Adam(cae.parameters(), lr=1e-3, weight_decay=1e-5, betas=(0.9, 0.999))
+        learner = A.CaeReconstructionLearner(None, None, cae, opt, None, 10, None, "/tmp/x", A.BatchDiceLoss([1.0]))
+        ms = list(learner.train_batches(batches, 3)) if prefetch else [learner.train_batch(b, 3) for b in batches]
+        torch.cuda.synchronize()
+        runs.append(([(m.loss, m.lesion.dc, m.core.dc, m.penu.dc, m.lesion.hd) for m in ms], [p.detach().clone() for p in cae.parameters()]))
+    assert runs[0][0] == runs[1][0], (runs[0][0], runs[1][0])
+    for a, b in zip(runs[0][1], runs[1][1]):
+        assert torch.equal(a, b)
+
+
 def test_tester_eval_batch_one():
     """Tester path: eval mode, batch size 1 (breaks in the reference on current torch)."""
     A = _api()
