@@ -651,7 +651,7 @@ static inline bool sp_tc4_wgrad_aligned(const SpConvDesc* d, const void* iside, 
 
 static inline int sp_tc4_wgrad_launch(const SpConvDesc* d, int nPerG, const float* iside, const float* i_scale, const float* i_shift,
                                       const float* oside, const float* o_scale, const float* o_shift, float* dw, float beta, float* ws,
-                                      cudaStream_t st, long long* prof = nullptr, int drain_every = 6) {
+                                      cudaStream_t st, long long* prof = nullptr, int drain_every = 6) {   // 48 accumulations per drain: rel-L2 4.6e-7 (8 steps: 6.7e-7 and 4 % faster; 2 steps: 3.0e-7)
     using namespace sp_wtc4;
     const Wtc4Plan p = plan(d);
     static bool attr = false;
