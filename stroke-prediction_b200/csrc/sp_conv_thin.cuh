@@ -13,6 +13,7 @@
 
 #ifndef SP_THIN_FWD_MINB
 #define SP_THIN_FWD_MINB 2
+#define SP_THIN_FWD1_MINB 2   // three CTAs per SM (80 registers, 176 B of spills): 0.687 -> 0.739 ms, not taken
 #define SP_THIN_BWD_MINB 2
 #define SP_THIN_WGRAD_MINB 1
 #endif
@@ -26,7 +27,7 @@ constexpr int NT = 256;
 // ---------------------------------------------------------------------------------------------------------------- forward
 // wp: packed [tap][ci][coP]; flip != 0 reads tap 26 - t.  blockIdx.y = pass over 16 output channels.
 template <int CI>
-__global__ void __launch_bounds__(NT, SP_THIN_FWD_MINB)
+__global__ void __launch_bounds__(NT, (CI == 1) ? SP_THIN_FWD1_MINB : SP_THIN_FWD_MINB)
 thin_fwd_kernel(SpConvDesc d, int nPerG, int coP, int tiles_w, int tiles_h, int tiles_d, const float* __restrict__ src,
                 const float* __restrict__ wp, int flip, const float* __restrict__ bias, const float* __restrict__ scale,
                 const float* __restrict__ shift, float* __restrict__ dst) {
