@@ -58,12 +58,13 @@ static_assert(W_STG_Z * 32 >= 2 * ZW, "staging roles");
 struct ColGeo {
     int n, oh0, j0, q;
 };
-// tile columns of parity 0 come first (total0 of them, tiles_w0 per row block), then those of parity 1
-__device__ __forceinline__ ColGeo col_geo(int col, int total0, int tiles_w0, int tiles_w1, int tiles_h) {
+// The two parities of one tile column are NEIGHBOURING work items (q = item & 1): the CTAs that run side by side read the same
+// 128-byte lines of X (two voxels of 64 B: one per parity) at the same time, so the second read hits L2.  Parity-major order
+// re-read every line from DRAM: 1.98 GB per launch for 0.79 GB of operands (ncu, profiles/r02_ncu_tc_kernels_in_step.csv).
+__device__ __forceinline__ ColGeo col_geo(int item, int tiles_w, int tiles_h) {
     ColGeo c;
-    c.q = col >= total0 ? 1 : 0;
-    if (c.q) col -= total0;
-    const int tiles_w = c.q ? tiles_w1 : tiles_w0;
+    c.q = item & 1;
+    int col = item >> 1;
     const int tw = col % tiles_w;
     col /= tiles_w;
     c.oh0 = (col % tiles_h) * THW;
@@ -73,7 +74,7 @@ __device__ __forceinline__ ColGeo col_geo(int col, int total0, int tiles_w0, int
 }
 
 __global__ void __launch_bounds__(NTHREADS_S2, 1)
-wgrad3_tc4s2_kernel(SpConvDesc d, int kk, int nPerG, int G, int total0, int tiles_w0, int tiles_w1, int tiles_h, int total_cols, int drain_every, int isstride,
+wgrad3_tc4s2_kernel(SpConvDesc d, int kk, int nPerG, int G, int tiles_w, int tiles_h, int total_cols, int drain_every, int isstride,
                     int osstride, const float* __restrict__ X, const float* __restrict__ i_scale, const float* __restrict__ i_shift,
                     const float* __restrict__ dZ, const float* __restrict__ o_scale, const float* __restrict__ o_shift,
                     float* __restrict__ ws, long long* __restrict__ prof, int nt) {
@@ -140,7 +141,7 @@ wgrad3_tc4s2_kernel(SpConvDesc d, int kk, int nPerG, int G, int total0, int tile
         for (int it = grp; it < nsteps; it += NGRP) {
             const int buf = it % NBUF, use = it / NBUF;
             const int cl = it / Do, od = it - cl * Do;
-            const ColGeo cg = col_geo((int)blockIdx.x + cl * (int)gridDim.x, total0, tiles_w0, tiles_w1, tiles_h);
+            const ColGeo cg = col_geo((int)blockIdx.x + cl * (int)gridDim.x, tiles_w, tiles_h);
             const int q = cg.q;
             bool waited = false;
             long long c1 = pr ? clock64() : 0;
@@ -399,15 +400,14 @@ __global__ void wgrad_reduce_s2_kernel(const float* __restrict__ ws, int chunks,
 }
 
 struct Plan {
-    int tiles_w[2], tiles_h, grid;
-    int64_t total0, total;      // tile columns of parity 0 / of both parities
+    int tiles_w, tiles_h, grid;
+    int64_t total;      // work items: (tile column, parity), parity fastest
 };
 static inline Plan plan(const SpConvDesc* d) {
     Plan p;
     p.tiles_h = (d->Ho + THW - 1) / THW;
-    for (int q = 0; q < 2; ++q) p.tiles_w[q] = ((d->Wi + 1 - q) / 2 + TU - 1) / TU;      // input columns of parity q, 32 per tile
-    p.total0 = (int64_t)p.tiles_w[0] * p.tiles_h * d->N;
-    p.total = p.total0 + (int64_t)p.tiles_w[1] * p.tiles_h * d->N;
+    p.tiles_w = ((d->Wi + 1) / 2 + TU - 1) / TU;                        // 32 input columns of one parity per tile (even columns: ceil(Wi / 2))
+    p.total = 2 * (int64_t)p.tiles_w * p.tiles_h * d->N;
     p.grid = sp_num_sms();
     const int cap = sp_wtc4_grid_cap_ref();
     if (cap > 0 && p.grid > cap) p.grid = cap;
@@ -453,7 +453,7 @@ static inline int sp_tc4s2_wgrad_launch(const SpConvDesc* d, int nPerG, const fl
             SpConvDesc s = *d;
             s.Ci = (d->Ci - 16 * c < 16) ? d->Ci - 16 * c : 16;
             s.Co = (d->Co - 16 * co < 16) ? d->Co - 16 * co : 16;
-            wgrad3_tc4s2_kernel<<<p.grid, NTHREADS_S2, SMEM, st>>>(s, d->k, nPerG, G, (int)p.total0, p.tiles_w[0], p.tiles_w[1], p.tiles_h, (int)p.total,
+            wgrad3_tc4s2_kernel<<<p.grid, NTHREADS_S2, SMEM, st>>>(s, d->k, nPerG, G, p.tiles_w, p.tiles_h, (int)p.total,
                                                                    drain_every, d->Ci, d->Co, iside + 16 * c, i_scale ? i_scale + 16 * c : nullptr,
                                                                    i_shift ? i_shift + 16 * c : nullptr, oside + 16 * co,
                                                                    o_scale ? o_scale + 16 * co : nullptr, o_shift ? o_shift + 16 * co : nullptr, ws,
