@@ -54,63 +54,52 @@ static inline int sp_num_sms() {
 static inline int64_t sp_cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 // ---- activations ----------------------------------------------------------------------------
-// expm1 on v <= 0 for the ELU epilogues (16 .. 24 evaluations per output voxel in the tensor-core tiers' epilogue warps), branch
-// free.  |v| < 1/4: degree-8 Taylor polynomial in Horner form (truncation v^9 / 9! < 1e-9 relative).  Otherwise exp(v) - 1 with
-// exp by Cody-Waite range reduction (n = rint(v log2 e), r = v - n ln 2 in two steps, |r| <= 0.347), a degree-7 polynomial
-// (r^8 / 8! < 5e-9) and the scaling 2^n applied to the exponent field; |result| >= 0.22, so the subtraction costs < 3e-7 relative.
-// Measured against fp64 on 2.2 M points: max relative error 1.3e-7 (libm's expm1f in fp32: 1.9e-7).
-__device__ __forceinline__ float sp_exp_nonpos(float v) {
-    v = fmaxf(v, -87.f);
-    const float t = fmaf(v, 1.442695041f, 12582912.f);           // 1.5 * 2^23: n = rint(v * log2 e) lands in the low mantissa bits
-    const float n = t - 12582912.f;
-    float r = fmaf(n, -0.693145752f, v);
-    r = fmaf(n, -1.428606765e-6f, r);
-    float p = fmaf(r, 1.f / 5040.f, 1.f / 720.f);
-    p = fmaf(r, p, 1.f / 120.f);
-    p = fmaf(r, p, 1.f / 24.f);
-    p = fmaf(r, p, 1.f / 6.f);
-    p = fmaf(r, p, 0.5f);
-    p = fmaf(r, p, 1.f);
-    p = fmaf(r, p, 1.f);
-    return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+// expm1 on v <= 0 for the ELU epilogues (16 .. 24 evaluations per output voxel in the tensor-core tiers' epilogue warps; 64 per
+// thread in the thin first-layer kernel, where the previous all-FMA form — Cody-Waite exponential + Taylor series, ~28
+// instructions per value — was more than half of the kernel's instruction stream), branch free, ~14 instructions:
+//   -1 < v <= 0: v * q(v), q = degree-6 Chebyshev fit of expm1(v) / v on [-1, 0] (fit error 2.4e-8; fp32 Horner: 1.5e-7 max relative)
+//   v <= -1:     ex2.approx(v * log2 e) - 1 on the MUFU pipe: |result| >= 0.63 and exp(v) <= 0.37, so the 2^-22 relative error
+//                bound of ex2.approx and the rounding of v * log2 e stay below 2.4e-7 relative to the result.
+// (libm's expm1f in fp32: 1.9e-7.)  tools/microbench/elu_err.cu measures it on the device.
+__device__ __forceinline__ float sp_ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
 }
+#define SP_EM1_C1 0.4999997913837433f
+#define SP_EM1_C2 0.16666345298290253f
+#define SP_EM1_C3 0.0416470430791378f
+#define SP_EM1_C4 0.008275879546999931f
+#define SP_EM1_C5 0.0013011073460802436f
+#define SP_EM1_C6 0.0001291868684347719f
 __device__ __forceinline__ float sp_expm1_neg(float v) {
-    const float p = fmaf(v, fmaf(v, fmaf(v, fmaf(v, fmaf(v, fmaf(v, fmaf(v, 1.f / 40320.f, 1.f / 5040.f), 1.f / 720.f), 1.f / 120.f),
-                                                  1.f / 24.f), 1.f / 6.f), 0.5f), 1.f);
-    return v > -0.25f ? v * p : sp_exp_nonpos(v) - 1.f;
+    const float q = fmaf(v, fmaf(v, fmaf(v, fmaf(v, fmaf(v, fmaf(v, SP_EM1_C6, SP_EM1_C5), SP_EM1_C4), SP_EM1_C3), SP_EM1_C2), SP_EM1_C1), 1.f);
+    const float e = sp_ex2_approx(v * 1.442695041f) - 1.f;
+    return v > -1.f ? v * q : e;
 }
-// ELU of N values at once, written level by level so that the N independent dependency chains (~26 dependent FMAs each) are
-// interleaved in the instruction stream.  Evaluated one value after the other (what the compiler emits for a loop over
-// sp_act_fwd) the epilogue warps of the tensor-core tiers issued one instruction every ~4 cycles: ncu stall_wait 3 : 1 selected.
+// ELU of N values at once, written level by level so that the N independent dependency chains are interleaved in the instruction
+// stream.  Evaluated one value after the other (what the compiler emits for a loop over sp_act_fwd) the epilogue warps of the
+// tensor-core tiers issued one instruction every ~4 cycles: ncu stall_wait 3 : 1 selected.
 template <int N>
 __device__ __forceinline__ void sp_elu_n(float* v, float alpha) {
-    float x[N], t[N], r[N], p[N], q[N];
+    float x[N], e[N], q[N];
 #pragma unroll
     for (int j = 0; j < N; ++j) x[j] = fminf(v[j], 0.f);
 #pragma unroll
-    for (int j = 0; j < N; ++j) t[j] = fmaf(fmaxf(x[j], -87.f), 1.442695041f, 12582912.f);
+    for (int j = 0; j < N; ++j) { e[j] = sp_ex2_approx(x[j] * 1.442695041f); q[j] = fmaf(x[j], SP_EM1_C6, SP_EM1_C5); }
 #pragma unroll
-    for (int j = 0; j < N; ++j) r[j] = fmaf(t[j] - 12582912.f, -0.693145752f, fmaxf(x[j], -87.f));
+    for (int j = 0; j < N; ++j) q[j] = fmaf(x[j], q[j], SP_EM1_C4);
 #pragma unroll
-    for (int j = 0; j < N; ++j) r[j] = fmaf(t[j] - 12582912.f, -1.428606765e-6f, r[j]);
+    for (int j = 0; j < N; ++j) q[j] = fmaf(x[j], q[j], SP_EM1_C3);
 #pragma unroll
-    for (int j = 0; j < N; ++j) { p[j] = fmaf(r[j], 1.f / 5040.f, 1.f / 720.f); q[j] = fmaf(x[j], 1.f / 40320.f, 1.f / 5040.f); }
+    for (int j = 0; j < N; ++j) q[j] = fmaf(x[j], q[j], SP_EM1_C2);
 #pragma unroll
-    for (int j = 0; j < N; ++j) { p[j] = fmaf(r[j], p[j], 1.f / 120.f); q[j] = fmaf(x[j], q[j], 1.f / 720.f); }
+    for (int j = 0; j < N; ++j) q[j] = fmaf(x[j], q[j], SP_EM1_C1);
 #pragma unroll
-    for (int j = 0; j < N; ++j) { p[j] = fmaf(r[j], p[j], 1.f / 24.f); q[j] = fmaf(x[j], q[j], 1.f / 120.f); }
-#pragma unroll
-    for (int j = 0; j < N; ++j) { p[j] = fmaf(r[j], p[j], 1.f / 6.f); q[j] = fmaf(x[j], q[j], 1.f / 24.f); }
-#pragma unroll
-    for (int j = 0; j < N; ++j) { p[j] = fmaf(r[j], p[j], 0.5f); q[j] = fmaf(x[j], q[j], 1.f / 6.f); }
-#pragma unroll
-    for (int j = 0; j < N; ++j) { p[j] = fmaf(r[j], p[j], 1.f); q[j] = fmaf(x[j], q[j], 0.5f); }
-#pragma unroll
-    for (int j = 0; j < N; ++j) { p[j] = fmaf(r[j], p[j], 1.f); q[j] = fmaf(x[j], q[j], 1.f); }
+    for (int j = 0; j < N; ++j) q[j] = fmaf(x[j], q[j], 1.f);
 #pragma unroll
     for (int j = 0; j < N; ++j) {
-        const float e = __int_as_float(__float_as_int(p[j]) + (__float_as_int(t[j]) << 23)) - 1.f;      // exp(x) - 1
-        const float m = x[j] > -0.25f ? x[j] * q[j] : e;                                                  // expm1(x), x <= 0
+        const float m = x[j] > -1.f ? x[j] * q[j] : e[j] - 1.f;                                          // expm1(x), x <= 0
         v[j] = fmaf(alpha, m, fmaxf(v[j], 0.f));
     }
 }
