@@ -200,13 +200,23 @@ class FusedUnit:
             return ops.conv_desc(N, out_size, self.cout, in_size, self.cin, self.k, self.s, self.pad, a, al)
         return ops.conv_desc(N, in_size, self.cin, out_size, self.cout, self.k, self.s, self.pad, a, al)
 
+    @staticmethod
+    def _geom(d, which):
+        return (which, d.N, d.Di, d.Hi, d.Wi, d.Ci, d.ldi, d.Do, d.Ho, d.Wo, d.Co, d.ldo, d.k, d.s, d.pd, d.ph, d.pw)
+
+    def has_pack(self, d, which):
+        """True when packed(d, which) would be served from the cache."""
+        w = self.conv.weight
+        hit = self._packed.get(self._geom(d, which))
+        return hit is not None and hit[0] == (w._version, w.data_ptr(), _weights_epoch)
+
     def packed(self, d, which):
         """Packed weights for direction `which` under geometry `d`.  The layout sp_pack_weights writes (FFMA / GEMM /
         tensor-core image, and the buffer size) depends on the tier the GEOMETRY selects, so the cache is keyed on the
         geometry as well as on the parameter version: the same unchanged weights at another volume size (validation,
         Tester, visualisation) get their own pack."""
         w = self.conv.weight
-        geom = (which, d.N, d.Di, d.Hi, d.Wi, d.Ci, d.ldi, d.Do, d.Ho, d.Wo, d.Co, d.ldo, d.k, d.s, d.pd, d.ph, d.pw)
+        geom = self._geom(d, which)
         key = (w._version, w.data_ptr(), _weights_epoch)
         hit = self._packed.get(geom)
         if hit is not None and hit[0] == key:
@@ -273,6 +283,52 @@ class SeqSaved:
         self.G = 1
 
 
+# After an optimizer step every weight image is stale: 2 packs per unit and step (forward and dgrad layout), ~10 us kernels that
+# sat between the convolutions on the compute stream (44 launches = 0.45 ms of the CAE step, 1.2 %).  Only the first unit of a
+# pass needs its image at once: the others — and every dgrad image — are packed on a side stream while that unit's BatchNorm
+# statistics and convolution run.
+PREPACK_AHEAD = True
+_pack_streams = {}
+
+
+def _prepack_ahead(plan, x, track):
+    """Launch the stale packs of `plan` (all but unit 0's forward image) on the pack stream.  Returns (event after the forward
+    images, event after the dgrad images); None where nothing was launched."""
+    units = plan.units
+    if not (PREPACK_AHEAD and x.is_cuda):
+        return None, None
+    N, size = x.shape[0], tuple(x.shape[2:])
+    fwd, bwd = [], []
+    for i, u in enumerate(units):
+        d = u.desc(N, size)
+        fw = 1 if u.transposed else 0
+        if i > 0 and not u.has_pack(d, fw):
+            fwd.append((u, d, fw))
+        if track and not u.has_pack(d, 1 - fw):
+            bwd.append((u, d, 1 - fw))
+        size = u.out_size(size)
+    if not fwd and not bwd:
+        return None, None
+    main = torch.cuda.current_stream(x.device)
+    side = _pack_streams.get(x.device)
+    if side is None:
+        side = _pack_streams[x.device] = torch.cuda.Stream(x.device)
+    side.wait_stream(main)       # the optimizer step that changed the weights is ahead of us on the compute stream
+    ev_f = ev_b = None
+    with torch.cuda.stream(side):
+        for u, d, w in fwd:
+            u.packed(d, w)
+        if fwd:
+            ev_f = torch.cuda.Event()
+            ev_f.record(side)
+        for u, d, w in bwd:
+            u.packed(d, w)
+        if bwd:
+            ev_b = torch.cuda.Event()
+            ev_b.record(side)
+    return ev_f, ev_b
+
+
 def seq_forward(plan, x, G=1, track=False):
     """x: NDHWC volume with N = G * B.  Returns (y, SeqSaved).  track: a backward pass will follow (counted for the
     plan_backward_hooks)."""
@@ -281,7 +337,12 @@ def seq_forward(plan, x, G=1, track=False):
     saved = SeqSaved()
     saved.G = G
     saved.acts.append(x)
-    for u in plan.units:
+    ev_fwd, ev_bwd = _prepack_ahead(plan, x, track)
+    if ev_bwd is not None:
+        plan.pack_event = ev_bwd
+    for iu, u in enumerate(plan.units):
+        if iu == 1 and ev_fwd is not None:
+            torch.cuda.current_stream(x.device).wait_event(ev_fwd)
         N, C, D, H, W = x.shape
         if C != u.cin:
             raise RuntimeError("channel mismatch: unit expects %d, got %d" % (u.cin, C))
@@ -329,6 +390,11 @@ def _seq_backward_impl(plan, saved, gy, need_input_grad, want):
     grads = {}
     units = plan.units
     last = units[-1]
+    # the dgrad images may have been launched on the pack stream by ANY forward pass of this plan (a later pass of the same step finds
+    # them in the cache and launches nothing): wait for the plan's latest pack event — a no-op once it has completed
+    ev = getattr(plan, 'pack_event', None)
+    if ev is not None and gy.is_cuda:
+        torch.cuda.current_stream(gy.device).wait_event(ev)
     # gradient w.r.t. the last conv output: gy * act'(y)
     def colsum_for(unit, like):
         """fp64 scratch for the bias gradient of `unit`, filled by the kernel that writes its output gradient."""
