@@ -153,6 +153,13 @@ int sp_bn_act_bwd_apply(const float* gxh, int ldg, const float* x, int ldx, cons
 /* colsum (optional, C doubles): receives the per-channel column sums of the values written to `out`, i.e. the bias
  * gradient of the convolution whose output gradient `out` is; sp_bias_from_colsum turns it into db = beta*db + colsum */
 int sp_bias_from_colsum(const double* colsum, int C, float* db, float beta, void* stream);
+/* BatchNorm parameter gradients of a network's FIRST unit (BatchNorm3d on the data -> Conv3d without padding: Unet3D.py:16-18
+ * block1, whose input needs no gradient, Learner.py:121) from the weight gradient instead of a dgrad + reduction:
+ * dw_hat = sp_wgrad taken with scale = invstd, shift = -mean*invstd (the normalised input), colsum = the fp64 bias gradient;
+ *   dgamma[ci] = beta_acc*dgamma + sum_{co,tap} w*dw_hat,  dbeta[ci] = beta_acc*dbeta + sum_{co,tap} w*colsum[co],
+ *   dw = beta_dw*dw + gamma[ci]*dw_hat + beta[ci]*colsum[co].   w, dw_hat, dw: torch layout [Co][Ci][k3]. */
+int sp_bn_grads_from_wgrad(const float* w, const float* dw_hat, const double* colsum, const float* gamma, const float* beta, int Co,
+                           int Ci, int k3, float* dw, float beta_dw, float* dgamma, float* dbeta, float beta_acc, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Resampling ops of the U-Net (Unet3D.py:39,41 MaxPool3d(2,2); :44,46 Upsample(x2, trilinear); :6-11,66-67,71-72

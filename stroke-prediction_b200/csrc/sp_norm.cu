@@ -314,6 +314,44 @@ bn_act_bwd_apply_vec_kernel(const float* __restrict__ gxh, int ldg, const float*
     }
 }
 
+// BatchNorm parameter gradients of a network's FIRST unit without its dgrad.  The input of that unit is data, so the gradient with
+// respect to the BN output (a full transposed correlation, 0.91 ms of the U-Net step, plus its reduction pass) is only needed for
+//   dgamma[ci] = sum_u dXbn[ci,u] * xhat[ci,u],   dbeta[ci] = sum_u dXbn[ci,u].
+// For a convolution without padding every tap of every output voxel reads a real input voxel, so with dXbn = corrT(dZ, W)
+//   dgamma[ci] = sum_{co,tap} W[co,ci,tap] * dWhat[co,ci,tap],   dWhat = sum_v dZ[co,v] * xhat[ci,v+tap]   (the weight gradient taken
+//                                                                against the NORMALISED input: scale = invstd, shift = -mean*invstd)
+//   dbeta[ci]  = sum_{co,tap} W[co,ci,tap] * S[co],              S[co] = sum_v dZ[co,v]                     (the bias gradient, fp64)
+// and the layer's own weight gradient follows from xbn = gamma * xhat + beta:  dW = gamma[ci] * dWhat + beta[ci] * S[co].
+// The sums run over all statistics groups at once (gamma / beta are shared, mean / invstd enter through dWhat).  One block per ci.
+__global__ void __launch_bounds__(128)
+bn_grads_from_wgrad_kernel(const float* __restrict__ W, const float* __restrict__ dWhat, const double* __restrict__ colsum,
+                           const float* __restrict__ gamma, const float* __restrict__ beta, int Co, int Ci, int k3,
+                           float* __restrict__ dW, float beta_dw, float* __restrict__ dgamma, float* __restrict__ dbeta, float beta_acc) {
+    __shared__ double sm[2][4];
+    const int ci = blockIdx.x;
+    const double gm = (double)gamma[ci], bt = (double)beta[ci];
+    double sg = 0.0, sb = 0.0;
+    for (int i = threadIdx.x; i < Co * k3; i += blockDim.x) {
+        const int co = i / k3, tap = i - co * k3;
+        const int64_t idx = ((int64_t)co * Ci + ci) * k3 + tap;
+        const double w = (double)W[idx], dh = (double)dWhat[idx], cs = colsum[co];
+        sg = fma(w, dh, sg);
+        sb = fma(w, cs, sb);
+        const float v = (float)(gm * dh + bt * cs);
+        dW[idx] = (beta_dw == 0.f) ? v : fmaf(beta_dw, dW[idx], v);
+    }
+    sg = sp_warp_sum(sg);
+    sb = sp_warp_sum(sb);
+    if ((threadIdx.x & 31) == 0) { sm[0][threadIdx.x >> 5] = sg; sm[1][threadIdx.x >> 5] = sb; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const float dg = (float)(sm[0][0] + sm[0][1] + sm[0][2] + sm[0][3]);
+        const float db = (float)(sm[1][0] + sm[1][1] + sm[1][2] + sm[1][3]);
+        if (dgamma) dgamma[ci] = (beta_acc == 0.f) ? dg : fmaf(beta_acc, dgamma[ci], dg);
+        if (dbeta) dbeta[ci] = (beta_acc == 0.f) ? db : fmaf(beta_acc, dbeta[ci], db);
+    }
+}
+
 __global__ void colsum_to_bias_kernel(const double* __restrict__ acc, int C, float* __restrict__ db, float beta) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c < C) db[c] = (beta == 0.f) ? (float)acc[c] : fmaf(beta, db[c], (float)acc[c]);
@@ -450,6 +488,16 @@ int sp_bias_from_colsum(const double* colsum, int C, float* db, float beta, void
     SP_REQUIRE(colsum && db && C > 0, "sp_bias_from_colsum: bad arguments");
     colsum_to_bias_kernel<<<(C + 255) / 256, 256, 0, sp_stream(stream)>>>(colsum, C, db, beta);
     SP_LAUNCH_OK("colsum_to_bias_kernel");
+    return 0;
+}
+
+int sp_bn_grads_from_wgrad(const float* w, const float* dw_hat, const double* colsum, const float* gamma, const float* beta, int Co,
+                           int Ci, int k3, float* dw, float beta_dw, float* dgamma, float* dbeta, float beta_acc, void* stream) {
+    SP_REQUIRE(w && dw_hat && colsum && gamma && beta && dw, "sp_bn_grads_from_wgrad: NULL pointer");
+    SP_REQUIRE(Co > 0 && Ci > 0 && k3 > 0, "sp_bn_grads_from_wgrad: bad extents %d %d %d", Co, Ci, k3);
+    bn_grads_from_wgrad_kernel<<<Ci, 128, 0, sp_stream(stream)>>>(w, dw_hat, colsum, gamma, beta, Co, Ci, k3, dw, beta_dw, dgamma, dbeta,
+                                                                   beta_acc);
+    SP_LAUNCH_OK("bn_grads_from_wgrad_kernel");
     return 0;
 }
 

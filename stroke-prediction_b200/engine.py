@@ -383,6 +383,41 @@ def seq_backward(plan, saved, gy, need_input_grad, want):
     return out
 
 
+# First unit of a network (BatchNorm3d on the data -> Conv3d without padding, e.g. Unet3D.py:16-18 block1): the input needs no
+# gradient, and the BatchNorm parameter gradients follow from the weight gradient taken against the normalised input
+# (include/stroke_b200.h: sp_bn_grads_from_wgrad) — no transposed correlation, no reduction pass over its result.
+FIRST_UNIT_SHORTCUT = True
+
+
+def _first_unit_shortcut(u, bnrec, x, gz, gz_colsum, d, G, want, grads):
+    """Weight / bias / BatchNorm gradients of unit 0 without its dgrad.  Returns False when the unit does not qualify."""
+    conv, bn = u.conv, u.bn
+    if not (FIRST_UNIT_SHORTCUT and bnrec is not None and bn is not None and bn.affine and not u.transposed
+            and tuple(u.pad) == (0, 0, 0) and gz_colsum is not None and conv.weight.is_contiguous()
+            and want(conv.weight) and conv.bias is not None and want(conv.bias) and (want(bn.weight) or want(bn.bias))):
+        return False
+    mean, invstd = bnrec[2], bnrec[3]
+    nshift = torch.mul(mean, invstd).neg_()
+    dwh = torch.empty_like(conv.weight, memory_format=torch.contiguous_format)
+    ops.wgrad(d, x, invstd, nshift, gz, None, None, G, dwh, 0.0)          # sum_v dZ[co, v] * xhat[ci, v + tap]
+    dw, beta_dw = _sink_view(conv.weight), 1.0
+    if dw is None:
+        dw, beta_dw = torch.empty_like(conv.weight, memory_format=torch.contiguous_format), 0.0
+        grads[conv.weight] = dw
+    dgamma, dbeta, beta_acc = _sink_view(bn.weight), _sink_view(bn.bias), 1.0
+    if dgamma is None or dbeta is None:
+        dgamma, dbeta, beta_acc = torch.empty_like(bn.weight), torch.empty_like(bn.bias), 0.0
+        grads[bn.weight], grads[bn.bias] = dgamma, dbeta
+    ops.bn_grads_from_wgrad(conv.weight.detach(), dwh, gz_colsum, bn.weight.detach(), bn.bias.detach(), dw, beta_dw, dgamma, dbeta,
+                            beta_acc)
+    db, beta = _sink_view(conv.bias), 1.0
+    if db is None:
+        db, beta = torch.empty_like(conv.bias), 0.0
+        grads[conv.bias] = db
+    ops.bias_from_colsum(gz_colsum, db, beta)
+    return True
+
+
 def _seq_backward_impl(plan, saved, gy, need_input_grad, want):
     """gy: gradient w.r.t. the chain output (post-activation).  `want(param)` tells whether a parameter gradient is
     needed.  Returns (gx or None, {param: grad})."""
@@ -420,6 +455,8 @@ def _seq_backward_impl(plan, saved, gy, need_input_grad, want):
             scale, shift = bnrec[0], bnrec[1]
         d = u.desc(N, (D, H, W), ACT_NONE, 0.0)
         conv = u.conv
+        if i == 0 and not need_input_grad and _first_unit_shortcut(u, bnrec, x, gz, gz_colsum, d, G, want, grads):
+            break
         # ---- parameter gradients
         if want(conv.weight):
             dw, beta = _sink_view(conv.weight), 1.0

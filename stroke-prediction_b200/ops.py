@@ -310,6 +310,17 @@ def bias_from_colsum(colsum, db, beta=0.0):
     return db
 
 
+def bn_grads_from_wgrad(w, dw_hat, colsum, gamma, beta, dw, beta_dw, dgamma, dbeta, beta_acc):
+    """First-unit shortcut (include/stroke_b200.h): BN parameter gradients and dW from the weight gradient against the normalised
+    input; w / dw_hat / dw in torch layout (Co, Ci, k, k, k)."""
+    _req_cuda(w, dw_hat, colsum, dw)
+    assert w.is_contiguous() and dw_hat.is_contiguous() and dw.is_contiguous() and colsum.dtype == torch.float64
+    Co, Ci = w.shape[0], w.shape[1]
+    k3 = w.numel() // (Co * Ci)
+    check(_L().sp_bn_grads_from_wgrad(_p(w), _p(dw_hat), _p(colsum), _p(gamma), _p(beta), Co, Ci, k3, _p(dw), beta_dw,
+                                      _p(dgamma), _p(dbeta), beta_acc, _stream()), "sp_bn_grads_from_wgrad")
+
+
 # ---------------------------------------------------------------------------------------------------- resampling
 def maxpool2_fwd(x):
     N, C, D, H, W = x.shape

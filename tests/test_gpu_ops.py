@@ -456,6 +456,27 @@ def test_raw_perfusion_statistics_do_not_cancel():
     _check_sequential(seq, x, check_input_grad=False)
 
 
+@pytest.mark.parametrize("cin,size,training", [(2, (12, 40, 44), True), (1, (6, 12, 14), True), (3, (10, 20, 36), True),
+                                               (2, (8, 14, 16), False)])
+def test_first_unit_bn_gradients_from_the_weight_gradient(cin, size, training):
+    """First unit of a network (Unet3D.py:16-18 block1: BatchNorm3d on the data -> Conv3d without padding): no input gradient is
+    needed, so dgamma / dbeta / dW come from the weight gradient against the normalised input (sp_bn_grads_from_wgrad) instead
+    of a dgrad + reduction.  Same bars as the dgrad path, which is run next to it; G = 2 statistics groups, data with a mean far
+    from zero (raw CBV / TTD), tcgen05 (2 channels, large planes) and FFMA weight-gradient tiers."""
+    engine, _, _ = _mods()
+    torch.manual_seed(77 + cin)
+    seq = nn.Sequential(nn.BatchNorm3d(cin), nn.Conv3d(cin, 16, 3), nn.LeakyReLU(0.01, True),
+                        nn.BatchNorm3d(16), nn.Conv3d(16, 16, 3), nn.LeakyReLU(0.01, True))
+    x = torch.randn(4, cin, *size) * 3.0 + 5.0
+    assert engine.FIRST_UNIT_SHORTCUT
+    _check_sequential(copy.deepcopy(seq), x, training=training, G=2, check_input_grad=False)
+    engine.FIRST_UNIT_SHORTCUT = False
+    try:
+        _check_sequential(copy.deepcopy(seq), x, training=training, G=2, check_input_grad=False)
+    finally:
+        engine.FIRST_UNIT_SHORTCUT = True
+
+
 # ---------------------------------------------------------------------------------------------------- resampling
 @pytest.mark.parametrize("size", [(4, 6, 8), (5, 7, 9), (2, 2, 2)])
 @pytest.mark.parametrize("C", [5, 8])            # 8: the 128-bit kernels
