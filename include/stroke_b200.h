@@ -157,9 +157,18 @@ int sp_bias_from_colsum(const double* colsum, int C, float* db, float beta, void
  * block1, whose input needs no gradient, Learner.py:121) from the weight gradient instead of a dgrad + reduction:
  * dw_hat = sp_wgrad taken with scale = invstd, shift = -mean*invstd (the normalised input), colsum = the fp64 bias gradient;
  *   dgamma[ci] = beta_acc*dgamma + sum_{co,tap} w*dw_hat,  dbeta[ci] = beta_acc*dbeta + sum_{co,tap} w*colsum[co],
- *   dw = beta_dw*dw + gamma[ci]*dw_hat + beta[ci]*colsum[co].   w, dw_hat, dw: torch layout [Co][Ci][k3]. */
-int sp_bn_grads_from_wgrad(const float* w, const float* dw_hat, const double* colsum, const float* gamma, const float* beta, int Co,
-                           int Ci, int k3, float* dw, float beta_dw, float* dgamma, float* dbeta, float beta_acc, void* stream);
+ *   dw = beta_dw*dw + gamma[ci]*dw_hat + beta[ci]*colsum[co].   w, dw_hat, dw: torch layout [Co][Ci][k3].
+ * tap_excl (optional, [Co][k3] doubles): with zero padding (applied after BatchNorm, Cae3D.py:40-41) colsum[co] is replaced by
+ * colsum[co] - tap_excl[co][tap], the sum over the output voxels whose tap reads a real input voxel. */
+int sp_bn_grads_from_wgrad(const float* w, const float* dw_hat, const double* colsum, const double* tap_excl, const float* gamma,
+                           const float* beta, int Co, int Ci, int k3, float* dw, float beta_dw, float* dgamma, float* dbeta,
+                           float beta_acc, void* stream);
+/* excl[co][tap] = sum of gz[co, v] over the output voxels v (N x Do x Ho x Wo, channel stride ldz) of a 3x3x3 stride-1 convolution
+ * with padding (pd, ph, pw) in 0..2 whose tap (kd, kh, kw) reads zero padding; only border voxels are read.  `excl` must hold
+ * SP_TAP_EXCL_REPLICAS * Co * 27 doubles (scratch copies that spread the atomics); the result is its first Co * 27 entries. */
+#define SP_TAP_EXCL_REPLICAS 16
+int sp_border_tap_sums(const float* gz, int ldz, int N, int Do, int Ho, int Wo, int Co, int pd, int ph, int pw, double* excl,
+                       void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Resampling ops of the U-Net (Unet3D.py:39,41 MaxPool3d(2,2); :44,46 Upsample(x2, trilinear); :6-11,66-67,71-72

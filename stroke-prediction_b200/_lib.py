@@ -70,8 +70,9 @@ SIGNATURES = {
     "sp_bn_act_bwd_apply": (c_int, [c_vp, c_int, c_vp, c_int, c_vp, c_int, c_i64, c_int, c_int, c_int, c_float,
                                     c_vp, c_int, c_int, c_vp, c_vp]),
     "sp_bias_from_colsum": (c_int, [c_vp, c_int, c_vp, c_float, c_vp]),
-    "sp_bn_grads_from_wgrad": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_vp, c_float, c_vp, c_vp, c_float,
+    "sp_bn_grads_from_wgrad": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_vp, c_float, c_vp, c_vp, c_float,
                                        c_vp]),
+    "sp_border_tap_sums": (c_int, [c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp]),
     "sp_maxpool2_fwd": (c_int, [c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_int, c_vp]),
     "sp_maxpool2_bwd": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp]),
     "sp_upsample2_fwd": (c_int, [c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_int, c_int, c_vp]),

@@ -322,10 +322,12 @@ bn_act_bwd_apply_vec_kernel(const float* __restrict__ gxh, int ldg, const float*
 //                                                                against the NORMALISED input: scale = invstd, shift = -mean*invstd)
 //   dbeta[ci]  = sum_{co,tap} W[co,ci,tap] * S[co],              S[co] = sum_v dZ[co,v]                     (the bias gradient, fp64)
 // and the layer's own weight gradient follows from xbn = gamma * xhat + beta:  dW = gamma[ci] * dWhat + beta[ci] * S[co].
+// With zero padding (applied AFTER BatchNorm, Cae3D.py:40-41) a tap of a border voxel may read padding: S becomes per tap,
+// S[co,tap] = S[co] - E[co,tap] with E = the sum of dZ over the output voxels whose tap falls outside (border_tap_sums_kernel).
 // The sums run over all statistics groups at once (gamma / beta are shared, mean / invstd enter through dWhat).  One block per ci.
 __global__ void __launch_bounds__(128)
 bn_grads_from_wgrad_kernel(const float* __restrict__ W, const float* __restrict__ dWhat, const double* __restrict__ colsum,
-                           const float* __restrict__ gamma, const float* __restrict__ beta, int Co, int Ci, int k3,
+                           const double* __restrict__ tap_excl, const float* __restrict__ gamma, const float* __restrict__ beta, int Co, int Ci, int k3,
                            float* __restrict__ dW, float beta_dw, float* __restrict__ dgamma, float* __restrict__ dbeta, float beta_acc) {
     __shared__ double sm[2][4];
     const int ci = blockIdx.x;
@@ -334,7 +336,8 @@ bn_grads_from_wgrad_kernel(const float* __restrict__ W, const float* __restrict_
     for (int i = threadIdx.x; i < Co * k3; i += blockDim.x) {
         const int co = i / k3, tap = i - co * k3;
         const int64_t idx = ((int64_t)co * Ci + ci) * k3 + tap;
-        const double w = (double)W[idx], dh = (double)dWhat[idx], cs = colsum[co];
+        const double w = (double)W[idx], dh = (double)dWhat[idx];
+        const double cs = colsum[co] - (tap_excl ? tap_excl[co * k3 + tap] : 0.0);      // S[co, tap]: the voxels whose tap reads a real input
         sg = fma(w, dh, sg);
         sb = fma(w, cs, sb);
         const float v = (float)(gm * dh + bt * cs);
@@ -350,6 +353,78 @@ bn_grads_from_wgrad_kernel(const float* __restrict__ W, const float* __restrict_
         if (dgamma) dgamma[ci] = (beta_acc == 0.f) ? dg : fmaf(beta_acc, dgamma[ci], dg);
         if (dbeta) dbeta[ci] = (beta_acc == 0.f) ? db : fmaf(beta_acc, dbeta[ci], db);
     }
+}
+
+// E[co][tap] = sum of gz[co, v] over the output voxels v of a 3x3x3 stride-1 convolution whose tap (kd, kh, kw) reads zero padding
+// (input coordinate o + k - p outside [0, I)).  Only border voxels contribute: a block walks (n, od, oh) rows and reads whole rows
+// on the d / h borders, the first / last pw voxels otherwise.  Thread = (output channel, w lane); 27 fp64 accumulators per thread.
+__global__ void __launch_bounds__(256)
+border_tap_sums_kernel(const float* __restrict__ gz, int ldz, int N, int Do, int Ho, int Wo, int Co, int CoP2, int pd, int ph, int pw,
+                       int Di, int Hi, int Wi, double* __restrict__ E) {
+    __shared__ double sm[256];
+    const int co = threadIdx.x % CoP2, wl = threadIdx.x / CoP2, lanes = 256 / CoP2;
+    double acc[27];
+#pragma unroll
+    for (int t = 0; t < 27; ++t) acc[t] = 0.0;
+    const int64_t rows = (int64_t)N * Do * Ho;
+    for (int64_t r = blockIdx.x; r < rows; r += gridDim.x) {
+        const int oh = (int)(r % Ho), od = (int)((r / Ho) % Do);
+        unsigned md = 0, mh = 0;                                  // bit k: tap k of this axis reads padding
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            if (od + k - pd < 0 || od + k - pd >= Di) md |= 1u << k;
+            if (oh + k - ph < 0 || oh + k - ph >= Hi) mh |= 1u << k;
+        }
+        const bool whole = (md | mh) != 0u || 2 * pw >= Wo;
+        if (!whole && pw == 0) continue;
+        const float* rowp = gz + r * (int64_t)Wo * ldz;
+        const int cnt = whole ? Wo : 2 * pw;
+        constexpr int U = 8;                                      // loads in flight per thread (the kernel is pure load latency)
+        for (int j0 = wl; j0 < cnt; j0 += U * lanes) {
+            float v[U];
+            unsigned m[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int j = j0 + u * lanes;
+                const int ow = whole ? j : (j < pw ? j : Wo - 2 * pw + j);
+                unsigned mw = 0;
+#pragma unroll
+                for (int k = 0; k < 3; ++k)
+                    if (ow + k - pw < 0 || ow + k - pw >= Wi) mw |= 1u << k;
+                const bool live = j < cnt && co < Co && (md | mh | mw) != 0u;
+                m[u] = live ? mw : 0xffffffffu;
+                v[u] = live ? __ldg(rowp + (int64_t)ow * ldz + co) : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (m[u] == 0xffffffffu) continue;
+                const double dv = (double)v[u];
+#pragma unroll
+                for (int t = 0; t < 27; ++t)
+                    if (((md >> (t / 9)) | (mh >> ((t / 3) % 3)) | (m[u] >> (t % 3))) & 1u) acc[t] += dv;
+            }
+        }
+    }
+#pragma unroll                   // (static indices: acc stays in registers)
+    for (int t = 0; t < 27; ++t) {
+        sm[threadIdx.x] = acc[t];
+        __syncthreads();
+        if (wl == 0 && co < Co) {
+            double sum = 0.0;
+            for (int l = 0; l < lanes; ++l) sum += sm[l * CoP2 + co];
+            // same-address fp64 atomics serialise (~0.2 us each): the blocks are spread over SP_TAP_EXCL_REPLICAS copies of E
+            if (sum != 0.0) atomicAdd(&E[(size_t)(blockIdx.x % SP_TAP_EXCL_REPLICAS) * 27 * Co + co * 27 + t], sum);
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void fold_replicas_kernel(double* __restrict__ E, int n, int replicas) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double s = E[i];
+    for (int k = 1; k < replicas; ++k) s += E[(size_t)k * n + i];
+    E[i] = s;
 }
 
 __global__ void colsum_to_bias_kernel(const double* __restrict__ acc, int C, float* __restrict__ db, float beta) {
@@ -491,13 +566,34 @@ int sp_bias_from_colsum(const double* colsum, int C, float* db, float beta, void
     return 0;
 }
 
-int sp_bn_grads_from_wgrad(const float* w, const float* dw_hat, const double* colsum, const float* gamma, const float* beta, int Co,
-                           int Ci, int k3, float* dw, float beta_dw, float* dgamma, float* dbeta, float beta_acc, void* stream) {
+int sp_bn_grads_from_wgrad(const float* w, const float* dw_hat, const double* colsum, const double* tap_excl, const float* gamma,
+                           const float* beta, int Co, int Ci, int k3, float* dw, float beta_dw, float* dgamma, float* dbeta,
+                           float beta_acc, void* stream) {
     SP_REQUIRE(w && dw_hat && colsum && gamma && beta && dw, "sp_bn_grads_from_wgrad: NULL pointer");
     SP_REQUIRE(Co > 0 && Ci > 0 && k3 > 0, "sp_bn_grads_from_wgrad: bad extents %d %d %d", Co, Ci, k3);
-    bn_grads_from_wgrad_kernel<<<Ci, 128, 0, sp_stream(stream)>>>(w, dw_hat, colsum, gamma, beta, Co, Ci, k3, dw, beta_dw, dgamma, dbeta,
-                                                                   beta_acc);
+    bn_grads_from_wgrad_kernel<<<Ci, 128, 0, sp_stream(stream)>>>(w, dw_hat, colsum, tap_excl, gamma, beta, Co, Ci, k3, dw, beta_dw,
+                                                                   dgamma, dbeta, beta_acc);
     SP_LAUNCH_OK("bn_grads_from_wgrad_kernel");
+    return 0;
+}
+
+int sp_border_tap_sums(const float* gz, int ldz, int N, int Do, int Ho, int Wo, int Co, int pd, int ph, int pw, double* excl,
+                       void* stream) {
+    SP_REQUIRE(gz && excl, "sp_border_tap_sums: NULL pointer");
+    SP_REQUIRE(N > 0 && Do > 0 && Ho > 0 && Wo > 0 && Co > 0 && Co <= 256 && ldz >= Co, "sp_border_tap_sums: bad shape");
+    SP_REQUIRE(pd >= 0 && pd <= 2 && ph >= 0 && ph <= 2 && pw >= 0 && pw <= 2, "sp_border_tap_sums: padding must be 0..2 (3x3x3, stride 1)");
+    SP_CUDA(cudaMemsetAsync(excl, 0, sizeof(double) * 27 * Co * SP_TAP_EXCL_REPLICAS, sp_stream(stream)));
+    if (pd == 0 && ph == 0 && pw == 0) return 0;
+    int CoP2 = 1;
+    while (CoP2 < Co) CoP2 *= 2;
+    const int64_t rows = (int64_t)N * Do * Ho;
+    int64_t blocks = (int64_t)sp_num_sms() * 4;
+    if (blocks > rows) blocks = rows;
+    border_tap_sums_kernel<<<(int)blocks, 256, 0, sp_stream(stream)>>>(gz, ldz, N, Do, Ho, Wo, Co, CoP2, pd, ph, pw, Do + 2 - 2 * pd,
+                                                                        Ho + 2 - 2 * ph, Wo + 2 - 2 * pw, excl);
+    SP_LAUNCH_OK("border_tap_sums_kernel");
+    fold_replicas_kernel<<<(27 * Co + 127) / 128, 128, 0, sp_stream(stream)>>>(excl, 27 * Co, SP_TAP_EXCL_REPLICAS);
+    SP_LAUNCH_OK("fold_replicas_kernel");
     return 0;
 }
 

@@ -392,8 +392,10 @@ FIRST_UNIT_SHORTCUT = True
 def _first_unit_shortcut(u, bnrec, x, gz, gz_colsum, d, G, want, grads):
     """Weight / bias / BatchNorm gradients of unit 0 without its dgrad.  Returns False when the unit does not qualify."""
     conv, bn = u.conv, u.bn
+    padded = max(u.pad)
     if not (FIRST_UNIT_SHORTCUT and bnrec is not None and bn is not None and bn.affine and not u.transposed
-            and tuple(u.pad) == (0, 0, 0) and gz_colsum is not None and conv.weight.is_contiguous()
+            and (padded == 0 or (u.k == 3 and u.s == 1 and padded <= 2 and min(u.pad) >= 0)) and gz_colsum is not None
+            and conv.weight.is_contiguous()
             and want(conv.weight) and conv.bias is not None and want(conv.bias) and (want(bn.weight) or want(bn.bias))):
         return False
     mean, invstd = bnrec[2], bnrec[3]
@@ -408,8 +410,10 @@ def _first_unit_shortcut(u, bnrec, x, gz, gz_colsum, d, G, want, grads):
     if dgamma is None or dbeta is None:
         dgamma, dbeta, beta_acc = torch.empty_like(bn.weight), torch.empty_like(bn.bias), 0.0
         grads[bn.weight], grads[bn.bias] = dgamma, dbeta
-    ops.bn_grads_from_wgrad(conv.weight.detach(), dwh, gz_colsum, bn.weight.detach(), bn.bias.detach(), dw, beta_dw, dgamma, dbeta,
-                            beta_acc)
+    # zero padding is applied after BatchNorm (Cae3D.py:40-41): taps of border voxels that read it see neither xhat nor beta
+    excl = ops.border_tap_sums(gz, u.pad) if padded > 0 else None
+    ops.bn_grads_from_wgrad(conv.weight.detach(), dwh, gz_colsum, excl, bn.weight.detach(), bn.bias.detach(), dw, beta_dw, dgamma,
+                            dbeta, beta_acc)
     db, beta = _sink_view(conv.bias), 1.0
     if db is None:
         db, beta = torch.empty_like(conv.bias), 0.0

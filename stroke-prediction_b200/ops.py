@@ -24,6 +24,7 @@ _KERNELS_PER_CALL = {
     "sp_dice_bwd": 1, "sp_absdiff_mean": 2, "sp_absdiff_bwd": 1, "sp_binary_counts": 1, "sp_latent_interp_fwd": 1,
     "sp_latent_interp_bwd": 1, "sp_adam_multi": 1, "sp_surface_distances": 13, "sp_signed_distance": 11,
     "sp_gauss3d": 3, "sp_elastic_warp": 1, "sp_zoom_plane_xy": 1, "sp_flip_w": 1, "sp_pad_volume": 1,
+    "sp_bias_from_colsum": 1, "sp_bn_grads_from_wgrad": 1, "sp_border_tap_sums": 2,
 }
 
 
@@ -310,14 +311,30 @@ def bias_from_colsum(colsum, db, beta=0.0):
     return db
 
 
-def bn_grads_from_wgrad(w, dw_hat, colsum, gamma, beta, dw, beta_dw, dgamma, dbeta, beta_acc):
+TAP_EXCL_REPLICAS = 16      # SP_TAP_EXCL_REPLICAS of include/stroke_b200.h
+
+
+def border_tap_sums(gz, pad):
+    """[Co, 27] fp64: per tap of a 3x3x3 stride-1 convolution with padding `pad`, the sum of gz over the output voxels whose tap
+    reads zero padding (include/stroke_b200.h)."""
+    _req_cuda(gz)
+    assert is_ndhwc(gz)
+    N, C, D, H, W = gz.shape
+    excl = torch.empty((TAP_EXCL_REPLICAS, C, 27), device=gz.device, dtype=torch.float64)
+    check(_L().sp_border_tap_sums(_p(gz), C, N, D, H, W, C, int(pad[0]), int(pad[1]), int(pad[2]), _p(excl), _stream()),
+          "sp_border_tap_sums")
+    return excl[0]
+
+
+def bn_grads_from_wgrad(w, dw_hat, colsum, tap_excl, gamma, beta, dw, beta_dw, dgamma, dbeta, beta_acc):
     """First-unit shortcut (include/stroke_b200.h): BN parameter gradients and dW from the weight gradient against the normalised
     input; w / dw_hat / dw in torch layout (Co, Ci, k, k, k)."""
-    _req_cuda(w, dw_hat, colsum, dw)
+    _req_cuda(w, dw_hat, colsum, dw, tap_excl)
     assert w.is_contiguous() and dw_hat.is_contiguous() and dw.is_contiguous() and colsum.dtype == torch.float64
     Co, Ci = w.shape[0], w.shape[1]
     k3 = w.numel() // (Co * Ci)
-    check(_L().sp_bn_grads_from_wgrad(_p(w), _p(dw_hat), _p(colsum), _p(gamma), _p(beta), Co, Ci, k3, _p(dw), beta_dw,
+    assert tap_excl is None or (tap_excl.dtype == torch.float64 and tuple(tap_excl.shape) == (Co, k3))
+    check(_L().sp_bn_grads_from_wgrad(_p(w), _p(dw_hat), _p(colsum), _p(tap_excl), _p(gamma), _p(beta), Co, Ci, k3, _p(dw), beta_dw,
                                       _p(dgamma), _p(dbeta), beta_acc, _stream()), "sp_bn_grads_from_wgrad")
 
 

@@ -456,17 +456,21 @@ def test_raw_perfusion_statistics_do_not_cancel():
     _check_sequential(seq, x, check_input_grad=False)
 
 
-@pytest.mark.parametrize("cin,size,training", [(2, (12, 40, 44), True), (1, (6, 12, 14), True), (3, (10, 20, 36), True),
-                                               (2, (8, 14, 16), False)])
-def test_first_unit_bn_gradients_from_the_weight_gradient(cin, size, training):
+@pytest.mark.parametrize("cin,size,training,pad", [
+    (2, (12, 40, 44), True, 0),                 # Unet3D.py:16-18 block1 (tcgen05 weight gradient on 2 channels)
+    (1, (6, 12, 14), True, 0), (3, (10, 20, 36), True, 0), (2, (8, 14, 16), False, 0),
+    (1, (9, 30, 34), True, (1, 0, 0)),          # Cae3D.py:40-41: depth padded after BatchNorm -> per-tap border sums
+    (2, (8, 14, 16), True, (1, 1, 1)), (1, (6, 9, 11), True, (1, 2, 2)), (3, (3, 1, 5), True, (1, 1, 2)),
+    (1, (8, 14, 16), False, (1, 0, 0))])
+def test_first_unit_bn_gradients_from_the_weight_gradient(cin, size, training, pad):
     """First unit of a network (Unet3D.py:16-18 block1: BatchNorm3d on the data -> Conv3d without padding): no input gradient is
     needed, so dgamma / dbeta / dW come from the weight gradient against the normalised input (sp_bn_grads_from_wgrad) instead
     of a dgrad + reduction.  Same bars as the dgrad path, which is run next to it; G = 2 statistics groups, data with a mean far
     from zero (raw CBV / TTD), tcgen05 (2 channels, large planes) and FFMA weight-gradient tiers."""
     engine, _, _ = _mods()
     torch.manual_seed(77 + cin)
-    seq = nn.Sequential(nn.BatchNorm3d(cin), nn.Conv3d(cin, 16, 3), nn.LeakyReLU(0.01, True),
-                        nn.BatchNorm3d(16), nn.Conv3d(16, 16, 3), nn.LeakyReLU(0.01, True))
+    seq = nn.Sequential(nn.BatchNorm3d(cin), nn.Conv3d(cin, 16, 3, padding=pad), nn.LeakyReLU(0.01, True),
+                        nn.BatchNorm3d(16), nn.Conv3d(16, 16, 3, padding=1), nn.LeakyReLU(0.01, True))
     x = torch.randn(4, cin, *size) * 3.0 + 5.0
     assert engine.FIRST_UNIT_SHORTCUT
     _check_sequential(copy.deepcopy(seq), x, training=training, G=2, check_input_grad=False)
