@@ -366,9 +366,33 @@ border_tap_sums_kernel(const float* __restrict__ gz, int ldz, int N, int Do, int
     double acc[27];
 #pragma unroll
     for (int t = 0; t < 27; ++t) acc[t] = 0.0;
-    const int64_t rows = (int64_t)N * Do * Ho;
-    for (int64_t r = blockIdx.x; r < rows; r += gridDim.x) {
-        const int oh = (int)(r % Ho), od = (int)((r / Ho) % Do);
+    // Candidate rows only (walking all N*Do*Ho rows cost 0.2 ms of index arithmetic on the CAE's first layer): [A] every row of the
+    // nd planes on the d border, [B] the nh rows on the h border of the other planes, [C] (pw > 0) the remaining rows, of which only
+    // the first / last pw voxels are read.
+    const int nd = (2 * pd < Do) ? 2 * pd : Do, nh = (2 * ph < Ho) ? 2 * ph : Ho;
+    const int perA = nd * Ho, perB = (Do - nd) * nh, perC = (pw > 0) ? (Do - nd) * (Ho - nh) : 0;
+    const int totA = N * perA, totB = N * perB, totC = N * perC;
+    for (int idx = blockIdx.x; idx < totA + totB + totC; idx += gridDim.x) {
+        int n, od, oh;
+        if (idx < totA) {
+            n = idx / perA;
+            const int rem = idx - n * perA, k = rem / Ho;
+            oh = rem - k * Ho;
+            od = (nd == Do || k < pd) ? k : Do - 2 * pd + k;
+        } else if (idx < totA + totB) {
+            const int i = idx - totA;
+            n = i / perB;
+            const int rem = i - n * perB, kd = rem / nh, j = rem - kd * nh;
+            od = pd + kd;
+            oh = (nh == Ho || j < ph) ? j : Ho - 2 * ph + j;
+        } else {
+            const int i = idx - totA - totB, perRow = Ho - nh;
+            n = i / perC;
+            const int rem = i - n * perC, kd = rem / perRow;
+            od = pd + kd;
+            oh = ph + (rem - kd * perRow);
+        }
+        const int64_t r = ((int64_t)n * Do + od) * Ho + oh;
         unsigned md = 0, mh = 0;                                  // bit k: tap k of this axis reads padding
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
@@ -586,6 +610,7 @@ int sp_border_tap_sums(const float* gz, int ldz, int N, int Do, int Ho, int Wo, 
     if (pd == 0 && ph == 0 && pw == 0) return 0;
     int CoP2 = 1;
     while (CoP2 < Co) CoP2 *= 2;
+    SP_REQUIRE((int64_t)N * Do * Ho < (1ll << 31), "sp_border_tap_sums: N * Do * Ho must fit 31 bits");
     const int64_t rows = (int64_t)N * Do * Ho;
     int64_t blocks = (int64_t)sp_num_sms() * 4;
     if (blocks > rows) blocks = rows;
