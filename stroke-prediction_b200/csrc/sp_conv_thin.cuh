@@ -5,7 +5,8 @@
 // wgrad of the CAE's first layer against 0.11 ms of HBM time).  Three specialised kernels:
 //   thin_fwd_kernel<CI>   forward: thread = 4 consecutive w voxels x 16 output channels, scalar input planes in shared memory
 //   thin_bwd_kernel       dgrad (flipped correlation 16 -> Ci channels): thread = 4 voxels x 1 channel, 16-channel halo tile in
-//                         shared memory, weights of one (kd, kh) row in registers
+//                         shared memory, weights of one (kd, kh) row in registers.  (Off the training path when the layer is the first
+//                         unit of a network and its input needs no gradient: sp_bn_grads_from_wgrad)
 //   thin_wgrad_kernel<CI> wgrad: thread = (row of output voxels, output-channel quad, ci) with all 27 taps in registers (108
 //                         accumulators), sliding 3x3x3 input window, O-side quad prefetched one voxel ahead
 #pragma once
